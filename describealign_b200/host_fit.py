@@ -1,0 +1,340 @@
+"""Host stage between the two device stages: the "rate-change fit".
+
+BASELINE.json's north star keeps this part in Python on the host and outside the timed
+window: the continuity filter, the per-feature gain fit, the 70->1 compression of the
+pass-1 path, the L1 linear programme and the grouping of its solution into line clusters
+(reference describealign.py:702-893), plus the two small host pieces of stage B - the
+corridor limits with the optional sub-frame offset refinement (describealign.py:895-930) and
+the node list built from the final path (describealign.py:995-1027).
+
+The arithmetic goes through the same numpy / scipy entry points the reference calls
+(np.convolve, np.linalg.lstsq, np.std, scipy.optimize.linprog with HiGHS) on operands of
+the same dtype and order, because the LP has degenerate optima and anything else would not
+reproduce the reference's segments.  Written from the functional description in
+SURVEY.md appendix A.6/A.7, not from the reference's source text.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+from dataclasses import dataclass
+
+import numpy as np
+import scipy.optimize
+import scipy.signal
+import scipy.sparse
+
+FRAMES_PER_SECOND = 210
+SPN = FRAMES_PER_SECOND // 10          # frames per node (describealign.py:596)
+CORRIDOR_RADIUS = FRAMES_PER_SECOND * 30   # +/- 30 s (describealign.py:863)
+
+FAILED_MSG = "Alignment failed, are the input files mismatched?"
+LP_FAILED_MSG = "Smooth Alignment L1-Min Optimization Failed!"
+
+
+def hann41() -> np.ndarray:
+    """41-tap f64 Hann window, normalised (describealign.py:597-598)."""
+    w = scipy.signal.windows.hann(2 * SPN + 1)[1:-1]
+    return w / np.sum(w)
+
+
+def local_mean(arr, window=None):
+    """describealign.py:599 (`get_mean`)."""
+    window = hann41() if window is None else window
+    return np.convolve(window, arr, mode="same")[:len(arr)]
+
+
+def min_path_length(n_video_energy: int, n_audio_energy: int) -> float:
+    """Shortest acceptable path (describealign.py:698, 991)."""
+    return max(min(n_video_energy, n_audio_energy) / 500.0, 5 * FRAMES_PER_SECOND)
+
+
+def continuity_error(x, y, deriv=False, window=None):
+    """Distance of every path point from a line extrapolated from its smoothed future or
+    past neighbours, whichever is closer (describealign.py:706-724)."""
+    window = hann41() if window is None else window
+    head = window[:SPN - 1]
+    head = head / np.sum(head)
+    half = SPN // 2
+    delay = SPN + half - 2
+
+    def lines(kernel):
+        xs = np.convolve(x, kernel, mode="valid")
+        ys = np.convolve(y, kernel, mode="valid")
+        slope = (ys[half:] - ys[:-half]) / (xs[half:] - xs[:-half])
+        return xs, ys, slope
+
+    xs, ys, slope_f = lines(head)
+    off_f = ys[:-half] - xs[:-half] * slope_f
+    xs, ys, slope_p = lines(head[::-1])
+    off_p = ys[half:] - xs[half:] * slope_p
+    shift = 1 if deriv else 0
+    err = np.full(len(x) - shift, np.inf)
+    k = delay - shift
+    err[:-k] = np.abs(slope_f * x[:-delay] + off_f - y[:-delay])
+    err[k:] = np.minimum(err[k:], np.abs(slope_p * x[delay:] + off_p - y[delay:]))
+    return err
+
+
+def scale_features(video_features, audio_features, x, y):
+    """Least-squares gain per feature, keep the first three, stack as (len, 3) float32
+    (describealign.py:733-741).  x = audio indices, y = video indices of the kept path."""
+    a_cols, v_cols = [], []
+    for v_feat, a_feat in list(zip(video_features, audio_features))[:3]:
+        a_std = np.std(a_feat)
+        gain = np.linalg.lstsq(v_feat[y][:, None], a_feat[x], rcond=None)[0]
+        a_cols.append(a_feat / a_std)
+        v_cols.append(v_feat * gain / a_std)
+    na = min(len(c) for c in a_cols)
+    nv = min(len(c) for c in v_cols)
+    audio_scaled = np.stack([c[:na] for c in a_cols], axis=1)
+    video_scaled = np.stack([c[:nv] for c in v_cols], axis=1)
+    return np.ascontiguousarray(audio_scaled), np.ascontiguousarray(video_scaled)
+
+
+def compress_path(x, y, window=None):
+    """Replace well-behaved runs of 70 path points by their mean point and merge entries
+    that share an audio index (describealign.py:743-767), quirks included."""
+    sx = local_mean(x, window)
+    sy = local_mean(y, window)
+    slope = np.diff(sy) / np.diff(sx)
+    offset = sy[:-1] - sx[:-1] * slope
+    err_y = slope * x[:-1] + offset - y[:-1]
+    cx, cy = list(x[0:10]), list(y[0:10])
+    start = None
+    for start in range(10, len(x) - 80, 70):
+        if np.all(np.abs(err_y[start:start + 70]) < 3):
+            cx.append(np.mean(x[start:start + 70]))
+            cy.append(np.mean(y[start:start + 70]))
+        else:
+            cx.extend(x[start:start + 70])
+            cy.extend(y[start:start + 70])
+    if start is None:
+        raise RuntimeError(FAILED_MSG)
+    # one further fixed slice is kept raw; points after it are dropped (reference quirk)
+    cx.extend(x[start + 70:start + 140])
+    cy.extend(y[start + 70:start + 140])
+    groups = OrderedDict()
+    for xi, yi in zip(cx, cy):
+        groups.setdefault(xi, []).append(yi)
+    ux = np.array(list(groups.keys()))
+    uy = np.array([np.mean(groups[k]) for k in ux])
+    return ux, uy
+
+
+@dataclass
+class RateFit:
+    x: np.ndarray           # fit points, audio frames
+    y: np.ndarray           # fit points, video frames
+    fit_err: np.ndarray
+    slopes: np.ndarray      # per interval, len n-1
+    median_slope: float
+
+
+def _lp_problem(x, y, window=None):
+    n = len(x)
+    dx = np.diff(x)
+    dy = np.diff(y)
+    inv = 1.0 / dx
+    jump_cost = np.full(n - 1, 10.0)
+    jump_cost /= np.maximum(1, np.sqrt(continuity_error(x, y, deriv=True, window=window) / 3.0))
+    cost = np.hstack([np.ones(2 * n), jump_cost, jump_cost,
+                      np.full(n, .01), np.full(n, .01),
+                      np.full(n - 1, 3), np.full(n - 1, 3),
+                      np.full(n - 1, .001), np.full(n - 1, .001),
+                      np.full(n - 2, 10.0 * 4000), np.full(n - 2, 10.0 * 4000), [0, ]])
+    # column offsets of the variable groups
+    c_fe_p, c_fe_m = 0, n
+    c_j_p, c_j_m = 2 * n, 3 * n - 1
+    c_sn_p, c_sn_m = 4 * n - 2, 5 * n - 2
+    c_snj_p, c_snj_m = 6 * n - 2, 7 * n - 3
+    c_rcj_p, c_rcj_m = 8 * n - 4, 9 * n - 5
+    c_rc_p, c_rc_m = 10 * n - 6, 11 * n - 8
+    c_med = 12 * n - 10
+    rows, cols, vals = [], [], []
+
+    def put(r, c, v):
+        rows.append(np.asarray(r, dtype=np.int64))
+        cols.append(np.asarray(c, dtype=np.int64))
+        vals.append(np.broadcast_to(np.asarray(v, dtype=np.float64), np.shape(r)).copy())
+
+    r1 = np.arange(n - 1)
+    # block 1: local slope of the fitted path = median slope + jumps  (n-1 rows)
+    for base, sign in ((c_fe_p, 1.0), (c_fe_m, -1.0)):
+        put(r1, base + r1, sign * -inv)
+        put(r1, base + r1 + 1, sign * inv)
+    for base, sign in ((c_j_p, 1.0), (c_j_m, -1.0), (c_snj_p, 1.0), (c_snj_m, -1.0),
+                       (c_rcj_p, 1.0), (c_rcj_m, -1.0)):
+        put(r1, base + r1, sign * inv)
+    put(r1, np.full(n - 1, c_med), 1.0)
+    # block 2: shot-noise jumps are the differences of the shot-noise terms  (n-1 rows)
+    r2 = (n - 1) + r1
+    put(r2, c_sn_p + r1, -1.0)
+    put(r2, c_sn_p + r1 + 1, 1.0)
+    put(r2, c_sn_m + r1, 1.0)
+    put(r2, c_sn_m + r1 + 1, -1.0)
+    put(r2, c_snj_p + r1, -1.0)
+    put(r2, c_snj_m + r1, 1.0)
+    # block 3: rate changes are the differences of consecutive rate-change jumps  (n-2 rows)
+    r3i = np.arange(n - 2)
+    r3 = 2 * (n - 1) + r3i
+    for base, sign in ((c_rcj_p, 1.0), (c_rcj_m, -1.0)):
+        put(r3, base + r3i, sign * -inv[:-1])
+        put(r3, base + r3i + 1, sign * inv[1:])
+    put(r3, c_rc_p + r3i, -1.0)
+    put(r3, c_rc_m + r3i, 1.0)
+    a_eq = scipy.sparse.coo_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))),
+                                   shape=(3 * n - 4, 12 * n - 9)).tocsc()
+    b_eq = np.hstack((dy / dx, np.zeros(2 * n - 3)))
+    bounds = [[0, None]] * (4 * n - 2) + [[0, 2.0]] * (2 * n) + [[0, None]] * (6 * n - 8) + [[None, None]]
+    return cost, a_eq, b_eq, bounds
+
+
+def rate_change_fit(x, y, window=None, linprog=None) -> RateFit:
+    """L1 fit of a piece-wise linear path with few rate changes (describealign.py:769-858)."""
+    linprog = scipy.optimize.linprog if linprog is None else linprog
+    n = len(x)
+    cost, a_eq, b_eq, bounds = _lp_problem(x, y, window)
+    fit = linprog(cost, A_eq=a_eq, b_eq=b_eq, bounds=bounds, method="highs-ds")
+    if not fit.success and fit.status == 4:
+        fit = linprog(cost, A_eq=a_eq, b_eq=b_eq, bounds=bounds, method="highs-ipm")
+    if not fit.success:
+        print(fit)
+        raise RuntimeError(LP_FAILED_MSG)
+    sol = fit.x
+    fit_err = sol[:n] - sol[n:2 * n]
+    slope_jumps = sol[8 * n - 4:9 * n - 5] - sol[9 * n - 5:10 * n - 6]
+    median_slope = sol[-1]
+    slopes = median_slope + slope_jumps / np.diff(x)
+    return RateFit(x=x, y=y, fit_err=fit_err, slopes=slopes, median_slope=median_slope)
+
+
+def line_clusters(fit: RateFit):
+    """Group the smooth path's points into co-linear clusters and fit a line to each
+    (describealign.py:861-893).  Returns a list of (x array, offset, slope)."""
+    smooth = list(zip(fit.x, fit.y - fit.fit_err))
+    slopes = np.hstack((fit.slopes[:1], fit.slopes, fit.slopes[-1:]))
+    groups = {}
+    for k, (px, py) in enumerate(smooth):
+        for slope in slopes[k:k + 2]:
+            if slope < .1 or slope > 10:
+                continue
+            key = (round(slope, 6), int(round(py - slope * px, 0)))
+            groups.setdefault(key, []).append((px, py))
+    clusters = []
+    taken = set()
+    for key, members in sorted(groups.items(), key=lambda kv: -len(kv[1])):
+        if key in taken:
+            continue
+        slope, offset = key
+        cluster = members
+        taken.add(key)
+        del groups[key]
+        for key2, members2 in list(groups.items()):
+            first, last = members2[0], members2[-1]
+            if abs(first[1] - (first[0] * slope + offset)) < 3 and abs(last[1] - (last[0] * slope + offset)) < 3:
+                cluster.extend(members2)
+                taken.add(key2)
+                del groups[key2]
+        clusters.append(cluster)
+    clusters = [sorted(c) for c in clusters]
+    clusters = [c for c in clusters if abs(c[0][0] - c[-1][0]) > 10 and len(c) > 5]
+    out = []
+    for c in clusters:
+        cx, cy = np.array(c).T
+        sol = np.linalg.lstsq(np.hstack((np.ones((len(cx), 1)), cx[:, None])), cy, rcond=None)[0]
+        out.append((cx, sol[0], sol[1]))
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# Stage-B host helpers
+# ------------------------------------------------------------------------------------------
+
+def x_limits(x_first, x_last, offset, slope, n_audio, n_video, extend=CORRIDOR_RADIUS, buffer_vert=4):
+    """Half-open audio-row range of a cluster's corridor (describealign.py:895-900)."""
+    lo = max(int(x_first) - extend, 0)
+    hi = min(int(x_last) + extend, n_audio - 1)
+    lo = max(lo, int(np.ceil((buffer_vert - offset) / slope)))
+    hi = min(hi, int(np.floor((n_video - buffer_vert - offset) / slope)))
+    return lo, hi
+
+
+def lerp_video(video_scaled: np.ndarray, y: np.ndarray) -> np.ndarray:
+    """Degree-1 spline through the video rows at fractional positions y, in the f64 form
+    that is bit-identical to scipy's make_interp_spline(k=1)."""
+    f = np.floor(y).astype(np.int64)
+    t = (y - f)[:, None]
+    v = video_scaled.astype(np.float64)
+    return v[f] * (1.0 - t) + v[f + 1] * t
+
+
+def plan_corridors(clusters, audio_scaled, video_scaled):
+    """Per cluster: the audio-row range to score and the (possibly refined) line.
+
+    Implements the control flow of describealign.py:912-932 up to the point where scoring
+    starts, including the sub-frame offset refinement (describealign.py:916-930) and the
+    quirk that the refinement branch shortens the corridor by one row.
+    Returns a list of (cluster_index, lo, hi, slope, offset) for clusters that are scored.
+    """
+    n_audio, n_video = len(audio_scaled), len(video_scaled)
+    plans = []
+    for idx, (cx, offset, slope) in enumerate(clusters):
+        lo, hi = x_limits(cx[0], cx[-1], offset, slope, n_audio, n_video, extend=0)
+        if hi < lo + 5:
+            continue
+        x_first, x_last = cx[0], cx[-1]
+        if hi > lo + 100:
+            rows = np.arange(lo, hi)
+            y = slope * rows + offset
+            a_m = audio_scaled[lo:hi]
+            v_m = lerp_video(video_scaled, y)
+            err = a_m[1:-1] - v_m[1:-1]
+            ok = np.mean(err, axis=-1) < 0.1
+            if np.count_nonzero(ok) > 50:
+                dv = ((v_m[2:] - v_m[:-2]) / 2.)[ok]
+                err = err[ok]
+                coef, resid, _, _ = np.linalg.lstsq(dv.reshape(-1, 1), err.flat, rcond=None)
+                explained = 1 - (resid / np.sum(err ** 2))
+                sigmas = np.sqrt(explained * np.prod(err.shape)) - 1.
+                if sigmas > 8 and abs(coef[0]) < 2:
+                    offset = offset + coef[0]
+            x_first, x_last = rows[0], rows[-1]
+        lo2, hi2 = x_limits(x_first, x_last, offset, slope, n_audio, n_video)
+        plans.append((idx, lo2, hi2, float(slope), float(offset)))
+    return plans
+
+
+def build_nodes(path, n_audio_energy: int, n_video_energy: int, n_audio_scaled: int, n_video_scaled: int):
+    """Similarity percentage and break-point nodes from the final path rows
+    (j, i, cluster, qual, cum) (describealign.py:993-1026).  Scales path[:, :2] in place."""
+    y, x, cluster, quals, _ = path.T
+    keep = (quals == 0) | (quals > .3)
+    sim_x = float(len(set(x[keep]))) / n_audio_scaled
+    sim_y = float(len(set(y[keep]))) / n_video_scaled
+    similarity = 100 * max(sim_x, sim_y)
+    nodes = []
+    if cluster[0] == cluster[1]:
+        nodes.append((x[0], y[0]))
+    for k in range(len(x) - 1):
+        if cluster[k] != cluster[k + 1]:
+            nodes.append((x[k] - .1, y[k] - .1))
+            nodes.append((x[k + 1] + .1, y[k + 1] + .1))
+    if cluster[-2] == cluster[-1]:
+        nodes.append((x[-1], y[-1]))
+    nx, ny = np.array(nodes).T / 210.
+    if (nx[1] - nx[0]) > 2:
+        s = (ny[1] - ny[0]) / (nx[1] - nx[0])
+        nx[0] = 0
+        ny[0] = ny[1] - (nx[1] * s)
+        if ny[0] < 0:
+            nx[0] = nx[1] - (ny[1] / s)
+            ny[0] = 0
+    if (nx[-1] - nx[-2]) > 2:
+        s = (ny[-1] - ny[-2]) / (nx[-1] - nx[-2])
+        nx[-1] = ((n_audio_energy - 1) / 210.)
+        ny[-1] = ny[-2] + ((nx[-1] - nx[-2]) * s)
+        if ny[-1] > ((n_video_energy - 1) / 210.):
+            ny[-1] = ((n_video_energy - 1) / 210.)
+            nx[-1] = nx[-2] + ((ny[-1] - ny[-2]) / s)
+    path[:, :2] /= 210.
+    return nx, ny, similarity
