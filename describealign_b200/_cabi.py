@@ -1,0 +1,254 @@
+"""ctypes binding of libdescribealign_b200.so (include/describealign_b200.h).
+
+There is no CPU fallback: if the shared library is missing or no CUDA device is present,
+every entry point raises.  The library is built in-tree by describealign_b200.build.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdescribealign_b200.so")
+
+PCM_S16, PCM_F16 = 0, 1
+VIDEO, AUDIO = 0, 1
+
+EXPORTS = [
+    "dab_abi_version", "dab_device_count", "dab_create", "dab_destroy", "dab_last_error",
+    "dab_pair_create", "dab_pair_destroy", "dab_pair_sync", "dab_pair_stream", "dab_pair_set_pcm",
+    "dab_pair_set_features", "dab_pair_feature_lens", "dab_pair_get_features", "dab_pair_stage_a",
+    "dab_pair_get_path1", "dab_pair_get_points1", "dab_pair_stage_b", "dab_pair_get_path2",
+    "dab_pair_get_points2", "dab_pair_get_stats", "dab_pair_get_timings", "dab_launch_count",
+]
+
+
+class Corridor(ctypes.Structure):
+    _fields_ = [("cluster", ctypes.c_int32), ("lo", ctypes.c_int32), ("hi", ctypes.c_int32),
+                ("reserved", ctypes.c_int32), ("slope", ctypes.c_double), ("offset", ctypes.c_double)]
+
+
+class Stats(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int64) for n in (
+        "n_video_frames", "n_audio_frames", "n_video_selected", "n_audio_queries", "n_table_entries",
+        "n_enumerated", "n_candidates", "n_points1", "n_path1", "n_points2", "n_path2")]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+TIMING_SLOTS = ("features_video", "features_audio", "prep_codes", "tables", "gate", "score",
+                "dp1_trace", "corridors", "dp2_trace")
+
+_lib = None
+
+
+class DabError(RuntimeError):
+    pass
+
+
+def load() -> ctypes.CDLL:
+    """Load the CUDA library; raise loudly if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise DabError(
+            f"{LIB_PATH} is missing: build it with `python -m describealign_b200.build` "
+            "(nvcc, sm_100a). describealign_b200 has no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, i64, i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int
+    lib.dab_abi_version.restype = i32
+    lib.dab_device_count.restype = i32
+    lib.dab_create.argtypes = [i32, ctypes.POINTER(vp)]
+    lib.dab_destroy.argtypes = [vp]
+    lib.dab_destroy.restype = None
+    lib.dab_last_error.argtypes = [vp]
+    lib.dab_last_error.restype = ctypes.c_char_p
+    lib.dab_pair_create.argtypes = [vp, ctypes.POINTER(vp)]
+    lib.dab_pair_destroy.argtypes = [vp]
+    lib.dab_pair_destroy.restype = None
+    lib.dab_pair_sync.argtypes = [vp]
+    lib.dab_pair_stream.argtypes = [vp]
+    lib.dab_pair_stream.restype = vp
+    lib.dab_pair_set_pcm.argtypes = [vp, i32, vp, i64, i32, i32, i32]
+    lib.dab_pair_set_features.argtypes = [vp, i32, vp, i64, vp, vp, vp, vp, i64]
+    lib.dab_pair_feature_lens.argtypes = [vp, i32, ctypes.POINTER(i64 * 5)]
+    lib.dab_pair_get_features.argtypes = [vp, i32, vp, vp, vp, vp, vp]
+    lib.dab_pair_stage_a.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(i64)]
+    lib.dab_pair_get_path1.argtypes = [vp, vp, vp]
+    lib.dab_pair_get_points1.argtypes = [vp, vp, vp, vp]
+    lib.dab_pair_stage_b.argtypes = [vp, vp, i64, vp, i64, vp, ctypes.c_int32, ctypes.c_int32,
+                                     ctypes.POINTER(i64), ctypes.POINTER(i64)]
+    lib.dab_pair_get_path2.argtypes = [vp, vp]
+    lib.dab_pair_get_points2.argtypes = [vp, vp, vp, vp, vp]
+    lib.dab_pair_get_stats.argtypes = [vp, ctypes.POINTER(Stats)]
+    lib.dab_pair_get_timings.argtypes = [vp, ctypes.POINTER(ctypes.c_float * 16)]
+    lib.dab_launch_count.argtypes = [vp]
+    lib.dab_launch_count.restype = i64
+    if lib.dab_abi_version() != 1:
+        raise DabError("libdescribealign_b200.so has an unexpected ABI version")
+    _lib = lib
+    return lib
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+class Context:
+    """One per process and GPU (dab_ctx)."""
+
+    def __init__(self, device: int = -1):
+        self.lib = load()
+        h = ctypes.c_void_p()
+        rc = self.lib.dab_create(int(device), ctypes.byref(h))
+        if rc != 0:
+            raise DabError(f"dab_create failed ({rc}): {self.lib.dab_last_error(None).decode()}")
+        self.handle = h
+
+    def check(self, rc: int):
+        if rc != 0:
+            raise DabError(f"describealign_b200 error {rc}: {self.lib.dab_last_error(self.handle).decode()}")
+
+    def launches(self) -> int:
+        return int(self.lib.dab_launch_count(self.handle))
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.dab_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Pair:
+    """Device-resident state of one (video, description) pair (dab_pair)."""
+
+    def __init__(self, ctx: Context):
+        self.ctx = ctx
+        self.lib = ctx.lib
+        h = ctypes.c_void_p()
+        ctx.check(self.lib.dab_pair_create(ctx.handle, ctypes.byref(h)))
+        self.handle = h
+        self._keep = []
+
+    # ---- features -------------------------------------------------------------------------
+    def set_pcm(self, track: int, pcm: np.ndarray):
+        """pcm: int16 (S, ch) / (S,) interleaved samples, or float16 of the same layout."""
+        if pcm.ndim == 1:
+            pcm = pcm[:, None]
+        if pcm.dtype == np.int16:
+            fmt = PCM_S16
+        elif pcm.dtype == np.float16:
+            fmt = PCM_F16
+        else:
+            raise TypeError("PCM must be int16 or float16")
+        pcm = np.ascontiguousarray(pcm)
+        self._keep.append(pcm)   # the copy is asynchronous for pinned memory
+        self.ctx.check(self.lib.dab_pair_set_pcm(self.handle, track, _ptr(pcm), pcm.shape[0], pcm.shape[1], fmt, 0))
+
+    def set_pcm_device(self, track: int, dev_ptr: int, samples: int, channels: int, fmt: int = PCM_S16):
+        self.ctx.check(self.lib.dab_pair_set_pcm(self.handle, track, ctypes.c_void_p(dev_ptr), samples, channels, fmt, 1))
+
+    def set_features(self, track: int, features):
+        e, z, b0, b1, b2 = features
+        e = np.ascontiguousarray(e, np.float32); z = np.ascontiguousarray(z, np.float32)
+        b0 = np.ascontiguousarray(b0, np.float32); b1 = np.ascontiguousarray(b1, np.float32)
+        b2 = np.ascontiguousarray(b2, np.float64)
+        n = min(len(z), len(b0), len(b1), len(b2))
+        if not (len(z) == len(b0) == len(b1) == len(b2)) or len(e) not in (n, n + 1):
+            raise ValueError("feature lengths must be n (zero crossings, bands) and n or n + 1 (energy)")
+        self.ctx.check(self.lib.dab_pair_set_features(self.handle, track, _ptr(e), len(e), _ptr(z), _ptr(b0),
+                                                      _ptr(b1), _ptr(b2), n))
+
+    def get_features(self, track: int):
+        lens = (ctypes.c_int64 * 5)()
+        self.ctx.check(self.lib.dab_pair_feature_lens(self.handle, track, ctypes.byref(lens)))
+        e = np.empty(lens[0], np.float32); z = np.empty(lens[1], np.float32)
+        b0 = np.empty(lens[2], np.float32); b1 = np.empty(lens[3], np.float32); b2 = np.empty(lens[4], np.float64)
+        self.ctx.check(self.lib.dab_pair_get_features(self.handle, track, _ptr(e), _ptr(z), _ptr(b0), _ptr(b1), _ptr(b2)))
+        self._keep.clear()
+        return [e, z, b0, b1, b2]
+
+    # ---- stage A ----------------------------------------------------------------------------
+    def stage_a(self):
+        npts, npath = ctypes.c_int64(), ctypes.c_int64()
+        self.ctx.check(self.lib.dab_pair_stage_a(self.handle, ctypes.byref(npts), ctypes.byref(npath)))
+        self._keep.clear()
+        self.n_points1, self.n_path1 = npts.value, npath.value
+        return npts.value, npath.value
+
+    def path1(self):
+        x = np.empty(self.n_path1, np.int32); y = np.empty(self.n_path1, np.int32)
+        self.ctx.check(self.lib.dab_pair_get_path1(self.handle, _ptr(x), _ptr(y)))
+        return x.astype(np.int64), y.astype(np.int64)
+
+    def points1(self):
+        n = self.n_points1
+        i = np.empty(n, np.int32); v = np.empty(n, np.int32); q = np.empty(n, np.float64)
+        self.ctx.check(self.lib.dab_pair_get_points1(self.handle, _ptr(i), _ptr(v), _ptr(q)))
+        return i, v, q
+
+    # ---- stage B ----------------------------------------------------------------------------
+    def stage_b(self, audio_scaled: np.ndarray, video_scaled: np.ndarray, plans, n_clusters: int):
+        a = np.ascontiguousarray(audio_scaled, np.float32)
+        v = np.ascontiguousarray(video_scaled, np.float32)
+        if a.ndim != 2 or a.shape[1] != 3 or v.ndim != 2 or v.shape[1] != 3:
+            raise ValueError("scaled features must be (n, 3) float32")
+        plans = [p for p in plans if p[2] > p[1]]
+        arr = (Corridor * max(len(plans), 1))()
+        for k, (idx, lo, hi, slope, offset) in enumerate(plans):
+            arr[k] = Corridor(int(idx), int(lo), int(hi), 0, float(slope), float(offset))
+        npts, npath = ctypes.c_int64(), ctypes.c_int64()
+        self.ctx.check(self.lib.dab_pair_stage_b(self.handle, _ptr(a), a.shape[0], _ptr(v), v.shape[0],
+                                                 ctypes.cast(arr, ctypes.c_void_p), len(plans), int(n_clusters),
+                                                 ctypes.byref(npts), ctypes.byref(npath)))
+        self.n_points2, self.n_path2 = npts.value, npath.value
+        return npts.value, npath.value
+
+    def path2(self):
+        rows = np.empty((self.n_path2, 5), np.float64)
+        self.ctx.check(self.lib.dab_pair_get_path2(self.handle, _ptr(rows)))
+        return rows
+
+    def points2(self):
+        n = self.n_points2
+        i = np.empty(n, np.int32); j = np.empty(n, np.float64); c = np.empty(n, np.int32); q = np.empty(n, np.float64)
+        self.ctx.check(self.lib.dab_pair_get_points2(self.handle, _ptr(i), _ptr(j), _ptr(c), _ptr(q)))
+        return i, j, c, q
+
+    # ---- introspection ------------------------------------------------------------------------
+    def stats(self) -> dict:
+        s = Stats()
+        self.ctx.check(self.lib.dab_pair_get_stats(self.handle, ctypes.byref(s)))
+        return s.as_dict()
+
+    def timings(self) -> dict:
+        ms = (ctypes.c_float * 16)()
+        self.ctx.check(self.lib.dab_pair_get_timings(self.handle, ctypes.byref(ms)))
+        return {name: float(ms[k]) for k, name in enumerate(TIMING_SLOTS)}
+
+    def sync(self):
+        self.ctx.check(self.lib.dab_pair_sync(self.handle))
+
+    @property
+    def stream(self) -> int:
+        return int(self.lib.dab_pair_stream(self.handle) or 0)
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.dab_pair_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,365 @@
+// C ABI of describealign_b200 (include/describealign_b200.h).
+#include <string.h>
+
+#include <new>
+
+#include "common.cuh"
+
+static std::string g_create_err;
+
+int dab_ensure(dab_ctx *ctx, DevBuf &b, size_t bytes) {
+  if (bytes <= b.cap && b.p) return DAB_OK;
+  if (b.p) {
+    DAB_CUDA(cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+  }
+  size_t want = bytes + bytes / 4 + 256;   // head-room so that similar pairs reuse the buffer
+  DAB_CUDA(cudaMalloc(&b.p, want));
+  b.cap = want;
+  return DAB_OK;
+}
+
+static void free_buf(DevBuf &b) {
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+}
+
+extern "C" {
+
+int dab_abi_version(void) { return DAB_ABI_VERSION; }
+
+int dab_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+const char *dab_last_error(const dab_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int dab_create(int device, dab_ctx **out) {
+  if (!out) return DAB_E_ARG;
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    g_create_err = std::string("no CUDA device available (describealign_b200 has no CPU fallback): ") +
+                   (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    return DAB_E_CUDA;
+  }
+  if (device < 0) {
+    if (cudaGetDevice(&device) != cudaSuccess) device = 0;
+  }
+  if (device >= n) { g_create_err = "device index out of range"; return DAB_E_ARG; }
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) { g_create_err = cudaGetErrorString(e); return DAB_E_CUDA; }
+  dab_ctx *ctx = new (std::nothrow) dab_ctx();
+  if (!ctx) return DAB_E_CUDA;
+  ctx->device = device;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+  *out = ctx;
+  return DAB_OK;
+}
+
+void dab_destroy(dab_ctx *ctx) { delete ctx; }
+
+int64_t dab_launch_count(const dab_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int dab_pair_create(dab_ctx *ctx, dab_pair **out) {
+  if (!ctx || !out) return DAB_E_ARG;
+  *out = nullptr;
+  DAB_CUDA(cudaSetDevice(ctx->device));
+  dab_pair *pr = new (std::nothrow) dab_pair();
+  if (!pr) return DAB_E_CUDA;
+  pr->ctx = ctx;
+  DAB_CUDA(cudaStreamCreateWithFlags(&pr->stream, cudaStreamNonBlocking));
+  for (int k = 0; k < 32; ++k) DAB_CUDA(cudaEventCreate(&pr->ev[k]));
+  DAB_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&pr->h_counters), sizeof(int64_t) * 32, cudaHostAllocDefault));
+  memset(pr->h_counters, 0, sizeof(int64_t) * 32);
+  *out = pr;
+  return DAB_OK;
+}
+
+void dab_pair_destroy(dab_pair *pr) {
+  if (!pr) return;
+  cudaSetDevice(pr->ctx->device);
+  if (pr->stream) cudaStreamSynchronize(pr->stream);
+  for (int t = 0; t < 2; ++t) {
+    Track &k = pr->trk[t];
+    DevBuf *bs[] = {&k.pcm, &k.energy, &k.zc, &k.b0, &k.b1, &k.b2, &k.ms, &k.nrm, &k.pack, &k.code, &k.nq_flag, &k.nq_list};
+    for (DevBuf *b : bs) free_buf(*b);
+  }
+  DevBuf *bs[] = {&pr->scan_tmp, &pr->tbl_count, &pr->tbl_start, &pr->tbl_items, &pr->row_count, &pr->row_off,
+                  &pr->cand_tmp, &pr->cand_s, &pr->cand_i, &pr->cand_q, &pr->keep_flag, &pr->keep_off, &pr->pt_i,
+                  &pr->pt_s, &pr->pt_q, &pr->counters, &pr->tree1, &pr->back1, &pr->len1, &pr->cp1, &pr->dpres,
+                  &pr->seglist, &pr->path1_x, &pr->path1_y, &pr->a_scaled, &pr->v_scaled, &pr->corridors,
+                  &pr->row2_count, &pr->row2_off, &pr->p2_i, &pr->p2_c, &pr->p2_rank, &pr->p2_j, &pr->p2_q,
+                  &pr->tree2, &pr->cache2, &pr->back2, &pr->len2, &pr->cp2, &pr->backid2, &pr->path2};
+  for (DevBuf *b : bs) free_buf(*b);
+  for (int k = 0; k < 32; ++k)
+    if (pr->ev[k]) cudaEventDestroy(pr->ev[k]);
+  if (pr->h_counters) cudaFreeHost(pr->h_counters);
+  if (pr->stream) cudaStreamDestroy(pr->stream);
+  delete pr;
+}
+
+int dab_pair_sync(dab_pair *pr) {
+  if (!pr) return DAB_E_ARG;
+  dab_ctx *ctx = pr->ctx;
+  DAB_CUDA(cudaStreamSynchronize(pr->stream));
+  return DAB_OK;
+}
+
+void *dab_pair_stream(dab_pair *pr) { return pr ? reinterpret_cast<void *>(pr->stream) : nullptr; }
+
+int dab_pair_set_pcm(dab_pair *pr, int track, const void *pcm, int64_t samples, int channels, int format,
+                     int on_device) {
+  if (!pr) return DAB_E_ARG;
+  dab_ctx *ctx = pr->ctx;
+  if (track < 0 || track > 1 || !pcm || samples < 0 || (channels != 1 && channels != 2) ||
+      (format != DAB_PCM_S16 && format != DAB_PCM_F16)) {
+    ctx->err = "dab_pair_set_pcm: invalid argument";
+    return DAB_E_ARG;
+  }
+  DAB_CUDA(cudaSetDevice(ctx->device));
+  Track &tk = pr->trk[track];
+  tk.S = samples;
+  tk.ch = channels;
+  tk.have_features = false;
+  const void *d_pcm = pcm;
+  cudaEvent_t e0 = pr->ev[2 * track], e1 = pr->ev[2 * track + 1];
+  if (!on_device) {
+    const size_t bytes = sizeof(int16_t) * (size_t)samples * (size_t)channels;
+    DAB_TRY(dab_ensure(ctx, tk.pcm, bytes + 16));
+    DAB_CUDA(cudaMemcpyAsync(tk.pcm.p, pcm, bytes, cudaMemcpyHostToDevice, pr->stream));
+    d_pcm = tk.pcm.p;
+  }
+  DAB_CUDA(cudaEventRecord(e0, pr->stream));
+  DAB_TRY(dab_run_features(pr, track, d_pcm, format));
+  DAB_CUDA(cudaEventRecord(e1, pr->stream));
+  pr->ev_used[track] = true;
+  return DAB_OK;
+}
+
+int dab_pair_set_features(dab_pair *pr, int track, const float *energy, int64_t n_energy, const float *zc,
+                          const float *band0, const float *band1, const double *band2, int64_t n) {
+  if (!pr) return DAB_E_ARG;
+  dab_ctx *ctx = pr->ctx;
+  if (track < 0 || track > 1 || !energy || !zc || !band0 || !band1 || !band2 || n < 0 ||
+      (n_energy != n && n_energy != n + 1)) {
+    ctx->err = "dab_pair_set_features: invalid argument (len(energy) must be n or n + 1)";
+    return DAB_E_ARG;
+  }
+  DAB_CUDA(cudaSetDevice(ctx->device));
+  Track &tk = pr->trk[track];
+  tk.L = n;
+  tk.Le = n_energy;
+  tk.S = n * 210;
+  DAB_TRY(dab_ensure(ctx, tk.energy, sizeof(float) * (size_t)(n_energy + 1)));
+  DAB_TRY(dab_ensure(ctx, tk.zc, sizeof(float) * (size_t)(n + 1)));
+  DAB_TRY(dab_ensure(ctx, tk.b0, sizeof(float) * (size_t)(n + 1)));
+  DAB_TRY(dab_ensure(ctx, tk.b1, sizeof(float) * (size_t)(n + 1)));
+  DAB_TRY(dab_ensure(ctx, tk.b2, sizeof(double) * (size_t)(n + 1)));
+  cudaStream_t st = pr->stream;
+  DAB_CUDA(cudaMemcpyAsync(tk.energy.p, energy, sizeof(float) * (size_t)n_energy, cudaMemcpyHostToDevice, st));
+  DAB_CUDA(cudaMemcpyAsync(tk.zc.p, zc, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, st));
+  DAB_CUDA(cudaMemcpyAsync(tk.b0.p, band0, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, st));
+  DAB_CUDA(cudaMemcpyAsync(tk.b1.p, band1, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, st));
+  DAB_CUDA(cudaMemcpyAsync(tk.b2.p, band2, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, st));
+  DAB_CUDA(cudaStreamSynchronize(st));   // the caller may free its arrays right after (describealign.py:1107)
+  tk.have_features = true;
+  return DAB_OK;
+}
+
+int dab_pair_feature_lens(dab_pair *pr, int track, int64_t lens[5]) {
+  if (!pr || track < 0 || track > 1 || !lens) return DAB_E_ARG;
+  Track &tk = pr->trk[track];
+  if (!tk.have_features) { pr->ctx->err = "no features computed for this track"; return DAB_E_STATE; }
+  lens[0] = tk.Le;
+  lens[1] = lens[2] = lens[3] = lens[4] = tk.L;
+  return DAB_OK;
+}
+
+int dab_pair_get_features(dab_pair *pr, int track, float *energy, float *zc, float *band0, float *band1,
+                          double *band2) {
+  if (!pr || track < 0 || track > 1) return DAB_E_ARG;
+  dab_ctx *ctx = pr->ctx;
+  Track &tk = pr->trk[track];
+  if (!tk.have_features) { ctx->err = "no features computed for this track"; return DAB_E_STATE; }
+  DAB_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = pr->stream;
+  if (energy && tk.Le > 0) DAB_CUDA(cudaMemcpyAsync(energy, tk.energy.p, sizeof(float) * (size_t)tk.Le, cudaMemcpyDeviceToHost, st));
+  if (tk.L > 0) {
+    if (zc) DAB_CUDA(cudaMemcpyAsync(zc, tk.zc.p, sizeof(float) * (size_t)tk.L, cudaMemcpyDeviceToHost, st));
+    if (band0) DAB_CUDA(cudaMemcpyAsync(band0, tk.b0.p, sizeof(float) * (size_t)tk.L, cudaMemcpyDeviceToHost, st));
+    if (band1) DAB_CUDA(cudaMemcpyAsync(band1, tk.b1.p, sizeof(float) * (size_t)tk.L, cudaMemcpyDeviceToHost, st));
+    if (band2) DAB_CUDA(cudaMemcpyAsync(band2, tk.b2.p, sizeof(double) * (size_t)tk.L, cudaMemcpyDeviceToHost, st));
+  }
+  DAB_CUDA(cudaStreamSynchronize(st));
+  return DAB_OK;
+}
+
+int dab_pair_stage_a(dab_pair *pr, int64_t *n_points, int64_t *n_path) {
+  if (!pr) return DAB_E_ARG;
+  dab_ctx *ctx = pr->ctx;
+  for (int t = 0; t < 2; ++t) {
+    if (!pr->trk[t].have_features) { ctx->err = "stage_a: features of both tracks are required first"; return DAB_E_STATE; }
+    const int64_t lmin = pr->trk[t].Le < pr->trk[t].L ? pr->trk[t].Le : pr->trk[t].L;
+    if (lmin < 2 * DAB_WIN) { ctx->err = "stage_a: track shorter than 82 frames"; return DAB_E_TOO_SHORT; }
+  }
+  DAB_CUDA(cudaSetDevice(ctx->device));
+  DAB_TRY(dab_run_stage_a(pr));
+  if (n_points) *n_points = pr->n_points1;
+  if (n_path) *n_path = pr->n_path1;
+  return DAB_OK;
+}
+
+int dab_pair_get_path1(dab_pair *pr, int32_t *x_audio, int32_t *y_video) {
+  if (!pr) return DAB_E_ARG;
+  dab_ctx *ctx = pr->ctx;
+  DAB_CUDA(cudaSetDevice(ctx->device));
+  const size_t bytes = sizeof(int32_t) * (size_t)pr->n_path1;
+  if (bytes) {
+    if (x_audio) DAB_CUDA(cudaMemcpyAsync(x_audio, pr->path1_x.p, bytes, cudaMemcpyDeviceToHost, pr->stream));
+    if (y_video) DAB_CUDA(cudaMemcpyAsync(y_video, pr->path1_y.p, bytes, cudaMemcpyDeviceToHost, pr->stream));
+  }
+  DAB_CUDA(cudaStreamSynchronize(pr->stream));
+  return DAB_OK;
+}
+
+}  // extern "C"
+
+namespace {
+__global__ void ranks_to_frames_kernel(const int32_t *pt_s, const int32_t *v_sel, int64_t n, int32_t *out) {
+  int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) out[k] = v_sel[pt_s[k]];
+}
+}  // namespace
+
+extern "C" {
+
+int dab_pair_get_points1(dab_pair *pr, int32_t *i_audio, int32_t *v_video, double *qual) {
+  if (!pr) return DAB_E_ARG;
+  dab_ctx *ctx = pr->ctx;
+  DAB_CUDA(cudaSetDevice(ctx->device));
+  const int64_t n = pr->n_points1;
+  if (n > 0) {
+    cudaStream_t st = pr->stream;
+    if (i_audio) DAB_CUDA(cudaMemcpyAsync(i_audio, pr->pt_i.p, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    if (qual) DAB_CUDA(cudaMemcpyAsync(qual, pr->pt_q.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    if (v_video) {
+      DAB_TRY(dab_ensure(ctx, pr->cand_tmp, sizeof(int32_t) * (size_t)(n + 1)));
+      ranks_to_frames_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(pr->pt_s.as<int32_t>(),
+                                                                      pr->trk[DAB_TRACK_VIDEO].nq_list.as<int32_t>(), n,
+                                                                      pr->cand_tmp.as<int32_t>());
+      ctx->launches += 1;
+      DAB_CUDA(cudaMemcpyAsync(v_video, pr->cand_tmp.p, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    }
+  }
+  DAB_CUDA(cudaStreamSynchronize(pr->stream));
+  return DAB_OK;
+}
+
+int dab_pair_stage_b(dab_pair *pr, const float *audio_scaled, int64_t n_audio, const float *video_scaled,
+                     int64_t n_video, const dab_corridor *corridors, int32_t n_corridors, int32_t n_clusters,
+                     int64_t *n_points, int64_t *n_path) {
+  if (!pr) return DAB_E_ARG;
+  dab_ctx *ctx = pr->ctx;
+  if (!audio_scaled || !video_scaled || n_audio <= 0 || n_video <= 8 || n_corridors < 0 || n_clusters < 0 ||
+      (n_corridors > 0 && !corridors)) {
+    ctx->err = "dab_pair_stage_b: invalid argument";
+    return DAB_E_ARG;
+  }
+  int64_t rows = 0;
+  for (int k = 0; k < n_corridors; ++k) {
+    const dab_corridor &c = corridors[k];
+    if (c.cluster < 0 || c.cluster >= n_clusters || c.lo < 0 || c.hi > n_audio ||
+        (k > 0 && c.cluster <= corridors[k - 1].cluster)) {
+      ctx->err = "dab_pair_stage_b: corridors must be in ascending cluster order with rows inside the audio track";
+      return DAB_E_ARG;
+    }
+    if (c.hi > c.lo) {
+      // the line must stay inside the video feature array for every scored row (:898-899)
+      const double j0 = c.slope * (double)c.lo + c.offset, j1 = c.slope * (double)(c.hi - 1) + c.offset;
+      const double jmin = j0 < j1 ? j0 : j1, jmax = j0 < j1 ? j1 : j0;
+      if (!(jmin >= 0.0) || !(jmax < (double)(n_video - 1))) {
+        ctx->err = "dab_pair_stage_b: corridor line leaves the video track";
+        return DAB_E_ARG;
+      }
+      rows += c.hi - c.lo;
+    }
+  }
+  DAB_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = pr->stream;
+  DAB_TRY(dab_ensure(ctx, pr->a_scaled, sizeof(float) * 3 * (size_t)n_audio));
+  DAB_TRY(dab_ensure(ctx, pr->v_scaled, sizeof(float) * 3 * (size_t)n_video));
+  DAB_TRY(dab_ensure(ctx, pr->corridors, sizeof(dab_corridor) * (size_t)(n_corridors + 1)));
+  DAB_CUDA(cudaMemcpyAsync(pr->a_scaled.p, audio_scaled, sizeof(float) * 3 * (size_t)n_audio, cudaMemcpyHostToDevice, st));
+  DAB_CUDA(cudaMemcpyAsync(pr->v_scaled.p, video_scaled, sizeof(float) * 3 * (size_t)n_video, cudaMemcpyHostToDevice, st));
+  if (n_corridors > 0)
+    DAB_CUDA(cudaMemcpyAsync(pr->corridors.p, corridors, sizeof(dab_corridor) * (size_t)n_corridors, cudaMemcpyHostToDevice, st));
+  // np.max of the energy columns (:908-909)
+  float amax = audio_scaled[0], vmax = video_scaled[0];
+  for (int64_t k = 1; k < n_audio; ++k) amax = audio_scaled[3 * k] > amax ? audio_scaled[3 * k] : amax;
+  for (int64_t k = 1; k < n_video; ++k) vmax = video_scaled[3 * k] > vmax ? video_scaled[3 * k] : vmax;
+  reinterpret_cast<float *>(pr->h_counters + 8)[0] = amax;
+  reinterpret_cast<float *>(pr->h_counters + 8)[1] = vmax;
+  pr->h_counters[11] = rows;
+  pr->stats.n_audio_frames = n_audio;
+  pr->stats.n_video_frames = n_video;
+  DAB_TRY(dab_run_stage_b(pr, n_corridors, n_clusters));
+  if (n_points) *n_points = pr->n_points2;
+  if (n_path) *n_path = pr->n_path2;
+  return DAB_OK;
+}
+
+int dab_pair_get_path2(dab_pair *pr, double *rows) {
+  if (!pr) return DAB_E_ARG;
+  dab_ctx *ctx = pr->ctx;
+  DAB_CUDA(cudaSetDevice(ctx->device));
+  if (rows && pr->n_path2 > 0)
+    DAB_CUDA(cudaMemcpyAsync(rows, pr->path2.p, sizeof(double) * 5 * (size_t)pr->n_path2, cudaMemcpyDeviceToHost, pr->stream));
+  DAB_CUDA(cudaStreamSynchronize(pr->stream));
+  return DAB_OK;
+}
+
+int dab_pair_get_points2(dab_pair *pr, int32_t *i_audio, double *j_video, int32_t *cluster, double *qual) {
+  if (!pr) return DAB_E_ARG;
+  dab_ctx *ctx = pr->ctx;
+  DAB_CUDA(cudaSetDevice(ctx->device));
+  const size_t n = (size_t)pr->n_points2;
+  cudaStream_t st = pr->stream;
+  if (n > 0) {
+    if (i_audio) DAB_CUDA(cudaMemcpyAsync(i_audio, pr->p2_i.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+    if (j_video) DAB_CUDA(cudaMemcpyAsync(j_video, pr->p2_j.p, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    if (cluster) DAB_CUDA(cudaMemcpyAsync(cluster, pr->p2_c.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+    if (qual) DAB_CUDA(cudaMemcpyAsync(qual, pr->p2_q.p, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+  }
+  DAB_CUDA(cudaStreamSynchronize(st));
+  return DAB_OK;
+}
+
+int dab_pair_get_stats(dab_pair *pr, dab_stats *out) {
+  if (!pr || !out) return DAB_E_ARG;
+  *out = pr->stats;
+  return DAB_OK;
+}
+
+int dab_pair_get_timings(dab_pair *pr, float ms[16]) {
+  if (!pr || !ms) return DAB_E_ARG;
+  dab_ctx *ctx = pr->ctx;
+  DAB_CUDA(cudaSetDevice(ctx->device));
+  DAB_CUDA(cudaStreamSynchronize(pr->stream));
+  for (int s = 0; s < 16; ++s) {
+    ms[s] = 0.0f;
+    if (s < 9 && pr->ev_used[s]) {
+      float t = 0.0f;
+      if (cudaEventElapsedTime(&t, pr->ev[2 * s], pr->ev[2 * s + 1]) == cudaSuccess) ms[s] = t;
+    }
+  }
+  return DAB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,192 @@
+// describealign_b200 - shared declarations of the CUDA implementation (sm_100a).
+// All arithmetic files are compiled with -fmad=false: the reference's numpy code never
+// contracts a*b+c, and where OpenBLAS does (its ddot kernels), fma() is written explicitly.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/describealign_b200.h"
+
+#define DAB_NCODE 823543  // 7^7 digit codes per hash table (reference describealign.py:610-628)
+#define DAB_WIN 41        // frames in the correlation / norm window (:597)
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct dab_ctx {
+  int device = 0;
+  std::string err;
+  int64_t launches = 0;
+  int sm_count = 148;
+};
+
+// Features and prep data of one track, device resident.
+struct Track {
+  int64_t S = 0;       // samples per channel
+  int ch = 1;
+  int64_t L = 0;       // frames = S / 210 (length of zc / bands)
+  int64_t Le = 0;      // length of the energy feature (L or L + 1)
+  bool have_features = false;
+  DevBuf pcm;          // staging for host PCM
+  DevBuf energy, zc, b0, b1, b2;   // f32 x4, f64
+  // stage A prep (features 0..2 keep ms / nrm for scoring; 3, 4 only feed the codes)
+  DevBuf ms;           // f64 [3][Lp]   Lp = min feature length
+  DevBuf nrm;          // f64 [3][Lp-40]
+  DevBuf pack;         // u32 [5][Lp-40] 3-bit digits (bits 0-20) + flags (bits 21-27, video)
+  DevBuf code;         // i32 [5][Lp-40] base-7 code (audio: lookup key)
+  DevBuf nq_flag;      // i32 [n] not-quiet flags, then reused
+  DevBuf nq_list;      // i32 selected frame list (video: every 4th not-quiet; audio: all not-quiet)
+  int64_t n_codes = 0; // Lp - 40
+  int64_t n_list = 0;
+};
+
+struct dab_pair {
+  dab_ctx *ctx = nullptr;
+  cudaStream_t stream = nullptr;
+  Track trk[2];
+  // scan scratch
+  DevBuf scan_tmp;
+  // tables
+  DevBuf tbl_count;   // i32 [5*NCODE + 1]
+  DevBuf tbl_start;   // i32 [5*NCODE + 1]
+  DevBuf tbl_items;   // i32 sel-ranks
+  // gate / scoring
+  DevBuf row_count, row_off;   // i32 [n_queries + 1]
+  DevBuf cand_tmp, cand_s, cand_i;  // i32 [n_cand]
+  DevBuf cand_q;               // f64 [n_cand]
+  DevBuf keep_flag, keep_off;  // i32 [n_cand + 1]
+  DevBuf pt_i, pt_s, pt_q;     // match points of pass 1
+  DevBuf counters;             // i64 [16] device counters
+  // dp1
+  DevBuf tree1;                // Node16 levels
+  DevBuf back1, len1, cp1;     // i32 [n_points]
+  DevBuf dpres;                // i32/i64 results (end id, path len)
+  DevBuf seglist;              // i32 checkpoints
+  DevBuf path1_x, path1_y;     // i32
+  int64_t n_points1 = 0, n_path1 = 0;
+  // stage B
+  DevBuf a_scaled, v_scaled;   // f32 (n,3)
+  DevBuf corridors;            // dab_corridor[]
+  DevBuf row2_count, row2_off; // i32 [n_audio + 1]
+  DevBuf p2_i, p2_c, p2_rank;  // i32
+  DevBuf p2_j, p2_q;           // f64
+  DevBuf tree2;                // frontier tree of pass 2
+  DevBuf cache2;               // prev_cache rows
+  DevBuf back2;                // per point: predecessor tuple
+  DevBuf len2, cp2, backid2;   // i32
+  DevBuf path2;                // f64 (n,5)
+  int64_t n_points2 = 0, n_path2 = 0;
+  dab_stats stats = {};
+  cudaEvent_t ev[32] = {};
+  bool ev_used[16] = {};
+  // pinned host mirror of small results
+  int64_t *h_counters = nullptr;
+};
+
+#define DAB_CUDA(call)                                                                     \
+  do {                                                                                     \
+    cudaError_t e__ = (call);                                                              \
+    if (e__ != cudaSuccess) {                                                              \
+      char b__[512];                                                                       \
+      snprintf(b__, sizeof b__, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__),   \
+               __FILE__, __LINE__);                                                        \
+      ctx->err = b__;                                                                      \
+      return DAB_E_CUDA;                                                                   \
+    }                                                                                      \
+  } while (0)
+
+#define DAB_TRY(expr)              \
+  do {                             \
+    int rc__ = (expr);             \
+    if (rc__ != DAB_OK) return rc__; \
+  } while (0)
+
+int dab_ensure(dab_ctx *ctx, DevBuf &b, size_t bytes);
+static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// exclusive scan of n int32 values; out[n] receives the total (out has n + 1 entries).
+int dab_exclusive_scan(dab_pair *pr, const int32_t *in, int32_t *out, int64_t n);
+
+// stage entry points implemented in the .cu files
+int dab_run_features(dab_pair *pr, int track, const void *d_pcm, int format);
+int dab_run_stage_a(dab_pair *pr);
+int dab_run_stage_b(dab_pair *pr, int32_t n_corridors, int32_t n_clusters);
+
+#define DAB_LAUNCHED(pr) ((pr)->ctx->launches++)
+
+// ------------------------------------------------------------------------------------------
+// OpenBLAS 0.3.30 SkylakeX ddot summation order (what np.dot / np.convolve do on f64 in the
+// reference, SURVEY.md B.2 iv): blocks of 32 through 4 x 8 FMA lanes folded to 4 x 4, blocks
+// of 16 through 4 x 4 FMA lanes, tail as one FMA chain.  X(i), Y(i) are accessor macros.
+// ------------------------------------------------------------------------------------------
+template <typename FX, typename FY>
+__device__ __forceinline__ double ddot_skx(FX X, FY Y, int n) {
+  double a[4][4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int l = 0; l < 4; ++l) a[k][l] = 0.0;
+  int n1 = n & ~15;
+  int n32 = n1 & ~31;
+  int i = 0;
+  if (n32) {
+    double z[4][8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int l = 0; l < 8; ++l) z[k][l] = 0.0;
+    for (; i < n32; i += 32) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int l = 0; l < 8; ++l) z[k][l] = fma(X(i + 8 * k + l), Y(i + 8 * k + l), z[k][l]);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int l = 0; l < 4; ++l) a[k][l] = z[k][l] + z[k][l + 4];
+  }
+  for (; i < n1; i += 16) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int l = 0; l < 4; ++l) a[k][l] = fma(X(i + 4 * k + l), Y(i + 4 * k + l), a[k][l]);
+  }
+  double s0 = ((a[0][0] + a[1][0]) + a[2][0]) + a[3][0];
+  double s1 = ((a[0][1] + a[1][1]) + a[2][1]) + a[3][1];
+  double s2 = ((a[0][2] + a[1][2]) + a[2][2]) + a[3][2];
+  double s3 = ((a[0][3] + a[1][3]) + a[2][3]) + a[3][3];
+  double dot = (s0 + s2) + (s1 + s3);
+  for (; i < n; ++i) dot = fma(Y(i), X(i), dot);
+  return dot;
+}
+
+// Fixed n = 41 specialisation: one 32-block, no 16-block, 9-element tail.
+template <typename FX, typename FY>
+__device__ __forceinline__ double ddot41_skx(FX X, FY Y) {
+  double z[4][8];
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int l = 0; l < 8; ++l) z[k][l] = fma(X(8 * k + l), Y(8 * k + l), 0.0);
+  double s[4];
+#pragma unroll
+  for (int l = 0; l < 4; ++l) {
+    double a0 = z[0][l] + z[0][l + 4];
+    double a1 = z[1][l] + z[1][l + 4];
+    double a2 = z[2][l] + z[2][l + 4];
+    double a3 = z[3][l] + z[3][l + 4];
+    s[l] = ((a0 + a1) + a2) + a3;
+  }
+  double dot = (s[0] + s[2]) + (s[1] + s[3]);
+#pragma unroll
+  for (int i = 32; i < 41; ++i) dot = fma(Y(i), X(i), dot);
+  return dot;
+}

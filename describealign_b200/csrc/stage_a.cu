@@ -1,0 +1,783 @@
+// Device stage A of align() (reference describealign.py:596-700):
+//   prep      41-tap Hann local-mean subtraction, 41-frame sliding L2 norm   (:599-608)
+//   codes     7 quantised samples per feature -> packed digits + flags       (:622-628, 638-644)
+//   select    not-quiet frames; video keeps every 4th of that list           (:629-630, 657-658)
+//   tables    5 direct-address tables over the 7^7 codes, video frames stored under every
+//             code reachable through their flagged digits                     (:615-633)
+//   gate      per audio query: (>= 2 of tables 0-2) and (table 3 or 4)         (:649-660)
+//   score     3 x 41-tap normalised correlation -> prob -> qual                (:662-673)
+//   dp1       frontier DP as a prefix-max over video rank, with back pointers  (:654-656, 674-682)
+//   trace     traceback through checkpointed back pointers                     (:690-697)
+//
+// Layout: every per-frame array is structure-of-arrays in HBM (feature-major) so that a warp
+// touching consecutive frames reads consecutive addresses.  The hash "dict of sets" of the
+// reference becomes a counting-sort CSR (start[code], items[]) per table: 7^7 = 823 543
+// codes x 5 tables x 4 B = 16.5 MB of starts, L2 resident.  The gate is evaluated as an
+// integer predicate on packed 3-bit digits, so a bucket entry costs five 4-byte loads.
+#include "common.cuh"
+#include "hann_tables.h"
+
+namespace {
+
+__constant__ double c_hflip[41];   // flipped 41-tap Hann (np.convolve flips; the window is not bit-symmetric)
+
+// ------------------------------------------------------------------------------------------
+// prep: ms = feat - conv_same(feat, hann41)   (f64, OpenBLAS ddot order incl. shorter edge dots)
+// ------------------------------------------------------------------------------------------
+struct PrepArgs {
+  const float *f32[4];
+  const double *f64;
+  int64_t len[5];     // per-feature length (energy may be one longer)
+  int64_t Lp;         // frames kept for ms / nrm storage (min length)
+  double *ms;         // [5][Lms]  Lms = max len (stride)
+  int64_t stride;
+};
+
+__device__ __forceinline__ double feat_at(const PrepArgs &a, int f, int64_t t) {
+  return f < 4 ? (double)a.f32[f][t] : a.f64[t];
+}
+
+__global__ void meansub_kernel(PrepArgs a) {
+  const int f = blockIdx.y;
+  const int64_t n = a.len[f];
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  int64_t lo = t - 20, hi = t + 21, klo = 0;
+  if (lo < 0) { klo = -lo; lo = 0; }
+  if (hi > n) hi = n;
+  const int m = (int)(hi - lo);
+  double mean;
+  if (f < 4) {
+    const float *src = a.f32[f] + lo;
+    auto X = [&](int i) { return (double)src[i]; };
+    auto Y = [&](int i) { return c_hflip[klo + i]; };
+    mean = (m == 41) ? ddot41_skx(X, Y) : ddot_skx(X, Y, m);
+  } else {
+    const double *src = a.f64 + lo;
+    auto X = [&](int i) { return src[i]; };
+    auto Y = [&](int i) { return c_hflip[klo + i]; };
+    mean = (m == 41) ? ddot41_skx(X, Y) : ddot_skx(X, Y, m);
+  }
+  a.ms[(int64_t)f * a.stride + t] = feat_at(a, f, t) - mean;
+}
+
+// nrm[t] = max(1e-3, sqrt(sum_{k<41} ms[t+k]^2)) and the digit codes of frame t.
+struct CodeArgs {
+  const double *ms;     // [5][stride]
+  int64_t stride;
+  int64_t len[5];
+  double *nrm;          // [3][nstride] (features 0..2 only are stored)
+  int64_t nstride;
+  uint32_t *pack;       // [5][nstride]
+  int32_t *code;        // [5][nstride]
+  int is_video;
+};
+
+__global__ void norm_codes_kernel(CodeArgs a) {
+  const int f = blockIdx.y;
+  const int64_t ncodes = a.len[f] - 40;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ncodes) return;
+  const double *m = a.ms + (int64_t)f * a.stride + t;
+  auto X = [&](int i) { double v = m[i]; return v * v; };
+  auto Y = [&](int) { return 1.0; };
+  double nr = sqrt(ddot41_skx(X, Y));
+  if (nr < 0.001) nr = 0.001;
+  if (f < 3) a.nrm[(int64_t)f * a.nstride + t] = nr;
+  uint32_t pk = 0;
+  int32_t code = 0, p7 = 1;
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+    double d = m[2 + 6 * k] / nr;
+    d = 8.0 * d;
+    int dig;
+    if (a.is_video) {
+      d = d + 3.3;
+      d = fmin(fmax(d, 0.0), 6.0);
+      double fl = floor(d);
+      if (d - fl > 0.6) pk |= 1u << (21 + k);
+      dig = (int)fl;
+    } else {
+      d = d + 3.5;
+      double fl = floor(d);
+      fl = fmin(fmax(fl, 0.0), 6.0);
+      dig = (int)fl;
+    }
+    pk |= (uint32_t)dig << (3 * k);
+    code += dig * p7;
+    p7 *= 7;
+  }
+  a.pack[(int64_t)f * a.nstride + t] = pk;
+  a.code[(int64_t)f * a.nstride + t] = code;
+}
+
+// ------------------------------------------------------------------------------------------
+// scans / compaction
+// ------------------------------------------------------------------------------------------
+constexpr int SCAN_THREADS = 512;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int *total, int *smem /* >= 32 ints */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int y = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += y;
+  }
+  if (lane == 31) smem[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    int w = (lane < (int)(blockDim.x >> 5)) ? smem[lane] : 0;
+    int winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int y = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += y;
+    }
+    smem[lane] = winc - w;
+    if (lane == 31) smem[32] = winc;
+  }
+  __syncthreads();
+  int res = inc - v + smem[warp];
+  *total = smem[32];
+  __syncthreads();
+  return res;
+}
+
+__global__ void scan_reduce_kernel(const int32_t *in, int64_t n, int32_t *block_sums) {
+  __shared__ int sm[33];
+  const int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
+  int s = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k) {
+    int64_t i = base + (int64_t)threadIdx.x * SCAN_ITEMS + k;
+    if (i < n) s += in[i];
+  }
+  int total;
+  block_exclusive_scan(s, &total, sm);
+  if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+// single block: exclusive scan of the block sums in place, total to sums[nblocks]
+__global__ void scan_sums_kernel(int32_t *sums, int nblocks) {
+  __shared__ int sm[33];
+  int carry = 0;
+  for (int base = 0; base < nblocks; base += SCAN_THREADS) {
+    int i = base + threadIdx.x;
+    int v = (i < nblocks) ? sums[i] : 0;
+    int total;
+    int ex = block_exclusive_scan(v, &total, sm);
+    if (i < nblocks) sums[i] = ex + carry;
+    carry += total;
+  }
+  if (threadIdx.x == 0) sums[nblocks] = carry;
+}
+
+__global__ void scan_apply_kernel(const int32_t *in, int32_t *out, int64_t n, const int32_t *block_sums, int nblocks) {
+  __shared__ int sm[33];
+  const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+  int v[SCAN_ITEMS];
+  int s = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k) {
+    v[k] = (base + k < n) ? in[base + k] : 0;
+    s += v[k];
+  }
+  int total;
+  int ex = block_exclusive_scan(s, &total, sm) + block_sums[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k) {
+    if (base + k < n) out[base + k] = ex;
+    ex += v[k];
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = block_sums[nblocks];
+}
+
+__global__ void notquiet_flag_kernel(const float *energy, int64_t n, int32_t *flag) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) flag[t] = energy[t] > 0.5f ? 1 : 0;
+}
+
+// list[rank / every] = t for flagged t whose rank % every == 0
+__global__ void compact_kernel(const int32_t *flag, const int32_t *off, int64_t n, int every, int32_t *list) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n && flag[t]) {
+    int r = off[t];
+    if (r % every == 0) list[r / every] = (int32_t)t;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// tables
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int32_t pack_to_code(uint32_t pk) {
+  int32_t c = 0, p7 = 1;
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+    c += (int32_t)((pk >> (3 * k)) & 7u) * p7;
+    p7 *= 7;
+  }
+  return c;
+}
+
+// One thread per (selected video frame, table).  FILL = false: count; FILL = true: place.
+template <bool FILL>
+__global__ void table_kernel(const uint32_t *pack, int64_t nstride, const int32_t *sel, int64_t nsel,
+                             int32_t *count, const int32_t *start, int32_t *items) {
+  const int f = blockIdx.y;
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nsel) return;
+  const uint32_t pk = pack[(int64_t)f * nstride + sel[s]];
+  const uint32_t fl = pk >> 21;
+  const int32_t base = pack_to_code(pk);
+  const int32_t P7[7] = {1, 7, 49, 343, 2401, 16807, 117649};
+  for (uint32_t sub = fl;; sub = (sub - 1) & fl) {
+    int32_t c = base;
+#pragma unroll
+    for (int k = 0; k < 7; ++k)
+      if (sub & (1u << k)) c += P7[k];
+    const int64_t slot = (int64_t)f * DAB_NCODE + c;
+    if (!FILL) {
+      atomicAdd(&count[slot], 1);
+    } else {
+      int pos = atomicSub(&count[slot], 1) - 1;   // consumes the counts back to zero
+      items[start[slot] + pos] = (int32_t)s;
+    }
+    if (sub == 0) break;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// gate
+// ------------------------------------------------------------------------------------------
+// low bit of every 3-bit field that is non-zero
+__device__ __forceinline__ uint32_t nz_fields(uint32_t m) { return (m | (m >> 1) | (m >> 2)) & 0x49249u; }
+
+// does audio digit pack `a` fall into video entry `v` (digits + flags)?  
+__device__ __forceinline__ bool digits_match(uint32_t a, uint32_t v) {
+  const uint32_t vd = v & 0x1FFFFFu;
+  const uint32_t fl = v >> 21;
+  // spread the 7 flag bits to the low bit of each 3-bit field
+  uint32_t sp = (fl & 1u) | ((fl & 2u) << 2) | ((fl & 4u) << 4) | ((fl & 8u) << 6) | ((fl & 16u) << 8) |
+                ((fl & 32u) << 10) | ((fl & 64u) << 12);
+  const uint32_t vplus = vd + sp;   // flagged digits are <= 5, no carry between fields
+  return (nz_fields(a ^ vd) & nz_fields(a ^ vplus)) == 0u;
+}
+
+struct GateArgs {
+  const int32_t *a_code;    // [5][a_nstride]
+  const uint32_t *a_pack;
+  int64_t a_nstride;
+  const int32_t *a_list;    // not-quiet audio frames
+  int64_t n_queries;
+  const uint32_t *v_pack;   // [5][v_nstride]
+  int64_t v_nstride;
+  const int32_t *v_sel;     // selected video frames (rank -> frame)
+  const int32_t *start;     // [5*NCODE + 1]
+  const int32_t *items;
+  int32_t *row_count;       // count pass output
+  const int32_t *row_off;   // fill pass input
+  int32_t *cand_tmp, *cand_s, *cand_i;
+  int64_t cand_cap;
+  unsigned long long *enumerated;
+};
+
+template <bool FILL>
+__global__ void gate_kernel(GateArgs g) {
+  const int lane = threadIdx.x & 31;
+  const int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (q >= g.n_queries) return;
+  const int32_t i = g.a_list[q];
+  uint32_t ap[5];
+  int32_t st[5], en[5];
+#pragma unroll
+  for (int f = 0; f < 5; ++f) {
+    ap[f] = g.a_pack[(int64_t)f * g.a_nstride + i] & 0x1FFFFFu;
+    const int64_t slot = (int64_t)f * DAB_NCODE + g.a_code[(int64_t)f * g.a_nstride + i];
+    st[f] = g.start[slot];
+    en[f] = g.start[slot + 1];
+  }
+  const int n0 = en[0] - st[0], n1 = en[1] - st[1], n2 = en[2] - st[2], n3 = en[3] - st[3], n4 = en[4] - st[4];
+  // every candidate lies in at least one bucket of any pair out of {0,1,2}, and in bucket 3 or 4
+  int fa = 0, fb = 1, best = n0 + n1;
+  if (n0 + n2 < best) { best = n0 + n2; fa = 0; fb = 2; }
+  if (n1 + n2 < best) { best = n1 + n2; fa = 1; fb = 2; }
+  if (n3 + n4 < best) { best = n3 + n4; fa = 3; fb = 4; }
+  int found = 0;
+  const int64_t off = FILL ? g.row_off[q] : 0;
+  for (int pass = 0; pass < 2; ++pass) {
+    const int fcur = pass == 0 ? fa : fb;
+    const int s0 = st[fcur], cnt = en[fcur] - st[fcur];
+    for (int base = 0; base < cnt; base += 32) {
+      const int e = base + lane;
+      bool ok = false;
+      int32_t s = 0;
+      if (e < cnt) {
+        s = g.items[s0 + e];
+        const int32_t v = g.v_sel[s];
+        bool m[5];
+#pragma unroll
+        for (int f = 0; f < 5; ++f) m[f] = digits_match(ap[f], g.v_pack[(int64_t)f * g.v_nstride + v]);
+        ok = ((int)m[0] + (int)m[1] + (int)m[2] >= 2) && (m[3] || m[4]);
+        if (pass == 1 && m[fa]) ok = false;   // already enumerated from the first bucket
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, ok);
+      if (FILL && ok) {
+        const int64_t pos = off + found + __popc(bal & ((1u << lane) - 1u));
+        if (pos < g.cand_cap) g.cand_tmp[pos] = s;
+      }
+      found += __popc(bal);
+    }
+  }
+  if (!FILL) {
+    if (lane == 0) g.row_count[q] = found;
+    // work counter (bucket entries visited): one atomic per 32 rows
+    if (lane == 0 && (q & 31) == 0) atomicAdd(g.enumerated, (unsigned long long)best * 32ull);
+    return;
+  }
+  if (off + found > g.cand_cap) return;
+  __syncwarp();
+  // order the row's candidates by video rank: position = number of smaller entries
+  for (int k = lane; k < found; k += 32) {
+    const int32_t x = g.cand_tmp[off + k];
+    int r = 0;
+    for (int j = 0; j < found; ++j) r += (g.cand_tmp[off + j] < x);
+    g.cand_s[off + r] = x;
+    g.cand_i[off + r] = i;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// scoring: thread per candidate
+// ------------------------------------------------------------------------------------------
+struct ScoreArgs {
+  const int32_t *cand_s, *cand_i;
+  int64_t n_cand;
+  const int32_t *v_sel;
+  const double *a_ms, *v_ms;     // [5][stride]
+  int64_t a_stride, v_stride;
+  const double *a_nrm, *v_nrm;   // [3][nstride]
+  int64_t a_nstride, v_nstride;
+  double *qual;                  // < 0: rejected
+  int32_t *keep;
+};
+
+__global__ void score_kernel(ScoreArgs s) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= s.n_cand) return;
+  const int32_t i = s.cand_i[c];
+  const int32_t v = s.v_sel[s.cand_s[c]];
+  double prob = 1.0;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const double *am = s.a_ms + (int64_t)j * s.a_stride + i;
+    const double *vm = s.v_ms + (int64_t)j * s.v_stride + v;
+    auto X = [&](int k) { return am[k]; };
+    auto Y = [&](int k) { return vm[k]; };
+    double corr = ddot41_skx(X, Y);
+    corr = corr / (s.a_nrm[(int64_t)j * s.a_nstride + i] * s.v_nrm[(int64_t)j * s.v_nstride + v]);
+    prob = prob * fmax(1e-8, 1.0 - corr);
+  }
+  prob = pow(prob, 2.9);
+  double qual = -1.0;
+  if (!(prob > 1e-8)) qual = fmin(50.0, pow(prob / 1e-12, -1.0 / 3));
+  s.qual[c] = qual;
+  s.keep[c] = qual >= 0.0 ? 1 : 0;
+}
+
+__global__ void gather_points_kernel(const int32_t *keep, const int32_t *off, int64_t n,
+                                     const int32_t *cand_i, const int32_t *cand_s, const double *qual,
+                                     int32_t *pt_i, int32_t *pt_s, double *pt_q) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < n && keep[c]) {
+    const int o = off[c];
+    pt_i[o] = cand_i[c];
+    pt_s[o] = cand_s[c];
+    pt_q[o] = qual[c];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// frontier DP #1: cum(p) = q(p) + max{cum(p') : p' earlier, rank' <= rank},
+// ties to the smallest rank; the seed has cum 0.  One warp walks the points in (i, v) order;
+// the prefix maximum lives in a 32-ary max tree over the video ranks: per level the warp
+// loads one 32-node row (512 B, coalesced), lanes left of the path contribute to the query and
+// the lane on the path keeps the old node for the update.  All four rows are fetched together,
+// so a point costs one memory round trip (usually L1 hits: consecutive path points share rows).
+// ------------------------------------------------------------------------------------------
+struct __align__(16) Node1 {
+  double cum;     // 0 = empty / seed
+  int32_t id;     // point id, -1 = seed
+  int32_t rank;
+};
+
+constexpr int DP_LEVELS = 4;
+constexpr int DP_CHECK = 256;   // checkpoint spacing for the parallel traceback
+
+struct Dp1Args {
+  const int32_t *pt_s;
+  const double *pt_q;
+  const int32_t *n_points_dev;   // device-resident count
+  Node1 *level[DP_LEVELS];
+  int32_t *back, *len, *cp;
+  int32_t *result;               // [0] end id, [1] path length
+};
+
+__device__ __forceinline__ bool key_better(double ca, int ra, double cb, int rb) {
+  return ca > cb || (ca == cb && ra < rb);
+}
+
+__global__ void __launch_bounds__(32, 1) dp1_kernel(Dp1Args a) {
+  const int lane = threadIdx.x;
+  const int n = *a.n_points_dev;
+  double best_all_cum = 0.0;
+  int best_all_id = -1, best_all_rank = 0x7fffffff;
+  int r_next = n > 0 ? a.pt_s[0] : 0;
+  double q_next = n > 0 ? a.pt_q[0] : 0.0;
+  for (int p = 0; p < n; ++p) {
+    const int r = r_next;
+    const double q = q_next;
+    if (p + 1 < n) { r_next = a.pt_s[p + 1]; q_next = a.pt_q[p + 1]; }
+    Node1 nd[DP_LEVELS];
+    int pos[DP_LEVELS];
+#pragma unroll
+    for (int k = 0; k < DP_LEVELS; ++k) {
+      const int g = r >> (5 * k);
+      pos[k] = g & 31;
+      nd[k] = a.level[k][(g & ~31) + lane];
+    }
+    // lane-local best over eligible nodes; higher levels hold smaller ranks
+    double bc = 0.0;
+    int bid = -1, brank = 0x7fffffff;
+#pragma unroll
+    for (int k = DP_LEVELS - 1; k >= 0; --k) {
+      const bool elig = (k == 0) ? (lane <= pos[0]) : (lane < pos[k]);
+      if (elig && key_better(nd[k].cum, nd[k].rank, bc, brank)) { bc = nd[k].cum; bid = nd[k].id; brank = nd[k].rank; }
+    }
+    // warp arg-max on (cum desc, rank asc); all cum >= 0 so the bit patterns order like integers
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(bc);
+    const unsigned hi = (unsigned)(bits >> 32), lo = (unsigned)bits;
+    const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
+    bool alive = hi == mhi;
+    const unsigned mlo = __reduce_max_sync(0xffffffffu, alive ? lo : 0u);
+    alive = alive && lo == mlo;
+    const unsigned mr = __reduce_min_sync(0xffffffffu, alive ? (unsigned)brank : 0xffffffffu);
+    alive = alive && (unsigned)brank == mr;
+    const int src = __ffs(__ballot_sync(0xffffffffu, alive)) - 1;
+    const double pc = __shfl_sync(0xffffffffu, bc, src);
+    const int pid = __shfl_sync(0xffffffffu, bid, src);
+    const double cum = pc + q;
+    // updates: leaf always (a later point on the same rank chains from the earlier one), upper
+    // levels when the new key wins
+    if (lane == pos[0]) {
+      Node1 me; me.cum = cum; me.id = p; me.rank = r;
+      a.level[0][r] = me;
+    }
+#pragma unroll
+    for (int k = 1; k < DP_LEVELS; ++k) {
+      if (lane == pos[k] && key_better(cum, r, nd[k].cum, nd[k].rank)) {
+        Node1 me; me.cum = cum; me.id = p; me.rank = r;
+        a.level[k][r >> (5 * k)] = me;
+      }
+    }
+    if (lane == 0) {
+      a.back[p] = pid;
+      const int ln = pid < 0 ? 1 : a.len[pid] + 1;
+      a.len[p] = ln;
+      a.cp[p] = (ln % DP_CHECK == 0 || pid < 0) ? p : a.cp[pid];
+    }
+    if (key_better(cum, r, best_all_cum, best_all_rank)) { best_all_cum = cum; best_all_id = p; best_all_rank = r; }
+    __syncwarp();
+  }
+  if (lane == 0) {
+    a.result[0] = best_all_id;
+    a.result[1] = best_all_id < 0 ? 0 : a.len[best_all_id];
+  }
+}
+
+// Traceback: thread 0 hops from checkpoint to checkpoint (path_len / 256 dependent steps),
+// then every segment between checkpoints is walked by its own thread.
+struct TraceArgs {
+  const int32_t *back, *len, *cp, *result;
+  const int32_t *pt_i, *pt_s, *v_sel;
+  int32_t *seg;          // scratch: segment start ids
+  int32_t *path_x, *path_y;
+};
+
+__global__ void trace1_kernel(TraceArgs a) {
+  __shared__ int nseg;
+  if (threadIdx.x == 0) {
+    int k = 0;
+    int cur = a.result[0];
+    while (cur >= 0) {
+      a.seg[k++] = cur;
+      const int c = a.cp[cur];      // last node of this segment (checkpoint or chain root)
+      cur = a.back[c];
+    }
+    nseg = k;
+  }
+  __syncthreads();
+  for (int s = threadIdx.x; s < nseg; s += blockDim.x) {
+    int cur = a.seg[s];
+    const int stop = a.cp[cur];
+    while (true) {
+      const int pos = a.len[cur] - 1;
+      a.path_x[pos] = a.pt_i[cur];
+      a.path_y[pos] = a.v_sel[a.pt_s[cur]];
+      if (cur == stop) break;
+      cur = a.back[cur];
+    }
+  }
+}
+
+__global__ void fill_nodes_kernel(Node1 *p, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { Node1 z; z.cum = 0.0; z.id = -1; z.rank = 0x7fffffff; p[i] = z; }
+}
+
+bool g_hann_ready[64] = {};
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// host drivers
+// ------------------------------------------------------------------------------------------
+int dab_exclusive_scan(dab_pair *pr, const int32_t *in, int32_t *out, int64_t n) {
+  dab_ctx *ctx = pr->ctx;
+  const int nblocks = (int)cdiv(n > 0 ? n : 1, SCAN_TILE);
+  DAB_TRY(dab_ensure(ctx, pr->scan_tmp, sizeof(int32_t) * (size_t)(nblocks + 1)));
+  int32_t *sums = pr->scan_tmp.as<int32_t>();
+  scan_reduce_kernel<<<nblocks, SCAN_THREADS, 0, pr->stream>>>(in, n, sums);
+  scan_sums_kernel<<<1, SCAN_THREADS, 0, pr->stream>>>(sums, nblocks);
+  scan_apply_kernel<<<nblocks, SCAN_THREADS, 0, pr->stream>>>(in, out, n, sums, nblocks);
+  pr->ctx->launches += 3;
+  DAB_CUDA(cudaGetLastError());
+  return DAB_OK;
+}
+
+static int prep_track(dab_pair *pr, int track) {
+  dab_ctx *ctx = pr->ctx;
+  Track &tk = pr->trk[track];
+  const int64_t Lmax = tk.Le > tk.L ? tk.Le : tk.L;
+  const int64_t Lmin = tk.Le < tk.L ? tk.Le : tk.L;
+  const int64_t nc = Lmax - 40;     // stride of the code arrays (energy may have one more)
+  tk.n_codes = Lmin - 40;
+  DAB_TRY(dab_ensure(ctx, tk.ms, sizeof(double) * (size_t)(5 * Lmax)));
+  DAB_TRY(dab_ensure(ctx, tk.nrm, sizeof(double) * (size_t)(3 * nc)));
+  DAB_TRY(dab_ensure(ctx, tk.pack, sizeof(uint32_t) * (size_t)(5 * nc)));
+  DAB_TRY(dab_ensure(ctx, tk.code, sizeof(int32_t) * (size_t)(5 * nc)));
+  PrepArgs pa;
+  pa.f32[0] = tk.energy.as<float>(); pa.f32[1] = tk.zc.as<float>();
+  pa.f32[2] = tk.b0.as<float>(); pa.f32[3] = tk.b1.as<float>();
+  pa.f64 = tk.b2.as<double>();
+  pa.len[0] = tk.Le; pa.len[1] = pa.len[2] = pa.len[3] = pa.len[4] = tk.L;
+  pa.Lp = Lmin; pa.ms = tk.ms.as<double>(); pa.stride = Lmax;
+  dim3 g1((unsigned)cdiv(Lmax, 256), 5);
+  meansub_kernel<<<g1, 256, 0, pr->stream>>>(pa);
+  CodeArgs ca;
+  ca.ms = tk.ms.as<double>(); ca.stride = Lmax;
+  for (int f = 0; f < 5; ++f) ca.len[f] = pa.len[f];
+  ca.nrm = tk.nrm.as<double>(); ca.nstride = nc;
+  ca.pack = tk.pack.as<uint32_t>(); ca.code = tk.code.as<int32_t>();
+  ca.is_video = track == DAB_TRACK_VIDEO;
+  dim3 g2((unsigned)cdiv(nc, 256), 5);
+  norm_codes_kernel<<<g2, 256, 0, pr->stream>>>(ca);
+  ctx->launches += 2;
+  // not-quiet selection: t < len(energy) - 41 with energy[t] > .5
+  const int64_t nqn = tk.Le - 41;
+  DAB_TRY(dab_ensure(ctx, tk.nq_flag, sizeof(int32_t) * (size_t)(2 * (nqn + 2))));
+  DAB_TRY(dab_ensure(ctx, tk.nq_list, sizeof(int32_t) * (size_t)(nqn + 2)));
+  int32_t *flag = tk.nq_flag.as<int32_t>();
+  int32_t *off = flag + (nqn + 1);
+  notquiet_flag_kernel<<<(unsigned)cdiv(nqn, 256), 256, 0, pr->stream>>>(tk.energy.as<float>(), nqn, flag);
+  ctx->launches += 1;
+  DAB_TRY(dab_exclusive_scan(pr, flag, off, nqn));
+  compact_kernel<<<(unsigned)cdiv(nqn, 256), 256, 0, pr->stream>>>(flag, off, nqn, track == DAB_TRACK_VIDEO ? 4 : 1,
+                                                                  tk.nq_list.as<int32_t>());
+  ctx->launches += 1;
+  DAB_CUDA(cudaMemcpyAsync(&pr->h_counters[track], off + nqn, sizeof(int32_t), cudaMemcpyDeviceToHost, pr->stream));
+  DAB_CUDA(cudaGetLastError());
+  return DAB_OK;
+}
+
+int dab_run_stage_a(dab_pair *pr) {
+  dab_ctx *ctx = pr->ctx;
+  int dev = 0;
+  DAB_CUDA(cudaGetDevice(&dev));
+  if (!(dev < 64 && g_hann_ready[dev])) {
+    double hf[41];
+    for (int k = 0; k < 41; ++k) hf[k] = DAB_HANN41_F64[40 - k];
+    DAB_CUDA(cudaMemcpyToSymbol(c_hflip, hf, sizeof(hf)));
+    if (dev < 64) g_hann_ready[dev] = true;
+  }
+  Track &V = pr->trk[DAB_TRACK_VIDEO], &A = pr->trk[DAB_TRACK_AUDIO];
+  cudaStream_t st = pr->stream;
+  pr->n_points1 = pr->n_path1 = 0;
+
+  DAB_CUDA(cudaEventRecord(pr->ev[4], st));
+  pr->h_counters[0] = pr->h_counters[1] = 0;
+  DAB_TRY(prep_track(pr, DAB_TRACK_VIDEO));
+  DAB_TRY(prep_track(pr, DAB_TRACK_AUDIO));
+  DAB_CUDA(cudaEventRecord(pr->ev[5], st));
+  DAB_CUDA(cudaStreamSynchronize(st));
+  const int64_t n_vnq = (int32_t)pr->h_counters[0];
+  const int64_t n_vsel = (n_vnq + 3) / 4;
+  const int64_t n_q = (int32_t)pr->h_counters[1];
+  V.n_list = n_vsel;
+  A.n_list = n_q;
+  pr->stats.n_video_frames = V.L; pr->stats.n_audio_frames = A.L;
+  pr->stats.n_video_selected = n_vsel; pr->stats.n_audio_queries = n_q;
+
+  // ---- tables ----
+  const int64_t nslots = 5LL * DAB_NCODE;
+  DAB_TRY(dab_ensure(ctx, pr->tbl_count, sizeof(int32_t) * (size_t)(nslots + 1)));
+  DAB_TRY(dab_ensure(ctx, pr->tbl_start, sizeof(int32_t) * (size_t)(nslots + 2)));
+  DAB_TRY(dab_ensure(ctx, pr->counters, sizeof(int64_t) * 16));
+  DAB_CUDA(cudaMemsetAsync(pr->tbl_count.p, 0, sizeof(int32_t) * (size_t)(nslots + 1), st));
+  DAB_CUDA(cudaMemsetAsync(pr->counters.p, 0, sizeof(int64_t) * 16, st));
+  const int64_t v_nstride = (V.Le > V.L ? V.Le : V.L) - 40;
+  const int64_t a_nstride = (A.Le > A.L ? A.Le : A.L) - 40;
+  DAB_CUDA(cudaEventRecord(pr->ev[6], st));
+  if (n_vsel > 0) {
+    dim3 gt((unsigned)cdiv(n_vsel, 128), 5);
+    table_kernel<false><<<gt, 128, 0, st>>>(V.pack.as<uint32_t>(), v_nstride, V.nq_list.as<int32_t>(), n_vsel,
+                                            pr->tbl_count.as<int32_t>(), nullptr, nullptr);
+    ctx->launches += 1;
+  }
+  DAB_TRY(dab_exclusive_scan(pr, pr->tbl_count.as<int32_t>(), pr->tbl_start.as<int32_t>(), nslots));
+  DAB_CUDA(cudaMemcpyAsync(&pr->h_counters[2], pr->tbl_start.as<int32_t>() + nslots, sizeof(int32_t),
+                           cudaMemcpyDeviceToHost, st));
+  DAB_CUDA(cudaStreamSynchronize(st));
+  const int64_t n_entries = (int32_t)pr->h_counters[2];
+  pr->stats.n_table_entries = n_entries;
+  DAB_TRY(dab_ensure(ctx, pr->tbl_items, sizeof(int32_t) * (size_t)(n_entries + 1)));
+  if (n_vsel > 0) {
+    dim3 gt((unsigned)cdiv(n_vsel, 128), 5);
+    table_kernel<true><<<gt, 128, 0, st>>>(V.pack.as<uint32_t>(), v_nstride, V.nq_list.as<int32_t>(), n_vsel,
+                                           pr->tbl_count.as<int32_t>(), pr->tbl_start.as<int32_t>(),
+                                           pr->tbl_items.as<int32_t>());
+    ctx->launches += 1;
+  }
+  DAB_CUDA(cudaEventRecord(pr->ev[7], st));
+
+  // ---- gate: count, scan, fill ----
+  DAB_TRY(dab_ensure(ctx, pr->row_count, sizeof(int32_t) * (size_t)(n_q + 2)));
+  DAB_TRY(dab_ensure(ctx, pr->row_off, sizeof(int32_t) * (size_t)(n_q + 2)));
+  GateArgs ga;
+  ga.a_code = A.code.as<int32_t>(); ga.a_pack = A.pack.as<uint32_t>(); ga.a_nstride = a_nstride;
+  ga.a_list = A.nq_list.as<int32_t>(); ga.n_queries = n_q;
+  ga.v_pack = V.pack.as<uint32_t>(); ga.v_nstride = v_nstride; ga.v_sel = V.nq_list.as<int32_t>();
+  ga.start = pr->tbl_start.as<int32_t>(); ga.items = pr->tbl_items.as<int32_t>();
+  ga.row_count = pr->row_count.as<int32_t>(); ga.row_off = pr->row_off.as<int32_t>();
+  ga.cand_tmp = ga.cand_s = ga.cand_i = nullptr; ga.cand_cap = 0;
+  ga.enumerated = reinterpret_cast<unsigned long long *>(pr->counters.as<int64_t>() + 3);
+  DAB_CUDA(cudaEventRecord(pr->ev[8], st));
+  int64_t n_cand = 0;
+  if (n_q > 0) {
+    const unsigned gb = (unsigned)cdiv(n_q * 32, 256);
+    gate_kernel<false><<<gb, 256, 0, st>>>(ga);
+    ctx->launches += 1;
+    DAB_TRY(dab_exclusive_scan(pr, pr->row_count.as<int32_t>(), pr->row_off.as<int32_t>(), n_q));
+    DAB_CUDA(cudaMemcpyAsync(&pr->h_counters[4], pr->row_off.as<int32_t>() + n_q, sizeof(int32_t),
+                             cudaMemcpyDeviceToHost, st));
+    DAB_CUDA(cudaMemcpyAsync(&pr->h_counters[3], pr->counters.as<int64_t>() + 3, sizeof(int64_t),
+                             cudaMemcpyDeviceToHost, st));
+    DAB_CUDA(cudaStreamSynchronize(st));
+    n_cand = (int32_t)pr->h_counters[4];
+    pr->stats.n_enumerated = pr->h_counters[3];
+    DAB_TRY(dab_ensure(ctx, pr->cand_tmp, sizeof(int32_t) * (size_t)(n_cand + 1)));
+    DAB_TRY(dab_ensure(ctx, pr->cand_s, sizeof(int32_t) * (size_t)(n_cand + 1)));
+    DAB_TRY(dab_ensure(ctx, pr->cand_i, sizeof(int32_t) * (size_t)(n_cand + 1)));
+    ga.cand_tmp = pr->cand_tmp.as<int32_t>(); ga.cand_s = pr->cand_s.as<int32_t>(); ga.cand_i = pr->cand_i.as<int32_t>();
+    ga.cand_cap = n_cand;
+    if (n_cand > 0) {
+      gate_kernel<true><<<gb, 256, 0, st>>>(ga);
+      ctx->launches += 1;
+    }
+  }
+  pr->stats.n_candidates = n_cand;
+  DAB_CUDA(cudaEventRecord(pr->ev[9], st));
+
+  // ---- scoring + compaction ----
+  DAB_CUDA(cudaEventRecord(pr->ev[10], st));
+  int64_t n_pts = 0;
+  if (n_cand > 0) {
+    DAB_TRY(dab_ensure(ctx, pr->cand_q, sizeof(double) * (size_t)(n_cand + 1)));
+    DAB_TRY(dab_ensure(ctx, pr->keep_flag, sizeof(int32_t) * (size_t)(n_cand + 2)));
+    DAB_TRY(dab_ensure(ctx, pr->keep_off, sizeof(int32_t) * (size_t)(n_cand + 2)));
+    ScoreArgs sa;
+    sa.cand_s = pr->cand_s.as<int32_t>(); sa.cand_i = pr->cand_i.as<int32_t>(); sa.n_cand = n_cand;
+    sa.v_sel = V.nq_list.as<int32_t>();
+    sa.a_ms = A.ms.as<double>(); sa.v_ms = V.ms.as<double>();
+    sa.a_stride = (A.Le > A.L ? A.Le : A.L); sa.v_stride = (V.Le > V.L ? V.Le : V.L);
+    sa.a_nrm = A.nrm.as<double>(); sa.v_nrm = V.nrm.as<double>();
+    sa.a_nstride = a_nstride; sa.v_nstride = v_nstride;
+    sa.qual = pr->cand_q.as<double>(); sa.keep = pr->keep_flag.as<int32_t>();
+    score_kernel<<<(unsigned)cdiv(n_cand, 128), 128, 0, st>>>(sa);
+    ctx->launches += 1;
+    DAB_TRY(dab_exclusive_scan(pr, pr->keep_flag.as<int32_t>(), pr->keep_off.as<int32_t>(), n_cand));
+    DAB_CUDA(cudaMemcpyAsync(&pr->h_counters[5], pr->keep_off.as<int32_t>() + n_cand, sizeof(int32_t),
+                             cudaMemcpyDeviceToHost, st));
+    DAB_CUDA(cudaStreamSynchronize(st));
+    n_pts = (int32_t)pr->h_counters[5];
+    DAB_TRY(dab_ensure(ctx, pr->pt_i, sizeof(int32_t) * (size_t)(n_pts + 1)));
+    DAB_TRY(dab_ensure(ctx, pr->pt_s, sizeof(int32_t) * (size_t)(n_pts + 1)));
+    DAB_TRY(dab_ensure(ctx, pr->pt_q, sizeof(double) * (size_t)(n_pts + 1)));
+    if (n_pts > 0) {
+      gather_points_kernel<<<(unsigned)cdiv(n_cand, 256), 256, 0, st>>>(
+          pr->keep_flag.as<int32_t>(), pr->keep_off.as<int32_t>(), n_cand, pr->cand_i.as<int32_t>(),
+          pr->cand_s.as<int32_t>(), pr->cand_q.as<double>(), pr->pt_i.as<int32_t>(), pr->pt_s.as<int32_t>(),
+          pr->pt_q.as<double>());
+      ctx->launches += 1;
+    }
+  }
+  pr->n_points1 = n_pts;
+  pr->stats.n_points1 = n_pts;
+  DAB_CUDA(cudaEventRecord(pr->ev[11], st));
+
+  // ---- DP #1 + traceback ----
+  DAB_CUDA(cudaEventRecord(pr->ev[12], st));
+  int64_t n_path = 0;
+  if (n_pts > 0) {
+    if (n_vsel > (1LL << (5 * DP_LEVELS))) { ctx->err = "too many hashed video frames for the DP tree"; return DAB_E_CAPACITY; }
+    int64_t lv[DP_LEVELS], tot = 0;
+    int64_t m = n_vsel;
+    for (int k = 0; k < DP_LEVELS; ++k) { lv[k] = cdiv(m > 0 ? m : 1, 32) * 32; tot += lv[k]; m = cdiv(m, 32); }
+    DAB_TRY(dab_ensure(ctx, pr->tree1, sizeof(Node1) * (size_t)tot));
+    fill_nodes_kernel<<<(unsigned)cdiv(tot, 256), 256, 0, st>>>(pr->tree1.as<Node1>(), tot);
+    DAB_TRY(dab_ensure(ctx, pr->back1, sizeof(int32_t) * (size_t)(n_pts + 1)));
+    DAB_TRY(dab_ensure(ctx, pr->len1, sizeof(int32_t) * (size_t)(n_pts + 1)));
+    DAB_TRY(dab_ensure(ctx, pr->cp1, sizeof(int32_t) * (size_t)(n_pts + 1)));
+    DAB_TRY(dab_ensure(ctx, pr->dpres, sizeof(int32_t) * 8));
+    DAB_TRY(dab_ensure(ctx, pr->seglist, sizeof(int32_t) * (size_t)(n_pts / DP_CHECK + 16)));
+    DAB_TRY(dab_ensure(ctx, pr->path1_x, sizeof(int32_t) * (size_t)(n_pts + 1)));
+    DAB_TRY(dab_ensure(ctx, pr->path1_y, sizeof(int32_t) * (size_t)(n_pts + 1)));
+    Dp1Args da;
+    da.pt_s = pr->pt_s.as<int32_t>(); da.pt_q = pr->pt_q.as<double>();
+    da.n_points_dev = pr->keep_off.as<int32_t>() + n_cand;
+    Node1 *base = pr->tree1.as<Node1>();
+    for (int k = 0; k < DP_LEVELS; ++k) { da.level[k] = base; base += lv[k]; }
+    da.back = pr->back1.as<int32_t>(); da.len = pr->len1.as<int32_t>(); da.cp = pr->cp1.as<int32_t>();
+    da.result = pr->dpres.as<int32_t>();
+    dp1_kernel<<<1, 32, 0, st>>>(da);
+    TraceArgs ta;
+    ta.back = da.back; ta.len = da.len; ta.cp = da.cp; ta.result = da.result;
+    ta.pt_i = pr->pt_i.as<int32_t>(); ta.pt_s = pr->pt_s.as<int32_t>(); ta.v_sel = V.nq_list.as<int32_t>();
+    ta.seg = pr->seglist.as<int32_t>(); ta.path_x = pr->path1_x.as<int32_t>(); ta.path_y = pr->path1_y.as<int32_t>();
+    trace1_kernel<<<1, 256, 0, st>>>(ta);
+    ctx->launches += 3;
+    DAB_CUDA(cudaMemcpyAsync(&pr->h_counters[6], pr->dpres.as<int32_t>(), 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    DAB_CUDA(cudaEventRecord(pr->ev[13], st));
+    DAB_CUDA(cudaStreamSynchronize(st));
+    n_path = reinterpret_cast<int32_t *>(&pr->h_counters[6])[1];
+  } else {
+    DAB_CUDA(cudaEventRecord(pr->ev[13], st));
+  }
+  pr->n_path1 = n_path;
+  pr->stats.n_path1 = n_path;
+  for (int s = 2; s <= 6; ++s) pr->ev_used[s] = true;
+  DAB_CUDA(cudaGetLastError());
+  return DAB_OK;
+}

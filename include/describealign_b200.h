@@ -1,0 +1,153 @@
+/*
+ * describealign_b200 - C ABI of the B200 alignment hot path.
+ *
+ * Drop-in boundary for the part of julbean/describealign between "PCM decoded" and the
+ * returned alignment (reference describealign.py:545-1027).  The reference has no FFI for
+ * this path - it is plain Python calling numpy - so the entry points below are what a
+ * binding for the reference's four hot-path functions needs (INTEGRATION.md shows the
+ * ctypes stub):
+ *
+ *   reference function (describealign.py)            replaced by
+ *   ------------------------------------------------------------------------------------
+ *   parse_audio_from_file tail  :156  (int16->f16)   dab_pair_set_pcm (conversion on device)
+ *   get_energy                  :545-555             dab_pair_set_pcm + dab_pair_get_features
+ *   get_zero_crossings          :557-566             "
+ *   get_freq_bands              :575-593             "
+ *   align, device stage A       :596-700             dab_pair_stage_a + dab_pair_get_path1
+ *   align, host stage           :702-893             stays in Python (describealign_b200/host_fit.py)
+ *   align, device stage B       :895-993             dab_pair_stage_b + dab_pair_get_path2
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success or a
+ * DAB_E_* code, with a message available from dab_last_error(); the caller owns every
+ * buffer it passes; "host" pointers may be pageable or pinned; nothing here is
+ * thread-safe per context (the reference calls the path from one thread, :1098-1122) but
+ * any number of pairs may be in flight on one context - calls that enqueue work are
+ * asynchronous on the pair's own CUDA stream and dab_pair_get_* / dab_pair_sync wait for it.
+ * There is no CPU fallback: without a CUDA device dab_create fails.
+ */
+#ifndef DESCRIBEALIGN_B200_H
+#define DESCRIBEALIGN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DAB_ABI_VERSION 1
+
+enum {
+  DAB_OK = 0,
+  DAB_E_CUDA = 1,       /* a CUDA runtime call failed */
+  DAB_E_ARG = 2,        /* invalid argument */
+  DAB_E_STATE = 3,      /* call sequence violated (e.g. stage_a before features) */
+  DAB_E_CAPACITY = 4,   /* an internal buffer overflowed even after growing */
+  DAB_E_TOO_SHORT = 5   /* track shorter than the 41-frame window */
+};
+
+/* sample formats accepted by dab_pair_set_pcm */
+enum {
+  DAB_PCM_S16 = 0,      /* interleaved int16, as ffmpeg's s16le stream (describealign.py:152) */
+  DAB_PCM_F16 = 1       /* interleaved IEEE half, i.e. the memory behind the reference's
+                           float16 (ch, S) array, which is an F-ordered view (describealign.py:156) */
+};
+
+enum { DAB_TRACK_VIDEO = 0, DAB_TRACK_AUDIO = 1 };
+
+typedef struct dab_ctx dab_ctx;    /* one per process and GPU */
+typedef struct dab_pair dab_pair;  /* one (video, description) pair: device-resident state */
+
+/* One scored corridor of stage B: audio rows [lo, hi) on the line j = slope * i + offset,
+ * belonging to line cluster `cluster` (describealign.py:931-941). */
+typedef struct {
+  int32_t cluster;
+  int32_t lo;
+  int32_t hi;
+  int32_t reserved;
+  double slope;
+  double offset;
+} dab_corridor;
+
+/* Work counters of the last stage_a / stage_b run (for measurement). */
+typedef struct {
+  int64_t n_video_frames, n_audio_frames;
+  int64_t n_video_selected;   /* hashed video frames (every 4th not-quiet) */
+  int64_t n_audio_queries;    /* not-quiet audio frames */
+  int64_t n_table_entries;    /* expanded entries per table, summed over the 5 tables */
+  int64_t n_enumerated;       /* bucket entries visited by the gate */
+  int64_t n_candidates;       /* candidates scored */
+  int64_t n_points1;          /* match points of pass 1 */
+  int64_t n_path1;
+  int64_t n_points2;
+  int64_t n_path2;
+} dab_stats;
+
+int dab_abi_version(void);
+int dab_device_count(void);
+
+/* device < 0: current device. */
+int dab_create(int device, dab_ctx **out);
+void dab_destroy(dab_ctx *ctx);
+const char *dab_last_error(const dab_ctx *ctx);   /* ctx may be NULL for dab_create failures */
+
+int dab_pair_create(dab_ctx *ctx, dab_pair **out);
+void dab_pair_destroy(dab_pair *pair);
+int dab_pair_sync(dab_pair *pair);
+/* the CUDA stream (cudaStream_t) the pair's work is enqueued on, for event timing */
+void *dab_pair_stream(dab_pair *pair);
+
+/* ---- features (reference :545-593) ------------------------------------------------------
+ * Computes the five 210 Hz feature vectors of one track from interleaved PCM of
+ * `samples` samples per channel, `channels` in {1, 2}.  `pcm` is a host pointer, or a
+ * device pointer when on_device != 0.  Results stay on the device inside the pair. */
+int dab_pair_set_pcm(dab_pair *pair, int track, const void *pcm, int64_t samples, int channels,
+                     int format, int on_device);
+
+/* Alternatively upload features computed elsewhere (the reference-level align() boundary,
+ * :595): energy[n_energy], zc[n], band0[n], band1[n] float32 and band2[n] float64 (host). */
+int dab_pair_set_features(dab_pair *pair, int track, const float *energy, int64_t n_energy,
+                          const float *zc, const float *band0, const float *band1, const double *band2,
+                          int64_t n);
+
+/* lens[0] = len(energy) (n or n + 1, :555), lens[1..4] = n. */
+int dab_pair_feature_lens(dab_pair *pair, int track, int64_t lens[5]);
+/* Copies features to host buffers of at least lens[] elements; any pointer may be NULL. */
+int dab_pair_get_features(dab_pair *pair, int track, float *energy, float *zc, float *band0,
+                          float *band1, double *band2);
+
+/* ---- stage A (reference :596-700) -------------------------------------------------------
+ * prep + codes + tables + gate + scoring + frontier DP #1 + traceback, all on the device.
+ * Blocks until the path length is known.  n_points / n_path may be NULL. */
+int dab_pair_stage_a(dab_pair *pair, int64_t *n_points, int64_t *n_path);
+/* pass-1 path, ascending: audio frame x[k], video frame y[k] (int32, n_path entries each). */
+int dab_pair_get_path1(dab_pair *pair, int32_t *x_audio, int32_t *y_video);
+/* pass-1 match points sorted by (audio frame, video frame); any pointer may be NULL. */
+int dab_pair_get_points1(dab_pair *pair, int32_t *i_audio, int32_t *v_video, double *qual);
+
+/* ---- stage B (reference :895-993) -------------------------------------------------------
+ * audio_scaled / video_scaled: float32 row-major (n, 3) arrays from the host stage (:740-741),
+ * host pointers.  corridors: the scored clusters in cluster order with their final
+ * (refined) lines.  n_clusters: number of line clusters (>= max cluster index + 1). */
+int dab_pair_stage_b(dab_pair *pair, const float *audio_scaled, int64_t n_audio,
+                     const float *video_scaled, int64_t n_video, const dab_corridor *corridors,
+                     int32_t n_corridors, int32_t n_clusters, int64_t *n_points, int64_t *n_path);
+/* final path rows (video j, audio i, cluster, qual, cum), float64 row-major (n_path, 5),
+ * in frames (the /210 scaling of :1026 is the caller's). */
+int dab_pair_get_path2(dab_pair *pair, double *rows);
+/* pass-2 points sorted by (i, j, cluster); any pointer may be NULL. */
+int dab_pair_get_points2(dab_pair *pair, int32_t *i_audio, double *j_video, int32_t *cluster, double *qual);
+
+int dab_pair_get_stats(dab_pair *pair, dab_stats *out);
+
+/* Device-side time of the kernels of the last stage_a / stage_b / set_pcm call on this pair,
+ * in milliseconds, measured with CUDA events on the pair's stream; slots:
+ * 0 features(video) 1 features(audio) 2 prep+codes 3 tables 4 gate 5 score 6 dp1+traceback
+ * 7 corridor scoring 8 dp2+traceback.  Slots not run since creation are 0. */
+int dab_pair_get_timings(dab_pair *pair, float ms[16]);
+/* number of kernel launches issued by this context since creation */
+int64_t dab_launch_count(const dab_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DESCRIBEALIGN_B200_H */
