@@ -1,0 +1,406 @@
+#!/usr/bin/env python
+"""Benchmark of the alignment hot path (BASELINE.json: audio-hours aligned per second).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--pairs B] [--impl ours|reference]
+
+A step = one pass of the hot path over one batch of B synthetic pairs per GPU of the C2 shape
+(22-min video audio vs 27-min description, 202 s start offset, injected skips):
+features of both tracks, device stage A (describealign.py:596-700) and device stage B
+(:895-993).  The host-side rate-change fit between the two device stages (:702-893) runs
+every step but outside the timed regions, as BASELINE.json prescribes.
+
+value   device-resident: PCM already in HBM when the timed region starts; CUDA events
+        bracketing each device stage on the streams the kernels are launched on.
+e2e     the same passes through the public API (AlignJob.load_pcm + stages) from pinned HOST
+        buffers, H2D/D2H copies inside the timed region.
+One rank per GPU (torchrun for N > 1); ranks process disjoint pairs (weak scaling), no
+data-path collective; timings are max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "audio_hours_aligned_per_second"
+UNIT = "audio-hours/s"
+WORKLOAD = "C2: synthetic 22-min video audio vs 27-min description, 202 s offset, 10 inserted skips, mono 44.1 kHz s16"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--pairs", type=int, default=4, help="pairs per GPU per step")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the C2 durations (debugging only)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def make_pairs(n, first_seed, scale):
+    """n C2 pairs with distinct seeds, generated in parallel worker processes."""
+    from concurrent.futures import ProcessPoolExecutor
+    from describealign_b200 import synth
+    seeds = [first_seed + k for k in range(n)]
+    if n == 1:
+        return [synth.config_pair("C2", seeds[0], scale)]
+    with ProcessPoolExecutor(max_workers=min(n, os.cpu_count() or 1)) as ex:
+        return list(ex.map(_make_one, [(s, scale) for s in seeds]))
+
+
+def _make_one(arg):
+    from describealign_b200 import synth
+    return synth.config_pair("C2", arg[0], arg[1])
+
+
+def audio_hours(pairs):
+    return sum(v.shape[0] + a.shape[0] for v, a in pairs) / 44100.0 / 3600.0
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[3 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        with open(p) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm (oracle port; the reference is Python and not present on the GPU box)
+# ------------------------------------------------------------------------------------------------
+
+def cpu_pass(pair, keep=False):
+    """One pass of the hot path on the CPU through the oracle; returns (seconds without the host
+    fit, seconds of the host fit, outputs or path length)."""
+    from describealign_b200 import host_fit
+    from oracle import align_oracle as ao, features as of
+    v, a = pair
+    t0 = time.perf_counter()
+    V, A = of.all_features(v), of.all_features(a)
+    sa = ao.stage_a(V, A, V[0], A[0])
+    t1 = time.perf_counter()
+    x, y = sa["path_x"], sa["path_y"]
+    kp = host_fit.continuity_error(x, y) < 3
+    kx, ky = x[kp], y[kp]
+    a_s, v_s = host_fit.scale_features(V, A, kx, ky)
+    fx, fy = host_fit.compress_path(kx, ky)
+    fit = host_fit.rate_change_fit(fx, fy)
+    clusters = host_fit.line_clusters(fit)
+    plans = host_fit.plan_corridors(clusters, a_s, v_s)
+    t2 = time.perf_counter()
+    sb = ao.stage_b(plans, len(clusters), a_s, v_s)
+    t3 = time.perf_counter()
+    out = len(sb["path"])
+    if keep:
+        path = sb["path"]
+        nx, ny, sim = host_fit.build_nodes(path, len(A[0]), len(V[0]), len(a_s), len(v_s))
+        out = {"V": V, "A": A, "path1": (x, y), "path": path, "nodes": (nx, ny), "similarity": sim}
+    return (t1 - t0) + (t3 - t2), t2 - t1, out
+
+
+def _cpu_worker(pair):
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    return cpu_pass(pair)
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the oracle port of the reference's CPU path on all host cores (one pair
+    per process, which is how the single-threaded reference would be run in parallel)."""
+    if rank != 0:
+        return
+    import oracle
+    oracle.build()
+    pairs = make_pairs(args.pairs * world, 0, args.scale)
+    hours = audio_hours(pairs)
+    cores = min(len(pairs), os.cpu_count() or 1)
+    from concurrent.futures import ProcessPoolExecutor
+    times = []
+    with ProcessPoolExecutor(max_workers=cores) as ex:
+        for step in range(args.warmup + args.steps):
+            res = list(ex.map(_cpu_worker, pairs))
+            # each worker times its own pass (host fit excluded, as in the GPU arm); with one
+            # process per pair running concurrently the step takes as long as the slowest one
+            dev = [r[0] for r in res]
+            step_s = max(dev) if cores >= len(pairs) else sum(dev) / cores
+            if step >= args.warmup:
+                times.append(max(step_s, 1e-9))
+    ms = 1e3 * float(np.mean(times))
+    value = hours / (ms / 1e3)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic", "impl": "reference",
+            "config": {"workload": WORKLOAD, "pairs_per_step": len(pairs), "audio_hours_per_step": hours,
+                       "scale": args.scale},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{len(pairs)} full C2 pairs per step, one oracle process per pair"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from describealign_b200 import api, build
+    build.build()
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    pairs = make_pairs(args.pairs, rank * args.pairs, args.scale)
+    hours_rank = audio_hours(pairs)
+    B = len(pairs)
+
+    # device-resident copies (int16 interleaved) and pinned host copies
+    dev = [(torch.from_numpy(np.ascontiguousarray(v)).cuda(), torch.from_numpy(np.ascontiguousarray(a)).cuda())
+           for v, a in pairs]
+    pinned = [(torch.from_numpy(np.ascontiguousarray(v)).pin_memory(), torch.from_numpy(np.ascontiguousarray(a)).pin_memory())
+              for v, a in pairs]
+    ctx = api.context()
+    jobs_pairs = [api._cabi.Pair(ctx) for _ in range(B)]
+    streams = [torch.cuda.ExternalStream(p.stream) for p in jobs_pairs]
+    cur = torch.cuda.current_stream()
+
+    from concurrent.futures import ThreadPoolExecutor
+    pool = ThreadPoolExecutor(max_workers=B)
+
+    def timed_phase(fn):
+        """Run fn(k) for every pair concurrently; returns device ms between a start event every
+        pair stream waits on and a stop event that waits on every pair stream."""
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record(cur)
+        for s in streams:
+            s.wait_event(start)
+        list(pool.map(fn, range(B)))
+        for s in streams:
+            e = torch.cuda.Event()
+            e.record(s)
+            cur.wait_event(e)
+        stop.record(cur)
+        stop.synchronize()
+        return start.elapsed_time(stop)
+
+    def one_step(host_input: bool):
+        jobs = [api.AlignJob(jobs_pairs[k]) for k in range(B)]
+
+        def stage_a(k):
+            if host_input:
+                jobs[k].load_pcm(pinned[k][0].numpy(), pinned[k][1].numpy())
+            else:
+                v, a = dev[k]
+                jobs[k].load_pcm_device((v.data_ptr(), v.shape[0], v.shape[1]), (a.data_ptr(), a.shape[0], a.shape[1]))
+            jobs[k].device_stage_a()
+
+        ms_a = timed_phase(stage_a)
+        list(pool.map(lambda k: jobs[k].host_stage(), range(B)))      # untimed (BASELINE.json)
+        ms_b = timed_phase(lambda k: jobs[k].device_stage_b())
+        return ms_a + ms_b, jobs
+
+    def run_steps(host_input):
+        for _ in range(args.warmup):
+            one_step(host_input)
+        barrier()
+        l0 = ctx.launches()
+        total, jobs = 0.0, None
+        for _ in range(args.steps):
+            ms, jobs = one_step(host_input)
+            total += ms
+        barrier()
+        return total / args.steps, ctx.launches() - l0, jobs
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_dev, launches, jobs = run_steps(False)
+    clocks = sampler.stop() if rank == 0 else None
+    timings = [j.pair.timings() for j in jobs]
+    stats = [j.pair.stats() for j in jobs]
+    ms_e2e, _, jobs_e = run_steps(True)
+    h2d = sum(j.h2d_bytes for j in jobs_e)
+    d2h = sum(j.d2h_bytes for j in jobs_e)
+
+    # parity inside the run: rank 0 checks its first pair against the oracle
+    parity = None
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        import oracle
+        oracle.build()
+        cpu_s, fit_s, o = cpu_pass(pairs[0], keep=True)
+        j0 = jobs[0]
+        nx, ny, sim, path, med = j0.finish()
+        ox, oy = o["nodes"]
+        opath = o["path"]
+        same_shape = path.shape == opath.shape
+        parity = {
+            "features_f32_identical": bool(all(np.array_equal(j0.video_features[k], o["V"][k]) and
+                                               np.array_equal(j0.audio_features[k], o["A"][k]) for k in range(4))),
+            "path1_identical": bool(np.array_equal(j0.x, o["path1"][0]) and np.array_equal(j0.y, o["path1"][1])),
+            "path2_rows": int(len(path)),
+            "path2_int_identical": bool(same_shape and np.array_equal(path[:, 1], opath[:, 1]) and
+                                        np.array_equal(path[:, 2], opath[:, 2]) and
+                                        np.allclose(path[:, 0], opath[:, 0], rtol=0, atol=1e-9)),
+            "nodes_max_abs_diff_s": float(max(np.max(np.abs(nx - ox)), np.max(np.abs(ny - oy)))) if len(nx) == len(ox) else None,
+            "similarity_diff": float(abs(sim - o["similarity"])),
+        }
+        h1 = audio_hours(pairs[:1])
+        cpu = {"value": h1 / cpu_s, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": "1 full C2 pair through the oracle (C features, C match + DPs, numpy corridors); host fit (%.2f s) excluded as in the GPU arm" % fit_s,
+               "seconds": cpu_s, "host_cpu": _cpu_model(), "host_cores": os.cpu_count()}
+
+    # max over ranks
+    t = torch.tensor([ms_dev, ms_e2e], device="cuda", dtype=torch.float64)
+    tot = torch.tensor([hours_rank, float(launches), float(h2d), float(d2h)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms_dev, ms_e2e = float(t[0]), float(t[1])
+    hours, launches_all, h2d_all, d2h_all = (float(x) for x in tot)
+
+    if rank == 0:
+        peaks, peak_src = measured_peaks()
+        # per-kernel device times of the last timed step, summed over this rank's pairs
+        agg = {k: sum(tm[k] for tm in timings) for k in timings[0]}
+        dominant = max(agg, key=agg.get)
+        # feature kernel roofline: algorithmic bytes = PCM read once + 24 B per output frame
+        feat_ms = agg["features_video"] + agg["features_audio"]
+        feat_bytes = sum(2 * (v.shape[0] * v.shape[1] + a.shape[0] * a.shape[1]) + 24 * (v.shape[0] // 210 + a.shape[0] // 210)
+                         for v, a in pairs)
+        feat_gbs = feat_bytes / (feat_ms * 1e-3) / 1e9 if feat_ms > 0 else None
+        # DP kernels: 24 B per point (i, v, qual in; back pointer out), SURVEY.md 8(d)
+        dp_pts = sum(s["n_points1"] for s in stats), sum(s["n_points2"] for s in stats)
+        dp_ms = agg["dp1_trace"], agg["dp2_trace"]
+        roof = {"features": {"bound": "hbm", "achieved": feat_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                             "frac": feat_gbs / peaks["hbm_gbs"] if feat_gbs else None, "ms": feat_ms,
+                             "algorithmic_bytes": feat_bytes},
+                "dp1_trace": {"bound": "hbm", "achieved": 24 * dp_pts[0] / (dp_ms[0] * 1e-3) / 1e9 if dp_ms[0] > 0 else None,
+                              "peak": peaks["hbm_gbs"], "unit": "GB/s", "ms": dp_ms[0], "points": dp_pts[0],
+                              "points_per_s": dp_pts[0] / (dp_ms[0] * 1e-3) if dp_ms[0] > 0 else None,
+                              "note": "latency-bound serial dependency, not bandwidth-bound"},
+                "dp2_trace": {"bound": "hbm", "achieved": 24 * dp_pts[1] / (dp_ms[1] * 1e-3) / 1e9 if dp_ms[1] > 0 else None,
+                              "peak": peaks["hbm_gbs"], "unit": "GB/s", "ms": dp_ms[1], "points": dp_pts[1],
+                              "points_per_s": dp_pts[1] / (dp_ms[1] * 1e-3) if dp_ms[1] > 0 else None,
+                              "note": "latency-bound serial dependency, not bandwidth-bound"}}
+        for v in roof.values():
+            if v.get("frac") is None and v.get("achieved") is not None:
+                v["frac"] = v["achieved"] / v["peak"]
+        dom_key = dominant if dominant in roof else ("features" if dominant.startswith("features") else None)
+        main_roof = dict(roof[dom_key]) if dom_key else dict(roof["features"])
+        main_roof.update({"kernel": dom_key or dominant, "peak_source": peak_src, "traffic": None})
+        line = {
+            "metric": METRIC, "value": hours / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32+f64 (u32 packed codes)", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "pairs_per_gpu_per_step": B, "audio_hours_per_step": hours,
+                       "l2_policy": "inputs larger than L2 (each pair streams 259 MB of PCM; 126 MB L2)",
+                       "timed": "device stage A (features, prep, tables, gate, score, DP1, traceback) + device stage B (corridors, DP2, traceback); host rate-change fit untimed",
+                       "scale": args.scale},
+            "ms_per_pair": ms_dev / B,
+            "e2e": {"value": hours / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": h2d_all, "d2h_bytes_per_step": d2h_all},
+            "gpu_launches": int(launches_all),
+            "roofline": main_roof,
+            "roofline_by_kernel": roof,
+            "kernel_ms_last_step": agg,
+            "work": {k: sum(s[k] for s in stats) for k in stats[0]},
+            "clocks": clocks,
+            "cpu_baseline": cpu,
+            "parity": parity,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for ln in f:
+                if ln.startswith("model name"):
+                    return ln.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

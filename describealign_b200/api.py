@@ -104,36 +104,109 @@ def get_freq_bands(arr):
 # align
 # ---------------------------------------------------------------------------------------------
 
-def _finish(pair, video_features, audio_features, n_video_energy, n_audio_energy, details=None):
-    """Everything after the features are on the device: stage A, host fit, stage B, nodes."""
-    print("  matching audio...  \r", end='')
-    _, n_path = pair.stage_a()
-    min_len = host_fit.min_path_length(n_video_energy, n_audio_energy)
-    if n_path < min_len:
-        raise RuntimeError(FAILED_MSG)
-    x, y = pair.path1()
+class AlignJob:
+    """One pair walking through the path: device stage A -> host fit -> device stage B.
 
-    print("  refining match: pass 1 of 2...\r", end='')
-    keep = host_fit.continuity_error(x, y) < 3
-    x, y = x[keep], y[keep]
-    audio_scaled, video_scaled = host_fit.scale_features(video_features, audio_features, x, y)
-    fit_x, fit_y = host_fit.compress_path(x, y)
-    fit = host_fit.rate_change_fit(fit_x, fit_y)
+    The three steps are separate methods so that a batch driver can keep several pairs in
+    flight (one CUDA stream per pair) and so that the benchmark can time the device stages
+    without the host-side rate-change fit, which BASELINE.json excludes from the metric.
+    """
 
-    print("  refining match: pass 2 of 2...\r", end='')
-    clusters = host_fit.line_clusters(fit)
-    plans = host_fit.plan_corridors(clusters, audio_scaled, video_scaled)
-    pair.stage_b(audio_scaled, video_scaled, plans, len(clusters))
-    path = pair.path2()
-    if len(path) < min_len:
-        raise RuntimeError(FAILED_MSG)
-    if details is not None:
-        details.update(kept_x=x, kept_y=y, fit=fit, clusters=clusters, plans=plans,
-                       audio_scaled=audio_scaled, video_scaled=video_scaled,
-                       stats=pair.stats(), timings=pair.timings())
-    nodes_x, nodes_y, similarity = host_fit.build_nodes(path, n_audio_energy, n_video_energy,
-                                                        len(audio_scaled), len(video_scaled))
-    return nodes_x, nodes_y, similarity, path, fit.median_slope
+    def __init__(self, pair: _cabi.Pair | None = None):
+        self.pair = pair if pair is not None else acquire_pair()
+        self._own = pair is None
+        self.video_features = self.audio_features = None
+        self.h2d_bytes = self.d2h_bytes = 0
+
+    # -- inputs ---------------------------------------------------------------------------
+    def load_pcm(self, video_pcm, audio_pcm):
+        """Host PCM: interleaved int16 (S, ch), or the reference's float16 (ch, S) arrays."""
+        def prep(p):
+            p = np.asarray(p)
+            if p.dtype == np.float16 and p.ndim == 2 and p.shape[0] in (1, 2) and p.shape[1] > 2:
+                return _interleaved(p)
+            return p
+        v, a = prep(video_pcm), prep(audio_pcm)
+        self.pair.set_pcm(VIDEO, v)
+        self.pair.set_pcm(AUDIO, a)
+        self.h2d_bytes += v.nbytes + a.nbytes
+        self._features_on_device = True
+
+    def load_pcm_device(self, video, audio):
+        """Device-resident PCM: (device pointer, samples per channel, channels) per track."""
+        self.pair.set_pcm_device(VIDEO, *video)
+        self.pair.set_pcm_device(AUDIO, *audio)
+        self._features_on_device = True
+
+    def load_features(self, video_features, audio_features):
+        self.pair.set_features(VIDEO, video_features)
+        self.pair.set_features(AUDIO, audio_features)
+        self.video_features, self.audio_features = video_features, audio_features
+        self.h2d_bytes += sum(np.asarray(f).nbytes for f in list(video_features) + list(audio_features))
+        self._features_on_device = False
+
+    # -- stages ---------------------------------------------------------------------------
+    def device_stage_a(self):
+        """Features (if PCM was given) + stage A on the device; brings back what the host fit
+        needs: the integer pass-1 path and the feature vectors."""
+        _, n_path = self.pair.stage_a()
+        if self.video_features is None:
+            self.video_features = self.pair.get_features(VIDEO)
+            self.audio_features = self.pair.get_features(AUDIO)
+            self.d2h_bytes += sum(f.nbytes for f in self.video_features + self.audio_features)
+        self.n_video_energy = len(self.video_features[0])
+        self.n_audio_energy = len(self.audio_features[0])
+        self.min_len = host_fit.min_path_length(self.n_video_energy, self.n_audio_energy)
+        if n_path < self.min_len:
+            raise RuntimeError(FAILED_MSG)
+        self.x, self.y = self.pair.path1()
+        self.d2h_bytes += 8 * n_path
+        return self.x, self.y
+
+    def host_stage(self):
+        """The untimed "rate-change fit" on the host (describealign.py:702-893)."""
+        keep = host_fit.continuity_error(self.x, self.y) < 3
+        self.kept_x, self.kept_y = self.x[keep], self.y[keep]
+        self.audio_scaled, self.video_scaled = host_fit.scale_features(
+            self.video_features, self.audio_features, self.kept_x, self.kept_y)
+        fit_x, fit_y = host_fit.compress_path(self.kept_x, self.kept_y)
+        self.fit = host_fit.rate_change_fit(fit_x, fit_y)
+        self.clusters = host_fit.line_clusters(self.fit)
+        self.plans = host_fit.plan_corridors(self.clusters, self.audio_scaled, self.video_scaled)
+
+    def device_stage_b(self):
+        self.pair.stage_b(self.audio_scaled, self.video_scaled, self.plans, len(self.clusters))
+        self.h2d_bytes += self.audio_scaled.nbytes + self.video_scaled.nbytes
+        self.path = self.pair.path2()
+        self.d2h_bytes += self.path.nbytes
+        if len(self.path) < self.min_len:
+            raise RuntimeError(FAILED_MSG)
+        return self.path
+
+    def finish(self, details=None):
+        if details is not None:
+            details.update(kept_x=self.kept_x, kept_y=self.kept_y, fit=self.fit, clusters=self.clusters,
+                           plans=self.plans, audio_scaled=self.audio_scaled, video_scaled=self.video_scaled,
+                           video_features=self.video_features, audio_features=self.audio_features,
+                           path1=(self.x, self.y), stats=self.pair.stats(), timings=self.pair.timings(),
+                           h2d_bytes=self.h2d_bytes, d2h_bytes=self.d2h_bytes)
+        nx, ny, sim = host_fit.build_nodes(self.path, self.n_audio_energy, self.n_video_energy,
+                                           len(self.audio_scaled), len(self.video_scaled))
+        return nx, ny, sim, self.path, self.fit.median_slope
+
+    def close(self):
+        if self._own and self.pair is not None:
+            release_pair(self.pair)
+        self.pair = None
+
+    def run(self, details=None):
+        print("  matching audio...  \r", end='')
+        self.device_stage_a()
+        print("  refining match: pass 1 of 2...\r", end='')
+        self.host_stage()
+        print("  refining match: pass 2 of 2...\r", end='')
+        self.device_stage_b()
+        return self.finish(details)
 
 
 def align(video_features, audio_desc_features, video_energy, audio_desc_energy, details=None):
@@ -147,34 +220,21 @@ def align(video_features, audio_desc_features, video_energy, audio_desc_energy, 
         if energy is not feats[0] and not np.array_equal(energy, feats[0]):
             raise NotImplementedError(f"{name}_energy must be {name}_features[0], as in describealign.py:1121")
     print("  memorizing video...        \r", end='')
-    pair = acquire_pair()
+    job = AlignJob()
     try:
-        pair.set_features(VIDEO, video_features)
-        pair.set_features(AUDIO, audio_desc_features)
-        return _finish(pair, video_features, audio_desc_features, len(video_energy), len(audio_desc_energy), details)
+        job.load_features(list(video_features), list(audio_desc_features))
+        return job.run(details)
     finally:
-        release_pair(pair)
+        job.close()
 
 
-def align_pcm(video_pcm: np.ndarray, audio_desc_pcm: np.ndarray, details=None):
-    """PCM in, alignment out (the block describealign.py:1096-1125 in one call).
-
-    video_pcm / audio_desc_pcm: interleaved int16 (S, ch) as decoded by ffmpeg, or the
-    reference's float16 (ch, S) arrays."""
-    def prep(p):
-        p = np.asarray(p)
-        if p.dtype == np.float16 and p.ndim == 2 and p.shape[0] in (1, 2) and p.shape[1] > 2:
-            return _interleaved(p)
-        return p
+def align_pcm(video_pcm, audio_desc_pcm, details=None):
+    """PCM in, alignment out (the block describealign.py:1096-1125 in one call): features
+    never leave the GPU except the copies the host-side fit needs."""
     print("  memorizing video...        \r", end='')
-    pair = acquire_pair()
+    job = AlignJob()
     try:
-        pair.set_pcm(VIDEO, prep(video_pcm))
-        pair.set_pcm(AUDIO, prep(audio_desc_pcm))
-        vf = pair.get_features(VIDEO)
-        af = pair.get_features(AUDIO)
-        if details is not None:
-            details.update(video_features=vf, audio_features=af)
-        return _finish(pair, vf, af, len(vf[0]), len(af[0]), details)
+        job.load_pcm(video_pcm, audio_desc_pcm)
+        return job.run(details)
     finally:
-        release_pair(pair)
+        job.close()
