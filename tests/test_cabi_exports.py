@@ -1,0 +1,105 @@
+"""CPU tests of the drop-in boundary: the C-ABI library builds, loads and exports every symbol
+include/describealign_b200.h declares; without a CUDA device the product path fails loudly
+(no CPU fallback); the host-side mirror has the reference's names and signatures.
+No compute is launched here.
+"""
+import ctypes
+import inspect
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "describealign_b200.h")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from describealign_b200 import _cabi, build
+    build.build()
+    return _cabi.load()
+
+
+def _declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(dab_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported(lib):
+    names = _declared_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} is declared in the header but not exported"
+
+
+def test_binding_covers_header():
+    from describealign_b200 import _cabi
+    assert sorted(_cabi.EXPORTS) == _declared_symbols()
+
+
+def test_abi_version_and_struct_layout(lib):
+    from describealign_b200 import _cabi
+    assert lib.dab_abi_version() == 1
+    assert ctypes.sizeof(_cabi.Corridor) == 32       # 4 x int32 + 2 x double
+    assert ctypes.sizeof(_cabi.Stats) == 11 * 8
+
+
+def test_no_cpu_fallback(lib):
+    """On a box without a GPU the context cannot be created and every API entry raises."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA device present")
+    from describealign_b200 import _cabi, api
+    h = ctypes.c_void_p()
+    assert lib.dab_create(-1, ctypes.byref(h)) != 0
+    assert b"no CPU fallback" in lib.dab_last_error(None)
+    with pytest.raises(_cabi.DabError):
+        api.get_energy(np.zeros((1, 4410), np.float16))
+    with pytest.raises(_cabi.DabError):
+        api.align_pcm(np.zeros((4410, 1), np.int16), np.zeros((4410, 1), np.int16))
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from describealign_b200 import _cabi
+    monkeypatch.setattr(_cabi, "_lib", None)
+    monkeypatch.setattr(_cabi, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_cabi.DabError, match="no CPU fallback"):
+        _cabi.load()
+
+
+def test_product_does_not_import_oracle():
+    """The oracle is test infrastructure: nothing under describealign_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "describealign_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+                assert "liboracle" not in src, f
+
+
+def test_mirror_has_reference_signatures():
+    """describealign.py:545, 557, 575, 595: same names and positional parameters."""
+    from describealign_b200 import api
+    assert list(inspect.signature(api.get_energy).parameters) == ["arr"]
+    assert list(inspect.signature(api.get_zero_crossings).parameters) == ["arr"]
+    assert list(inspect.signature(api.get_freq_bands).parameters) == ["arr"]
+    assert list(inspect.signature(api.align).parameters)[:4] == [
+        "video_features", "audio_desc_features", "video_energy", "audio_desc_energy"]
+
+
+def test_launcher_patches_a_module():
+    import types
+    from describealign_b200 import api, launcher
+    fake = types.ModuleType("describealign")
+    for n in ("get_energy", "get_zero_crossings", "get_freq_bands", "align"):
+        setattr(fake, n, lambda *a, **k: None)
+    launcher.patch(fake)
+    assert fake.align is api.align and fake.get_freq_bands is api.get_freq_bands
+    assert callable(fake._reference_align)
+    broken = types.ModuleType("describealign")
+    with pytest.raises(AttributeError):
+        launcher.patch(broken)
