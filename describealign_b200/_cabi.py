@@ -17,7 +17,7 @@ PCM_S16, PCM_F16 = 0, 1
 VIDEO, AUDIO = 0, 1
 
 EXPORTS = [
-    "dab_abi_version", "dab_device_count", "dab_create", "dab_destroy", "dab_last_error",
+    "dab_abi_version", "dab_device_count", "dab_create", "dab_destroy", "dab_set_option", "dab_last_error",
     "dab_pair_create", "dab_pair_destroy", "dab_pair_sync", "dab_pair_stream", "dab_pair_set_pcm",
     "dab_pair_set_features", "dab_pair_feature_lens", "dab_pair_get_features", "dab_pair_stage_a",
     "dab_pair_get_path1", "dab_pair_get_points1", "dab_pair_stage_b", "dab_pair_get_path2",
@@ -33,14 +33,15 @@ class Corridor(ctypes.Structure):
 class Stats(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int64) for n in (
         "n_video_frames", "n_audio_frames", "n_video_selected", "n_audio_queries", "n_table_entries",
-        "n_enumerated", "n_candidates", "n_points1", "n_path1", "n_points2", "n_path2")]
+        "n_enumerated", "n_candidates", "n_points1", "n_path1", "n_points2", "n_path2",
+        "n_dp2_queries", "n_dp2_refills", "n_dp2_neighbour")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
 
 
 TIMING_SLOTS = ("features_video", "features_audio", "prep_codes", "tables", "gate", "score",
-                "dp1_trace", "corridors", "dp2_trace")
+                "dp1_trace", "corridors", "dp2_trace", "dp2")
 
 _lib = None
 
@@ -65,6 +66,7 @@ def load() -> ctypes.CDLL:
     lib.dab_create.argtypes = [i32, ctypes.POINTER(vp)]
     lib.dab_destroy.argtypes = [vp]
     lib.dab_destroy.restype = None
+    lib.dab_set_option.argtypes = [vp, ctypes.c_char_p, i64]
     lib.dab_last_error.argtypes = [vp]
     lib.dab_last_error.restype = ctypes.c_char_p
     lib.dab_pair_create.argtypes = [vp, ctypes.POINTER(vp)]
@@ -112,6 +114,9 @@ class Context:
     def check(self, rc: int):
         if rc != 0:
             raise DabError(f"describealign_b200 error {rc}: {self.lib.dab_last_error(self.handle).decode()}")
+
+    def set_option(self, name: str, value: int):
+        self.check(self.lib.dab_set_option(self.handle, name.encode(), int(value)))
 
     def launches(self) -> int:
         return int(self.lib.dab_launch_count(self.handle))

@@ -65,6 +65,13 @@ int dab_create(int device, dab_ctx **out) {
 
 void dab_destroy(dab_ctx *ctx) { delete ctx; }
 
+int dab_set_option(dab_ctx *ctx, const char *name, int64_t value) {
+  if (!ctx || !name) return DAB_E_ARG;
+  if (strcmp(name, "dp2_generic") == 0) { ctx->opt_dp2_generic = value != 0; return DAB_OK; }
+  ctx->err = std::string("dab_set_option: unknown option ") + name;
+  return DAB_E_ARG;
+}
+
 int64_t dab_launch_count(const dab_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
 int dab_pair_create(dab_ctx *ctx, dab_pair **out) {
@@ -96,7 +103,8 @@ void dab_pair_destroy(dab_pair *pr) {
                   &pr->pt_s, &pr->pt_q, &pr->counters, &pr->tree1, &pr->back1, &pr->len1, &pr->cp1, &pr->dpres,
                   &pr->seglist, &pr->path1_x, &pr->path1_y, &pr->a_scaled, &pr->v_scaled, &pr->corridors,
                   &pr->row2_count, &pr->row2_off, &pr->p2_i, &pr->p2_c, &pr->p2_rank, &pr->p2_j, &pr->p2_q,
-                  &pr->tree2, &pr->cache2, &pr->back2, &pr->len2, &pr->cp2, &pr->backid2, &pr->path2};
+                  &pr->tree2, &pr->cache2, &pr->back2, &pr->len2, &pr->cp2, &pr->backid2, &pr->path2,
+                  &pr->p2_k, &pr->pm2, &pr->pmoff2, &pr->lift_up, &pr->lift_dep};
   for (DevBuf *b : bs) free_buf(*b);
   for (int k = 0; k < 32; ++k)
     if (pr->ev[k]) cudaEventDestroy(pr->ev[k]);
@@ -293,6 +301,7 @@ int dab_pair_stage_b(dab_pair *pr, const float *audio_scaled, int64_t n_audio, c
   }
   DAB_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = pr->stream;
+  pr->h_cor.assign(corridors, corridors + n_corridors);
   DAB_TRY(dab_ensure(ctx, pr->a_scaled, sizeof(float) * 3 * (size_t)n_audio));
   DAB_TRY(dab_ensure(ctx, pr->v_scaled, sizeof(float) * 3 * (size_t)n_video));
   DAB_TRY(dab_ensure(ctx, pr->corridors, sizeof(dab_corridor) * (size_t)(n_corridors + 1)));
@@ -357,6 +366,10 @@ int dab_pair_get_timings(dab_pair *pr, float ms[16]) {
     if (s < 9 && pr->ev_used[s]) {
       float t = 0.0f;
       if (cudaEventElapsedTime(&t, pr->ev[2 * s], pr->ev[2 * s + 1]) == cudaSuccess) ms[s] = t;
+    }
+    if (s == 9 && pr->ev_used[8]) {
+      float t = 0.0f;
+      if (cudaEventElapsedTime(&t, pr->ev[16], pr->ev[18]) == cudaSuccess) ms[s] = t;
     }
   }
   return DAB_OK;

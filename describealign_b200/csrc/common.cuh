@@ -25,6 +25,7 @@ struct dab_ctx {
   std::string err;
   int64_t launches = 0;
   int sm_count = 148;
+  int opt_dp2_generic = 0;   // force the tree DP for pass 2 (testing)
 };
 
 // Features and prep data of one track, device resident.
@@ -75,7 +76,10 @@ struct dab_pair {
   DevBuf a_scaled, v_scaled;   // f32 (n,3)
   DevBuf corridors;            // dab_corridor[]
   DevBuf row2_count, row2_off; // i32 [n_audio + 1]
-  DevBuf p2_i, p2_c, p2_rank;  // i32
+  DevBuf p2_i, p2_c, p2_rank, p2_k;  // i32
+  DevBuf pm2, pmoff2;          // corridor-state DP: per-corridor running maxima, row offsets
+  DevBuf lift_up, lift_dep;    // pointer-jumping traceback
+  std::vector<dab_corridor> h_cor;   // host copy of the corridors of the current stage_b call
   DevBuf p2_j, p2_q;           // f64
   DevBuf tree2;                // frontier tree of pass 2
   DevBuf cache2;               // prev_cache rows

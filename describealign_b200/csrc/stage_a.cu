@@ -402,10 +402,7 @@ __global__ void gather_points_kernel(const int32_t *keep, const int32_t *off, in
 // ------------------------------------------------------------------------------------------
 // frontier DP #1: cum(p) = q(p) + max{cum(p') : p' earlier, rank' <= rank},
 // ties to the smallest rank; the seed has cum 0.  One warp walks the points in (i, v) order;
-// the prefix maximum lives in a 32-ary max tree over the video ranks: per level the warp
-// loads one 32-node row (512 B, coalesced), lanes left of the path contribute to the query and
-// the lane on the path keeps the old node for the update.  All four rows are fetched together,
-// so a point costs one memory round trip (usually L1 hits: consecutive path points share rows).
+// the prefix maximum lives in a 32-ary max tree over the video ranks (HBM/L2 resident).
 // ------------------------------------------------------------------------------------------
 struct __align__(16) Node1 {
   double cum;     // 0 = empty / seed
@@ -421,7 +418,7 @@ struct Dp1Args {
   const double *pt_q;
   const int32_t *n_points_dev;   // device-resident count
   Node1 *level[DP_LEVELS];
-  int32_t *back, *len, *cp;
+  int4 *meta;                    // per point (back pointer, chain length, checkpoint id, -)
   int32_t *result;               // [0] end id, [1] path length
 };
 
@@ -429,78 +426,152 @@ __device__ __forceinline__ bool key_better(double ca, int ra, double cb, int rb)
   return ca > cb || (ca == cb && ra < rb);
 }
 
+__device__ __forceinline__ Node1 load_node_cg(const Node1 *p) {
+  // L2 read (bypasses L1): the node may have been rewritten by another lane's fire-and-forget store
+  const int4 v = __ldcg(reinterpret_cast<const int4 *>(p));
+  Node1 n;
+  n.cum = __hiloint2double(v.y, v.x);
+  n.id = v.z;
+  n.rank = v.w;
+  return n;
+}
+
+// The walk keeps the frontier's top entry (largest cum; ties -> smallest rank) in registers.
+// A point whose rank is >= the top's rank has the top as its predecessor and becomes the new
+// top (quals are > 0): no tree loads, one f64 add on the dependent chain, and one predicated
+// 16-byte store per lane role - lane 0 the leaf, lane 4 the back record, lanes 1-3 the old top
+// into its level-k ancestor, but only when the top leaves that ancestor's block (the ancestors of
+// the current top are implied by the registers; every other node is exact).  Only points left
+// of the top (false matches, backward jumps) run the full prefix-max query: one 32-node row per
+// level (512 B, coalesced), lanes left of the path feed the query and the lane on the path keeps
+// the old node for the conditional update.
 __global__ void __launch_bounds__(32, 1) dp1_kernel(Dp1Args a) {
+  __shared__ int s_r[2][32];
+  __shared__ double s_q[2][32];
   const int lane = threadIdx.x;
   const int n = *a.n_points_dev;
-  double best_all_cum = 0.0;
-  int best_all_id = -1, best_all_rank = 0x7fffffff;
-  int r_next = n > 0 ? a.pt_s[0] : 0;
-  double q_next = n > 0 ? a.pt_q[0] : 0.0;
-  for (int p = 0; p < n; ++p) {
-    const int r = r_next;
-    const double q = q_next;
-    if (p + 1 < n) { r_next = a.pt_s[p + 1]; q_next = a.pt_q[p + 1]; }
-    Node1 nd[DP_LEVELS];
-    int pos[DP_LEVELS];
-#pragma unroll
-    for (int k = 0; k < DP_LEVELS; ++k) {
-      const int g = r >> (5 * k);
-      pos[k] = g & 31;
-      nd[k] = a.level[k][(g & ~31) + lane];
-    }
-    // lane-local best over eligible nodes; higher levels hold smaller ranks
-    double bc = 0.0;
-    int bid = -1, brank = 0x7fffffff;
-#pragma unroll
-    for (int k = DP_LEVELS - 1; k >= 0; --k) {
-      const bool elig = (k == 0) ? (lane <= pos[0]) : (lane < pos[k]);
-      if (elig && key_better(nd[k].cum, nd[k].rank, bc, brank)) { bc = nd[k].cum; bid = nd[k].id; brank = nd[k].rank; }
-    }
-    // warp arg-max on (cum desc, rank asc); all cum >= 0 so the bit patterns order like integers
-    const unsigned long long bits = (unsigned long long)__double_as_longlong(bc);
-    const unsigned hi = (unsigned)(bits >> 32), lo = (unsigned)bits;
-    const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
-    bool alive = hi == mhi;
-    const unsigned mlo = __reduce_max_sync(0xffffffffu, alive ? lo : 0u);
-    alive = alive && lo == mlo;
-    const unsigned mr = __reduce_min_sync(0xffffffffu, alive ? (unsigned)brank : 0xffffffffu);
-    alive = alive && (unsigned)brank == mr;
-    const int src = __ffs(__ballot_sync(0xffffffffu, alive)) - 1;
-    const double pc = __shfl_sync(0xffffffffu, bc, src);
-    const int pid = __shfl_sync(0xffffffffu, bid, src);
-    const double cum = pc + q;
-    // updates: leaf always (a later point on the same rank chains from the earlier one), upper
-    // levels when the new key wins
-    if (lane == pos[0]) {
-      Node1 me; me.cum = cum; me.id = p; me.rank = r;
-      a.level[0][r] = me;
-    }
-#pragma unroll
-    for (int k = 1; k < DP_LEVELS; ++k) {
-      if (lane == pos[k] && key_better(cum, r, nd[k].cum, nd[k].rank)) {
-        Node1 me; me.cum = cum; me.id = p; me.rank = r;
-        a.level[k][r >> (5 * k)] = me;
+  double top_cum = 0.0;
+  int top_id = -1, top_rank = -1, top_len = 0, top_cp = -1;
+  const int role = lane < DP_LEVELS ? lane : 0;
+  int4 *const my_level = reinterpret_cast<int4 *>(a.level[role]);
+  const int my_shift = 5 * role;
+  int rr = lane < n ? a.pt_s[lane] : 0;
+  double qq = lane < n ? a.pt_q[lane] : 0.0;
+  for (int base = 0; base < n; base += 32) {
+    const int buf = (base >> 5) & 1;
+    s_r[buf][lane] = rr;
+    s_q[buf][lane] = qq;
+    __syncwarp();
+    if (base + 32 + lane < n) { rr = a.pt_s[base + 32 + lane]; qq = a.pt_q[base + 32 + lane]; }
+    const int cnt = n - base < 32 ? n - base : 32;
+    int r_nx = s_r[buf][0];
+    double q_nx = s_q[buf][0];
+    for (int t = 0; t < cnt; ++t) {
+      const int p = base + t;
+      const int r = r_nx;
+      const double q = q_nx;
+      if (t + 1 < cnt) { r_nx = s_r[buf][t + 1]; q_nx = s_q[buf][t + 1]; }
+      if (r >= top_rank) {
+        const double cum = top_cum + q;
+        const int ln = top_len + 1;
+        const int cpv = (ln % DP_CHECK == 0 || top_id < 0) ? p : top_cp;
+        // lane 0: leaf <- new top.  lanes 1..3: ancestor of the OLD top when the top leaves its block.
+        // lane 4: back record.
+        int4 val;
+        int4 *dst;
+        bool doit;
+        if (lane == DP_LEVELS) {
+          val.x = top_id; val.y = ln; val.z = cpv; val.w = 0;
+          dst = a.meta + p;
+          doit = true;
+        } else if (lane == 0) {
+          val.x = __double2loint(cum); val.y = __double2hiint(cum); val.z = p; val.w = r;
+          dst = my_level + r;
+          doit = true;
+        } else {
+          val.x = __double2loint(top_cum); val.y = __double2hiint(top_cum); val.z = top_id; val.w = top_rank;
+          dst = my_level + (top_rank >> my_shift);
+          doit = lane < DP_LEVELS && top_id >= 0 && (r >> my_shift) != (top_rank >> my_shift);
+        }
+        if (doit) *dst = val;
+        top_cum = cum; top_id = p; top_rank = r; top_len = ln; top_cp = cpv;
+        continue;
       }
+      __syncwarp();   // orders the stores above before the loads below
+      Node1 nd[DP_LEVELS];
+      int pos[DP_LEVELS];
+#pragma unroll
+      for (int k = 0; k < DP_LEVELS; ++k) {
+        const int g = r >> (5 * k);
+        pos[k] = g & 31;
+        nd[k] = load_node_cg(&a.level[k][(g & ~31) + lane]);
+      }
+      // lane-local best over eligible nodes; higher levels hold smaller ranks
+      double bc = 0.0;
+      int bid = -1, brank = 0x7fffffff;
+#pragma unroll
+      for (int k = DP_LEVELS - 1; k >= 0; --k) {
+        const bool elig = (k == 0) ? (lane <= pos[0]) : (lane < pos[k]);
+        if (elig && key_better(nd[k].cum, nd[k].rank, bc, brank)) { bc = nd[k].cum; bid = nd[k].id; brank = nd[k].rank; }
+      }
+      // warp arg-max on (cum desc, rank asc); all cum >= 0 so the bit patterns order like integers
+      const unsigned long long bits = (unsigned long long)__double_as_longlong(bc);
+      const unsigned hi = (unsigned)(bits >> 32), lo = (unsigned)bits;
+      const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
+      bool alive = hi == mhi;
+      const unsigned mlo = __reduce_max_sync(0xffffffffu, alive ? lo : 0u);
+      alive = alive && lo == mlo;
+      const unsigned mr = __reduce_min_sync(0xffffffffu, alive ? (unsigned)brank : 0xffffffffu);
+      alive = alive && (unsigned)brank == mr;
+      const int src = __ffs(__ballot_sync(0xffffffffu, alive)) - 1;
+      const double pc = __shfl_sync(0xffffffffu, bc, src);
+      const int pid = __shfl_sync(0xffffffffu, bid, src);
+      const double cum = pc + q;
+      // updates: leaf always (a later point on the same rank chains from the earlier one), upper
+      // levels when the new key wins.  (A node on the current top's path may be stale-low; the
+      // top is written over it when it leaves the block, and it is >= everything in that block.)
+      if (lane == pos[0]) {
+        Node1 me; me.cum = cum; me.id = p; me.rank = r;
+        a.level[0][r] = me;
+      }
+#pragma unroll
+      for (int k = 1; k < DP_LEVELS; ++k) {
+        if (lane == pos[k] && key_better(cum, r, nd[k].cum, nd[k].rank)) {
+          Node1 me; me.cum = cum; me.id = p; me.rank = r;
+          a.level[k][r >> (5 * k)] = me;
+        }
+      }
+      int ln = 1, cpv = p;
+      if (pid >= 0) {
+        const int4 pm = __ldcg(a.meta + pid);
+        ln = pm.y + 1;
+        cpv = (ln % DP_CHECK == 0) ? p : pm.z;
+      }
+      if (lane == 0) { int4 m; m.x = pid; m.y = ln; m.z = cpv; m.w = 0; a.meta[p] = m; }
+      if (key_better(cum, r, top_cum, top_rank)) {
+        // the old top's ancestors are flushed where the new top lies in another block
+        if (lane >= 1 && lane < DP_LEVELS && top_id >= 0 && (r >> my_shift) != (top_rank >> my_shift)) {
+          int4 val;
+          val.x = __double2loint(top_cum); val.y = __double2hiint(top_cum); val.z = top_id; val.w = top_rank;
+          my_level[top_rank >> my_shift] = val;
+        }
+        top_cum = cum; top_id = p; top_rank = r; top_len = ln; top_cp = cpv;
+      }
+      __syncwarp();
     }
-    if (lane == 0) {
-      a.back[p] = pid;
-      const int ln = pid < 0 ? 1 : a.len[pid] + 1;
-      a.len[p] = ln;
-      a.cp[p] = (ln % DP_CHECK == 0 || pid < 0) ? p : a.cp[pid];
-    }
-    if (key_better(cum, r, best_all_cum, best_all_rank)) { best_all_cum = cum; best_all_id = p; best_all_rank = r; }
     __syncwarp();
   }
   if (lane == 0) {
-    a.result[0] = best_all_id;
-    a.result[1] = best_all_id < 0 ? 0 : a.len[best_all_id];
+    a.result[0] = top_id;
+    a.result[1] = top_id < 0 ? 0 : top_len;
   }
 }
 
 // Traceback: thread 0 hops from checkpoint to checkpoint (path_len / 256 dependent steps),
 // then every segment between checkpoints is walked by its own thread.
 struct TraceArgs {
-  const int32_t *back, *len, *cp, *result;
+  const int4 *meta;              // (back, len, cp, -)
+  const int32_t *result;
   const int32_t *pt_i, *pt_s, *v_sel;
   int32_t *seg;          // scratch: segment start ids
   int32_t *path_x, *path_y;
@@ -513,21 +584,22 @@ __global__ void trace1_kernel(TraceArgs a) {
     int cur = a.result[0];
     while (cur >= 0) {
       a.seg[k++] = cur;
-      const int c = a.cp[cur];      // last node of this segment (checkpoint or chain root)
-      cur = a.back[c];
+      const int c = a.meta[cur].z;  // last node of this segment (checkpoint or chain root)
+      cur = a.meta[c].x;
     }
     nseg = k;
   }
   __syncthreads();
   for (int s = threadIdx.x; s < nseg; s += blockDim.x) {
     int cur = a.seg[s];
-    const int stop = a.cp[cur];
+    const int stop = a.meta[cur].z;
     while (true) {
-      const int pos = a.len[cur] - 1;
+      const int4 m = a.meta[cur];
+      const int pos = m.y - 1;
       a.path_x[pos] = a.pt_i[cur];
       a.path_y[pos] = a.v_sel[a.pt_s[cur]];
       if (cur == stop) break;
-      cur = a.back[cur];
+      cur = m.x;
     }
   }
 }
@@ -747,9 +819,7 @@ int dab_run_stage_a(dab_pair *pr) {
     for (int k = 0; k < DP_LEVELS; ++k) { lv[k] = cdiv(m > 0 ? m : 1, 32) * 32; tot += lv[k]; m = cdiv(m, 32); }
     DAB_TRY(dab_ensure(ctx, pr->tree1, sizeof(Node1) * (size_t)tot));
     fill_nodes_kernel<<<(unsigned)cdiv(tot, 256), 256, 0, st>>>(pr->tree1.as<Node1>(), tot);
-    DAB_TRY(dab_ensure(ctx, pr->back1, sizeof(int32_t) * (size_t)(n_pts + 1)));
-    DAB_TRY(dab_ensure(ctx, pr->len1, sizeof(int32_t) * (size_t)(n_pts + 1)));
-    DAB_TRY(dab_ensure(ctx, pr->cp1, sizeof(int32_t) * (size_t)(n_pts + 1)));
+    DAB_TRY(dab_ensure(ctx, pr->back1, sizeof(int4) * (size_t)(n_pts + 1)));
     DAB_TRY(dab_ensure(ctx, pr->dpres, sizeof(int32_t) * 8));
     DAB_TRY(dab_ensure(ctx, pr->seglist, sizeof(int32_t) * (size_t)(n_pts / DP_CHECK + 16)));
     DAB_TRY(dab_ensure(ctx, pr->path1_x, sizeof(int32_t) * (size_t)(n_pts + 1)));
@@ -759,11 +829,11 @@ int dab_run_stage_a(dab_pair *pr) {
     da.n_points_dev = pr->keep_off.as<int32_t>() + n_cand;
     Node1 *base = pr->tree1.as<Node1>();
     for (int k = 0; k < DP_LEVELS; ++k) { da.level[k] = base; base += lv[k]; }
-    da.back = pr->back1.as<int32_t>(); da.len = pr->len1.as<int32_t>(); da.cp = pr->cp1.as<int32_t>();
+    da.meta = pr->back1.as<int4>();
     da.result = pr->dpres.as<int32_t>();
     dp1_kernel<<<1, 32, 0, st>>>(da);
     TraceArgs ta;
-    ta.back = da.back; ta.len = da.len; ta.cp = da.cp; ta.result = da.result;
+    ta.meta = da.meta; ta.result = da.result;
     ta.pt_i = pr->pt_i.as<int32_t>(); ta.pt_s = pr->pt_s.as<int32_t>(); ta.v_sel = V.nq_list.as<int32_t>();
     ta.seg = pr->seglist.as<int32_t>(); ta.path_x = pr->path1_x.as<int32_t>(); ta.path_y = pr->path1_y.as<int32_t>();
     trace1_kernel<<<1, 256, 0, st>>>(ta);

@@ -15,6 +15,14 @@ namespace {
 
 constexpr int MAXC = 32;   // corridors that may overlap one audio row
 
+struct __align__(16) P2Rec {     // one pass-2 point, as the DP walks it
+  double j, q;
+  int32_t i;
+  int32_t kf;      // corridor index | neighbour flag << 8
+  int32_t cell;    // int(j)
+  int32_t ro;      // row offset inside its corridor
+};
+
 struct ScoreBArgs {
   const float *a_scaled;   // (n_a, 3)
   const float *v_scaled;   // (n_v, 3)
@@ -25,8 +33,10 @@ struct ScoreBArgs {
   int32_t *row_count;
   const int32_t *row_off;
   int32_t *p_i, *p_c, *p_rank;
+  P2Rec *rec;
   double *p_j, *p_q;
   int32_t *overflow;
+  int32_t want_rank;       // the generic DP needs rank(j); the corridor-state DP does not
 };
 
 __device__ __forceinline__ double line_at(const dab_corridor &c, int64_t i) {
@@ -39,7 +49,7 @@ __global__ void corridor_kernel(ScoreBArgs s) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= s.n_a) return;
   double js[MAXC];
-  int cs[MAXC];
+  int cs[MAXC], ks[MAXC];
   int n = 0;
   for (int k = 0; k < s.n_cor; ++k) {
     const dab_corridor c = s.cor[k];
@@ -50,14 +60,14 @@ __global__ void corridor_kernel(ScoreBArgs s) {
     for (int m = 0; m < n; ++m) dup = dup || ((long long)js[m] == cell);
     if (dup) continue;     // an earlier (lower-index) cluster already claimed (i, int(j))
     if (n == MAXC) { atomicExch(s.overflow, 1); break; }
-    js[n] = j; cs[n] = c.cluster; ++n;
+    js[n] = j; cs[n] = c.cluster; ks[n] = k; ++n;
   }
   if (!FILL) { s.row_count[i] = n; return; }
   // insertion sort by j (cells are unique within the row, hence so are the j)
   for (int a = 1; a < n; ++a) {
-    double j = js[a]; int c = cs[a]; int b = a - 1;
-    while (b >= 0 && js[b] > j) { js[b + 1] = js[b]; cs[b + 1] = cs[b]; --b; }
-    js[b + 1] = j; cs[b + 1] = c;
+    double j = js[a]; int c = cs[a]; int kk = ks[a]; int b = a - 1;
+    while (b >= 0 && js[b] > j) { js[b + 1] = js[b]; cs[b + 1] = cs[b]; ks[b + 1] = ks[b]; --b; }
+    js[b + 1] = j; cs[b + 1] = c; ks[b + 1] = kk;
   }
   const int64_t off = s.row_off[i];
   const float a0 = s.a_scaled[i * 3 + 0], a1 = s.a_scaled[i * 3 + 1], a2 = s.a_scaled[i * 3 + 2];
@@ -82,20 +92,40 @@ __global__ void corridor_kernel(ScoreBArgs s) {
     q = q + (double)ag;
     // rank of j over all corridor rows
     int rank = 1;
-    for (int k = 0; k < s.n_cor; ++k) {
-      const dab_corridor c = s.cor[k];
-      int lo = c.lo, hi = c.hi;        // first row in [lo, hi) whose coordinate is >= j
-      while (lo < hi) {
-        const int mid = lo + ((hi - lo) >> 1);
-        if (line_at(c, mid) < j) lo = mid + 1; else hi = mid;
+    if (s.want_rank) {
+      for (int k = 0; k < s.n_cor; ++k) {
+        const dab_corridor c = s.cor[k];
+        int lo = c.lo, hi = c.hi;        // first row in [lo, hi) whose coordinate is >= j
+        while (lo < hi) {
+          const int mid = lo + ((hi - lo) >> 1);
+          if (line_at(c, mid) < j) lo = mid + 1; else hi = mid;
+        }
+        rank += lo - c.lo;
       }
-      rank += lo - c.lo;
+    }
+    // neighbourhood flag for the corridor-state DP: could a point of another corridor have
+    // written one of the prev_cache cells int(j)-2 .. int(j) during rows i-2 .. i?  (A superset
+    // test on the lines themselves: it ignores which duplicates were dropped.)
+    int near = 0;
+    const long long cell = (long long)j;
+    for (int k = 0; k < s.n_cor; ++k) {
+      if (k == ks[m]) continue;
+      const dab_corridor c = s.cor[k];
+      for (int64_t r = i - 2; r <= i; ++r) {
+        if (r < c.lo || r >= c.hi) continue;
+        const long long oc = (long long)line_at(c, r);
+        near |= (oc >= cell - 2 && oc <= cell);
+      }
     }
     s.p_i[off + m] = (int32_t)i;
     s.p_j[off + m] = j;
     s.p_c[off + m] = cs[m];
     s.p_q[off + m] = q;
     s.p_rank[off + m] = rank;
+    P2Rec rc;
+    rc.j = j; rc.q = q; rc.i = (int32_t)i; rc.kf = ks[m] | (near << 8); rc.cell = (int32_t)cell;
+    rc.ro = (int32_t)(i - s.cor[ks[m]].lo);
+    s.rec[off + m] = rc;
   }
 }
 
@@ -302,25 +332,403 @@ __global__ void init_dp2_kernel(Node2 *nodes, int64_t n_nodes, Cell2 *cache, int
   if (t < n_clusters) { cb_val[t] = -1000.0; cb_id[t] = -1; }
 }
 
+// ------------------------------------------------------------------------------------------
+// DP #2, corridor-state formulation (the fast path; the tree kernel above stays as the generic
+// fallback for > 32 corridors or lines with non-positive slope).
+//
+// Every point lies on one of <= 32 corridor lines j = slope * i + offset with slope > 0, so
+//   * prev_cache (describealign.py:956, 966-973) only ever yields points of rows i-2 .. i: the
+//     last three points of each corridor are enough state ("history");
+//   * the frontier (describealign.py:946, 961-962, 976-981) seen from (i, j) is
+//         F(j) = max over corridors c' of PM_c'[ #rows of c' processed so far with j' <= j ]
+//     where PM_c' is the running maximum of cum - 1000 along corridor c' (ties: earliest row),
+//     because j' grows with the row inside a corridor.  PM_c' is append-only, lives in HBM,
+//     its last 16 rows in shared memory;
+//   * when the frontier's top entry lies at j' <= j it IS F(j): no query at all.  A query is
+//     only needed for points below the top's coordinate whose own candidates do not already
+//     beat the top value; then lane c' looks PM_c' up (head / recent ring / a small per-lane
+//     window cache of older rows, refilled 16 rows at a time) and the warp arg-max-reduces.
+// One warp walks the points in (i, j) order; the state of the corridor being extended lives in
+// registers (uniform across lanes), the other corridors' state in shared memory.  The dependent
+// chain per point is compare + select + one f64 add.  cum values are bit-identical to the
+// reference because every cum is still "chosen predecessor value + qual".
+// ------------------------------------------------------------------------------------------
+struct __align__(16) PmEntry {
+  double val;
+  int32_t id;
+  int32_t pad;
+};
+
+struct __align__(16) BackRec {   // per point result: value it started from, predecessor id
+  double best;
+  int32_t pred;
+  int32_t pad;
+};
+
+// state of one corridor (shared memory copy; the corridor being extended lives in registers)
+struct __align__(16) CorState {
+  double h_cum0, h_cum1;                         // history: last three points of this corridor
+  int32_t h_row0, h_row1, h_cell0, h_cell1;
+  int32_t h_id0, h_id1, h_row2, h_cell2;
+  double h_cum2; int32_t h_id2; int32_t filled;  // filled: last PM row written
+  double cl_v; int32_t cl_i; int32_t pm_i;       // cluster best (cum - 50), PM head id
+  double pm_v; long long pm_base;                // PM head (cum - 1000), first PM row in a.pm
+};
+
+constexpr int RING = 16;     // most recent PM rows kept in shared memory
+constexpr int WAYS = 4;      // window cache: ways per lane
+constexpr int WLEN = 16;     // rows per window
+
+struct Dp2LArgs {
+  const P2Rec *rec;
+  const double *p_j;
+  int32_t n_points;
+  const dab_corridor *cor;
+  int32_t n_cor;
+  const int64_t *pm_off;     // [n_cor] first PM row of each corridor
+  PmEntry *pm;
+  BackRec *back;
+  int32_t *result;           // [0] end id ; double top value at +2
+  unsigned long long *counters;   // [0] frontier queries, [1] window refills, [2] neighbour points
+};
+
+__global__ void __launch_bounds__(32, 1) dp2_corridor_kernel(Dp2LArgs a) {
+  __shared__ CorState s_st[32];
+  __shared__ double s_pmv[32];                 // SoA mirrors of what the query lanes read
+  __shared__ int s_pmi[32], s_filled[32];
+  __shared__ int s_lo[32], s_hi[32], s_cluster[32];
+  __shared__ double s_slope[32], s_off[32], s_inv[32];
+  __shared__ PmEntry s_ring[32][RING];
+  __shared__ PmEntry s_win[32][WAYS * WLEN];
+  __shared__ P2Rec s_rec[2][32];
+
+  const int lane = threadIdx.x;
+  const int n = a.n_points;
+  const int n_cor = a.n_cor;
+  const double NEG = -INFINITY;
+  {
+    const bool v = lane < n_cor;
+    dab_corridor c;
+    if (v) c = a.cor[lane];
+    s_lo[lane] = v ? c.lo : 0x7fffffff;
+    s_hi[lane] = v ? c.hi : 0x7fffffff;
+    s_cluster[lane] = v ? c.cluster : -1;
+    s_slope[lane] = v ? c.slope : 1.0;
+    s_off[lane] = v ? c.offset : 0.0;
+    s_inv[lane] = v ? 1.0 / c.slope : 1.0;
+    CorState z;
+    z.h_cum0 = z.h_cum1 = z.h_cum2 = NEG;
+    z.h_row0 = z.h_row1 = z.h_row2 = -100;
+    z.h_cell0 = z.h_cell1 = z.h_cell2 = -100;
+    z.h_id0 = z.h_id1 = z.h_id2 = -2;
+    z.filled = -1;
+    z.cl_v = -1000.0; z.cl_i = -1;               // clusters_best_so_far seed (describealign.py:948)
+    z.pm_v = NEG; z.pm_i = -2;
+    z.pm_base = v ? a.pm_off[lane] : 0;
+    s_st[lane] = z;
+    s_pmv[lane] = NEG; s_pmi[lane] = -2; s_filled[lane] = -1;
+  }
+  __syncwarp();
+  // lane-private window tags (lane l caches older PM rows of corridor l)
+  int wbase[WAYS], wnext = 0;
+#pragma unroll
+  for (int w = 0; w < WAYS; ++w) wbase[w] = -0x40000000;
+  unsigned n_query = 0, n_refill = 0, n_near = 0;
+
+  // state of the current corridor (uniform registers)
+  int cur = 0;
+  CorState st = s_st[0];
+  int c_cluster = s_cluster[0];
+  // frontier top: seed (0, 0, -1, 0, 0) (describealign.py:947)
+  double top_v = 0.0, top_j = 0.0;
+  int top_i = -1;
+
+  // every lane writes the same values to the same addresses: no divergence, and each lane's later
+  // reads see at least its own writes, so no barrier is needed
+  auto spill = [&]() {
+    s_st[cur] = st;
+    s_pmv[cur] = st.pm_v; s_pmi[cur] = st.pm_i; s_filled[cur] = st.filled;
+  };
+
+  // F(j) for a point of corridor k at row i: lane c' contributes PM_c'[rows of c' with j' <= j]
+  auto frontier_query = [&](int i, double j, int k, double &fv_out, int &fi_out) {
+        spill();                        // the other lanes' view of every corridor but `cur` is current
+        double v = NEG;
+        int id = -2;
+        if (lane == k) { v = 0.0; id = -1; }          // the frontier's seed entry, j' = 0
+        else if (lane < n_cor && s_lo[lane] <= i) {
+          const int lo = s_lo[lane], rows = s_hi[lane] - lo;
+          const double sl = s_slope[lane], of = s_off[lane];
+          // rows of this corridor whose coordinate is <= j
+          double est = floor((j - of) * s_inv[lane]) - (double)lo + 1.0;
+          int kk = est < 0.0 ? 0 : (est > (double)rows ? rows : (int)est);
+          while (kk < rows && __dadd_rn(__dmul_rn(sl, (double)(lo + kk)), of) <= j) ++kk;
+          while (kk > 0 && __dadd_rn(__dmul_rn(sl, (double)(lo + kk - 1)), of) > j) --kk;
+          const int done = (i + 1 < lo + rows ? i + 1 : lo + rows) - lo;   // rows <= i
+          const int idx = kk < done ? kk : done;
+          const int f = s_filled[lane];
+          if (idx > 0 && f >= 0) {
+            const int x = idx - 1;
+            if (x >= f) { v = s_pmv[lane]; id = s_pmi[lane]; }
+            else if (x > f - RING) { const PmEntry e = s_ring[lane][x & (RING - 1)]; v = e.val; id = e.id; }
+            else {
+              int hit = -1;
+#pragma unroll
+              for (int w = 0; w < WAYS; ++w) if (x >= wbase[w] && x < wbase[w] + WLEN) hit = w;
+              if (hit < 0) {
+                hit = wnext; wnext = (wnext + 1) & (WAYS - 1);
+                ++n_refill;
+                const PmEntry *src = a.pm + s_st[lane].pm_base + x;      // rows x .. x+15 < f are final
+#pragma unroll
+                for (int e = 0; e < WLEN; ++e) {
+                  const int4 raw = __ldcg(reinterpret_cast<const int4 *>(src + e));
+                  *reinterpret_cast<int4 *>(&s_win[lane][hit * WLEN + e]) = raw;
+                }
+#pragma unroll
+                for (int w = 0; w < WAYS; ++w) if (w == hit) wbase[w] = x;
+              }
+              int wb = 0;
+#pragma unroll
+              for (int w = 0; w < WAYS; ++w) if (w == hit) wb = wbase[w];
+              const PmEntry e = s_win[lane][hit * WLEN + (x - wb)];
+              v = e.val; id = e.id;
+            }
+          }
+        }
+        // warp arg-max on (val desc, j' asc, id asc)
+        const unsigned long long ob = order_bits(v);
+        const unsigned hi = (unsigned)(ob >> 32), lo32 = (unsigned)ob;
+        const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
+        bool alive = hi == mhi;
+        const unsigned mlo = __reduce_max_sync(0xffffffffu, alive ? lo32 : 0u);
+        alive = alive && lo32 == mlo;
+        unsigned bal = __ballot_sync(0xffffffffu, alive);
+        if (__popc(bal) > 1) {
+          // equal values (flat stretches that started from the same jump): smallest j', then id
+          const double jj = !alive ? INFINITY : (id < 0 ? 0.0 : a.p_j[id]);
+          const unsigned long long jb = (unsigned long long)__double_as_longlong(jj);   // jj >= 0
+          const unsigned jh = (unsigned)(jb >> 32), jl = (unsigned)jb;
+          const unsigned nh = __reduce_min_sync(0xffffffffu, alive ? jh : 0xffffffffu);
+          alive = alive && jh == nh;
+          const unsigned nl = __reduce_min_sync(0xffffffffu, alive ? jl : 0xffffffffu);
+          alive = alive && jl == nl;
+          const unsigned ni = __reduce_min_sync(0xffffffffu, alive ? (unsigned)(id + 2) : 0xffffffffu);
+          alive = alive && (unsigned)(id + 2) == ni;
+          bal = __ballot_sync(0xffffffffu, alive);
+        }
+        const int src = __ffs(bal) - 1;
+        const double fv = __shfl_sync(0xffffffffu, v, src);
+        const int fi = __shfl_sync(0xffffffffu, id, src);
+        fv_out = fv; fi_out = fi;
+  };
+
+  P2Rec rr;
+  if (lane < n) rr = a.rec[lane];
+  for (int base = 0; base < n; base += 32) {
+    const int buf = (base >> 5) & 1;
+    s_rec[buf][lane] = rr;
+    __syncwarp();
+    if (base + 32 + lane < n) rr = a.rec[base + 32 + lane];
+    const int cnt = n - base < 32 ? n - base : 32;
+    P2Rec nx = s_rec[buf][0];
+    for (int t = 0; t < cnt; ++t) {
+      const int p = base + t;
+      const P2Rec pt = nx;
+      if (t + 1 < cnt) nx = s_rec[buf][t + 1];
+      const int i = pt.i, cell = pt.cell, ro = pt.ro;
+      const double j = pt.j, q = pt.q;
+      const int k = pt.kf & 0xff;
+      const bool near = pt.kf > 0xff;
+      if (k != cur) {
+        spill();
+        cur = k;
+        st = s_st[k];
+        c_cluster = s_cluster[k];
+      }
+      double best;
+      int pred;
+      if (!near) {
+        // own-corridor prev_cache candidates: rows i-1 / i-2 of this line, latest write per cell
+        const bool vis1 = st.h_row0 >= i - 2 && st.h_cell0 >= cell - 2;
+        const bool vis2 = st.h_row1 >= i - 2 && st.h_cell1 >= cell - 2 && st.h_cell1 != st.h_cell0;
+        // candidates in the reference's order [frontier, cluster best, cell(s)]: the LAST one that
+        // attains the maximum wins (every test is ">=", describealign.py:960-973)
+        double m = st.cl_v;
+        int mi = st.cl_i;
+        if (vis2 && st.h_cum1 >= m) { m = st.h_cum1; mi = st.h_id1; }
+        if (vis1 && st.h_cum0 >= m) { m = st.h_cum0; mi = st.h_id0; }
+        best = m; pred = mi;
+        if (top_j <= j) {
+          if (top_v > m) { best = top_v; pred = top_i; }     // the top entry is F(j) itself
+        } else if (m < top_v) {                               // else F(j) <= top value <= m
+          ++n_query;
+          double fv; int fi;
+          frontier_query(i, j, k, fv, fi);
+          if (fv > m) { best = fv; pred = fi; }
+        }
+      } else {
+        ++n_near;
+        best = NEG; pred = -2;
+        if (top_j <= j) { best = top_v; pred = top_i; }
+        else { ++n_query; frontier_query(i, j, k, best, pred); }
+      }
+      if (near) {
+        // generic prev_cache evaluation over the histories of all corridors
+        if (st.cl_v >= best) { best = st.cl_v; pred = st.cl_i; }
+        spill();
+#pragma unroll 1
+        for (int x = cell - 2; x <= cell; ++x) {
+          int brow = -1, bh = 0;
+          if (lane < n_cor) {
+            const CorState *o = &s_st[lane];
+            if (o->h_cell0 == x && o->h_row0 > brow) { brow = o->h_row0; bh = 0; }
+            if (o->h_cell1 == x && o->h_row1 > brow) { brow = o->h_row1; bh = 1; }
+            if (o->h_cell2 == x && o->h_row2 > brow) { brow = o->h_row2; bh = 2; }
+          }
+          const int mrow = (int)__reduce_max_sync(0xffffffffu, (unsigned)(brow + 1)) - 1;
+          if (mrow < 0 || mrow < i - 2) continue;         // nothing written recently enough
+          const int src = __ffs(__ballot_sync(0xffffffffu, brow == mrow)) - 1;
+          const int sh = __shfl_sync(0xffffffffu, bh, src);
+          const CorState *o = &s_st[src];
+          double pc = sh == 0 ? o->h_cum0 : (sh == 1 ? o->h_cum1 : o->h_cum2);
+          const int pid = sh == 0 ? o->h_id0 : (sh == 1 ? o->h_id1 : o->h_id2);
+          const double pj = __dadd_rn(__dmul_rn(s_slope[src], (double)mrow), s_off[src]);
+          if (s_cluster[src] != c_cluster) {
+            const double d = (j - pj) - (double)(i - mrow);
+            pc = pc - (100.0 + 100.0 * (d * d));
+          }
+          if (pj <= j && pc >= best) { best = pc; pred = pid; }
+        }
+      }
+      {
+        const double cum = best + q;
+        // ---- updates ---------------------------------------------------------------------
+        st.h_row2 = st.h_row1; st.h_cell2 = st.h_cell1; st.h_id2 = st.h_id1; st.h_cum2 = st.h_cum1;
+        st.h_row1 = st.h_row0; st.h_cell1 = st.h_cell0; st.h_id1 = st.h_id0; st.h_cum1 = st.h_cum0;
+        st.h_row0 = i; st.h_cell0 = cell; st.h_id0 = p; st.h_cum0 = cum;
+        const double cj = cum - 50.0;
+        if (st.cl_v < cj) { st.cl_v = cj; st.cl_i = p; }
+        const double jump = cum - 1000.0;
+        if (ro - st.filled > 1) {
+          // rows without a point (their cell was claimed by an earlier cluster) repeat the head
+          PmEntry e; e.val = st.pm_v; e.id = st.pm_i; e.pad = 0;
+          for (int r = st.filled + 1; r < ro; ++r) {
+            if (lane == 0) a.pm[st.pm_base + r] = e;
+            s_ring[k][r & (RING - 1)] = e;
+          }
+        }
+        if (jump > st.pm_v) { st.pm_v = jump; st.pm_i = p; }
+        st.filled = ro;
+        PmEntry e; e.val = st.pm_v; e.id = st.pm_i; e.pad = 0;
+        s_ring[k][ro & (RING - 1)] = e;
+        // lane 0 appends the PM row, lane 1 the back record: one predicated 16-byte store
+        int4 *dst = lane == 0 ? reinterpret_cast<int4 *>(a.pm + st.pm_base + ro) : reinterpret_cast<int4 *>(a.back + p);
+        int4 val;
+        if (lane == 0) { val.x = __double2loint(e.val); val.y = __double2hiint(e.val); val.z = e.id; val.w = 0; }
+        else { val.x = __double2loint(best); val.y = __double2hiint(best); val.z = pred; val.w = 0; }
+        if (lane < 2) *dst = val;
+        if (jump > top_v || (jump == top_v && j < top_j)) { top_v = jump; top_j = j; top_i = p; }
+      }
+    }
+    __syncwarp();
+  }
+  if (lane == 0) {
+    a.result[0] = top_i;
+    *reinterpret_cast<double *>(a.result + 2) = top_v;
+    a.counters[0] = n_query; a.counters[1] = n_refill; a.counters[2] = n_near;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Traceback by pointer jumping (binary lifting): up[k][p] = 2^k-th predecessor, node n = root.
+// depth doubles alongside; the ancestors of the end point are marked level by level from the
+// top; each marked point writes its own path row at position depth - 1.
+// ------------------------------------------------------------------------------------------
+__global__ void lift_init_kernel(const BackRec *back, int32_t n, int32_t *up0, int32_t *dep0, int32_t *mark,
+                                 const int32_t *result) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p > n) return;
+  if (p == n) { up0[p] = n; dep0[p] = 0; mark[p] = 0; return; }
+  const int b = back[p].pred;
+  up0[p] = b < 0 ? n : b;
+  dep0[p] = 1;
+  mark[p] = (p == result[0]) ? 1 : 0;
+}
+
+__global__ void lift_step_kernel(const int32_t *up_in, const int32_t *dep_in, int32_t n, int32_t *up_out,
+                                 int32_t *dep_out) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p > n) return;
+  const int u = up_in[p];
+  up_out[p] = up_in[u];
+  dep_out[p] = dep_in[p] + dep_in[u];
+}
+
+__global__ void lift_mark_kernel(const int32_t *up_k, int32_t n, int32_t *mark) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n || !mark[p]) return;
+  const int u = up_k[p];
+  if (u != n) mark[u] = 1;
+}
+
+struct EmitArgs {
+  const int32_t *mark, *dep, *result;
+  const BackRec *back;
+  const int32_t *p_i, *p_c;
+  const double *p_j, *p_q;
+  int32_t n;
+  double *rows;
+  int32_t *n_path;
+};
+
+__global__ void lift_emit_kernel(EmitArgs a) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= a.n || !a.mark[p]) return;
+  const int pos = a.dep[p] - 1;
+  double *row = a.rows + (int64_t)pos * 5;
+  row[0] = a.p_j[p]; row[1] = (double)a.p_i[p]; row[2] = (double)a.p_c[p]; row[3] = a.p_q[p];
+  // 5th column of a row = the (penalised) value its successor started from (describealign.py:983);
+  // the end row carries the frontier value of the end point
+  if (pos > 0) a.rows[(int64_t)(pos - 1) * 5 + 4] = a.back[p].best;
+  if (p == a.result[0]) {
+    row[4] = *reinterpret_cast<const double *>(a.result + 2);
+    *a.n_path = pos + 1;
+  }
+}
+
 }  // namespace
+
+// The corridor-state DP needs: at most 32 corridors, positive slopes, every coordinate >= 3 (so the
+// seeded prev_cache cell 0 is never in reach; x_limits keeps lines >= 4, describealign.py:898).
+static bool corridor_dp_eligible(const dab_pair *pr, int32_t n_cor) {
+  if (pr->ctx->opt_dp2_generic || n_cor > 32) return false;
+  for (int k = 0; k < n_cor; ++k) {
+    const dab_corridor &c = pr->h_cor[k];
+    if (!(c.slope > 0.0)) return false;
+    if (c.hi > c.lo && !(c.slope * (double)c.lo + c.offset >= 3.0)) return false;
+  }
+  return true;
+}
 
 int dab_run_stage_b(dab_pair *pr, int32_t n_cor, int32_t n_clusters) {
   dab_ctx *ctx = pr->ctx;
   cudaStream_t st = pr->stream;
   const int64_t n_a = pr->stats.n_audio_frames, n_v = pr->stats.n_video_frames;  // set by the caller
   pr->n_points2 = pr->n_path2 = 0;
+  const bool fast = corridor_dp_eligible(pr, n_cor);
   ScoreBArgs sb;
   sb.a_scaled = pr->a_scaled.as<float>(); sb.v_scaled = pr->v_scaled.as<float>();
   sb.n_a = n_a; sb.n_v = n_v;
   sb.cor = pr->corridors.as<dab_corridor>(); sb.n_cor = n_cor;
   sb.a_max = reinterpret_cast<float *>(pr->h_counters + 8)[0];
   sb.v_max = reinterpret_cast<float *>(pr->h_counters + 8)[1];
+  sb.want_rank = fast ? 0 : 1;
   DAB_TRY(dab_ensure(ctx, pr->row2_count, sizeof(int32_t) * (size_t)(n_a + 2)));
   DAB_TRY(dab_ensure(ctx, pr->row2_off, sizeof(int32_t) * (size_t)(n_a + 2)));
-  DAB_TRY(dab_ensure(ctx, pr->dpres, sizeof(int32_t) * 8));
-  DAB_CUDA(cudaMemsetAsync(pr->dpres.p, 0, sizeof(int32_t) * 8, st));
+  DAB_TRY(dab_ensure(ctx, pr->dpres, sizeof(int32_t) * 16));
+  DAB_CUDA(cudaMemsetAsync(pr->dpres.p, 0, sizeof(int32_t) * 16, st));
   sb.row_count = pr->row2_count.as<int32_t>(); sb.row_off = pr->row2_off.as<int32_t>();
-  sb.p_i = sb.p_c = sb.p_rank = nullptr; sb.p_j = sb.p_q = nullptr;
+  sb.p_i = sb.p_c = sb.p_rank = nullptr; sb.rec = nullptr; sb.p_j = sb.p_q = nullptr;
   sb.overflow = pr->dpres.as<int32_t>() + 6;
   DAB_CUDA(cudaEventRecord(pr->ev[14], st));
   int64_t n_pts = 0;
@@ -337,9 +745,11 @@ int dab_run_stage_b(dab_pair *pr, int32_t n_cor, int32_t n_clusters) {
     DAB_TRY(dab_ensure(ctx, pr->p2_i, sizeof(int32_t) * (size_t)(n_pts + 1)));
     DAB_TRY(dab_ensure(ctx, pr->p2_c, sizeof(int32_t) * (size_t)(n_pts + 1)));
     DAB_TRY(dab_ensure(ctx, pr->p2_rank, sizeof(int32_t) * (size_t)(n_pts + 1)));
+    DAB_TRY(dab_ensure(ctx, pr->p2_k, sizeof(P2Rec) * (size_t)(n_pts + 1)));
     DAB_TRY(dab_ensure(ctx, pr->p2_j, sizeof(double) * (size_t)(n_pts + 1)));
     DAB_TRY(dab_ensure(ctx, pr->p2_q, sizeof(double) * (size_t)(n_pts + 1)));
     sb.p_i = pr->p2_i.as<int32_t>(); sb.p_c = pr->p2_c.as<int32_t>(); sb.p_rank = pr->p2_rank.as<int32_t>();
+    sb.rec = pr->p2_k.as<P2Rec>();
     sb.p_j = pr->p2_j.as<double>(); sb.p_q = pr->p2_q.as<double>();
     if (n_pts > 0) {
       corridor_kernel<true><<<gb, 128, 0, st>>>(sb);
@@ -352,7 +762,56 @@ int dab_run_stage_b(dab_pair *pr, int32_t n_cor, int32_t n_clusters) {
 
   DAB_CUDA(cudaEventRecord(pr->ev[16], st));
   int64_t n_path = 0;
-  if (n_pts > 0) {
+  if (n_pts > 0 && fast) {
+    // ---- corridor-state DP + pointer-jumping traceback ----
+    int64_t pm_off[32], rows = 0;
+    for (int k = 0; k < n_cor; ++k) { pm_off[k] = rows; rows += pr->h_cor[k].hi > pr->h_cor[k].lo ? pr->h_cor[k].hi - pr->h_cor[k].lo : 0; }
+    int levels = 1;                      // up[0 .. levels-1], 2^(levels-1) >= n_pts
+    while ((1LL << (levels - 1)) < n_pts) ++levels;
+    const int64_t np1 = n_pts + 1;
+    DAB_TRY(dab_ensure(ctx, pr->pm2, sizeof(PmEntry) * (size_t)(rows + WLEN + 1)));
+    DAB_TRY(dab_ensure(ctx, pr->pmoff2, sizeof(int64_t) * 32 + sizeof(unsigned long long) * 4));
+    DAB_TRY(dab_ensure(ctx, pr->back2, sizeof(BackRec) * (size_t)(n_pts + 2)));
+    DAB_TRY(dab_ensure(ctx, pr->lift_up, sizeof(int32_t) * (size_t)(levels * np1)));
+    DAB_TRY(dab_ensure(ctx, pr->lift_dep, sizeof(int32_t) * (size_t)(3 * np1)));
+    DAB_TRY(dab_ensure(ctx, pr->path2, sizeof(double) * 5 * (size_t)(n_pts + 1)));
+    DAB_CUDA(cudaMemcpyAsync(pr->pmoff2.p, pm_off, sizeof(int64_t) * (size_t)n_cor, cudaMemcpyHostToDevice, st));
+    Dp2LArgs la;
+    la.rec = pr->p2_k.as<P2Rec>(); la.p_j = pr->p2_j.as<double>();
+    la.n_points = (int32_t)n_pts;
+    la.cor = pr->corridors.as<dab_corridor>(); la.n_cor = n_cor;
+    la.pm_off = pr->pmoff2.as<int64_t>(); la.pm = pr->pm2.as<PmEntry>();
+    la.back = pr->back2.as<BackRec>();
+    la.result = pr->dpres.as<int32_t>();
+    la.counters = reinterpret_cast<unsigned long long *>(pr->pmoff2.as<int64_t>() + 32);
+    dp2_corridor_kernel<<<1, 32, 0, st>>>(la);
+    DAB_CUDA(cudaEventRecord(pr->ev[18], st));
+    int32_t *up = pr->lift_up.as<int32_t>();
+    int32_t *dep0 = pr->lift_dep.as<int32_t>(), *dep1 = dep0 + np1, *mark = dep1 + np1;
+    const unsigned gl = (unsigned)cdiv(np1, 256);
+    lift_init_kernel<<<gl, 256, 0, st>>>(la.back, (int32_t)n_pts, up, dep0, mark, la.result);
+    int32_t *din = dep0, *dout = dep1;
+    for (int k = 1; k < levels; ++k) {
+      lift_step_kernel<<<gl, 256, 0, st>>>(up + (int64_t)(k - 1) * np1, din, (int32_t)n_pts, up + (int64_t)k * np1, dout);
+      int32_t *t = din; din = dout; dout = t;
+    }
+    for (int k = levels - 1; k >= 0; --k) lift_mark_kernel<<<gl, 256, 0, st>>>(up + (int64_t)k * np1, (int32_t)n_pts, mark);
+    EmitArgs ea;
+    ea.mark = mark; ea.dep = din; ea.back = la.back; ea.result = la.result;
+    ea.p_i = pr->p2_i.as<int32_t>(); ea.p_c = pr->p2_c.as<int32_t>(); ea.p_j = la.p_j; ea.p_q = pr->p2_q.as<double>();
+    ea.n = (int32_t)n_pts; ea.rows = pr->path2.as<double>(); ea.n_path = pr->dpres.as<int32_t>() + 1;
+    lift_emit_kernel<<<gl, 256, 0, st>>>(ea);
+    ctx->launches += 2 + 2 * levels;
+    DAB_CUDA(cudaMemcpyAsync(&pr->h_counters[12], pr->dpres.as<int32_t>(), 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    DAB_CUDA(cudaMemcpyAsync(&pr->h_counters[16], la.counters, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    DAB_CUDA(cudaEventRecord(pr->ev[17], st));
+    DAB_CUDA(cudaStreamSynchronize(st));
+    n_path = reinterpret_cast<int32_t *>(&pr->h_counters[12])[1];
+    pr->stats.n_dp2_queries = pr->h_counters[16];
+    pr->stats.n_dp2_refills = pr->h_counters[17];
+    pr->stats.n_dp2_neighbour = pr->h_counters[18];
+  } else if (n_pts > 0) {
+    // ---- generic tree DP ----
     // rank domain: 1 + total corridor rows
     int64_t dom = 1;
     {
@@ -390,6 +849,7 @@ int dab_run_stage_b(dab_pair *pr, int32_t n_cor, int32_t n_clusters) {
     da.back_id = back_id; da.len = pr->len2.as<int32_t>(); da.cp = pr->cp2.as<int32_t>();
     da.back_cum = back_cum; da.result = pr->dpres.as<int32_t>();
     dp2_kernel<<<1, 32, 0, st>>>(da);
+    DAB_CUDA(cudaEventRecord(pr->ev[18], st));
     Trace2Args ta;
     ta.back_id = back_id; ta.len = da.len; ta.cp = da.cp; ta.result = da.result; ta.back_cum = back_cum;
     ta.p_i = da.p_i; ta.p_c = da.p_c; ta.p_j = da.p_j; ta.p_q = da.p_q;
@@ -401,6 +861,7 @@ int dab_run_stage_b(dab_pair *pr, int32_t n_cor, int32_t n_clusters) {
     DAB_CUDA(cudaStreamSynchronize(st));
     n_path = reinterpret_cast<int32_t *>(&pr->h_counters[12])[1];
   } else {
+    DAB_CUDA(cudaEventRecord(pr->ev[18], st));
     DAB_CUDA(cudaEventRecord(pr->ev[17], st));
   }
   pr->n_path2 = n_path;

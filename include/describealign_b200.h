@@ -80,6 +80,9 @@ typedef struct {
   int64_t n_path1;
   int64_t n_points2;
   int64_t n_path2;
+  int64_t n_dp2_queries;      /* pass-2 points that needed a real frontier query */
+  int64_t n_dp2_refills;      /* 16-row refills of the per-corridor running-max windows */
+  int64_t n_dp2_neighbour;    /* pass-2 points with another corridor within 2 cells / 2 rows */
 } dab_stats;
 
 int dab_abi_version(void);
@@ -88,6 +91,9 @@ int dab_device_count(void);
 /* device < 0: current device. */
 int dab_create(int device, dab_ctx **out);
 void dab_destroy(dab_ctx *ctx);
+/* Tuning / testing switches.  "dp2_generic" = 1 forces the tree-based pass-2 DP instead of the
+ * corridor-state DP (both are exact; the tests compare them).  Unknown names return DAB_E_ARG. */
+int dab_set_option(dab_ctx *ctx, const char *name, int64_t value);
 const char *dab_last_error(const dab_ctx *ctx);   /* ctx may be NULL for dab_create failures */
 
 int dab_pair_create(dab_ctx *ctx, dab_pair **out);
@@ -142,7 +148,7 @@ int dab_pair_get_stats(dab_pair *pair, dab_stats *out);
 /* Device-side time of the kernels of the last stage_a / stage_b / set_pcm call on this pair,
  * in milliseconds, measured with CUDA events on the pair's stream; slots:
  * 0 features(video) 1 features(audio) 2 prep+codes 3 tables 4 gate 5 score 6 dp1+traceback
- * 7 corridor scoring 8 dp2+traceback.  Slots not run since creation are 0. */
+ * 7 corridor scoring 8 dp2+traceback 9 dp2 alone.  Slots not run since creation are 0. */
 int dab_pair_get_timings(dab_pair *pair, float ms[16]);
 /* number of kernel launches issued by this context since creation */
 int64_t dab_launch_count(const dab_ctx *ctx);

@@ -149,3 +149,97 @@ def test_mismatched_inputs_fail_like_the_reference(gpu_ctx):
     _, a = synth.make_pair(60.0, 1.0, seed=202)
     with pytest.raises(RuntimeError, match="Alignment failed, are the input files mismatched"):
         api.align_pcm(v, a)
+
+
+def _random_stage_b_case(seed, n_a=9000, n_v=9000, n_cor=6, crossing=True):
+    """Synthetic pass-2 input: smooth random scaled features and hand-made corridors (different
+    slopes so that lines cross and share cells, one line duplicated a quarter cell away so that
+    the 'first cluster to claim (i, int(j)) wins' rule fires).  The audio is made to follow a
+    different corridor in each stretch of ~600 rows, with short corrupted runs inside, so that
+    the best path uses global jumps, same-cluster jumps and cross-cluster local steps."""
+    rng = np.random.default_rng(seed)
+
+    def feats(n):
+        x = rng.standard_normal((n + 40, 3)).cumsum(axis=0)
+        x = x[40:] - x[:-40]
+        return np.ascontiguousarray((x / 6.0).astype(np.float32))
+    audio, video = feats(n_a), feats(n_v)
+    plans = []
+    for k in range(n_cor):
+        slope = float(rng.uniform(0.7, 1.25)) if crossing else 1.0
+        offset = float(rng.uniform(4.0, 0.15 * n_v)) + (0.0 if crossing else 40.0 * k)
+        if k == 2:                       # same line as corridor 1, shifted by a fraction of a cell
+            slope, offset = plans[1][3], plans[1][4] + 0.25
+        lo = int(rng.integers(0, n_a // 8))
+        hi = int(rng.integers(7 * n_a // 8, n_a))
+        lo = max(lo, int(np.ceil((4 - offset) / slope)), 0)
+        hi = min(hi, int(np.floor((n_v - 4 - offset) / slope)))
+        plans.append((k, lo, hi, slope, offset))
+    seg = 600
+    for s0 in range(0, n_a, seg):
+        idx, lo, hi, slope, offset = plans[int(rng.integers(0, n_cor))]
+        a0, a1 = max(s0, lo), min(s0 + seg, hi)
+        if a1 - a0 < 50:
+            continue
+        rows = np.arange(a0, a1)
+        y = slope * rows + offset
+        f = np.floor(y).astype(np.int64)
+        t = (y - f)[:, None]
+        good = video[f] * (1 - t) + video[f + 1] * t + 0.01 * rng.standard_normal((a1 - a0, 3))
+        b0 = int(rng.integers(0, a1 - a0 - 40))
+        good[b0:b0 + 30] += rng.standard_normal((30, 3))          # a corrupted run: cluster jump
+        audio[a0:a1] = good.astype(np.float32)
+    # energy column: keep most frames within 2.5 of the maximum so that the gates stay open
+    audio[:, 0] = np.clip(audio[:, 0], -1.0, 1.0)
+    video[:, 0] = np.clip(video[:, 0], -1.0, 1.0)
+    return audio, video, plans, n_cor
+
+
+@pytest.mark.parametrize("seed,crossing", [(1, True), (2, True), (3, False), (4, True), (5, True)])
+@pytest.mark.parametrize("generic", [0, 1])
+def test_stage_b_adversarial_vs_oracle(gpu_ctx, seed, crossing, generic):
+    """Corridor scoring + DP #2 + traceback on inputs built to hit the rare branches (crossing
+    lines, shared cells, dropped duplicates, negative quals, cluster jumps), for the
+    corridor-state DP and for the generic tree DP; both must equal the oracle bit for bit in the
+    integer columns and to 1e-9 in the float ones."""
+    from describealign_b200 import _cabi
+    from oracle import align_oracle as ao
+    audio, video, plans, n_clusters = _random_stage_b_case(seed, crossing=crossing)
+    want = ao.stage_b(plans, n_clusters, audio, video)
+    gpu_ctx.set_option("dp2_generic", generic)
+    try:
+        pair = _cabi.Pair(gpu_ctx)
+        pair.stage_b(audio, video, plans, n_clusters)
+        i, j, c, q = pair.points2()
+        path = pair.path2()
+        stats = pair.stats()
+        pair.close()
+    finally:
+        gpu_ctx.set_option("dp2_generic", 0)
+    assert np.array_equal(i, want["points_i"]) and np.array_equal(c, want["points_c"])
+    np.testing.assert_array_equal(j, want["points_j"])
+    np.testing.assert_allclose(q, want["points_q"], rtol=0, atol=1e-9)
+    wp = want["path"]
+    assert path.shape == wp.shape, (path.shape, wp.shape)
+    np.testing.assert_array_equal(path[:, :3], wp[:, :3])
+    np.testing.assert_allclose(path[:, 3:], wp[:, 3:], rtol=0, atol=1e-8)
+    if not generic and crossing:
+        assert stats["n_dp2_neighbour"] > 0, "the test is meant to exercise the shared-cell branch"
+
+
+def test_end_to_end_dp2_variants_agree(gpu_ctx, golden_align):
+    """Same pair through both pass-2 DPs: identical paths (the corridor-state DP is the product
+    path; the tree DP is the generic fallback)."""
+    from describealign_b200 import api
+    _, meta = golden_align
+    v, a = golden_pair_pcm(meta, "pair_warp")
+    out = []
+    for generic in (0, 1):
+        api.context().set_option("dp2_generic", generic)
+        try:
+            out.append(api.align_pcm(v, a))
+        finally:
+            api.context().set_option("dp2_generic", 0)
+    np.testing.assert_array_equal(out[0][3], out[1][3])
+    np.testing.assert_array_equal(out[0][0], out[1][0])
+    np.testing.assert_array_equal(out[0][1], out[1][1])
