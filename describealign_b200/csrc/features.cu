@@ -3,16 +3,21 @@
 // :568-573, get_freq_bands :575-593) in ONE pass over the PCM.
 //
 // One CTA produces FT consecutive output frames.  It stages the samples of frames
-// [t0-7, t0+FT+7) plus 40 samples of filter halo in shared memory as float16 (the
-// reference's own sample type, :156), derives every intermediate of the polyphase filter
-// bank (lp1 @8820 Hz, lp2 @1260 Hz, the three residual band energies, 105-sample block
-// energies, per-frame zero-crossing counts) in shared memory, and writes only the five
-// outputs.  HBM traffic: the PCM once (+ halo re-reads, served from L2) and 24 B per frame.
+// [t0-8, t0+FT+8) plus 40 samples of filter halo in shared memory as float16 (the
+// reference's own sample type, :156) with 16-byte loads, derives every intermediate of the
+// polyphase filter bank (lp1 @8820 Hz, lp2 @1260 Hz, the three residual band energies,
+// 105-sample block energies, per-frame zero-crossing counts) in shared memory, and writes
+// only the five outputs.  HBM traffic: the PCM once (+ halo re-reads, served from L2) and
+// 24 B per frame.  The Hann tables live in shared memory as well: they are indexed by the
+// phase, which differs between the threads of a warp, and divergent __constant__ reads
+// serialise (the first version of this kernel spent 85 % of its cycles in that unit).
 //
 // Bit-exactness: every sum is evaluated in the order numpy / OpenBLAS
 // use in the reference - parallelism is across outputs, never across the taps of one
 // output - with separately rounded multiplies and adds (-fmad=false), f32 products
 // accumulated in f64 where numpy does, and glibc's log10f restated in IEEE operations.
+// The arithmetic cost of those fixed orders (about 6 500 instructions per frame, of which
+// 630 f32->f64 conversions) is what bounds this kernel, not HBM.
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -20,19 +25,32 @@
 
 namespace {
 
-constexpr int FT = 96;            // output frames per CTA
-constexpr int FH = 7;             // halo frames each side (15-tap smoothing at the frame rate)
-constexpr int NF = FT + 2 * FH;   // frames staged
+constexpr int FH = 8;             // halo frames each side (7 needed; 8 keeps tiles 16-byte aligned)
 constexpr int PADS = 40;          // halo samples each side (lp2 needs lp1 +-7, lp1 needs +-5 samples)
-constexpr int NS = NF * 210 + 2 * PADS;
-constexpr int N1 = NF * 42 + 14;  // lp1 entries staged (+-7)
 constexpr int THREADS = 512;
+constexpr int NTAB = 772;         // 630 + 90 + 21 + 15 + 13 = 769 floats, padded
 
-__constant__ float c_w13[13];
-__constant__ float c_w15[15];
-__constant__ float c_w21[21];
-__constant__ float c_w90[90];
-__constant__ float c_w630[630];
+template <int CH> struct Tile {
+  static constexpr int FT = CH == 1 ? 104 : 48;      // output frames per CTA
+  static constexpr int NF = FT + 2 * FH;              // frames staged
+  static constexpr int NS = NF * 210 + 2 * PADS;      // samples staged (multiple of 8)
+  static constexpr int N1 = NF * 42 + 14;             // lp1 entries staged (+-7)
+  // shared memory carve-up, in bytes, every section 16-byte aligned
+  static constexpr int O_TAB = 0;
+  static constexpr int O_SIG = O_TAB + NTAB * 4;
+  static constexpr int O_RAW = O_SIG + NS * 2;                                  // stereo only: half2 per sample
+  static constexpr int O_LP1 = O_RAW + (CH == 2 ? NF * 210 * 4 : 0);
+  static constexpr int O_BE0 = O_LP1 + ((N1 * 4 + 15) & ~15);
+  static constexpr int O_LP2 = O_BE0 + NF * 42 * 4;
+  static constexpr int O_BE1 = O_LP2 + NF * 6 * 4;
+  static constexpr int O_BE2 = O_BE1 + NF * 6 * 4;
+  static constexpr int O_EB = O_BE2 + NF * 8;
+  static constexpr int O_ZI = O_EB + 2 * NF * 4;
+  static constexpr int O_P1 = O_ZI + NF * 4;                                    // band-1 phase sums FT*6
+  static constexpr int BYTES = O_P1 + FT * 6 * 4;
+};
+
+__device__ float g_tables[NTAB];   // w630 | w90 | w21 | w15 | w13
 __constant__ double c_logf_invc[16];
 __constant__ double c_logf_logc[16];
 
@@ -76,21 +94,23 @@ __device__ __forceinline__ float glibc_log10f(float x) {
   return z + y * 3.0102920532e-01f;
 }
 
+// one PCM element as float16: int16 -> float16 (RNE) as describealign.py:156, or the half itself
 template <int FMT>
-__device__ __forceinline__ float sample_f32(const void *pcm, int64_t idx) {
-  if (FMT == DAB_PCM_S16) {
-    short s = reinterpret_cast<const short *>(pcm)[idx];
-    return __half2float(__short2half_rn(s));   // int16 -> float16 (RNE) as describealign.py:156
-  } else {
-    return __half2float(reinterpret_cast<const __half *>(pcm)[idx]);
-  }
+__device__ __forceinline__ __half elem_half(const void *pcm, int64_t idx) {
+  if (FMT == DAB_PCM_S16) return __short2half_rn(reinterpret_cast<const short *>(pcm)[idx]);
+  return reinterpret_cast<const __half *>(pcm)[idx];
 }
 
 template <int FMT>
-__device__ __forceinline__ bool sample_neg(const void *pcm, int64_t idx) {
-  // np.signbit on the float16 array (:558); -0.0 cannot come out of an int16 conversion but an
-  // F16 caller may pass it, so test the sign bit, not "< 0".
-  return (reinterpret_cast<const unsigned short *>(pcm)[idx] & 0x8000u) != 0;
+__device__ __forceinline__ __half bits_half(unsigned short b) {
+  if (FMT == DAB_PCM_S16) return __short2half_rn((short)b);
+  return __ushort_as_half(b);
+}
+
+// np.mean over the two float16 channels: float32 accumulate, divide, round to float16 (:576)
+__device__ __forceinline__ __half mid_half(__half l, __half r) {
+  const float s = __half2float(l) + __half2float(r);
+  return __float2half_rn(s / 2.0f);
 }
 
 struct FeatArgs {
@@ -99,22 +119,54 @@ struct FeatArgs {
   int64_t L;      // S / 210
   int64_t nb;     // S / 105
   int64_t Le;     // ceil(nb / 2)
+  int vec_ok;     // pcm is 16-byte aligned
   float *energy, *zc, *b0, *b1;
   double *b2;
 };
 
+// einsum('ijk,ijk->j') lane l of one 105 * CH element block (SURVEY.md B.2 i): elements
+// l, l+4, ... accumulated in steps of 16 elements visiting the four 4-wide chunks in the order
+// 3, 2, 1, 0, then the tail in increasing order.  X(e) returns element e of the block as float.
+template <int CNT, typename FX>
+__device__ __forceinline__ float energy_lane(FX X, int l) {
+  float acc = 0.0f;
+  int q = 0;
+#pragma unroll 2
+  for (; q + 16 <= CNT; q += 16) {
+#pragma unroll
+    for (int c4 = 3; c4 >= 0; --c4) {
+      const float x = X(q + 4 * c4 + l);
+      acc = acc + x * x;
+    }
+  }
+#pragma unroll
+  for (; q < CNT; q += 4) {
+    if (q + l < CNT) {
+      const float x = X(q + l);
+      acc = acc + x * x;
+    }
+  }
+  return acc;
+}
+
 template <int FMT, int CH>
-__global__ void __launch_bounds__(THREADS) features_kernel(FeatArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  __half *sig = reinterpret_cast<__half *>(smem_raw);                 // NS (padded to even)
-  float *lp1 = reinterpret_cast<float *>(sig + ((NS + 7) & ~7));      // N1
-  float *be0 = lp1 + N1;                                               // NF*42
-  float *ph = be0 + NF * 42;                                           // FT*42 phase sums for band 0
-  float *lp2 = ph + FT * 42;                                           // NF*6
-  float *be1 = lp2 + NF * 6;                                           // NF*6
-  float *eb = be1 + NF * 6;                                            // 2*NF block energies
-  float *zf = eb + 2 * NF;                                             // NF zero-crossing counts
-  double *be2 = reinterpret_cast<double *>(zf + NF + (NF & 1));        // NF
+__global__ void __launch_bounds__(THREADS, 2) features_kernel(FeatArgs a) {
+  using T = Tile<CH>;
+  constexpr int FT = T::FT, NF = T::NF, NS = T::NS, N1 = T::N1;
+  extern __shared__ __align__(16) unsigned char smem[];
+  float *tab = reinterpret_cast<float *>(smem + T::O_TAB);
+  const float *w630 = tab, *w90 = tab + 630, *w21 = tab + 720, *w15 = tab + 741, *w13 = tab + 756;
+  __half *sig = reinterpret_cast<__half *>(smem + T::O_SIG);
+  __half2 *raw = reinterpret_cast<__half2 *>(smem + T::O_RAW);   // stereo: (left, right) of frame samples
+  float *lp1 = reinterpret_cast<float *>(smem + T::O_LP1);
+  float *ph = lp1;                                                  // band-0 phase sums reuse lp1's space
+  float *be0 = reinterpret_cast<float *>(smem + T::O_BE0);
+  float *lp2 = reinterpret_cast<float *>(smem + T::O_LP2);
+  float *be1 = reinterpret_cast<float *>(smem + T::O_BE1);
+  double *be2 = reinterpret_cast<double *>(smem + T::O_BE2);
+  float *eb = reinterpret_cast<float *>(smem + T::O_EB);
+  int *zi = reinterpret_cast<int *>(smem + T::O_ZI);
+  float *p1 = reinterpret_cast<float *>(smem + T::O_P1);
 
   const int tid = threadIdx.x;
   const int64_t t0 = (int64_t)blockIdx.x * FT;          // first output frame of this tile
@@ -122,92 +174,132 @@ __global__ void __launch_bounds__(THREADS) features_kernel(FeatArgs a) {
   const int64_t s0 = f0 * 210 - PADS;                   // first staged sample (may be < 0)
   const int64_t Sb = a.L * 210;                         // band signal length (:577)
 
-  // ---- stage the mono / mid signal as float16, zero outside [0, Sb) ----------------------
-  for (int k = tid; k < NS; k += THREADS) {
-    int64_t g = s0 + k;
-    __half h = __float2half_rn(0.0f);
-    if (g >= 0 && g < Sb) {
-      if (CH == 1) {
-        h = __float2half_rn(sample_f32<FMT>(a.pcm, g));  // exact: value is already a float16
-      } else {
-        float l = sample_f32<FMT>(a.pcm, 2 * g), r = sample_f32<FMT>(a.pcm, 2 * g + 1);
-        float s = l + r;                                 // np.mean over 2 float16 channels: f32
-        h = __float2half_rn(s / 2.0f);                   // accumulate, divide, round to float16
-      }
-    }
-    sig[k] = h;
-  }
+  // ---- tables, zero-crossing counters ------------------------------------------------------
+  for (int k = tid; k < NTAB; k += THREADS) tab[k] = g_tables[k];
+  for (int k = tid; k < NF; k += THREADS) zi[k] = 0;
 
-  // ---- block energies (einsum order, SURVEY.md B.2 i) and zero-crossing counts, from global --
-  for (int k = tid; k < 2 * NF; k += THREADS) {
-    int64_t b = 2 * f0 + k;
-    float e = 0.0f;
-    if (b >= 0 && b < a.nb) {
-      const int cnt = 105 * CH;
-      const int64_t base = b * cnt;
-      float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
-      int q = 0;
-      for (; q + 16 <= cnt; q += 16) {
+  // ---- stage the mono / mid signal as float16, zero outside [0, Sb) ------------------------
+  // 8 samples per step; s0 is a multiple of 8 samples, so a 16-byte aligned source stays aligned
+  for (int v = tid; v < NS / 8; v += THREADS) {
+    const int64_t g = s0 + 8 * (int64_t)v;
+    __align__(16) __half h[8];
+    if (a.vec_ok && g >= 0 && g + 8 <= Sb) {
+      if (CH == 1) {
+        const uint4 w = __ldg(reinterpret_cast<const uint4 *>(reinterpret_cast<const unsigned short *>(a.pcm) + g));
+        const unsigned u[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-        for (int c4 = 3; c4 >= 0; --c4) {
-          float x0 = sample_f32<FMT>(a.pcm, base + q + 4 * c4 + 0);
-          float x1 = sample_f32<FMT>(a.pcm, base + q + 4 * c4 + 1);
-          float x2 = sample_f32<FMT>(a.pcm, base + q + 4 * c4 + 2);
-          float x3 = sample_f32<FMT>(a.pcm, base + q + 4 * c4 + 3);
-          l0 = l0 + x0 * x0; l1 = l1 + x1 * x1; l2 = l2 + x2 * x2; l3 = l3 + x3 * x3;
+        for (int e = 0; e < 4; ++e) {
+          h[2 * e] = bits_half<FMT>((unsigned short)(u[e] & 0xffffu));
+          h[2 * e + 1] = bits_half<FMT>((unsigned short)(u[e] >> 16));
+        }
+      } else {
+        const uint4 *src = reinterpret_cast<const uint4 *>(reinterpret_cast<const unsigned short *>(a.pcm) + 2 * g);
+        const uint4 w0 = __ldg(src), w1 = __ldg(src + 1);
+        const unsigned u[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        const int fr = 8 * v - PADS;                      // index into raw (frame samples only)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const __half l = bits_half<FMT>((unsigned short)(u[e] & 0xffffu));
+          const __half r = bits_half<FMT>((unsigned short)(u[e] >> 16));
+          h[e] = mid_half(l, r);
+          if (fr + e >= 0 && fr + e < NF * 210) raw[fr + e] = __halves2half2(l, r);
         }
       }
-      for (; q < cnt; q += 4) {
-        float x0 = (q + 0 < cnt) ? sample_f32<FMT>(a.pcm, base + q + 0) : 0.f;
-        float x1 = (q + 1 < cnt) ? sample_f32<FMT>(a.pcm, base + q + 1) : 0.f;
-        float x2 = (q + 2 < cnt) ? sample_f32<FMT>(a.pcm, base + q + 2) : 0.f;
-        float x3 = (q + 3 < cnt) ? sample_f32<FMT>(a.pcm, base + q + 3) : 0.f;
-        l0 = l0 + x0 * x0; l1 = l1 + x1 * x1; l2 = l2 + x2 * x2; l3 = l3 + x3 * x3;
-      }
-      e = ((l0 + l1) + (l2 + l3)) / (float)cnt;
-    }
-    eb[k] = e;
-  }
-  for (int k = tid; k < NF; k += THREADS) {
-    int64_t f = f0 + k;
-    float z = 0.0f;
-    if (f >= 0 && f < a.L) {
-      int count = 0;
-      for (int c = 0; c < CH; ++c) {
-        int64_t n = f * 210;
-        bool prev = (n == 0) ? false : sample_neg<FMT>(a.pcm, (n - 1) * CH + c);
-        for (int q = 0; q < 210; ++q) {
-          bool cur = sample_neg<FMT>(a.pcm, (n + q) * CH + c);
-          count += (cur != prev);
-          prev = cur;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int64_t ge = g + e;
+        __half x = __float2half_rn(0.0f), l = x, r = x;
+        if (ge >= 0 && ge < Sb) {
+          if (CH == 1) x = elem_half<FMT>(a.pcm, ge);
+          else { l = elem_half<FMT>(a.pcm, 2 * ge); r = elem_half<FMT>(a.pcm, 2 * ge + 1); x = mid_half(l, r); }
+        }
+        h[e] = x;
+        if (CH == 2) {
+          const int fr = 8 * v - PADS + e;
+          if (fr >= 0 && fr < NF * 210) raw[fr] = __halves2half2(l, r);
         }
       }
-      z = (float)count;
-      if (CH == 1) z = z * 2.0f;
     }
-    zf[k] = z;
+    *reinterpret_cast<uint4 *>(sig + 8 * v) = *reinterpret_cast<const uint4 *>(h);
   }
   __syncthreads();
+  const float w15r[15] = {w15[0], w15[1], w15[2], w15[3], w15[4], w15[5], w15[6], w15[7],
+                          w15[8], w15[9], w15[10], w15[11], w15[12], w15[13], w15[14]};
+
+  // ---- block energies (einsum order): 4 lane threads per 105-sample block --------------------
+  for (int k = tid; k < 2 * NF * 4; k += THREADS) {
+    const int kb = k >> 2, l = k & 3;
+    const int64_t b = 2 * f0 + kb;
+    float acc = 0.0f;
+    const bool valid = b >= 0 && b < a.nb;
+    if (valid) {
+      if ((b + 1) * 105 <= Sb) {
+        if (CH == 1) {
+          const __half *src = sig + PADS + kb * 105;
+          acc = energy_lane<105>([&](int e) { return __half2float(src[e]); }, l);
+        } else {
+          const __half *src = reinterpret_cast<const __half *>(raw + kb * 105);
+          acc = energy_lane<210>([&](int e) { return __half2float(src[e]); }, l);
+        }
+      } else {
+        // the one block past the band signal (S mod 210 >= 105) is not staged: read it from HBM
+        const int64_t base = b * 105 * CH;
+        acc = energy_lane<105 * CH>([&](int e) { return __half2float(elem_half<FMT>(a.pcm, base + e)); }, l);
+      }
+    }
+    const float o1 = __shfl_xor_sync(0xffffffffu, acc, 1);
+    const float s01 = (l & 1) ? o1 + acc : acc + o1;        // l0 + l1  /  l2 + l3 (left operand = lower lane)
+    const float o2 = __shfl_xor_sync(0xffffffffu, s01, 2);
+    if (l == 0) eb[kb] = valid ? (s01 + o2) / (float)(105 * CH) : 0.0f;
+  }
+
+  // ---- zero crossings: 14 chunks of 15 samples per frame and channel ----------------------------
+  for (int k = tid; k < NF * 14 * CH; k += THREADS) {
+    const int kf = k / (14 * CH), rem = k - kf * 14 * CH;
+    const int c = CH == 1 ? 0 : rem / 14, ck = CH == 1 ? rem : rem - c * 14;
+    const int64_t f = f0 + kf;
+    if (f >= 0 && f < a.L) {
+      int cnt = 0;
+      if (CH == 1) {
+        const unsigned short *src = reinterpret_cast<const unsigned short *>(sig) + PADS + kf * 210 + ck * 15;
+        unsigned prev = src[-1] >> 15;          // staged zero (+0) in front of sample 0: np.diff prepend=False
+#pragma unroll
+        for (int e = 0; e < 15; ++e) { const unsigned cur = src[e] >> 15; cnt += (int)(cur ^ prev); prev = cur; }
+      } else {
+        const unsigned short *src = reinterpret_cast<const unsigned short *>(raw) + 2 * (kf * 210 + ck * 15) + c;
+        unsigned prev;
+        if (kf == 0 && ck == 0) {
+          const int64_t n = f * 210;
+          prev = n == 0 ? 0u : (unsigned)(__half_as_ushort(elem_half<FMT>(a.pcm, (n - 1) * 2 + c)) >> 15);
+        } else {
+          prev = src[-2] >> 15;
+        }
+#pragma unroll
+        for (int e = 0; e < 15; ++e) { const unsigned cur = src[2 * e] >> 15; cnt += (int)(cur ^ prev); prev = cur; }
+      }
+      atomicAdd(&zi[kf], cnt);
+    }
+  }
 
   // ---- lp1 = downsample_blur(m, 5, 3): 5 phases x 3 taps, f32 accumulators (B.2 ii) ---------
   const int64_t n1_first = f0 * 42 - 7;          // global lp1 index of lp1[0]
   const int64_t len1 = a.L * 42;
   for (int k = tid; k < N1; k += THREADS) {
-    int64_t n = n1_first + k;
+    const int64_t n = n1_first + k;
     float total = 0.0f;
     if (n >= 0 && n < len1) {
-      // sample index of m[(n-1+j)*5 + p] relative to the staged window
-      const int rel = (int)((n - 1) * 5 - s0);
+      // staged index of m[(n-1)*5]; samples outside [0, Sb) are staged as zero, which is exactly
+      // the zero padding of the phase signals
+      const __half *src = sig + (int)((n - 1) * 5 - s0);
+      float x[15];
+#pragma unroll
+      for (int e = 0; e < 15; ++e) x[e] = __half2float(src[e]);
 #pragma unroll
       for (int p = 0; p < 5; ++p) {
         float acc = 0.0f;
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          // taps outside [0, len1) are zero padding of the phase signal
-          int64_t nn = n - 1 + j;
-          float x = (nn >= 0 && nn < len1) ? __half2float(sig[rel + j * 5 + p]) : 0.0f;
-          acc = acc + x * c_w15[p + (2 - j) * 5];
-        }
+        for (int j = 0; j < 3; ++j) acc = acc + x[j * 5 + p] * w15r[p + (2 - j) * 5];
         total = total + acc;
       }
     }
@@ -217,15 +309,15 @@ __global__ void __launch_bounds__(THREADS) features_kernel(FeatArgs a) {
 
   // ---- band-0 residual energy at 8820 Hz and lp2 = downsample_blur(lp1, 7, 3) ----------------
   for (int k = tid; k < NF * 42; k += THREADS) {
-    int64_t n = f0 * 42 + k;
+    const int64_t n = f0 * 42 + k;
     float acc = 0.0f;
     if (n >= 0 && n < len1) {
       const float lo = lp1[k + 7];
-      const int rel = (int)(n * 5 - s0);
+      const __half *src = sig + (int)(n * 5 - s0);
 #pragma unroll
       for (int i = 0; i < 5; ++i) {
-        float d = __half2float(sig[rel + i]) - lo;
-        float sq = d * d;
+        const float d = __half2float(src[i]) - lo;
+        const float sq = d * d;
         acc = (i == 0) ? sq : acc + sq;
       }
     }
@@ -233,19 +325,15 @@ __global__ void __launch_bounds__(THREADS) features_kernel(FeatArgs a) {
   }
   const int64_t len2 = a.L * 6;
   for (int k = tid; k < NF * 6; k += THREADS) {
-    int64_t n2 = f0 * 6 + k;
+    const int64_t n2 = f0 * 6 + k;
     float total = 0.0f;
     if (n2 >= 0 && n2 < len2) {
-      const int rel = (int)((n2 - 1) * 7 - n1_first);
+      const float *src = lp1 + (int)((n2 - 1) * 7 - n1_first);   // lp1 is zero outside [0, len1)
 #pragma unroll
       for (int p = 0; p < 7; ++p) {
         float acc = 0.0f;
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          int64_t nn = n2 - 1 + j;
-          float x = (nn >= 0 && nn < len2) ? lp1[rel + j * 7 + p] : 0.0f;
-          acc = acc + x * c_w21[p + (2 - j) * 7];
-        }
+        for (int j = 0; j < 3; ++j) acc = acc + src[j * 7 + p] * w21[p + (2 - j) * 7];
         total = total + acc;
       }
     }
@@ -255,101 +343,120 @@ __global__ void __launch_bounds__(THREADS) features_kernel(FeatArgs a) {
 
   // ---- band-1 residual energy at 1260 Hz, band-2 energy per frame (f64, :583/:588) ----------
   for (int k = tid; k < NF * 6; k += THREADS) {
-    int64_t n2 = f0 * 6 + k;
+    const int64_t n2 = f0 * 6 + k;
     float acc = 0.0f;
     if (n2 >= 0 && n2 < len2) {
       const float lo = lp2[k];
-      const int rel = (int)(n2 * 7 - n1_first);
+      const float *src = lp1 + (int)(n2 * 7 - n1_first);
 #pragma unroll
       for (int i = 0; i < 7; ++i) {
-        float d = lp1[rel + i] - lo;
-        float sq = d * d;
+        const float d = src[i] - lo;
+        const float sq = d * d;
         acc = (i == 0) ? sq : acc + sq;
       }
     }
     be1[k] = acc;
   }
   for (int k = tid; k < NF; k += THREADS) {
-    int64_t f = f0 + k;
+    const int64_t f = f0 + k;
     double acc = 0.0;
     if (f >= 0 && f < a.L) {
 #pragma unroll
       for (int i = 0; i < 6; ++i) {
-        double x = (double)lp2[k * 6 + i];
-        double sq = x * x;
+        const double x = (double)lp2[k * 6 + i];
+        const double sq = x * x;
         acc = (i == 0) ? sq : acc + sq;
       }
     }
     be2[k] = acc;
   }
-  __syncthreads();
+  __syncthreads();   // lp1 is dead from here on: ph reuses its space
 
-  // ---- band 0: 42 phases x 15 taps; each phase = f32 products accumulated in f64 (B.2 iii) ----
-  for (int k = tid; k < FT * 42; k += THREADS) {
-    const int t = k / 42, p = k - t * 42;
-    // output frame t0 + t uses be0 frames (t0 + t - 7 + j), j = 0..14 -> staged frame index t + j
-    double acc = 0.0;
+  // ---- band 0: 42 phases x 15 taps and band 1: 6 phases x 15 taps; each phase = f32 products
+  //      accumulated in f64 (B.2 iii).  One thread per (phase, run of TC frames), window in registers.
+  {
+    constexpr int TC = 8;
+    constexpr int NCH = (FT + TC - 1) / TC;
+    for (int u = tid; u < 48 * NCH; u += THREADS) {
+      const int ch = u / 48, pp = u - ch * 48;
+      const bool b0 = pp < 42;
+      const int p = b0 ? pp : pp - 42;
+      const int np = b0 ? 42 : 6;
+      const float *src = (b0 ? be0 : be1) + p;
+      const float *w = (b0 ? w630 : w90) + p;
+      float *dst = (b0 ? ph : p1) + p;
+      const int tb = ch * TC;
+      // output frame t0 + t uses staged frames t + 1 .. t + 15 (tap j <-> frame t + 1 + j)
+      float win[14 + TC], wr[15];
 #pragma unroll
-    for (int j = 0; j < 15; ++j) {
-      float prod = be0[(t + j) * 42 + p] * c_w630[p + (14 - j) * 42];
-      acc += (double)prod;
+      for (int e = 0; e < 14 + TC; ++e) win[e] = (tb + 1 + e < NF) ? src[(tb + 1 + e) * np] : 0.0f;
+#pragma unroll
+      for (int j = 0; j < 15; ++j) wr[j] = w[(14 - j) * np];
+#pragma unroll
+      for (int t = 0; t < TC; ++t) {
+        if (tb + t < FT) {
+          double acc = 0.0;
+#pragma unroll
+          for (int j = 0; j < 15; ++j) {
+            const float prod = win[t + j] * wr[j];
+            acc += (double)prod;
+          }
+          dst[(tb + t) * np] = (float)acc;
+        }
+      }
     }
-    ph[k] = (float)acc;
   }
   __syncthreads();
 
-  // ---- outputs --------------------------------------------------------------------------------
-  for (int t = tid; t < FT; t += THREADS) {
+  // ---- outputs: three thread roles per frame -----------------------------------------------------
+  for (int u = tid; u < 3 * FT; u += THREADS) {
+    const int role = u / FT, t = u - role * FT;
     const int64_t f = t0 + t;
-    if (f < a.L) {
-      // band 0: phases added sequentially in f32 (B.2 v), /210, log10(1+x)/2
-      float tot = 0.0f;
-      for (int p = 0; p < 42; ++p) tot = tot + ph[t * 42 + p];
-      a.b0[f] = glibc_log10f(1.0f + tot / 210.0f) / 2.0f;
-      // band 1: 6 phases x 15 taps
-      tot = 0.0f;
-      for (int p = 0; p < 6; ++p) {
+    if (role == 0) {
+      if (f < a.L) {
+        // band 0: phases added sequentially in f32 (B.2 v), /210, log10(1+x)/2
+        float tot = 0.0f;
+#pragma unroll 6
+        for (int p = 0; p < 42; ++p) tot = tot + ph[t * 42 + p];
+        a.b0[f] = glibc_log10f(1.0f + tot / 210.0f) / 2.0f;
+      }
+    } else if (role == 1) {
+      if (f < a.L) {
+        float tot = 0.0f;
+#pragma unroll
+        for (int p = 0; p < 6; ++p) tot = tot + p1[t * 6 + p];
+        a.b1[f] = glibc_log10f(1.0f + tot / 210.0f) / 2.0f;
+        // zero crossings: 13-tap Hann over frames f-6 .. f+6
         double acc = 0.0;
 #pragma unroll
-        for (int j = 0; j < 15; ++j) {
-          float prod = be1[(t + j) * 6 + p] * c_w90[p + (14 - j) * 6];
+        for (int j = 0; j < 13; ++j) {
+          float z = (float)zi[t + FH - 6 + j];
+          if (CH == 1) z = z * 2.0f;
+          const float prod = z * w13[12 - j];
           acc += (double)prod;
         }
-        tot = tot + (float)acc;
+        a.zc[f] = (float)acc;
       }
-      a.b1[f] = glibc_log10f(1.0f + tot / 210.0f) / 2.0f;
-      // band 2: one 15-tap f64 filter = OpenBLAS ddot tail, a sequential FMA chain (B.2 iv)
-      double acc = 0.0;
+    } else {
+      if (f < a.L) {
+        // band 2: one 15-tap f64 filter = OpenBLAS ddot tail, a sequential FMA chain (B.2 iv)
+        double acc = 0.0;
 #pragma unroll
-      for (int j = 0; j < 15; ++j) acc = fma((double)c_w15[14 - j], be2[t + j], acc);
-      a.b2[f] = log10(1.0 + acc / 210.0) / 2.0;
-      // zero crossings: 13-tap Hann over frames f-6 .. f+6
-      acc = 0.0;
-#pragma unroll
-      for (int j = 0; j < 13; ++j) {
-        float prod = zf[t + FH - 6 + j] * c_w13[12 - j];
-        acc += (double)prod;
+        for (int j = 0; j < 15; ++j) acc = fma((double)w15r[14 - j], be2[t + 1 + j], acc);
+        a.b2[f] = log10(1.0 + acc / 210.0) / 2.0;
       }
-      a.zc[f] = (float)acc;
-    }
-    if (f < a.Le) {
-      // energy: 13-tap Hann over blocks 2f-6 .. 2f+6, log10(1+x)/2, every second block (:553-555)
-      double acc = 0.0;
+      if (f < a.Le) {
+        // energy: 13-tap Hann over blocks 2f-6 .. 2f+6, log10(1+x)/2, every second block (:553-555)
+        double acc = 0.0;
 #pragma unroll
-      for (int j = 0; j < 13; ++j) {
-        float prod = eb[2 * (t + FH) - 6 + j] * c_w13[12 - j];
-        acc += (double)prod;
+        for (int j = 0; j < 13; ++j) {
+          const float prod = eb[2 * (t + FH) - 6 + j] * w13[12 - j];
+          acc += (double)prod;
+        }
+        a.energy[f] = glibc_log10f(1.0f + (float)acc) / 2.0f;
       }
-      a.energy[f] = glibc_log10f(1.0f + (float)acc) / 2.0f;
     }
   }
-}
-
-size_t feat_smem_bytes() {
-  size_t b = (size_t)((NS + 7) & ~7) * 2;
-  b += sizeof(float) * (size_t)(N1 + NF * 42 + FT * 42 + NF * 6 + NF * 6 + 2 * NF + NF + (NF & 1));
-  b += sizeof(double) * NF;
-  return b;
 }
 
 bool g_const_ready[64] = {};
@@ -358,11 +465,13 @@ int upload_constants(dab_ctx *ctx) {
   int dev = 0;
   DAB_CUDA(cudaGetDevice(&dev));
   if (dev < 64 && g_const_ready[dev]) return DAB_OK;
-  DAB_CUDA(cudaMemcpyToSymbol(c_w13, DAB_HANN13_F32, sizeof(DAB_HANN13_F32)));
-  DAB_CUDA(cudaMemcpyToSymbol(c_w15, DAB_HANN15_F32, sizeof(DAB_HANN15_F32)));
-  DAB_CUDA(cudaMemcpyToSymbol(c_w21, DAB_HANN21_F32, sizeof(DAB_HANN21_F32)));
-  DAB_CUDA(cudaMemcpyToSymbol(c_w90, DAB_HANN90_F32, sizeof(DAB_HANN90_F32)));
-  DAB_CUDA(cudaMemcpyToSymbol(c_w630, DAB_HANN630_F32, sizeof(DAB_HANN630_F32)));
+  float tab[NTAB] = {};
+  memcpy(tab, DAB_HANN630_F32, sizeof(DAB_HANN630_F32));
+  memcpy(tab + 630, DAB_HANN90_F32, sizeof(DAB_HANN90_F32));
+  memcpy(tab + 720, DAB_HANN21_F32, sizeof(DAB_HANN21_F32));
+  memcpy(tab + 741, DAB_HANN15_F32, sizeof(DAB_HANN15_F32));
+  memcpy(tab + 756, DAB_HANN13_F32, sizeof(DAB_HANN13_F32));
+  DAB_CUDA(cudaMemcpyToSymbol(g_tables, tab, sizeof(tab)));
   DAB_CUDA(cudaMemcpyToSymbol(c_logf_invc, h_logf_invc, sizeof(h_logf_invc)));
   DAB_CUDA(cudaMemcpyToSymbol(c_logf_logc, h_logf_logc, sizeof(h_logf_logc)));
   if (dev < 64) g_const_ready[dev] = true;
@@ -370,9 +479,11 @@ int upload_constants(dab_ctx *ctx) {
 }
 
 template <int FMT, int CH>
-int launch(dab_pair *pr, const FeatArgs &fa, int64_t tiles) {
+int launch(dab_pair *pr, const FeatArgs &fa, int64_t frames) {
   dab_ctx *ctx = pr->ctx;
-  size_t smem = feat_smem_bytes();
+  const int64_t tiles = cdiv(frames, Tile<CH>::FT);
+  if (tiles <= 0) return DAB_OK;
+  const size_t smem = Tile<CH>::BYTES;
   DAB_CUDA(cudaFuncSetAttribute(features_kernel<FMT, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   features_kernel<FMT, CH><<<(unsigned)tiles, THREADS, smem, pr->stream>>>(fa);
   DAB_LAUNCHED(pr);
@@ -396,16 +507,15 @@ int dab_run_features(dab_pair *pr, int track, const void *d_pcm, int format) {
   DAB_TRY(dab_ensure(ctx, tk.b2, sizeof(double) * (size_t)(L + 1)));
   FeatArgs fa;
   fa.pcm = d_pcm; fa.S = tk.S; fa.L = L; fa.nb = nb; fa.Le = Le;
+  fa.vec_ok = (reinterpret_cast<uintptr_t>(d_pcm) & 15u) == 0;
   fa.energy = tk.energy.as<float>(); fa.zc = tk.zc.as<float>();
   fa.b0 = tk.b0.as<float>(); fa.b1 = tk.b1.as<float>(); fa.b2 = tk.b2.as<double>();
-  const int64_t tiles = cdiv(Le > L ? Le : L, FT);
-  if (tiles > 0) {
-    if (format == DAB_PCM_S16 && tk.ch == 1) DAB_TRY((launch<DAB_PCM_S16, 1>(pr, fa, tiles)));
-    else if (format == DAB_PCM_S16 && tk.ch == 2) DAB_TRY((launch<DAB_PCM_S16, 2>(pr, fa, tiles)));
-    else if (format == DAB_PCM_F16 && tk.ch == 1) DAB_TRY((launch<DAB_PCM_F16, 1>(pr, fa, tiles)));
-    else if (format == DAB_PCM_F16 && tk.ch == 2) DAB_TRY((launch<DAB_PCM_F16, 2>(pr, fa, tiles)));
-    else { ctx->err = "unsupported PCM format / channel count"; return DAB_E_ARG; }
-  }
+  const int64_t frames = Le > L ? Le : L;
+  if (format == DAB_PCM_S16 && tk.ch == 1) DAB_TRY((launch<DAB_PCM_S16, 1>(pr, fa, frames)));
+  else if (format == DAB_PCM_S16 && tk.ch == 2) DAB_TRY((launch<DAB_PCM_S16, 2>(pr, fa, frames)));
+  else if (format == DAB_PCM_F16 && tk.ch == 1) DAB_TRY((launch<DAB_PCM_F16, 1>(pr, fa, frames)));
+  else if (format == DAB_PCM_F16 && tk.ch == 2) DAB_TRY((launch<DAB_PCM_F16, 2>(pr, fa, frames)));
+  else { ctx->err = "unsupported PCM format / channel count"; return DAB_E_ARG; }
   tk.have_features = true;
   return DAB_OK;
 }
