@@ -22,6 +22,7 @@ EXPORTS = [
     "dab_pair_set_features", "dab_pair_feature_lens", "dab_pair_get_features", "dab_pair_stage_a",
     "dab_pair_get_path1", "dab_pair_get_points1", "dab_pair_stage_b", "dab_pair_get_path2",
     "dab_pair_get_points2", "dab_pair_get_stats", "dab_pair_get_timings", "dab_launch_count",
+    "dab_pair_stage_a_match", "dab_pair_export_points1", "dab_pair_import_points1", "dab_pair_dp1",
 ]
 
 
@@ -82,6 +83,10 @@ def load() -> ctypes.CDLL:
     lib.dab_pair_stage_a.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(i64)]
     lib.dab_pair_get_path1.argtypes = [vp, vp, vp]
     lib.dab_pair_get_points1.argtypes = [vp, vp, vp, vp]
+    lib.dab_pair_stage_a_match.argtypes = [vp, i64, i64, ctypes.POINTER(i64)]
+    lib.dab_pair_export_points1.argtypes = [vp, vp, vp, vp, i32]
+    lib.dab_pair_import_points1.argtypes = [vp, vp, vp, vp, i64, i32]
+    lib.dab_pair_dp1.argtypes = [vp, ctypes.POINTER(i64)]
     lib.dab_pair_stage_b.argtypes = [vp, vp, i64, vp, i64, vp, ctypes.c_int32, ctypes.c_int32,
                                      ctypes.POINTER(i64), ctypes.POINTER(i64)]
     lib.dab_pair_get_path2.argtypes = [vp, vp]
@@ -173,6 +178,11 @@ class Pair:
         self.ctx.check(self.lib.dab_pair_set_features(self.handle, track, _ptr(e), len(e), _ptr(z), _ptr(b0),
                                                       _ptr(b1), _ptr(b2), n))
 
+    def feature_lens(self, track: int):
+        lens = (ctypes.c_int64 * 5)()
+        self.ctx.check(self.lib.dab_pair_feature_lens(self.handle, track, ctypes.byref(lens)))
+        return [int(x) for x in lens]
+
     def get_features(self, track: int):
         lens = (ctypes.c_int64 * 5)()
         self.ctx.check(self.lib.dab_pair_feature_lens(self.handle, track, ctypes.byref(lens)))
@@ -200,6 +210,39 @@ class Pair:
         i = np.empty(n, np.int32); v = np.empty(n, np.int32); q = np.empty(n, np.float64)
         self.ctx.check(self.lib.dab_pair_get_points1(self.handle, _ptr(i), _ptr(v), _ptr(q)))
         return i, v, q
+
+    # ---- stage A in two steps (row-sharded match stage of one long pair) ------------------------
+    def stage_a_match(self, row_lo: int = 0, row_hi: int = 2 ** 62):
+        """prep + tables for the whole pair; gate + scoring for audio frames row_lo <= i < row_hi."""
+        npts = ctypes.c_int64()
+        self.ctx.check(self.lib.dab_pair_stage_a_match(self.handle, int(row_lo), int(row_hi), ctypes.byref(npts)))
+        self._keep.clear()
+        self.n_points1, self.n_path1 = npts.value, 0
+        return npts.value
+
+    def export_points1_device(self, i_ptr: int, v_ptr: int, q_ptr: int):
+        """Copy this pair's match points into device buffers (e.g. torch tensors used for NCCL)."""
+        self.ctx.check(self.lib.dab_pair_export_points1(self.handle, ctypes.c_void_p(i_ptr), ctypes.c_void_p(v_ptr),
+                                                        ctypes.c_void_p(q_ptr), 1))
+
+    def import_points1(self, i, v, q):
+        """Replace the pair's match points by host arrays sorted by (audio frame, video frame)."""
+        i = np.ascontiguousarray(i, np.int32); v = np.ascontiguousarray(v, np.int32); q = np.ascontiguousarray(q, np.float64)
+        if not (len(i) == len(v) == len(q)):
+            raise ValueError("point arrays must have equal lengths")
+        self.ctx.check(self.lib.dab_pair_import_points1(self.handle, _ptr(i), _ptr(v), _ptr(q), len(i), 0))
+        self.n_points1 = len(i)
+
+    def import_points1_device(self, i_ptr: int, v_ptr: int, q_ptr: int, n: int):
+        self.ctx.check(self.lib.dab_pair_import_points1(self.handle, ctypes.c_void_p(i_ptr), ctypes.c_void_p(v_ptr),
+                                                        ctypes.c_void_p(q_ptr), int(n), 1))
+        self.n_points1 = int(n)
+
+    def dp1(self):
+        npath = ctypes.c_int64()
+        self.ctx.check(self.lib.dab_pair_dp1(self.handle, ctypes.byref(npath)))
+        self.n_path1 = npath.value
+        return npath.value
 
     # ---- stage B ----------------------------------------------------------------------------
     def stage_b(self, audio_scaled: np.ndarray, video_scaled: np.ndarray, plans, n_clusters: int):

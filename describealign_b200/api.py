@@ -149,7 +149,12 @@ class AlignJob:
     def device_stage_a(self):
         """Features (if PCM was given) + stage A on the device; brings back what the host fit
         needs: the integer pass-1 path and the feature vectors."""
-        _, n_path = self.pair.stage_a()
+        self.pair.stage_a()
+        return self.after_stage_a()
+
+    def after_stage_a(self):
+        """Length rule of describealign.py:698-699 and the copies the host fit needs."""
+        n_path = self.pair.n_path1
         if self.video_features is None:
             self.video_features = self.pair.get_features(VIDEO)
             self.audio_features = self.pair.get_features(AUDIO)

@@ -136,6 +136,7 @@ int dab_pair_set_pcm(dab_pair *pr, int track, const void *pcm, int64_t samples, 
   tk.S = samples;
   tk.ch = channels;
   tk.have_features = false;
+  pr->matched = false;
   const void *d_pcm = pcm;
   cudaEvent_t e0 = pr->ev[2 * track], e1 = pr->ev[2 * track + 1];
   if (!on_device) {
@@ -165,6 +166,7 @@ int dab_pair_set_features(dab_pair *pr, int track, const float *energy, int64_t 
   tk.L = n;
   tk.Le = n_energy;
   tk.S = n * 210;
+  pr->matched = false;
   DAB_TRY(dab_ensure(ctx, tk.energy, sizeof(float) * (size_t)(n_energy + 1)));
   DAB_TRY(dab_ensure(ctx, tk.zc, sizeof(float) * (size_t)(n + 1)));
   DAB_TRY(dab_ensure(ctx, tk.b0, sizeof(float) * (size_t)(n + 1)));
@@ -219,6 +221,7 @@ int dab_pair_stage_a(dab_pair *pr, int64_t *n_points, int64_t *n_path) {
   }
   DAB_CUDA(cudaSetDevice(ctx->device));
   DAB_TRY(dab_run_stage_a(pr));
+  pr->matched = true;
   if (n_points) *n_points = pr->n_points1;
   if (n_path) *n_path = pr->n_path1;
   return DAB_OK;
@@ -248,25 +251,77 @@ __global__ void ranks_to_frames_kernel(const int32_t *pt_s, const int32_t *v_sel
 
 extern "C" {
 
-int dab_pair_get_points1(dab_pair *pr, int32_t *i_audio, int32_t *v_video, double *qual) {
-  if (!pr) return DAB_E_ARG;
+static int export_points1(dab_pair *pr, int32_t *i_audio, int32_t *v_video, double *qual, int dst_on_device) {
   dab_ctx *ctx = pr->ctx;
   DAB_CUDA(cudaSetDevice(ctx->device));
+  const cudaMemcpyKind kind = dst_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
   const int64_t n = pr->n_points1;
   if (n > 0) {
     cudaStream_t st = pr->stream;
-    if (i_audio) DAB_CUDA(cudaMemcpyAsync(i_audio, pr->pt_i.p, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
-    if (qual) DAB_CUDA(cudaMemcpyAsync(qual, pr->pt_q.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    if (i_audio) DAB_CUDA(cudaMemcpyAsync(i_audio, pr->pt_i.p, sizeof(int32_t) * (size_t)n, kind, st));
+    if (qual) DAB_CUDA(cudaMemcpyAsync(qual, pr->pt_q.p, sizeof(double) * (size_t)n, kind, st));
     if (v_video) {
       DAB_TRY(dab_ensure(ctx, pr->cand_tmp, sizeof(int32_t) * (size_t)(n + 1)));
       ranks_to_frames_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(pr->pt_s.as<int32_t>(),
                                                                       pr->trk[DAB_TRACK_VIDEO].nq_list.as<int32_t>(), n,
                                                                       pr->cand_tmp.as<int32_t>());
       ctx->launches += 1;
-      DAB_CUDA(cudaMemcpyAsync(v_video, pr->cand_tmp.p, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
+      DAB_CUDA(cudaMemcpyAsync(v_video, pr->cand_tmp.p, sizeof(int32_t) * (size_t)n, kind, st));
     }
   }
   DAB_CUDA(cudaStreamSynchronize(pr->stream));
+  return DAB_OK;
+}
+
+int dab_pair_get_points1(dab_pair *pr, int32_t *i_audio, int32_t *v_video, double *qual) {
+  if (!pr) return DAB_E_ARG;
+  return export_points1(pr, i_audio, v_video, qual, 0);
+}
+
+int dab_pair_export_points1(dab_pair *pr, int32_t *i_audio, int32_t *v_video, double *qual, int dst_on_device) {
+  if (!pr) return DAB_E_ARG;
+  return export_points1(pr, i_audio, v_video, qual, dst_on_device);
+}
+
+static int check_stage_a_inputs(dab_pair *pr, const char *who) {
+  dab_ctx *ctx = pr->ctx;
+  for (int t = 0; t < 2; ++t) {
+    if (!pr->trk[t].have_features) { ctx->err = std::string(who) + ": features of both tracks are required first"; return DAB_E_STATE; }
+    const int64_t lmin = pr->trk[t].Le < pr->trk[t].L ? pr->trk[t].Le : pr->trk[t].L;
+    if (lmin < 2 * DAB_WIN) { ctx->err = std::string(who) + ": track shorter than 82 frames"; return DAB_E_TOO_SHORT; }
+  }
+  return DAB_OK;
+}
+
+int dab_pair_stage_a_match(dab_pair *pr, int64_t row_lo, int64_t row_hi, int64_t *n_points) {
+  if (!pr) return DAB_E_ARG;
+  dab_ctx *ctx = pr->ctx;
+  if (row_lo < 0 || row_hi < row_lo) { ctx->err = "dab_pair_stage_a_match: invalid row range"; return DAB_E_ARG; }
+  DAB_TRY(check_stage_a_inputs(pr, "stage_a_match"));
+  DAB_CUDA(cudaSetDevice(ctx->device));
+  DAB_TRY(dab_run_stage_a_match(pr, row_lo, row_hi));
+  pr->matched = true;
+  if (n_points) *n_points = pr->n_points1;
+  return DAB_OK;
+}
+
+int dab_pair_import_points1(dab_pair *pr, const int32_t *i_audio, const int32_t *v_video, const double *qual,
+                            int64_t n, int src_on_device) {
+  if (!pr) return DAB_E_ARG;
+  dab_ctx *ctx = pr->ctx;
+  if (n < 0 || (n > 0 && (!i_audio || !v_video || !qual))) { ctx->err = "dab_pair_import_points1: invalid argument"; return DAB_E_ARG; }
+  if (!pr->matched) { ctx->err = "import_points1: run stage_a_match on this pair first (it builds the hashed-frame list)"; return DAB_E_STATE; }
+  DAB_CUDA(cudaSetDevice(ctx->device));
+  return dab_run_import_points1(pr, i_audio, v_video, qual, n, src_on_device);
+}
+
+int dab_pair_dp1(dab_pair *pr, int64_t *n_path) {
+  if (!pr) return DAB_E_ARG;
+  dab_ctx *ctx = pr->ctx;
+  if (!pr->matched) { ctx->err = "dp1: no match points (run stage_a_match / import_points1 first)"; return DAB_E_STATE; }
+  DAB_CUDA(cudaSetDevice(ctx->device));
+  DAB_TRY(dab_run_stage_a_dp(pr));
+  if (n_path) *n_path = pr->n_path1;
   return DAB_OK;
 }
 

@@ -72,6 +72,7 @@ struct dab_pair {
   DevBuf seglist;              // i32 checkpoints
   DevBuf path1_x, path1_y;     // i32
   int64_t n_points1 = 0, n_path1 = 0;
+  bool matched = false;        // tables / hashed-frame list of the current features are built
   // stage B
   DevBuf a_scaled, v_scaled;   // f32 (n,3)
   DevBuf corridors;            // dab_corridor[]
@@ -121,6 +122,10 @@ int dab_exclusive_scan(dab_pair *pr, const int32_t *in, int32_t *out, int64_t n)
 // stage entry points implemented in the .cu files
 int dab_run_features(dab_pair *pr, int track, const void *d_pcm, int format);
 int dab_run_stage_a(dab_pair *pr);
+int dab_run_stage_a_match(dab_pair *pr, int64_t row_lo, int64_t row_hi);   // prep .. match points of audio rows [lo, hi)
+int dab_run_stage_a_dp(dab_pair *pr);                                       // DP #1 + traceback over the pair's points
+int dab_run_import_points1(dab_pair *pr, const int32_t *i_audio, const int32_t *v_video, const double *qual,
+                           int64_t n, int src_on_device);
 int dab_run_stage_b(dab_pair *pr, int32_t n_corridors, int32_t n_clusters);
 
 #define DAB_LAUNCHED(pr) ((pr)->ctx->launches++)

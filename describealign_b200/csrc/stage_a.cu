@@ -416,7 +416,7 @@ constexpr int DP_CHECK = 256;   // checkpoint spacing for the parallel traceback
 struct Dp1Args {
   const int32_t *pt_s;
   const double *pt_q;
-  const int32_t *n_points_dev;   // device-resident count
+  int32_t n_points;
   Node1 *level[DP_LEVELS];
   int4 *meta;                    // per point (back pointer, chain length, checkpoint id, -)
   int32_t *result;               // [0] end id, [1] path length
@@ -449,7 +449,7 @@ __global__ void __launch_bounds__(32, 1) dp1_kernel(Dp1Args a) {
   __shared__ int s_r[2][32];
   __shared__ double s_q[2][32];
   const int lane = threadIdx.x;
-  const int n = *a.n_points_dev;
+  const int n = a.n_points;
   double top_cum = 0.0;
   int top_id = -1, top_rank = -1, top_len = 0, top_cp = -1;
   const int role = lane < DP_LEVELS ? lane : 0;
@@ -629,7 +629,7 @@ int dab_exclusive_scan(dab_pair *pr, const int32_t *in, int32_t *out, int64_t n)
   return DAB_OK;
 }
 
-static int prep_track(dab_pair *pr, int track) {
+static int prep_track(dab_pair *pr, int track, int64_t row_lo = 0, int64_t row_hi = 0) {
   dab_ctx *ctx = pr->ctx;
   Track &tk = pr->trk[track];
   const int64_t Lmax = tk.Le > tk.L ? tk.Le : tk.L;
@@ -670,11 +670,17 @@ static int prep_track(dab_pair *pr, int track) {
                                                                   tk.nq_list.as<int32_t>());
   ctx->launches += 1;
   DAB_CUDA(cudaMemcpyAsync(&pr->h_counters[track], off + nqn, sizeof(int32_t), cudaMemcpyDeviceToHost, pr->stream));
+  if (track == DAB_TRACK_AUDIO) {
+    // list positions of the first not-quiet frame >= row_lo / >= row_hi (row-sharded match stage)
+    const int64_t lo = row_lo < 0 ? 0 : (row_lo > nqn ? nqn : row_lo), hi = row_hi < lo ? lo : (row_hi > nqn ? nqn : row_hi);
+    DAB_CUDA(cudaMemcpyAsync(&pr->h_counters[20], off + lo, sizeof(int32_t), cudaMemcpyDeviceToHost, pr->stream));
+    DAB_CUDA(cudaMemcpyAsync(&pr->h_counters[21], off + hi, sizeof(int32_t), cudaMemcpyDeviceToHost, pr->stream));
+  }
   DAB_CUDA(cudaGetLastError());
   return DAB_OK;
 }
 
-int dab_run_stage_a(dab_pair *pr) {
+int dab_run_stage_a_match(dab_pair *pr, int64_t row_lo, int64_t row_hi) {
   dab_ctx *ctx = pr->ctx;
   int dev = 0;
   DAB_CUDA(cudaGetDevice(&dev));
@@ -691,14 +697,16 @@ int dab_run_stage_a(dab_pair *pr) {
   DAB_CUDA(cudaEventRecord(pr->ev[4], st));
   pr->h_counters[0] = pr->h_counters[1] = 0;
   DAB_TRY(prep_track(pr, DAB_TRACK_VIDEO));
-  DAB_TRY(prep_track(pr, DAB_TRACK_AUDIO));
+  DAB_TRY(prep_track(pr, DAB_TRACK_AUDIO, row_lo, row_hi));
   DAB_CUDA(cudaEventRecord(pr->ev[5], st));
   DAB_CUDA(cudaStreamSynchronize(st));
   const int64_t n_vnq = (int32_t)pr->h_counters[0];
   const int64_t n_vsel = (n_vnq + 3) / 4;
-  const int64_t n_q = (int32_t)pr->h_counters[1];
+  const int64_t n_q_all = (int32_t)pr->h_counters[1];
+  const int64_t q_lo = (int32_t)pr->h_counters[20], q_hi = (int32_t)pr->h_counters[21];
+  const int64_t n_q = q_hi - q_lo;          // queries of this shard (all of them unless row-sharded)
   V.n_list = n_vsel;
-  A.n_list = n_q;
+  A.n_list = n_q_all;
   pr->stats.n_video_frames = V.L; pr->stats.n_audio_frames = A.L;
   pr->stats.n_video_selected = n_vsel; pr->stats.n_audio_queries = n_q;
 
@@ -739,7 +747,7 @@ int dab_run_stage_a(dab_pair *pr) {
   DAB_TRY(dab_ensure(ctx, pr->row_off, sizeof(int32_t) * (size_t)(n_q + 2)));
   GateArgs ga;
   ga.a_code = A.code.as<int32_t>(); ga.a_pack = A.pack.as<uint32_t>(); ga.a_nstride = a_nstride;
-  ga.a_list = A.nq_list.as<int32_t>(); ga.n_queries = n_q;
+  ga.a_list = A.nq_list.as<int32_t>() + q_lo; ga.n_queries = n_q;
   ga.v_pack = V.pack.as<uint32_t>(); ga.v_nstride = v_nstride; ga.v_sel = V.nq_list.as<int32_t>();
   ga.start = pr->tbl_start.as<int32_t>(); ga.items = pr->tbl_items.as<int32_t>();
   ga.row_count = pr->row_count.as<int32_t>(); ga.row_off = pr->row_off.as<int32_t>();
@@ -808,8 +816,17 @@ int dab_run_stage_a(dab_pair *pr) {
   pr->n_points1 = n_pts;
   pr->stats.n_points1 = n_pts;
   DAB_CUDA(cudaEventRecord(pr->ev[11], st));
+  for (int s = 2; s <= 5; ++s) pr->ev_used[s] = true;
+  DAB_CUDA(cudaGetLastError());
+  return DAB_OK;
+}
 
-  // ---- DP #1 + traceback ----
+// ---- DP #1 + traceback over pr->pt_* (n_points1 points sorted by (audio frame, video rank)) ----
+int dab_run_stage_a_dp(dab_pair *pr) {
+  dab_ctx *ctx = pr->ctx;
+  Track &V = pr->trk[DAB_TRACK_VIDEO];
+  cudaStream_t st = pr->stream;
+  const int64_t n_pts = pr->n_points1, n_vsel = V.n_list;
   DAB_CUDA(cudaEventRecord(pr->ev[12], st));
   int64_t n_path = 0;
   if (n_pts > 0) {
@@ -826,7 +843,7 @@ int dab_run_stage_a(dab_pair *pr) {
     DAB_TRY(dab_ensure(ctx, pr->path1_y, sizeof(int32_t) * (size_t)(n_pts + 1)));
     Dp1Args da;
     da.pt_s = pr->pt_s.as<int32_t>(); da.pt_q = pr->pt_q.as<double>();
-    da.n_points_dev = pr->keep_off.as<int32_t>() + n_cand;
+    da.n_points = (int32_t)n_pts;
     Node1 *base = pr->tree1.as<Node1>();
     for (int k = 0; k < DP_LEVELS; ++k) { da.level[k] = base; base += lv[k]; }
     da.meta = pr->back1.as<int4>();
@@ -847,7 +864,63 @@ int dab_run_stage_a(dab_pair *pr) {
   }
   pr->n_path1 = n_path;
   pr->stats.n_path1 = n_path;
-  for (int s = 2; s <= 6; ++s) pr->ev_used[s] = true;
+  pr->ev_used[6] = true;
   DAB_CUDA(cudaGetLastError());
+  return DAB_OK;
+}
+
+int dab_run_stage_a(dab_pair *pr) {
+  DAB_TRY(dab_run_stage_a_match(pr, 0, INT64_MAX));
+  return dab_run_stage_a_dp(pr);
+}
+
+// ---- row-sharded match stage: exchange of match points -----------------------------------
+namespace {
+// video frame -> rank in the selected-frame list (binary search; every frame of a point is in the list)
+__global__ void frames_to_ranks_kernel(const int32_t *v_frame, int64_t n, const int32_t *v_sel, int32_t n_sel,
+                                       int32_t *rank, int32_t *bad) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int32_t v = v_frame[k];
+  int lo = 0, hi = n_sel;
+  while (lo < hi) {
+    const int mid = lo + ((hi - lo) >> 1);
+    if (v_sel[mid] < v) lo = mid + 1; else hi = mid;
+  }
+  if (lo >= n_sel || v_sel[lo] != v) { atomicExch(bad, 1); lo = 0; }
+  rank[k] = lo;
+}
+}  // namespace
+
+int dab_run_import_points1(dab_pair *pr, const int32_t *i_audio, const int32_t *v_video, const double *qual,
+                           int64_t n, int src_on_device) {
+  dab_ctx *ctx = pr->ctx;
+  Track &V = pr->trk[DAB_TRACK_VIDEO];
+  cudaStream_t st = pr->stream;
+  const cudaMemcpyKind kind = src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  DAB_TRY(dab_ensure(ctx, pr->pt_i, sizeof(int32_t) * (size_t)(n + 1)));
+  DAB_TRY(dab_ensure(ctx, pr->pt_s, sizeof(int32_t) * (size_t)(n + 1)));
+  DAB_TRY(dab_ensure(ctx, pr->pt_q, sizeof(double) * (size_t)(n + 1)));
+  DAB_TRY(dab_ensure(ctx, pr->cand_tmp, sizeof(int32_t) * (size_t)(n + 1)));
+  DAB_TRY(dab_ensure(ctx, pr->dpres, sizeof(int32_t) * 16));
+  if (n > 0) {
+    DAB_CUDA(cudaMemcpyAsync(pr->pt_i.p, i_audio, sizeof(int32_t) * (size_t)n, kind, st));
+    DAB_CUDA(cudaMemcpyAsync(pr->cand_tmp.p, v_video, sizeof(int32_t) * (size_t)n, kind, st));
+    DAB_CUDA(cudaMemcpyAsync(pr->pt_q.p, qual, sizeof(double) * (size_t)n, kind, st));
+    DAB_CUDA(cudaMemsetAsync(pr->dpres.as<int32_t>() + 8, 0, sizeof(int32_t), st));
+    frames_to_ranks_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(pr->cand_tmp.as<int32_t>(), n, V.nq_list.as<int32_t>(),
+                                                                    (int32_t)V.n_list, pr->pt_s.as<int32_t>(),
+                                                                    pr->dpres.as<int32_t>() + 8);
+    ctx->launches += 1;
+    DAB_CUDA(cudaMemcpyAsync(&pr->h_counters[22], pr->dpres.as<int32_t>() + 8, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    DAB_CUDA(cudaStreamSynchronize(st));
+    if ((int32_t)pr->h_counters[22] != 0) {
+      ctx->err = "import_points1: a point's video frame is not one of this pair's hashed video frames";
+      return DAB_E_ARG;
+    }
+  }
+  pr->n_points1 = n;
+  pr->stats.n_points1 = n;
+  pr->n_path1 = 0;
   return DAB_OK;
 }

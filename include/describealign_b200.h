@@ -130,6 +130,19 @@ int dab_pair_get_path1(dab_pair *pair, int32_t *x_audio, int32_t *y_video);
 /* pass-1 match points sorted by (audio frame, video frame); any pointer may be NULL. */
 int dab_pair_get_points1(dab_pair *pair, int32_t *i_audio, int32_t *v_video, double *qual);
 
+/* ---- stage A in two steps, for one very long pair split over several GPUs ----
+ * dab_pair_stage_a_match: prep + codes + tables for the whole pair, then gate + scoring only for the
+ * audio frames row_lo <= i < row_hi (pass 0, INT64_MAX for all rows); the match points stay on the
+ * device.  Ranks exchange them with dab_pair_export_points1 / dab_pair_import_points1 (pointers may be
+ * device pointers, e.g. NCCL buffers, when *_on_device != 0); imported points must be sorted by
+ * (audio frame, video frame) - concatenating the shards in row order gives exactly that.
+ * dab_pair_dp1 then runs frontier DP #1 + traceback (reference :674-700) on the pair's points. */
+int dab_pair_stage_a_match(dab_pair *pair, int64_t row_lo, int64_t row_hi, int64_t *n_points);
+int dab_pair_export_points1(dab_pair *pair, int32_t *i_audio, int32_t *v_video, double *qual, int dst_on_device);
+int dab_pair_import_points1(dab_pair *pair, const int32_t *i_audio, const int32_t *v_video, const double *qual,
+                            int64_t n, int src_on_device);
+int dab_pair_dp1(dab_pair *pair, int64_t *n_path);
+
 /* ---- stage B (reference :895-993) -------------------------------------------------------
  * audio_scaled / video_scaled: float32 row-major (n, 3) arrays from the host stage (:740-741),
  * host pointers.  corridors: the scored clusters in cluster order with their final

@@ -62,12 +62,16 @@ def not_quiet(energy):
     return np.flatnonzero(np.asarray(energy)[:-41] > .5).astype(np.int32)
 
 
-def stage_a(video_features, audio_features, video_energy, audio_energy, want_debug=False):
+def match_points(video_features, audio_features, video_energy, audio_energy, rows=None):
+    """Match points (describealign.py:649-673) of the audio frames rows[0] <= i < rows[1] (all
+    rows when None), sorted by (i, v).  Returns (i, v, q, Lv, debug dict)."""
     L = lib()
     v_ms, v_nrm, v_code, v_flags = prep_track(video_features, True)
     a_ms, a_nrm, a_code, _ = prep_track(audio_features, False)
     v_sel = np.ascontiguousarray(not_quiet(video_energy)[::4])
     a_nq = np.ascontiguousarray(not_quiet(audio_energy))
+    if rows is not None:
+        a_nq = np.ascontiguousarray(a_nq[(a_nq >= rows[0]) & (a_nq < rows[1])])
     Lv = max(len(c) for c in v_code)
     cap = max(1 << 20, 4 * len(a_nq))
     stats = np.zeros(2, np.int64)
@@ -79,18 +83,32 @@ def stage_a(video_features, audio_features, video_energy, audio_energy, want_deb
         if n <= cap:
             break
         cap = int(n)
-    pi, pv, pq = pi[:n].copy(), pv[:n].copy(), pq[:n].copy()
+    dbg = dict(v_ms=v_ms, v_nrm=v_nrm, v_code=v_code, v_flags=v_flags, a_ms=a_ms, a_nrm=a_nrm,
+               a_code=a_code, v_sel=v_sel, a_nq=a_nq, touched=int(stats[0]), scored=int(stats[1]))
+    return pi[:n].copy(), pv[:n].copy(), pq[:n].copy(), Lv, dbg
+
+
+def dp1(pi, pv, pq, Lv):
+    """Frontier DP #1 + traceback (describealign.py:674-697) over points sorted by (i, v)."""
+    n = len(pi)
+    pi = np.ascontiguousarray(pi, np.int32); pv = np.ascontiguousarray(pv, np.int32)
+    pq = np.ascontiguousarray(pq, np.float64)
     path_i = np.zeros(max(n, 1), np.int32); path_v = np.zeros(max(n, 1), np.int32)
     cum = np.zeros(max(n, 1)); back = np.zeros(max(n, 1), np.int32)
-    plen = L.oracle_dp1(_p(pi), _p(pv), _p(pq), n, Lv, _p(path_i), _p(path_v), _p(cum), _p(back))
+    plen = lib().oracle_dp1(_p(pi), _p(pv), _p(pq), n, Lv, _p(path_i), _p(path_v), _p(cum), _p(back))
+    return path_i[:plen].astype(np.int64), path_v[:plen].astype(np.int64), cum[:n], back[:n]
+
+
+def stage_a(video_features, audio_features, video_energy, audio_energy, want_debug=False):
+    pi, pv, pq, Lv, dbg = match_points(video_features, audio_features, video_energy, audio_energy)
+    path_x, path_y, cum, back = dp1(pi, pv, pq, Lv)
     out = {
         "points_i": pi, "points_v": pv, "points_q": pq,
-        "path_x": path_i[:plen].astype(np.int64), "path_y": path_v[:plen].astype(np.int64),
-        "touched": int(stats[0]), "scored": int(stats[1]),
+        "path_x": path_x, "path_y": path_y,
+        "touched": dbg["touched"], "scored": dbg["scored"],
     }
     if want_debug:
-        out.update(v_ms=v_ms, v_nrm=v_nrm, v_code=v_code, v_flags=v_flags, a_ms=a_ms, a_nrm=a_nrm,
-                   a_code=a_code, v_sel=v_sel, a_nq=a_nq, cum=cum[:n], back=back[:n])
+        out.update(dbg, cum=cum, back=back)
     return out
 
 

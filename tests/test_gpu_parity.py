@@ -243,3 +243,51 @@ def test_end_to_end_dp2_variants_agree(gpu_ctx, golden_align):
     np.testing.assert_array_equal(out[0][3], out[1][3])
     np.testing.assert_array_equal(out[0][0], out[1][0])
     np.testing.assert_array_equal(out[0][1], out[1][1])
+
+
+def test_stage_a_row_shards_reassemble(gpu_ctx, golden_align):
+    """Row-sharded match stage (the long-pair protocol): the shards' match points,
+    concatenated in row order and imported back, give the reference's pass-1 path."""
+    from describealign_b200 import _cabi, batch
+    from oracle import features as of
+    data, meta = golden_align
+    g = data["pair_a"]
+    v, a = golden_pair_pcm(meta, "pair_a")
+    V, A = of.all_features(v), of.all_features(a)
+    pair = _cabi.Pair(gpu_ctx)
+    pair.set_features(_cabi.VIDEO, V)
+    pair.set_features(_cabi.AUDIO, A)
+    parts = []
+    for lo, hi in batch.row_shards(len(A[0]), 3):
+        n = pair.stage_a_match(lo, hi)
+        pi, pv, pq = pair.points1()
+        assert len(pi) == n and (n == 0 or (pi.min() >= lo and pi.max() < hi))
+        parts.append((pi, pv, pq))
+    pi = np.concatenate([p[0] for p in parts]); pv = np.concatenate([p[1] for p in parts])
+    pq = np.concatenate([p[2] for p in parts])
+    assert np.array_equal(pi, g["points1_i"]) and np.array_equal(pv, g["points1_v"])
+    np.testing.assert_allclose(pq, g["points1_q"], rtol=1e-12, atol=0)
+    pair.import_points1(pi, pv, pq)
+    pair.dp1()
+    x, y = pair.path1()
+    assert np.array_equal(x, g["path1_x"]) and np.array_equal(y, g["path1_y"])
+    # a frame that is not a hashed video frame is rejected, not silently mapped
+    bad = pv.copy(); bad[0] = bad[0] + 1 if bad[0] + 1 not in set(pv[:50].tolist()) else bad[0] + 2
+    with pytest.raises(_cabi.DabError):
+        pair.import_points1(pi, bad, pq)
+    pair.close()
+
+
+def test_long_pair_two_gpus():
+    """align_long_pair under torchrun with NCCL (needs 2 GPUs; the 1-GPU box skips it)."""
+    import subprocess, sys, os
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533",
+                          os.path.join(root, "tools", "run_long_pair.py"), "--seconds", "240", "--check"],
+                         capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert "long pair ok" in res.stdout
