@@ -18,10 +18,18 @@ constexpr int MAXC = 32;   // corridors that may overlap one audio row
 struct __align__(16) P2Rec {     // one pass-2 point, as the DP walks it
   double j, q;
   int32_t i;
-  int32_t kf;      // corridor index | neighbour flag << 8
+  int32_t kf;      // corridor index | P2_* flags
   int32_t cell;    // int(j)
   int32_t ro;      // row offset inside its corridor
 };
+
+// static facts about a point, worked out by the (parallel) scoring kernel so that the serial DP
+// does not have to:
+constexpr int P2_NEAR = 1 << 8;    // a point of another corridor may share its prev_cache cells
+constexpr int P2_VIS1 = 1 << 9;    // the corridor's previous point is a prev_cache candidate
+constexpr int P2_VIS2 = 1 << 10;   // ... and so is the one before it
+constexpr int P2_GAP = 1 << 11;    // the corridor has no point on row i - 1 (its cell was claimed)
+constexpr int P2_MAYQ = 1 << 12;   // another corridor has processed rows to the right of j
 
 struct ScoreBArgs {
   const float *a_scaled;   // (n_a, 3)
@@ -42,6 +50,22 @@ struct ScoreBArgs {
 __device__ __forceinline__ double line_at(const dab_corridor &c, int64_t i) {
   // numpy: slope * x + offset on an int64 arange -> f64 multiply, then add (no fma)
   return __dadd_rn(__dmul_rn(c.slope, (double)i), c.offset);
+}
+
+// corridors holding a point on row r, in cluster order, with the cells they claimed (:937-941)
+__device__ __forceinline__ int claim_row(const ScoreBArgs &s, int64_t r, int *ks, long long *cells) {
+  int n = 0;
+  if (r < 0 || r >= s.n_a) return 0;
+  for (int k = 0; k < s.n_cor; ++k) {
+    const dab_corridor c = s.cor[k];
+    if (r < c.lo || r >= c.hi) continue;
+    const long long cell = (long long)line_at(c, r);
+    bool dup = false;
+    for (int m = 0; m < n; ++m) dup = dup || (cells[m] == cell);
+    if (dup || n == MAXC) continue;
+    ks[n] = k; cells[n] = cell; ++n;
+  }
+  return n;
 }
 
 template <bool FILL>
@@ -71,6 +95,10 @@ __global__ void corridor_kernel(ScoreBArgs s) {
   }
   const int64_t off = s.row_off[i];
   const float a0 = s.a_scaled[i * 3 + 0], a1 = s.a_scaled[i * 3 + 1], a2 = s.a_scaled[i * 3 + 2];
+  // which corridors had a point on the two rows before (for the prev_cache visibility flags)
+  int ks1[MAXC], ks2[MAXC];
+  long long cells1[MAXC], cells2[MAXC];
+  const int n1 = claim_row(s, i - 1, ks1, cells1), n2 = claim_row(s, i - 2, ks2, cells2);
   for (int m = 0; m < n; ++m) {
     const double j = js[m];
     const double fl = floor(j);
@@ -122,9 +150,30 @@ __global__ void corridor_kernel(ScoreBArgs s) {
     s.p_c[off + m] = cs[m];
     s.p_q[off + m] = q;
     s.p_rank[off + m] = rank;
+    // own-corridor prev_cache candidates (describealign.py:966-973): the corridor's points on rows
+    // i-1 / i-2, as long as their cell is within two of this one and was not overwritten
+    bool has1 = false, has2 = false;
+    long long cell_a = 0, cell_b = 0;
+    for (int e = 0; e < n1; ++e) if (ks1[e] == ks[m]) { has1 = true; cell_a = cells1[e]; }
+    for (int e = 0; e < n2; ++e) if (ks2[e] == ks[m]) { has2 = true; cell_b = cells2[e]; }
+    const bool vis1 = has1 ? cell_a >= cell - 2 : (has2 && cell_b >= cell - 2);
+    const bool vis2 = has1 && has2 && cell_b >= cell - 2 && cell_b != cell_a;
+    const int ro = (int)(i - s.cor[ks[m]].lo);
+    const bool gap = !has1 && ro > 0;
+    // can the frontier's best entry lie to the right of this point?  Only if another corridor has
+    // processed rows (< i) with a larger coordinate.
+    bool mayq = false;
+    for (int k = 0; k < s.n_cor; ++k) {
+      if (k == ks[m]) continue;
+      const dab_corridor c = s.cor[k];
+      if (c.hi <= c.lo || c.lo > i - 1) continue;
+      const int64_t r = i - 1 < c.hi - 1 ? i - 1 : c.hi - 1;
+      mayq = mayq || line_at(c, r) > j;
+    }
     P2Rec rc;
-    rc.j = j; rc.q = q; rc.i = (int32_t)i; rc.kf = ks[m] | (near << 8); rc.cell = (int32_t)cell;
-    rc.ro = (int32_t)(i - s.cor[ks[m]].lo);
+    rc.j = j; rc.q = q; rc.i = (int32_t)i; rc.cell = (int32_t)cell; rc.ro = ro;
+    rc.kf = ks[m] | (near ? P2_NEAR : 0) | (vis1 ? P2_VIS1 : 0) | (vis2 ? P2_VIS2 : 0) | (gap ? P2_GAP : 0) |
+            (mayq ? P2_MAYQ : 0);
     s.rec[off + m] = rc;
   }
 }
@@ -538,7 +587,7 @@ __global__ void __launch_bounds__(32, 1) dp2_corridor_kernel(Dp2LArgs a) {
       const int i = pt.i, cell = pt.cell, ro = pt.ro;
       const double j = pt.j, q = pt.q;
       const int k = pt.kf & 0xff;
-      const bool near = pt.kf > 0xff;
+      const bool near = (pt.kf & P2_NEAR) != 0;
       if (k != cur) {
         spill();
         cur = k;
@@ -640,6 +689,241 @@ __global__ void __launch_bounds__(32, 1) dp2_corridor_kernel(Dp2LArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------
+// DP #2, lane-per-corridor formulation (the product path).  Same mathematics as
+// dp2_corridor_kernel above, but lane l of the walking warp OWNS corridor l: its last cums, its
+// cluster best, its running-max head and its line live in that lane's registers, so there is no
+// state to spill when consecutive points alternate between overlapping corridors, and the
+// per-point code is one branch-free instruction stream: every lane evaluates "its" candidates,
+// only the lane that owns the point's corridor commits (selects, predicated stores).  The facts
+// that do not depend on cum values - which earlier points are prev_cache candidates, whether rows
+// of the corridor were skipped, whether the frontier's best entry can lie right of the point -
+// were worked out by corridor_kernel (P2_* flags).  Cross-lane traffic per point: one 64-bit
+// shuffle (the committed cum - 1000 for the frontier top).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32, 1) dp2_lane_kernel(Dp2LArgs a) {
+  __shared__ PmEntry s_ring[RING][32];          // [row & 15][corridor]: last 16 running-max rows
+  __shared__ PmEntry s_win[32][WAYS * WLEN];    // per-lane window cache of older rows
+  __shared__ P2Rec s_rec[2][32];
+
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x;
+  const int n = a.n_points;
+  const int n_cor = a.n_cor;
+  const double NEG = -INFINITY;
+
+  // ---- this lane's corridor -----------------------------------------------------------------
+  const bool have = lane < n_cor;
+  int lo = 0x7fffffff, rows = 0, cluster = -1;
+  double sl = 1.0, of = 0.0, inv = 1.0;
+  PmEntry *pm = a.pm;
+  if (have) {
+    const dab_corridor c = a.cor[lane];
+    lo = c.lo; rows = c.hi > c.lo ? c.hi - c.lo : 0; cluster = c.cluster;
+    sl = c.slope; of = c.offset; inv = 1.0 / c.slope;
+    pm = a.pm + a.pm_off[lane];
+  }
+  double c0 = NEG, c1 = NEG, c2 = NEG;          // cums of the corridor's last three points
+  int id0 = -2, id1 = -2, id2 = -2;
+  double cl_v = -1000.0; int cl_i = -1;          // clusters_best_so_far seed (describealign.py:948)
+  double pm_v = NEG; int pm_i = -2;              // head of the running maximum of cum - 1000
+  int filled = -1;                               // last running-max row written
+  int wbase[WAYS], wnext = 0;
+#pragma unroll
+  for (int w = 0; w < WAYS; ++w) wbase[w] = -0x40000000;
+  // frontier top: seed (0, 0, -1, 0, 0) (describealign.py:947); uniform across lanes
+  double top_v = 0.0, top_j = 0.0;
+  int top_i = -1;
+  unsigned n_query = 0, n_refill = 0, n_near = 0;
+
+  // F(j) seen from a point of corridor k on row i: lane c' contributes PM_c'[rows of c' with j' <= j]
+  auto frontier_query = [&](int i, double j, int k, double &fv_out, int &fi_out) {
+    double v = NEG;
+    int id = -2;
+    if (lane == k) { v = 0.0; id = -1; }          // the frontier's seed entry, j' = 0
+    else if (have && lo <= i) {
+      double est = floor((j - of) * inv) - (double)lo + 1.0;
+      int kk = est < 0.0 ? 0 : (est > (double)rows ? rows : (int)est);
+      while (kk < rows && __dadd_rn(__dmul_rn(sl, (double)(lo + kk)), of) <= j) ++kk;
+      while (kk > 0 && __dadd_rn(__dmul_rn(sl, (double)(lo + kk - 1)), of) > j) --kk;
+      const int done = (i + 1 < lo + rows ? i + 1 : lo + rows) - lo;   // rows <= i
+      const int idx = kk < done ? kk : done;
+      const int f = filled;
+      if (idx > 0 && f >= 0) {
+        const int x = idx - 1;
+        if (x >= f) { v = pm_v; id = pm_i; }
+        else if (x > f - RING) { const PmEntry e = s_ring[x & (RING - 1)][lane]; v = e.val; id = e.id; }
+        else {
+          int hit = -1;
+#pragma unroll
+          for (int w = 0; w < WAYS; ++w) if (x >= wbase[w] && x < wbase[w] + WLEN) hit = w;
+          if (hit < 0) {
+            hit = wnext; wnext = (wnext + 1) & (WAYS - 1);
+            ++n_refill;
+            const PmEntry *src = pm + x;                   // rows x .. x+15 < f are final
+#pragma unroll
+            for (int e = 0; e < WLEN; ++e) {
+              const int4 raw = __ldcg(reinterpret_cast<const int4 *>(src + e));
+              *reinterpret_cast<int4 *>(&s_win[lane][hit * WLEN + e]) = raw;
+            }
+#pragma unroll
+            for (int w = 0; w < WAYS; ++w) if (w == hit) wbase[w] = x;
+          }
+          int wb = 0;
+#pragma unroll
+          for (int w = 0; w < WAYS; ++w) if (w == hit) wb = wbase[w];
+          const PmEntry e = s_win[lane][hit * WLEN + (x - wb)];
+          v = e.val; id = e.id;
+        }
+      }
+    }
+    // warp arg-max on (val desc, j' asc, id asc)
+    const unsigned long long ob = order_bits(v);
+    const unsigned hi = (unsigned)(ob >> 32), lo32 = (unsigned)ob;
+    const unsigned mhi = __reduce_max_sync(FULL, hi);
+    bool alive = hi == mhi;
+    const unsigned mlo = __reduce_max_sync(FULL, alive ? lo32 : 0u);
+    alive = alive && lo32 == mlo;
+    unsigned bal = __ballot_sync(FULL, alive);
+    if (__popc(bal) > 1) {
+      const double jj = !alive ? INFINITY : (id < 0 ? 0.0 : a.p_j[id]);
+      const unsigned long long jb = (unsigned long long)__double_as_longlong(jj);   // jj >= 0
+      const unsigned jh = (unsigned)(jb >> 32), jl = (unsigned)jb;
+      const unsigned nh = __reduce_min_sync(FULL, alive ? jh : 0xffffffffu);
+      alive = alive && jh == nh;
+      const unsigned nl = __reduce_min_sync(FULL, alive ? jl : 0xffffffffu);
+      alive = alive && jl == nl;
+      const unsigned ni = __reduce_min_sync(FULL, alive ? (unsigned)(id + 2) : 0xffffffffu);
+      alive = alive && (unsigned)(id + 2) == ni;
+      bal = __ballot_sync(FULL, alive);
+    }
+    const int src = __ffs(bal) - 1;
+    fv_out = __shfl_sync(FULL, v, src);
+    fi_out = __shfl_sync(FULL, id, src);
+  };
+
+  P2Rec rr;
+  if (lane < n) rr = a.rec[lane];
+  for (int base = 0; base < n; base += 32) {
+    const int buf = (base >> 5) & 1;
+    s_rec[buf][lane] = rr;
+    __syncwarp();
+    if (base + 32 + lane < n) rr = a.rec[base + 32 + lane];
+    const int cnt = n - base < 32 ? n - base : 32;
+    P2Rec nx = s_rec[buf][0];
+#pragma unroll 1
+    for (int t = 0; t < cnt; ++t) {
+      const int p = base + t;
+      const P2Rec pt = nx;
+      nx = s_rec[buf][(t + 1) & 31];             // (garbage past cnt: never used)
+      const double j = pt.j, q = pt.q;
+      const int kf = pt.kf, k = kf & 0xff, ro = pt.ro;
+      const bool mine = lane == k;
+
+      // ---- candidates in the reference's order [frontier, cluster best, cells]; every test is
+      //      ">=", so the LAST candidate attaining the maximum wins (describealign.py:960-973)
+      double best;
+      int pred;
+      if (!(kf & P2_NEAR)) {
+        double m = cl_v;
+        int mi = cl_i;
+        const bool t2 = (kf & P2_VIS2) && c1 >= m;
+        m = t2 ? c1 : m; mi = t2 ? id1 : mi;
+        const bool t1 = (kf & P2_VIS1) && c0 >= m;
+        m = t1 ? c0 : m; mi = t1 ? id0 : mi;
+        const bool left = top_j <= j;              // the top entry is F(j) itself
+        const bool tt = left && top_v > m;
+        best = tt ? top_v : m; pred = tt ? top_i : mi;
+        if (kf & P2_MAYQ) {
+          // the top lies right of the point: F(j) <= top value, needed only if that beats m
+          if (__ballot_sync(FULL, mine && !left && m < top_v)) {
+            ++n_query;
+            double fv; int fi;
+            frontier_query(pt.i, j, k, fv, fi);
+            if (fv > m) { best = fv; pred = fi; }
+          }
+        }
+      } else {
+        // ---- a point of another corridor may sit in this point's prev_cache cells: generic
+        //      evaluation over the last three points of every corridor (uniform values)
+        ++n_near;
+        const int i = pt.i, cell = pt.cell;
+        double ub = NEG; int up = -2;
+        if (top_j <= j) { ub = top_v; up = top_i; }
+        else { ++n_query; frontier_query(i, j, k, ub, up); }
+        const double clk = __shfl_sync(FULL, cl_v, k);
+        const int cik = __shfl_sync(FULL, cl_i, k);
+        const int cluster_k = __shfl_sync(FULL, cluster, k);
+        if (clk >= ub) { ub = clk; up = cik; }
+        // rows / cells of this lane's last three points
+        int hr0 = -100, hr1 = -100, hr2 = -100, hc0 = -100, hc1 = -100, hc2 = -100;
+        if (id0 >= 0) { const P2Rec r = a.rec[id0]; hr0 = r.i; hc0 = r.cell; }
+        if (id1 >= 0) { const P2Rec r = a.rec[id1]; hr1 = r.i; hc1 = r.cell; }
+        if (id2 >= 0) { const P2Rec r = a.rec[id2]; hr2 = r.i; hc2 = r.cell; }
+#pragma unroll 1
+        for (int x = cell - 2; x <= cell; ++x) {
+          int brow = -1, bh = 0;
+          if (hc0 == x && hr0 > brow) { brow = hr0; bh = 0; }
+          if (hc1 == x && hr1 > brow) { brow = hr1; bh = 1; }
+          if (hc2 == x && hr2 > brow) { brow = hr2; bh = 2; }
+          const int mrow = (int)__reduce_max_sync(FULL, (unsigned)(brow + 1)) - 1;
+          if (mrow < 0 || mrow < i - 2) continue;         // nothing written recently enough
+          const int src = __ffs(__ballot_sync(FULL, brow == mrow)) - 1;
+          const double myc = bh == 0 ? c0 : (bh == 1 ? c1 : c2);
+          const int myid = bh == 0 ? id0 : (bh == 1 ? id1 : id2);
+          double pc = __shfl_sync(FULL, myc, src);
+          const int pid = __shfl_sync(FULL, myid, src);
+          const double pj = __shfl_sync(FULL, __dadd_rn(__dmul_rn(sl, (double)mrow), of), src);
+          if (__shfl_sync(FULL, cluster, src) != cluster_k) {
+            const double d = (j - pj) - (double)(i - mrow);
+            pc = pc - (100.0 + 100.0 * (d * d));
+          }
+          if (pj <= j && pc >= ub) { ub = pc; up = pid; }
+        }
+        best = ub; pred = up;
+      }
+
+      // ---- commit (lane k) ---------------------------------------------------------------------
+      const double cum = best + q;
+      c2 = mine ? c1 : c2; id2 = mine ? id1 : id2;
+      c1 = mine ? c0 : c1; id1 = mine ? id0 : id1;
+      c0 = mine ? cum : c0; id0 = mine ? p : id0;
+      const double cj = cum - 50.0;
+      const bool ucl = mine && cl_v < cj;
+      cl_v = ucl ? cj : cl_v; cl_i = ucl ? p : cl_i;
+      const double jump = cum - 1000.0;
+      if (kf & P2_GAP) {
+        // rows without a point (their cell was claimed by an earlier cluster) repeat the head
+        if (mine) {
+          PmEntry e; e.val = pm_v; e.id = pm_i; e.pad = 0;
+          for (int r = filled + 1; r < ro; ++r) { pm[r] = e; s_ring[r & (RING - 1)][lane] = e; }
+        }
+        __syncwarp();
+      }
+      const bool upm = mine && jump > pm_v;
+      pm_v = upm ? jump : pm_v; pm_i = upm ? p : pm_i;
+      filled = mine ? ro : filled;
+      if (mine) {
+        PmEntry e; e.val = pm_v; e.id = pm_i; e.pad = 0;
+        s_ring[ro & (RING - 1)][lane] = e;
+        pm[ro] = e;
+        BackRec b; b.best = best; b.pred = pred; b.pad = 0;
+        a.back[p] = b;
+      }
+      const double jk = __shfl_sync(FULL, jump, k);
+      const bool ut = jk > top_v || (jk == top_v && j < top_j);
+      top_v = ut ? jk : top_v; top_j = ut ? j : top_j; top_i = ut ? p : top_i;
+    }
+    __syncwarp();
+  }
+  n_refill = __reduce_add_sync(FULL, n_refill);
+  if (lane == 0) {
+    a.result[0] = top_i;
+    *reinterpret_cast<double *>(a.result + 2) = top_v;
+    a.counters[0] = n_query; a.counters[1] = n_refill; a.counters[2] = n_near;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // Traceback by pointer jumping (binary lifting): up[k][p] = 2^k-th predecessor, node n = root.
 // depth doubles alongside; the ancestors of the end point are marked level by level from the
 // top; each marked point writes its own path row at position depth - 1.
@@ -701,7 +985,7 @@ __global__ void lift_emit_kernel(EmitArgs a) {
 // The corridor-state DP needs: at most 32 corridors, positive slopes, every coordinate >= 3 (so the
 // seeded prev_cache cell 0 is never in reach; x_limits keeps lines >= 4, describealign.py:898).
 static bool corridor_dp_eligible(const dab_pair *pr, int32_t n_cor) {
-  if (pr->ctx->opt_dp2_generic || n_cor > 32) return false;
+  if (pr->ctx->opt_dp2_generic || pr->ctx->opt_dp2_impl == 2 || n_cor > 32) return false;
   for (int k = 0; k < n_cor; ++k) {
     const dab_corridor &c = pr->h_cor[k];
     if (!(c.slope > 0.0)) return false;
@@ -784,7 +1068,8 @@ int dab_run_stage_b(dab_pair *pr, int32_t n_cor, int32_t n_clusters) {
     la.back = pr->back2.as<BackRec>();
     la.result = pr->dpres.as<int32_t>();
     la.counters = reinterpret_cast<unsigned long long *>(pr->pmoff2.as<int64_t>() + 32);
-    dp2_corridor_kernel<<<1, 32, 0, st>>>(la);
+    if (pr->ctx->opt_dp2_impl == 1) dp2_corridor_kernel<<<1, 32, 0, st>>>(la);
+    else dp2_lane_kernel<<<1, 32, 0, st>>>(la);
     DAB_CUDA(cudaEventRecord(pr->ev[18], st));
     int32_t *up = pr->lift_up.as<int32_t>();
     int32_t *dep0 = pr->lift_dep.as<int32_t>(), *dep1 = dep0 + np1, *mark = dep1 + np1;

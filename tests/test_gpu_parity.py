@@ -151,7 +151,7 @@ def test_mismatched_inputs_fail_like_the_reference(gpu_ctx):
         api.align_pcm(v, a)
 
 
-def _random_stage_b_case(seed, n_a=9000, n_v=9000, n_cor=6, crossing=True):
+def _random_stage_b_case(seed, n_a=9000, n_v=9000, n_cor=6, crossing=True, slopes=(0.7, 1.25)):
     """Synthetic pass-2 input: smooth random scaled features and hand-made corridors (different
     slopes so that lines cross and share cells, one line duplicated a quarter cell away so that
     the 'first cluster to claim (i, int(j)) wins' rule fires).  The audio is made to follow a
@@ -166,7 +166,7 @@ def _random_stage_b_case(seed, n_a=9000, n_v=9000, n_cor=6, crossing=True):
     audio, video = feats(n_a), feats(n_v)
     plans = []
     for k in range(n_cor):
-        slope = float(rng.uniform(0.7, 1.25)) if crossing else 1.0
+        slope = float(rng.uniform(*slopes)) if crossing else 1.0
         offset = float(rng.uniform(4.0, 0.15 * n_v)) + (0.0 if crossing else 40.0 * k)
         if k == 2:                       # same line as corridor 1, shifted by a fraction of a cell
             slope, offset = plans[1][3], plans[1][4] + 0.25
@@ -196,17 +196,18 @@ def _random_stage_b_case(seed, n_a=9000, n_v=9000, n_cor=6, crossing=True):
 
 
 @pytest.mark.parametrize("seed,crossing", [(1, True), (2, True), (3, False), (4, True), (5, True)])
-@pytest.mark.parametrize("generic", [0, 1])
-def test_stage_b_adversarial_vs_oracle(gpu_ctx, seed, crossing, generic):
+@pytest.mark.parametrize("impl", [0, 1, 2])
+def test_stage_b_adversarial_vs_oracle(gpu_ctx, seed, crossing, impl):
     """Corridor scoring + DP #2 + traceback on inputs built to hit the rare branches (crossing
     lines, shared cells, dropped duplicates, negative quals, cluster jumps), for the
     corridor-state DP and for the generic tree DP; both must equal the oracle bit for bit in the
-    integer columns and to 1e-9 in the float ones."""
+    integer columns and to 1e-9 in the float ones.  impl 0 = lane-per-corridor kernel (product
+    path), 1 = corridor-state kernel, 2 = generic tree DP."""
     from describealign_b200 import _cabi
     from oracle import align_oracle as ao
     audio, video, plans, n_clusters = _random_stage_b_case(seed, crossing=crossing)
     want = ao.stage_b(plans, n_clusters, audio, video)
-    gpu_ctx.set_option("dp2_generic", generic)
+    gpu_ctx.set_option("dp2_impl", impl)
     try:
         pair = _cabi.Pair(gpu_ctx)
         pair.stage_b(audio, video, plans, n_clusters)
@@ -215,7 +216,7 @@ def test_stage_b_adversarial_vs_oracle(gpu_ctx, seed, crossing, generic):
         stats = pair.stats()
         pair.close()
     finally:
-        gpu_ctx.set_option("dp2_generic", 0)
+        gpu_ctx.set_option("dp2_impl", 0)
     assert np.array_equal(i, want["points_i"]) and np.array_equal(c, want["points_c"])
     np.testing.assert_array_equal(j, want["points_j"])
     np.testing.assert_allclose(q, want["points_q"], rtol=0, atol=1e-9)
@@ -223,26 +224,53 @@ def test_stage_b_adversarial_vs_oracle(gpu_ctx, seed, crossing, generic):
     assert path.shape == wp.shape, (path.shape, wp.shape)
     np.testing.assert_array_equal(path[:, :3], wp[:, :3])
     np.testing.assert_allclose(path[:, 3:], wp[:, 3:], rtol=0, atol=1e-8)
-    if not generic and crossing:
+    if impl != 2 and crossing:
         assert stats["n_dp2_neighbour"] > 0, "the test is meant to exercise the shared-cell branch"
 
 
+@pytest.mark.parametrize("seed,slopes,n_v", [(11, (0.3, 0.6), 6000), (12, (1.8, 3.0), 30000), (13, (0.95, 1.05), 9000)])
+@pytest.mark.parametrize("impl", [0, 1, 2])
+def test_stage_b_slopes_vs_oracle(gpu_ctx, seed, slopes, n_v, impl):
+    """Shallow lines (several rows per prev_cache cell), steep lines (cells more than two apart,
+    so no local step is possible) and near-parallel lines, against the oracle."""
+    from describealign_b200 import _cabi
+    from oracle import align_oracle as ao
+    audio, video, plans, n_clusters = _random_stage_b_case(seed, n_v=n_v, slopes=slopes)
+    want = ao.stage_b(plans, n_clusters, audio, video)
+    gpu_ctx.set_option("dp2_impl", impl)
+    try:
+        pair = _cabi.Pair(gpu_ctx)
+        pair.stage_b(audio, video, plans, n_clusters)
+        i, j, c, q = pair.points2()
+        path = pair.path2()
+        pair.close()
+    finally:
+        gpu_ctx.set_option("dp2_impl", 0)
+    assert np.array_equal(i, want["points_i"]) and np.array_equal(c, want["points_c"])
+    np.testing.assert_array_equal(j, want["points_j"])
+    wp = want["path"]
+    assert path.shape == wp.shape, (path.shape, wp.shape)
+    np.testing.assert_array_equal(path[:, :3], wp[:, :3])
+    np.testing.assert_allclose(path[:, 3:], wp[:, 3:], rtol=0, atol=1e-8)
+
+
 def test_end_to_end_dp2_variants_agree(gpu_ctx, golden_align):
-    """Same pair through both pass-2 DPs: identical paths (the corridor-state DP is the product
-    path; the tree DP is the generic fallback)."""
+    """Same pair through the three pass-2 DPs: identical paths (the lane-per-corridor DP is the
+    product path; the tree DP is the generic fallback)."""
     from describealign_b200 import api
     _, meta = golden_align
     v, a = golden_pair_pcm(meta, "pair_warp")
     out = []
-    for generic in (0, 1):
-        api.context().set_option("dp2_generic", generic)
+    for impl in (0, 1, 2):
+        api.context().set_option("dp2_impl", impl)
         try:
             out.append(api.align_pcm(v, a))
         finally:
-            api.context().set_option("dp2_generic", 0)
-    np.testing.assert_array_equal(out[0][3], out[1][3])
-    np.testing.assert_array_equal(out[0][0], out[1][0])
-    np.testing.assert_array_equal(out[0][1], out[1][1])
+            api.context().set_option("dp2_impl", 0)
+    for other in out[1:]:
+        np.testing.assert_array_equal(out[0][3], other[3])
+        np.testing.assert_array_equal(out[0][0], other[0])
+        np.testing.assert_array_equal(out[0][1], other[1])
 
 
 def test_stage_a_row_shards_reassemble(gpu_ctx, golden_align):
