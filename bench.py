@@ -3,13 +3,13 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--pairs B] [--impl ours|reference]
 
-A step = one pass of the hot path over one batch of B synthetic pairs per GPU of the C2 shape
+A step = one pass of the hot path over one batch of B synthetic pairs per GPU (W in flight) of the C2 shape
 (22-min video audio vs 27-min description, 202 s start offset, injected skips):
 features of both tracks, device stage A (describealign.py:596-700) and device stage B
 (:895-993).  The host-side rate-change fit between the two device stages (:702-893) is outside
 the timed regions, as BASELINE.json prescribes; it is solved once per pair and reused for as long
-as stage A returns the identical pass-1 path.  All B pairs of a step are in flight at once (one
-CUDA stream each): the frontier DPs are one warp per pair, so throughput comes from overlap.
+as stage A returns the identical pass-1 path.  W pairs are in flight at once (one CUDA stream
+each): the frontier DPs are one warp per pair, so throughput comes from overlapping pairs.
 
 value   device-resident: PCM already in HBM when the timed region starts; CUDA events
         bracketing each device stage on the streams the kernels are launched on.
@@ -47,7 +47,9 @@ def parse_args():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--pairs", type=int, default=16, help="pairs per GPU per step (all in flight at once)")
+    ap.add_argument("--pairs", type=int, default=56, help="pairs per GPU per step")
+    ap.add_argument("--workers", type=int, default=28, help="pairs in flight per GPU (one CUDA stream each)")
+    ap.add_argument("--distinct", type=int, default=8, help="distinct synthetic pairs per GPU; a step cycles over them")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the C2 durations (debugging only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -222,79 +224,96 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    pairs = make_pairs(args.pairs, rank * args.pairs, args.scale)
+    # B pairs per step, cycling over a few distinct synthetic pairs (generating one takes ~35 s of CPU)
+    B = args.pairs
+    distinct = max(1, min(B, args.distinct))
+    base_pairs = make_pairs(distinct, rank * distinct, args.scale)
+    pairs = [base_pairs[k % distinct] for k in range(B)]
     hours_rank = audio_hours(pairs)
-    B = len(pairs)
 
-    # device-resident copies (int16 interleaved) and pinned host copies
+    # device-resident copies (int16 interleaved) and pinned host copies of the distinct pairs
     dev = [(torch.from_numpy(np.ascontiguousarray(v)).cuda(), torch.from_numpy(np.ascontiguousarray(a)).cuda())
-           for v, a in pairs]
+           for v, a in base_pairs]
     pinned = [(torch.from_numpy(np.ascontiguousarray(v)).pin_memory(), torch.from_numpy(np.ascontiguousarray(a)).pin_memory())
-              for v, a in pairs]
+              for v, a in base_pairs]
     ctx = api.context()
-    jobs_pairs = [api._cabi.Pair(ctx) for _ in range(B)]
-    streams = [torch.cuda.ExternalStream(p.stream) for p in jobs_pairs]
+    # W pairs in flight: one dab_pair (device buffers + CUDA stream) per worker slot.  The frontier DPs
+    # are one warp per pair and ~0.1 s long, so throughput comes from keeping W of them running while
+    # the data-parallel kernels of other pairs fill the SMs; W stays below the 32 hardware queues.
+    W = max(1, min(B, args.workers))
+    slot_pairs = [api._cabi.Pair(ctx) for _ in range(W)]
+    streams = [torch.cuda.ExternalStream(p.stream) for p in slot_pairs]
     cur = torch.cuda.current_stream()
 
+    import queue
     from concurrent.futures import ThreadPoolExecutor
-    pool = ThreadPoolExecutor(max_workers=B)
-
-    def timed_phase(fn):
-        """Run fn(k) for every pair concurrently; returns device ms between a start event every
-        pair stream waits on and a stop event that waits on every pair stream."""
-        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        start.record(cur)
-        for s in streams:
-            s.wait_event(start)
-        list(pool.map(fn, range(B)))
-        for s in streams:
-            e = torch.cuda.Event()
-            e.record(s)
-            cur.wait_event(e)
-        stop.record(cur)
-        stop.synchronize()
-        return start.elapsed_time(stop)
-
-    def one_step(host_input: bool):
-        jobs = [api.AlignJob(jobs_pairs[k]) for k in range(B)]
-
-        def stage_a(k):
-            if host_input:
-                jobs[k].load_pcm(pinned[k][0].numpy(), pinned[k][1].numpy())
-            else:
-                v, a = dev[k]
-                jobs[k].load_pcm_device((v.data_ptr(), v.shape[0], v.shape[1]), (a.data_ptr(), a.shape[0], a.shape[1]))
-            jobs[k].device_stage_a()
-
-        ms_a = timed_phase(stage_a)
-        list(pool.map(lambda k: host_stage(k, jobs[k]), range(B)))    # untimed (BASELINE.json)
-        ms_b = timed_phase(lambda k: jobs[k].device_stage_b())
-        phase_ms["a"] += ms_a
-        phase_ms["b"] += ms_b
-        return ms_a + ms_b, jobs
-
-    phase_ms = {"a": 0.0, "b": 0.0}
-
+    pool = ThreadPoolExecutor(max_workers=W)
     host_cache = {}
 
     def host_stage(k, job):
-        """The rate-change fit is outside the metric; its result only depends on the pass-1 path,
-        so it is solved once per pair and reused while stage A keeps returning that same path."""
-        c = host_cache.get(k)
+        """The rate-change fit is outside the metric (BASELINE.json); its result only depends on the
+        pass-1 path, so it is solved once per distinct pair (during warm-up) and reused for as long as
+        stage A keeps returning that same path.  Inside the timed region it is a dictionary lookup."""
+        c = host_cache.get(k % distinct)
         if c is not None and np.array_equal(c["x"], job.x) and np.array_equal(c["y"], job.y):
             for name in ("kept_x", "kept_y", "audio_scaled", "video_scaled", "fit", "clusters", "plans"):
                 setattr(job, name, c[name])
             return
         job.host_stage()
-        host_cache[k] = {"x": job.x, "y": job.y, **{name: getattr(job, name) for name in
-                         ("kept_x", "kept_y", "audio_scaled", "video_scaled", "fit", "clusters", "plans")}}
+        host_cache[k % distinct] = {"x": job.x, "y": job.y, **{name: getattr(job, name) for name in
+                                    ("kept_x", "kept_y", "audio_scaled", "video_scaled", "fit", "clusters", "plans")}}
+
+    def one_step(host_input: bool):
+        """All B pairs through stage A -> (cached) host fit -> stage B, W at a time.  Returns the
+        device time between a start event every pair stream waits on and a stop event that waits on
+        every pair stream."""
+        jobs = [None] * B
+        slots = queue.SimpleQueue()
+        for pr in slot_pairs:
+            slots.put(pr)
+
+        def work(k):
+            pr = slots.get()
+            t_in = time.perf_counter()
+            try:
+                job = api.AlignJob(pr)
+                jobs[k] = job
+                if host_input:
+                    hv, ha = pinned[k % distinct]
+                    job.load_pcm(hv.numpy(), ha.numpy())
+                else:
+                    v, a = dev[k % distinct]
+                    job.load_pcm_device((v.data_ptr(), v.shape[0], v.shape[1]), (a.data_ptr(), a.shape[0], a.shape[1]))
+                job.device_stage_a()
+                host_stage(k, job)
+                job.device_stage_b()
+                job.kernel_ms = pr.timings()
+                job.work = pr.stats()
+                job.host_ms["whole_pair"] = 1e3 * (time.perf_counter() - t_in)
+            finally:
+                slots.put(pr)
+
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record(cur)
+        for st in streams:
+            st.wait_event(start)
+        list(pool.map(work, range(B)))
+        for st in streams:
+            e = torch.cuda.Event()
+            e.record(st)
+            cur.wait_event(e)
+        stop.record(cur)
+        stop.synchronize()
+        return start.elapsed_time(stop), jobs
+
+    alloc0 = {}
 
     def run_steps(host_input):
         for _ in range(args.warmup):
             one_step(host_input)
         barrier()
         l0 = ctx.launches()
-        phase_ms["a"] = phase_ms["b"] = 0.0
+        alloc0.update(api._cabi.alloc_stats())
         total, jobs = 0.0, None
         for _ in range(args.steps):
             ms, jobs = one_step(host_input)
@@ -306,10 +325,14 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0:
         sampler.start()
     ms_dev, launches, jobs = run_steps(False)
-    phases_dev = {k: v / args.steps for k, v in phase_ms.items()}
+    alloc1 = api._cabi.alloc_stats()
+    alloc_timed = {k: alloc1[k] - alloc0[k] for k in alloc1}
     clocks = sampler.stop() if rank == 0 else None
-    timings = [j.pair.timings() for j in jobs]
-    stats = [j.pair.stats() for j in jobs]
+    timings = [j.kernel_ms for j in jobs]
+    host_calls = {k: {"mean": float(np.mean([j.host_ms.get(k, 0.0) for j in jobs])),
+                      "max": float(np.max([j.host_ms.get(k, 0.0) for j in jobs]))}
+                  for k in sorted(set().union(*[j.host_ms.keys() for j in jobs]))}
+    stats = [j.work for j in jobs]
     ms_e2e, _, jobs_e = run_steps(True)
     h2d = sum(j.h2d_bytes for j in jobs_e)
     d2h = sum(j.d2h_bytes for j in jobs_e)
@@ -321,14 +344,21 @@ def run_ours(args, rank, world, local_rank):
         import oracle
         oracle.build()
         cpu_s, fit_s, o = cpu_pass(pairs[0], keep=True)
-        j0 = jobs[0]
-        nx, ny, sim, path, med = j0.finish()
+        # one more (untimed) pass of pair 0 through the public API, keeping its intermediates
+        det = {}
+        nx, ny, sim, path, med = api.align_pcm(pairs[0][0], pairs[0][1], details=det)
+
+        class _J:
+            video_features, audio_features = det["video_features"], det["audio_features"]
+            x, y = det["path1"]
+        j0 = _J
         ox, oy = o["nodes"]
         opath = o["path"]
         same_shape = path.shape == opath.shape
         parity = {
             "features_f32_identical": bool(all(np.array_equal(j0.video_features[k], o["V"][k]) and
-                                               np.array_equal(j0.audio_features[k], o["A"][k]) for k in range(4))),
+                                               np.array_equal(j0.audio_features[k], o["A"][k])
+                                               for k in range(min(4, len(j0.video_features))))),
             "path1_identical": bool(np.array_equal(j0.x, o["path1"][0]) and np.array_equal(j0.y, o["path1"][1])),
             "path2_rows": int(len(path)),
             "path2_int_identical": bool(same_shape and np.array_equal(path[:, 1], opath[:, 1]) and
@@ -385,18 +415,21 @@ def run_ours(args, rank, world, local_rank):
             "metric": METRIC, "value": hours / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32+f64 (u32 packed codes)", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "pairs_per_gpu_per_step": B, "audio_hours_per_step": hours,
-                       "l2_policy": "inputs larger than L2 (each pair streams 259 MB of PCM; 126 MB L2)",
-                       "timed": "device stage A (features, prep, tables, gate, score, DP1, traceback) + device stage B (corridors, DP2, traceback); host rate-change fit untimed",
+            "config": {"workload": WORKLOAD, "pairs_per_gpu_per_step": B, "pairs_in_flight_per_gpu": W,
+                       "distinct_pairs_per_gpu": distinct, "audio_hours_per_step": hours,
+                       "l2_policy": "inputs larger than L2 (each pair streams 259 MB of PCM, %d distinct pairs per step; 126 MB L2)" % distinct,
+                       "timed": "one region per step: every pair through device stage A (features, prep, tables, gate, score, DP1, traceback) and device stage B (corridors, DP2, traceback), W pairs in flight; the host rate-change fit between them is solved during warm-up and is a cache lookup inside the region (untimed by BASELINE.json)",
                        "scale": args.scale},
             "ms_per_pair": ms_dev / B,
-            "ms_per_step_by_stage": {"stage_a": phases_dev["a"], "stage_b": phases_dev["b"]},
+            "pairs_in_flight": W,
             "e2e": {"value": hours / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": h2d_all, "d2h_bytes_per_step": d2h_all},
             "gpu_launches": int(launches_all),
             "roofline": main_roof,
             "roofline_by_kernel": roof,
             "kernel_ms_last_step": agg,
+            "host_call_ms_last_step": host_calls,
+            "allocator_activity_in_timed_steps": alloc_timed,
             "work": {k: sum(s[k] for s in stats) for k in stats[0]},
             "clocks": clocks,
             "cpu_baseline": cpu,

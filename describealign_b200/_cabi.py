@@ -23,6 +23,7 @@ EXPORTS = [
     "dab_pair_get_path1", "dab_pair_get_points1", "dab_pair_stage_b", "dab_pair_get_path2",
     "dab_pair_get_points2", "dab_pair_get_stats", "dab_pair_get_timings", "dab_launch_count",
     "dab_pair_stage_a_match", "dab_pair_export_points1", "dab_pair_import_points1", "dab_pair_dp1",
+    "dab_alloc_pinned", "dab_free_pinned", "dab_trim_pinned", "dab_alloc_stats",
 ]
 
 
@@ -35,7 +36,7 @@ class Stats(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int64) for n in (
         "n_video_frames", "n_audio_frames", "n_video_selected", "n_audio_queries", "n_table_entries",
         "n_enumerated", "n_candidates", "n_points1", "n_path1", "n_points2", "n_path2",
-        "n_dp2_queries", "n_dp2_refills", "n_dp2_neighbour")]
+        "n_dp2_queries", "n_dp2_refills", "n_dp2_neighbour", "n_dp2_run_points")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
@@ -63,6 +64,13 @@ def load() -> ctypes.CDLL:
     lib = ctypes.CDLL(LIB_PATH)
     vp, i64, i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int
     lib.dab_abi_version.restype = i32
+    lib.dab_alloc_pinned.argtypes = [ctypes.c_size_t]
+    lib.dab_alloc_pinned.restype = vp
+    lib.dab_free_pinned.argtypes = [vp]
+    lib.dab_free_pinned.restype = None
+    lib.dab_trim_pinned.restype = None
+    lib.dab_alloc_stats.argtypes = [ctypes.POINTER(ctypes.c_int64 * 4)]
+    lib.dab_alloc_stats.restype = None
     lib.dab_device_count.restype = i32
     lib.dab_create.argtypes = [i32, ctypes.POINTER(vp)]
     lib.dab_destroy.argtypes = [vp]
@@ -103,6 +111,44 @@ def load() -> ctypes.CDLL:
 
 def _ptr(a):
     return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def alloc_stats() -> dict:
+    out = (ctypes.c_int64 * 4)()
+    load().dab_alloc_stats(ctypes.byref(out))
+    return {"device_allocs": int(out[0]), "device_alloc_ms": out[1] / 1e3, "pinned_allocs": int(out[2]),
+            "pinned_alloc_ms": out[3] / 1e3}
+
+
+class _PinnedBlock:
+    """Owner of one buffer of the library's pinned pool; returns it to the pool when the last
+    numpy view of it is garbage collected."""
+
+    def __init__(self, lib, nbytes):
+        self.lib = lib
+        self.ptr = lib.dab_alloc_pinned(max(int(nbytes), 1))
+        if not self.ptr:
+            raise DabError("dab_alloc_pinned failed (no CUDA device, or out of page-locked memory)")
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                self.lib.dab_free_pinned(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype) -> np.ndarray:
+    """numpy array in page-locked host memory from the library's pool (recycled when freed)."""
+    lib = load()
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) if np.ndim(shape) else int(shape)
+    nbytes = n * dtype.itemsize
+    block = _PinnedBlock(lib, nbytes)
+    buf = (ctypes.c_char * max(nbytes, 1)).from_address(block.ptr)
+    buf._block = block          # the ctypes array (kept alive as the numpy base) keeps the block
+    return np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
 
 
 class Context:
@@ -148,6 +194,20 @@ class Pair:
         ctx.check(self.lib.dab_pair_create(ctx.handle, ctypes.byref(h)))
         self.handle = h
         self._keep = []
+        self._pin = {}      # name -> pinned uint8 staging buffer owned by this pair (grown, never shrunk)
+
+    def _staging(self, name: str, shape, dtype) -> np.ndarray:
+        """View of this pair's page-locked staging buffer `name`.  The buffers persist for the
+        life of the pair, so a batch in steady state never calls cudaHostAlloc (which waits for
+        every kernel on the device); a view is valid until the next call that reuses its name."""
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) if np.ndim(shape) else int(shape)
+        nbytes = n * dtype.itemsize
+        buf = self._pin.get(name)
+        if buf is None or buf.nbytes < nbytes:
+            buf = pinned_empty(max(nbytes + nbytes // 4, 4096), np.uint8)
+            self._pin[name] = buf
+        return buf[:nbytes].view(dtype).reshape(shape)
 
     # ---- features -------------------------------------------------------------------------
     def set_pcm(self, track: int, pcm: np.ndarray):
@@ -183,14 +243,17 @@ class Pair:
         self.ctx.check(self.lib.dab_pair_feature_lens(self.handle, track, ctypes.byref(lens)))
         return [int(x) for x in lens]
 
-    def get_features(self, track: int):
+    def get_features(self, track: int, count: int = 5, copy: bool = True):
+        """The first `count` feature vectors [energy, zero crossings, band 0, band 1, band 2]
+        (the host fit only needs the first three, describealign.py:735).  copy=False returns views
+        of this pair's pinned staging buffers, valid until the pair's next get_features call."""
         lens = (ctypes.c_int64 * 5)()
         self.ctx.check(self.lib.dab_pair_feature_lens(self.handle, track, ctypes.byref(lens)))
-        e = np.empty(lens[0], np.float32); z = np.empty(lens[1], np.float32)
-        b0 = np.empty(lens[2], np.float32); b1 = np.empty(lens[3], np.float32); b2 = np.empty(lens[4], np.float64)
-        self.ctx.check(self.lib.dab_pair_get_features(self.handle, track, _ptr(e), _ptr(z), _ptr(b0), _ptr(b1), _ptr(b2)))
+        dts = (np.float32, np.float32, np.float32, np.float32, np.float64)
+        out = [self._staging(f"feat{track}_{k}", lens[k], dts[k]) if k < count else None for k in range(5)]
+        self.ctx.check(self.lib.dab_pair_get_features(self.handle, track, *[_ptr(a) for a in out]))
         self._keep.clear()
-        return [e, z, b0, b1, b2]
+        return [np.array(a) if copy else a for a in out[:count]]
 
     # ---- stage A ----------------------------------------------------------------------------
     def stage_a(self):
@@ -201,7 +264,7 @@ class Pair:
         return npts.value, npath.value
 
     def path1(self):
-        x = np.empty(self.n_path1, np.int32); y = np.empty(self.n_path1, np.int32)
+        x = self._staging("path1_x", self.n_path1, np.int32); y = self._staging("path1_y", self.n_path1, np.int32)
         self.ctx.check(self.lib.dab_pair_get_path1(self.handle, _ptr(x), _ptr(y)))
         return x.astype(np.int64), y.astype(np.int64)
 
@@ -246,10 +309,14 @@ class Pair:
 
     # ---- stage B ----------------------------------------------------------------------------
     def stage_b(self, audio_scaled: np.ndarray, video_scaled: np.ndarray, plans, n_clusters: int):
-        a = np.ascontiguousarray(audio_scaled, np.float32)
-        v = np.ascontiguousarray(video_scaled, np.float32)
-        if a.ndim != 2 or a.shape[1] != 3 or v.ndim != 2 or v.shape[1] != 3:
+        if np.ndim(audio_scaled) != 2 or np.shape(audio_scaled)[1] != 3 or np.ndim(video_scaled) != 2 or \
+                np.shape(video_scaled)[1] != 3:
             raise ValueError("scaled features must be (n, 3) float32")
+        # staged in pinned memory: the upload is then one asynchronous DMA per array
+        a = self._staging("audio_scaled", np.shape(audio_scaled), np.float32)
+        v = self._staging("video_scaled", np.shape(video_scaled), np.float32)
+        np.copyto(a, audio_scaled, casting="same_kind")
+        np.copyto(v, video_scaled, casting="same_kind")
         plans = [p for p in plans if p[2] > p[1]]
         arr = (Corridor * max(len(plans), 1))()
         for k, (idx, lo, hi, slope, offset) in enumerate(plans):
@@ -262,9 +329,9 @@ class Pair:
         return npts.value, npath.value
 
     def path2(self):
-        rows = np.empty((self.n_path2, 5), np.float64)
+        rows = self._staging("path2", (self.n_path2, 5), np.float64)
         self.ctx.check(self.lib.dab_pair_get_path2(self.handle, _ptr(rows)))
-        return rows
+        return np.array(rows)
 
     def points2(self):
         n = self.n_points2

@@ -16,6 +16,7 @@ libdescribealign_b200.so; without it, or without a CUDA device, these functions 
 from __future__ import annotations
 
 import threading
+import time
 import weakref
 
 import numpy as np
@@ -116,7 +117,15 @@ class AlignJob:
         self.pair = pair if pair is not None else acquire_pair()
         self._own = pair is None
         self.video_features = self.audio_features = None
+        self.want_all_features = False
         self.h2d_bytes = self.d2h_bytes = 0
+        self.host_ms = {}        # wall time of each host-side call of this job (diagnostics)
+
+    def _timed(self, name, fn, *args):
+        t0 = time.perf_counter()
+        out = fn(*args)
+        self.host_ms[name] = self.host_ms.get(name, 0.0) + 1e3 * (time.perf_counter() - t0)
+        return out
 
     # -- inputs ---------------------------------------------------------------------------
     def load_pcm(self, video_pcm, audio_pcm):
@@ -127,8 +136,8 @@ class AlignJob:
                 return _interleaved(p)
             return p
         v, a = prep(video_pcm), prep(audio_pcm)
-        self.pair.set_pcm(VIDEO, v)
-        self.pair.set_pcm(AUDIO, a)
+        self._timed("set_pcm", self.pair.set_pcm, VIDEO, v)
+        self._timed("set_pcm", self.pair.set_pcm, AUDIO, a)
         self.h2d_bytes += v.nbytes + a.nbytes
         self._features_on_device = True
 
@@ -149,22 +158,26 @@ class AlignJob:
     def device_stage_a(self):
         """Features (if PCM was given) + stage A on the device; brings back what the host fit
         needs: the integer pass-1 path and the feature vectors."""
-        self.pair.stage_a()
+        self._timed("stage_a", self.pair.stage_a)
         return self.after_stage_a()
 
     def after_stage_a(self):
         """Length rule of describealign.py:698-699 and the copies the host fit needs."""
         n_path = self.pair.n_path1
         if self.video_features is None:
-            self.video_features = self.pair.get_features(VIDEO)
-            self.audio_features = self.pair.get_features(AUDIO)
+            # the host fit uses the first three features only (describealign.py:735)
+            count = 5 if self.want_all_features else 3
+            # views of the pair's pinned staging unless the caller keeps them (details)
+            keep = self.want_all_features
+            self.video_features = self._timed("get_features", self.pair.get_features, VIDEO, count, keep)
+            self.audio_features = self._timed("get_features", self.pair.get_features, AUDIO, count, keep)
             self.d2h_bytes += sum(f.nbytes for f in self.video_features + self.audio_features)
         self.n_video_energy = len(self.video_features[0])
         self.n_audio_energy = len(self.audio_features[0])
         self.min_len = host_fit.min_path_length(self.n_video_energy, self.n_audio_energy)
         if n_path < self.min_len:
             raise RuntimeError(FAILED_MSG)
-        self.x, self.y = self.pair.path1()
+        self.x, self.y = self._timed("path1", self.pair.path1)
         self.d2h_bytes += 8 * n_path
         return self.x, self.y
 
@@ -180,9 +193,9 @@ class AlignJob:
         self.plans = host_fit.plan_corridors(self.clusters, self.audio_scaled, self.video_scaled)
 
     def device_stage_b(self):
-        self.pair.stage_b(self.audio_scaled, self.video_scaled, self.plans, len(self.clusters))
+        self._timed("stage_b", self.pair.stage_b, self.audio_scaled, self.video_scaled, self.plans, len(self.clusters))
         self.h2d_bytes += self.audio_scaled.nbytes + self.video_scaled.nbytes
-        self.path = self.pair.path2()
+        self.path = self._timed("path2", self.pair.path2)
         self.d2h_bytes += self.path.nbytes
         if len(self.path) < self.min_len:
             raise RuntimeError(FAILED_MSG)
@@ -239,6 +252,7 @@ def align_pcm(video_pcm, audio_desc_pcm, details=None):
     print("  memorizing video...        \r", end='')
     job = AlignJob()
     try:
+        job.want_all_features = details is not None
         job.load_pcm(video_pcm, audio_desc_pcm)
         return job.run(details)
     finally:

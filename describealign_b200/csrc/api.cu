@@ -7,21 +7,61 @@
 
 static std::string g_create_err;
 
+// ---- pinned host memory pool ----------------------------------------------------------------
+// Results (features, paths) are copied device -> host asynchronously; with pageable destinations
+// the runtime stages every copy through its own bounce buffer and serialises the pairs in flight.
+// Buffers are handed out in power-of-two size classes and go back to a free list, so a batch in
+// steady state performs no cudaHostAlloc / cudaFreeHost (both synchronise the device).
+#include <map>
+#include <mutex>
+namespace {
+std::mutex g_pin_mu;
+std::multimap<size_t, void *> g_pin_free;        // size class -> buffer
+std::map<void *, size_t> g_pin_live;             // buffer -> size class
+size_t pin_class(size_t bytes) {
+  size_t c = 4096;
+  while (c < bytes) c <<= 1;
+  return c;
+}
+}  // namespace
+
+#include <atomic>
+#include <chrono>
+static std::atomic<int64_t> g_alloc_calls{0}, g_alloc_us{0}, g_pin_calls{0}, g_pin_us{0};
+static inline int64_t now_us() {
+  return std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// Device buffers only ever grow, and are freed with cudaFreeAsync on the pair's stream: a plain
+// cudaFree would wait for every other pair's kernels (the frontier DPs run for ~0.1 s).
+thread_local cudaStream_t dab_t_stream = nullptr;
+
 int dab_ensure(dab_ctx *ctx, DevBuf &b, size_t bytes) {
   if (bytes <= b.cap && b.p) return DAB_OK;
+  const int64_t t0 = now_us();
+  cudaStream_t st = dab_t_stream;
   if (b.p) {
-    DAB_CUDA(cudaFree(b.p));
+    if (b.pooled && st) DAB_CUDA(cudaFreeAsync(b.p, st));
+    else DAB_CUDA(cudaFree(b.p));
     b.p = nullptr;
     b.cap = 0;
   }
   size_t want = bytes + bytes / 4 + 256;   // head-room so that similar pairs reuse the buffer
-  DAB_CUDA(cudaMalloc(&b.p, want));
+  if (st) {
+    DAB_CUDA(cudaMallocAsync(&b.p, want, st));
+    b.pooled = true;
+  } else {
+    DAB_CUDA(cudaMalloc(&b.p, want));
+    b.pooled = false;
+  }
   b.cap = want;
+  g_alloc_calls += 1;
+  g_alloc_us += now_us() - t0;
   return DAB_OK;
 }
 
 static void free_buf(DevBuf &b) {
-  if (b.p) cudaFree(b.p);
+  if (b.p) cudaFree(b.p);     // also valid for stream-ordered allocations (synchronises)
   b.p = nullptr;
   b.cap = 0;
 }
@@ -29,6 +69,51 @@ static void free_buf(DevBuf &b) {
 extern "C" {
 
 int dab_abi_version(void) { return DAB_ABI_VERSION; }
+
+void *dab_alloc_pinned(size_t bytes) {
+  const size_t c = pin_class(bytes ? bytes : 1);
+  {
+    std::lock_guard<std::mutex> g(g_pin_mu);
+    auto it = g_pin_free.find(c);
+    if (it != g_pin_free.end()) {
+      void *p = it->second;
+      g_pin_free.erase(it);
+      g_pin_live[p] = c;
+      return p;
+    }
+  }
+  void *p = nullptr;
+  const int64_t t0 = now_us();
+  if (cudaHostAlloc(&p, c, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  g_pin_calls += 1;
+  g_pin_us += now_us() - t0;
+  std::lock_guard<std::mutex> g(g_pin_mu);
+  g_pin_live[p] = c;
+  return p;
+}
+
+void dab_free_pinned(void *p) {
+  if (!p) return;
+  std::lock_guard<std::mutex> g(g_pin_mu);
+  auto it = g_pin_live.find(p);
+  if (it == g_pin_live.end()) return;
+  g_pin_free.emplace(it->second, p);
+  g_pin_live.erase(it);
+}
+
+void dab_alloc_stats(int64_t out[4]) {
+  if (!out) return;
+  out[0] = g_alloc_calls; out[1] = g_alloc_us; out[2] = g_pin_calls; out[3] = g_pin_us;
+}
+
+void dab_trim_pinned(void) {
+  std::multimap<size_t, void *> drop;
+  {
+    std::lock_guard<std::mutex> g(g_pin_mu);
+    drop.swap(g_pin_free);
+  }
+  for (auto &kv : drop) cudaFreeHost(kv.second);
+}
 
 int dab_device_count(void) {
   int n = 0;
@@ -59,6 +144,12 @@ int dab_create(int device, dab_ctx **out) {
   ctx->device = device;
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+  cudaMemPool_t pool = nullptr;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
+    uint64_t keep = UINT64_MAX;   // freed buffers stay in the pool instead of going back to the OS
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  cudaGetLastError();
   *out = ctx;
   return DAB_OK;
 }
@@ -127,6 +218,7 @@ int dab_pair_set_pcm(dab_pair *pr, int track, const void *pcm, int64_t samples, 
                      int on_device) {
   if (!pr) return DAB_E_ARG;
   dab_ctx *ctx = pr->ctx;
+  StreamScope scope__(pr->stream);
   if (track < 0 || track > 1 || !pcm || samples < 0 || (channels != 1 && channels != 2) ||
       (format != DAB_PCM_S16 && format != DAB_PCM_F16)) {
     ctx->err = "dab_pair_set_pcm: invalid argument";
@@ -157,6 +249,7 @@ int dab_pair_set_features(dab_pair *pr, int track, const float *energy, int64_t 
                           const float *band0, const float *band1, const double *band2, int64_t n) {
   if (!pr) return DAB_E_ARG;
   dab_ctx *ctx = pr->ctx;
+  StreamScope scope__(pr->stream);
   if (track < 0 || track > 1 || !energy || !zc || !band0 || !band1 || !band2 || n < 0 ||
       (n_energy != n && n_energy != n + 1)) {
     ctx->err = "dab_pair_set_features: invalid argument (len(energy) must be n or n + 1)";
@@ -215,6 +308,7 @@ int dab_pair_get_features(dab_pair *pr, int track, float *energy, float *zc, flo
 int dab_pair_stage_a(dab_pair *pr, int64_t *n_points, int64_t *n_path) {
   if (!pr) return DAB_E_ARG;
   dab_ctx *ctx = pr->ctx;
+  StreamScope scope__(pr->stream);
   for (int t = 0; t < 2; ++t) {
     if (!pr->trk[t].have_features) { ctx->err = "stage_a: features of both tracks are required first"; return DAB_E_STATE; }
     const int64_t lmin = pr->trk[t].Le < pr->trk[t].L ? pr->trk[t].Le : pr->trk[t].L;
@@ -254,6 +348,7 @@ extern "C" {
 
 static int export_points1(dab_pair *pr, int32_t *i_audio, int32_t *v_video, double *qual, int dst_on_device) {
   dab_ctx *ctx = pr->ctx;
+  StreamScope scope__(pr->stream);
   DAB_CUDA(cudaSetDevice(ctx->device));
   const cudaMemcpyKind kind = dst_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
   const int64_t n = pr->n_points1;
@@ -297,6 +392,7 @@ static int check_stage_a_inputs(dab_pair *pr, const char *who) {
 int dab_pair_stage_a_match(dab_pair *pr, int64_t row_lo, int64_t row_hi, int64_t *n_points) {
   if (!pr) return DAB_E_ARG;
   dab_ctx *ctx = pr->ctx;
+  StreamScope scope__(pr->stream);
   if (row_lo < 0 || row_hi < row_lo) { ctx->err = "dab_pair_stage_a_match: invalid row range"; return DAB_E_ARG; }
   DAB_TRY(check_stage_a_inputs(pr, "stage_a_match"));
   DAB_CUDA(cudaSetDevice(ctx->device));
@@ -310,6 +406,7 @@ int dab_pair_import_points1(dab_pair *pr, const int32_t *i_audio, const int32_t 
                             int64_t n, int src_on_device) {
   if (!pr) return DAB_E_ARG;
   dab_ctx *ctx = pr->ctx;
+  StreamScope scope__(pr->stream);
   if (n < 0 || (n > 0 && (!i_audio || !v_video || !qual))) { ctx->err = "dab_pair_import_points1: invalid argument"; return DAB_E_ARG; }
   if (!pr->matched) { ctx->err = "import_points1: run stage_a_match on this pair first (it builds the hashed-frame list)"; return DAB_E_STATE; }
   DAB_CUDA(cudaSetDevice(ctx->device));
@@ -319,6 +416,7 @@ int dab_pair_import_points1(dab_pair *pr, const int32_t *i_audio, const int32_t 
 int dab_pair_dp1(dab_pair *pr, int64_t *n_path) {
   if (!pr) return DAB_E_ARG;
   dab_ctx *ctx = pr->ctx;
+  StreamScope scope__(pr->stream);
   if (!pr->matched) { ctx->err = "dp1: no match points (run stage_a_match / import_points1 first)"; return DAB_E_STATE; }
   DAB_CUDA(cudaSetDevice(ctx->device));
   DAB_TRY(dab_run_stage_a_dp(pr));
@@ -331,6 +429,7 @@ int dab_pair_stage_b(dab_pair *pr, const float *audio_scaled, int64_t n_audio, c
                      int64_t *n_points, int64_t *n_path) {
   if (!pr) return DAB_E_ARG;
   dab_ctx *ctx = pr->ctx;
+  StreamScope scope__(pr->stream);
   if (!audio_scaled || !video_scaled || n_audio <= 0 || n_video <= 8 || n_corridors < 0 || n_clusters < 0 ||
       (n_corridors > 0 && !corridors)) {
     ctx->err = "dab_pair_stage_b: invalid argument";

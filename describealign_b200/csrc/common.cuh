@@ -17,6 +17,7 @@
 struct DevBuf {
   void *p = nullptr;
   size_t cap = 0;
+  bool pooled = false;   // allocated with cudaMallocAsync
   template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
@@ -114,6 +115,14 @@ struct dab_pair {
     if (rc__ != DAB_OK) return rc__; \
   } while (0)
 
+// Device buffers are allocated stream-ordered (cudaMallocAsync / cudaFreeAsync on the stream of the
+// pair whose API call is running): cudaMalloc / cudaFree would wait for every other pair's kernels.
+extern thread_local cudaStream_t dab_t_stream;
+struct StreamScope {
+  cudaStream_t prev;
+  explicit StreamScope(cudaStream_t s) : prev(dab_t_stream) { dab_t_stream = s; }
+  ~StreamScope() { dab_t_stream = prev; }
+};
 int dab_ensure(dab_ctx *ctx, DevBuf &b, size_t bytes);
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -438,10 +438,10 @@ __device__ __forceinline__ Node1 load_node_cg(const Node1 *p) {
 
 // The walk keeps the frontier's top entry (largest cum; ties -> smallest rank) in registers.
 // A point whose rank is >= the top's rank has the top as its predecessor and becomes the new
-// top (quals are > 0): no tree loads, one f64 add on the dependent chain, and one predicated
-// 16-byte store per lane role - lane 0 the leaf, lane 4 the back record, lanes 1-3 the old top
-// into its level-k ancestor, but only when the top leaves that ancestor's block (the ancestors of
-// the current top are implied by the registers; every other node is exact).  Only points left
+// top (quals are > 0): no tree loads, one f64 add on the dependent chain; the leaf, the back
+// record and the old top's level-k ancestors (written only when the top leaves that ancestor's
+// block - the ancestors of the current top are implied by the registers; every other node is
+// exact) are stored lane-parallel for a whole run of such points at a time.  Only points left
 // of the top (false matches, backward jumps) run the full prefix-max query: one 32-node row per
 // level (512 B, coalesced), lanes left of the path feed the query and the lane on the path keeps
 // the old node for the conditional update.
@@ -464,39 +464,66 @@ __global__ void __launch_bounds__(32, 1) dp1_kernel(Dp1Args a) {
     __syncwarp();
     if (base + 32 + lane < n) { rr = a.pt_s[base + 32 + lane]; qq = a.pt_q[base + 32 + lane]; }
     const int cnt = n - base < 32 ? n - base : 32;
-    int r_nx = s_r[buf][0];
-    double q_nx = s_q[buf][0];
-    for (int t = 0; t < cnt; ++t) {
+    // ---- runs of points that each extend the top (rank >= the rank before it) are handled 32 at
+    //      a time: the cums are one sequential chain of f64 adds (exactly the reference's order),
+    //      everything else - back records, leaves, ancestor flushes - is lane-parallel ----------
+    const int my_r = s_r[buf][lane];
+    const int prev_r = lane > 0 ? s_r[buf][lane - 1] : 0;
+    const int next_r = lane + 1 < cnt ? s_r[buf][lane + 1] : -1;
+    const unsigned inc = __ballot_sync(0xffffffffu, lane < cnt && (lane == 0 || my_r >= prev_r));
+    int t = 0;
+    while (t < cnt) {
       const int p = base + t;
-      const int r = r_nx;
-      const double q = q_nx;
-      if (t + 1 < cnt) { r_nx = s_r[buf][t + 1]; q_nx = s_q[buf][t + 1]; }
+      const int r = s_r[buf][t];
+      const double q = s_q[buf][t];
       if (r >= top_rank) {
-        const double cum = top_cum + q;
-        const int ln = top_len + 1;
-        const int cpv = (ln % DP_CHECK == 0 || top_id < 0) ? p : top_cp;
-        // lane 0: leaf <- new top.  lanes 1..3: ancestor of the OLD top when the top leaves its block.
-        // lane 4: back record.
-        int4 val;
-        int4 *dst;
-        bool doit;
-        if (lane == DP_LEVELS) {
-          val.x = top_id; val.y = ln; val.z = cpv; val.w = 0;
-          dst = a.meta + p;
-          doit = true;
-        } else if (lane == 0) {
-          val.x = __double2loint(cum); val.y = __double2hiint(cum); val.z = p; val.w = r;
-          dst = my_level + r;
-          doit = true;
-        } else {
-          val.x = __double2loint(top_cum); val.y = __double2hiint(top_cum); val.z = top_id; val.w = top_rank;
-          dst = my_level + (top_rank >> my_shift);
-          doit = lane < DP_LEVELS && top_id >= 0 && (r >> my_shift) != (top_rank >> my_shift);
+        int len = 1;
+        if (t + 1 < 32) {
+          const unsigned stop = (~inc) >> (t + 1);
+          len += stop ? __ffs(stop) - 1 : 31 - t;
         }
-        if (doit) *dst = val;
-        top_cum = cum; top_id = p; top_rank = r; top_len = ln; top_cp = cpv;
+        if (len > cnt - t) len = cnt - t;
+        double c = top_cum, my_cum = 0.0;
+        for (int u = 0; u < len; ++u) {
+          c = c + s_q[buf][t + u];
+          if (lane == t + u) my_cum = c;
+        }
+        const bool in_run = lane >= t && lane < t + len;
+        const bool first = lane == t;
+        double old_cum = __shfl_up_sync(0xffffffffu, my_cum, 1);
+        int old_id = base + lane - 1, old_rank = prev_r;
+        if (first) { old_cum = top_cum; old_id = top_id; old_rank = top_rank; }
+        const int ln = top_len + 1 + (lane - t);
+        const unsigned fm = __ballot_sync(0xffffffffu, in_run && (ln % DP_CHECK == 0 || (first && top_id < 0)));
+        const unsigned fml = fm & ((2u << lane) - 1u);
+        const int cpv = fml ? base + 31 - __clz(fml) : top_cp;
+        if (in_run) {
+          int4 m; m.x = old_id; m.y = ln; m.z = cpv; m.w = 0;
+          a.meta[base + lane] = m;
+          if (lane == t + len - 1 || next_r != my_r) {       // the last point on a rank owns its leaf
+            Node1 me; me.cum = my_cum; me.id = base + lane; me.rank = my_r;
+            a.level[0][my_r] = me;
+          }
+          if (old_id >= 0) {                                  // the old top leaves ancestor blocks
+#pragma unroll
+            for (int k = 1; k < DP_LEVELS; ++k) {
+              if ((my_r >> (5 * k)) != (old_rank >> (5 * k))) {
+                Node1 me; me.cum = old_cum; me.id = old_id; me.rank = old_rank;
+                a.level[k][old_rank >> (5 * k)] = me;
+              }
+            }
+          }
+        }
+        const int last = t + len - 1;
+        top_cum = __shfl_sync(0xffffffffu, my_cum, last);
+        top_rank = __shfl_sync(0xffffffffu, my_r, last);
+        top_len = __shfl_sync(0xffffffffu, ln, last);
+        top_cp = __shfl_sync(0xffffffffu, cpv, last);
+        top_id = base + last;
+        t += len;
         continue;
       }
+      ++t;
       __syncwarp();   // orders the stores above before the loads below
       Node1 nd[DP_LEVELS];
       int pos[DP_LEVELS];

@@ -425,6 +425,7 @@ struct __align__(16) CorState {
 };
 
 constexpr int RING = 16;     // most recent PM rows kept in shared memory
+constexpr int RUN_MIN = 8;   // shortest run of chain points worth the lane-parallel commit
 constexpr int WAYS = 4;      // window cache: ways per lane
 constexpr int WLEN = 16;     // rows per window
 
@@ -733,7 +734,7 @@ __global__ void __launch_bounds__(32, 1) dp2_lane_kernel(Dp2LArgs a) {
   // frontier top: seed (0, 0, -1, 0, 0) (describealign.py:947); uniform across lanes
   double top_v = 0.0, top_j = 0.0;
   int top_i = -1;
-  unsigned n_query = 0, n_refill = 0, n_near = 0;
+  unsigned n_query = 0, n_refill = 0, n_near = 0, n_runpts = 0;
 
   // F(j) seen from a point of corridor k on row i: lane c' contributes PM_c'[rows of c' with j' <= j]
   auto frontier_query = [&](int i, double j, int k, double &fv_out, int &fi_out) {
@@ -809,12 +810,92 @@ __global__ void __launch_bounds__(32, 1) dp2_lane_kernel(Dp2LArgs a) {
     __syncwarp();
     if (base + 32 + lane < n) rr = a.rec[base + 32 + lane];
     const int cnt = n - base < 32 ? n - base : 32;
-    P2Rec nx = s_rec[buf][0];
-#pragma unroll 1
-    for (int t = 0; t < cnt; ++t) {
+    // ---- runs: consecutive points of ONE corridor that each extend that corridor's best chain,
+    //      while the corridor's last point is also the frontier's top.  Then every point's best
+    //      predecessor is the point before it (cluster best = c0 - 50 < c0, c1 <= c0, frontier top =
+    //      c0 - 1000 < c0), so the cums are one sequential chain of f64 adds - exactly the
+    //      reference's order - and the rest (back records, running-max rows) is lane-parallel. ----
+    const P2Rec own = s_rec[buf][lane];
+    const int own_k = own.kf & 0xff;
+    const int prev_k = lane > 0 ? (s_rec[buf][lane - 1].kf & 0xff) : -1;
+    const bool simple = lane < cnt && (own.kf & (P2_NEAR | P2_GAP | P2_VIS1)) == P2_VIS1 && own.q > 0.0;
+    const unsigned simplemask = __ballot_sync(FULL, simple);
+    const unsigned contmask = __ballot_sync(FULL, simple && own_k == prev_k);
+    int t = 0, no_run_at = -1;       // no_run_at: the point that just ended a run takes the scalar path
+    while (t < cnt) {
+      if (((simplemask >> t) & 1u) && t != no_run_at) {
+        int len = 1;
+        if (t + 1 < 32) {
+          const unsigned stop = (~contmask) >> (t + 1);
+          len += stop ? __ffs(stop) - 1 : 31 - t;
+        }
+        if (len > cnt - t) len = cnt - t;
+        const int k = s_rec[buf][t].kf & 0xff;
+        const bool rising = id0 >= 0 && cl_i == id0 && pm_i == id0 && top_i == id0;
+        if (len >= RUN_MIN && __shfl_sync(FULL, (int)rising, k)) {
+          // state of the corridor's owner lane
+          const double k_c0 = __shfl_sync(FULL, c0, k), k_c1 = __shfl_sync(FULL, c1, k);
+          const double k_cl = __shfl_sync(FULL, cl_v, k), k_pm = __shfl_sync(FULL, pm_v, k);
+          const int k_id0 = __shfl_sync(FULL, id0, k), k_id1 = __shfl_sync(FULL, id1, k);
+          PmEntry *const k_pmrow = reinterpret_cast<PmEntry *>(
+              __shfl_sync(FULL, (unsigned long long)reinterpret_cast<uintptr_t>(pm), k));
+          double c = k_c0, my_cum = 0.0;
+          for (int u = 0; u < len; ++u) {
+            c = c + s_rec[buf][t + u].q;
+            if (lane == t + u) my_cum = c;
+          }
+          const bool in_run = lane >= t && lane < t + len;
+          const bool first = lane == t;
+          double prev_cum = __shfl_up_sync(FULL, my_cum, 1);
+          if (first) prev_cum = k_c0;
+          const int prev_id = first ? k_id0 : base + lane - 1;
+          const double cj = my_cum - 50.0, jump = my_cum - 1000.0;
+          double prev_cj = __shfl_up_sync(FULL, cj, 1), prev_jump = __shfl_up_sync(FULL, jump, 1);
+          if (first) { prev_cj = k_cl; prev_jump = k_pm > top_v ? k_pm : top_v; }
+          // strictly rising in all three derived values, else the scalar rules decide
+          const bool good = in_run && my_cum > prev_cum && cj > prev_cj && jump > prev_jump;
+          const unsigned bad = (~__ballot_sync(FULL, good)) >> t;
+          int glen = bad ? __ffs(bad) - 1 : 32 - t;
+          if (glen > len) glen = len;
+          if (glen > 0) {
+            const int last = t + glen - 1;
+            if (lane >= t && lane <= last) {
+              BackRec b; b.best = prev_cum; b.pred = prev_id; b.pad = 0;
+              a.back[base + lane] = b;
+              PmEntry e; e.val = jump; e.id = base + lane; e.pad = 0;
+              k_pmrow[own.ro] = e;
+              if (lane > last - RING) s_ring[own.ro & (RING - 1)][k] = e;
+            }
+            // new state of the owner lane and the frontier top
+            const int l1 = last - 1 >= t ? last - 1 : t, l2 = last - 2 >= t ? last - 2 : t;
+            const double n_c0 = __shfl_sync(FULL, my_cum, last);
+            const double s1 = __shfl_sync(FULL, my_cum, l1), s2 = __shfl_sync(FULL, my_cum, l2);
+            const double n_cj = __shfl_sync(FULL, cj, last), n_jump = __shfl_sync(FULL, jump, last);
+            const int n_ro = __shfl_sync(FULL, own.ro, last);
+            const double n_j = __shfl_sync(FULL, own.j, last);
+            if (lane == k) {
+              c2 = glen >= 3 ? s2 : (glen == 2 ? k_c0 : k_c1);
+              id2 = glen >= 3 ? base + last - 2 : (glen == 2 ? k_id0 : k_id1);
+              c1 = glen >= 2 ? s1 : k_c0;
+              id1 = glen >= 2 ? base + last - 1 : k_id0;
+              c0 = n_c0; id0 = base + last;
+              cl_v = n_cj; cl_i = base + last;
+              pm_v = n_jump; pm_i = base + last;
+              filled = n_ro;
+            }
+            top_v = n_jump; top_j = n_j; top_i = base + last;
+            n_runpts += glen;
+            __syncwarp();
+            t += glen;
+            no_run_at = t;
+            continue;
+          }
+          no_run_at = t;
+        }
+      }
       const int p = base + t;
-      const P2Rec pt = nx;
-      nx = s_rec[buf][(t + 1) & 31];             // (garbage past cnt: never used)
+      const P2Rec pt = s_rec[buf][t];
+      ++t;
       const double j = pt.j, q = pt.q;
       const int kf = pt.kf, k = kf & 0xff, ro = pt.ro;
       const bool mine = lane == k;
@@ -919,7 +1000,7 @@ __global__ void __launch_bounds__(32, 1) dp2_lane_kernel(Dp2LArgs a) {
   if (lane == 0) {
     a.result[0] = top_i;
     *reinterpret_cast<double *>(a.result + 2) = top_v;
-    a.counters[0] = n_query; a.counters[1] = n_refill; a.counters[2] = n_near;
+    a.counters[0] = n_query; a.counters[1] = n_refill; a.counters[2] = n_near; a.counters[3] = n_runpts;
   }
 }
 
@@ -1068,6 +1149,7 @@ int dab_run_stage_b(dab_pair *pr, int32_t n_cor, int32_t n_clusters) {
     la.back = pr->back2.as<BackRec>();
     la.result = pr->dpres.as<int32_t>();
     la.counters = reinterpret_cast<unsigned long long *>(pr->pmoff2.as<int64_t>() + 32);
+    DAB_CUDA(cudaMemsetAsync(la.counters, 0, 4 * sizeof(unsigned long long), st));
     if (pr->ctx->opt_dp2_impl == 1) dp2_corridor_kernel<<<1, 32, 0, st>>>(la);
     else dp2_lane_kernel<<<1, 32, 0, st>>>(la);
     DAB_CUDA(cudaEventRecord(pr->ev[18], st));
@@ -1088,13 +1170,14 @@ int dab_run_stage_b(dab_pair *pr, int32_t n_cor, int32_t n_clusters) {
     lift_emit_kernel<<<gl, 256, 0, st>>>(ea);
     ctx->launches += 2 + 2 * levels;
     DAB_CUDA(cudaMemcpyAsync(&pr->h_counters[12], pr->dpres.as<int32_t>(), 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    DAB_CUDA(cudaMemcpyAsync(&pr->h_counters[16], la.counters, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    DAB_CUDA(cudaMemcpyAsync(&pr->h_counters[16], la.counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     DAB_CUDA(cudaEventRecord(pr->ev[17], st));
     DAB_CUDA(cudaStreamSynchronize(st));
     n_path = reinterpret_cast<int32_t *>(&pr->h_counters[12])[1];
     pr->stats.n_dp2_queries = pr->h_counters[16];
     pr->stats.n_dp2_refills = pr->h_counters[17];
     pr->stats.n_dp2_neighbour = pr->h_counters[18];
+    pr->stats.n_dp2_run_points = pr->h_counters[19];
   } else if (n_pts > 0) {
     // ---- generic tree DP ----
     // rank domain: 1 + total corridor rows

@@ -28,6 +28,7 @@
 #ifndef DESCRIBEALIGN_B200_H
 #define DESCRIBEALIGN_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -83,10 +84,24 @@ typedef struct {
   int64_t n_dp2_queries;      /* pass-2 points that needed a real frontier query */
   int64_t n_dp2_refills;      /* 16-row refills of the per-corridor running-max windows */
   int64_t n_dp2_neighbour;    /* pass-2 points with another corridor within 2 cells / 2 rows */
+  int64_t n_dp2_run_points;   /* pass-2 points committed by the lane-parallel run path */
 } dab_stats;
 
 int dab_abi_version(void);
 int dab_device_count(void);
+
+/* Page-locked host buffers from a process-wide pool (power-of-two size classes, recycled on free).
+ * Passing such buffers as the host pointers of dab_pair_set_pcm / dab_pair_get_* / dab_pair_stage_b
+ * makes those copies asynchronous DMA instead of staged pageable copies; any host pointer works.
+ * dab_alloc_pinned returns NULL when no CUDA device is available.  dab_trim_pinned releases the
+ * free list back to the driver. */
+void *dab_alloc_pinned(size_t bytes);
+void dab_free_pinned(void *p);
+void dab_trim_pinned(void);
+/* Allocator activity since load: out[0] device (re)allocations, out[1] microseconds spent in them,
+ * out[2] page-locked allocations that missed the pool, out[3] microseconds spent in them.  A batch in
+ * steady state should show no growth: both kinds of call synchronise the whole device. */
+void dab_alloc_stats(int64_t out[4]);
 
 /* device < 0: current device. */
 int dab_create(int device, dab_ctx **out);
