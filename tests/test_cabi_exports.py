@@ -44,7 +44,7 @@ def test_abi_version_and_struct_layout(lib):
     from describealign_b200 import _cabi
     assert lib.dab_abi_version() == 1
     assert ctypes.sizeof(_cabi.Corridor) == 32       # 4 x int32 + 2 x double
-    assert ctypes.sizeof(_cabi.Stats) == 14 * 8
+    assert ctypes.sizeof(_cabi.Stats) == 15 * 8
 
 
 def test_no_cpu_fallback(lib):
