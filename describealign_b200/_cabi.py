@@ -23,7 +23,7 @@ EXPORTS = [
     "dab_pair_get_path1", "dab_pair_get_points1", "dab_pair_stage_b", "dab_pair_get_path2",
     "dab_pair_get_points2", "dab_pair_get_stats", "dab_pair_get_timings", "dab_launch_count",
     "dab_pair_stage_a_match", "dab_pair_export_points1", "dab_pair_import_points1", "dab_pair_dp1",
-    "dab_alloc_pinned", "dab_free_pinned", "dab_trim_pinned", "dab_alloc_stats",
+    "dab_alloc_pinned", "dab_free_pinned", "dab_trim_pinned", "dab_alloc_stats", "dab_host_copy",
 ]
 
 
@@ -43,7 +43,8 @@ class Stats(ctypes.Structure):
 
 
 TIMING_SLOTS = ("features_video", "features_audio", "prep_codes", "tables", "gate", "score",
-                "dp1_trace", "corridors", "dp2_trace", "dp2")
+                "dp1_trace", "corridors", "dp2_trace", "dp2",
+                "host_in_set_pcm", "host_in_stage_a", "host_in_stage_b", "host_in_get")
 
 _lib = None
 
@@ -69,6 +70,8 @@ def load() -> ctypes.CDLL:
     lib.dab_free_pinned.argtypes = [vp]
     lib.dab_free_pinned.restype = None
     lib.dab_trim_pinned.restype = None
+    lib.dab_host_copy.argtypes = [vp, vp, ctypes.c_size_t]
+    lib.dab_host_copy.restype = None
     lib.dab_alloc_stats.argtypes = [ctypes.POINTER(ctypes.c_int64 * 4)]
     lib.dab_alloc_stats.restype = None
     lib.dab_device_count.restype = i32
@@ -111,6 +114,20 @@ def load() -> ctypes.CDLL:
 
 def _ptr(a):
     return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def host_copy(dst: np.ndarray, src: np.ndarray):
+    """dst[...] = src for two C-contiguous arrays of equal byte size, outside the interpreter lock
+    (numpy's own copy holds it, which serialises the worker threads of a batch)."""
+    if dst.nbytes != src.nbytes or not dst.flags.c_contiguous or not src.flags.c_contiguous:
+        raise ValueError("host_copy needs C-contiguous arrays of equal size")
+    if dst.nbytes:
+        load().dab_host_copy(_ptr(dst), _ptr(src), dst.nbytes)
+    return dst
+
+
+def copied(src: np.ndarray) -> np.ndarray:
+    return host_copy(np.empty(src.shape, src.dtype), src)
 
 
 def alloc_stats() -> dict:
@@ -253,7 +270,7 @@ class Pair:
         out = [self._staging(f"feat{track}_{k}", lens[k], dts[k]) if k < count else None for k in range(5)]
         self.ctx.check(self.lib.dab_pair_get_features(self.handle, track, *[_ptr(a) for a in out]))
         self._keep.clear()
-        return [np.array(a) if copy else a for a in out[:count]]
+        return [copied(a) if copy else a for a in out[:count]]
 
     # ---- stage A ----------------------------------------------------------------------------
     def stage_a(self):
@@ -315,8 +332,11 @@ class Pair:
         # staged in pinned memory: the upload is then one asynchronous DMA per array
         a = self._staging("audio_scaled", np.shape(audio_scaled), np.float32)
         v = self._staging("video_scaled", np.shape(video_scaled), np.float32)
-        np.copyto(a, audio_scaled, casting="same_kind")
-        np.copyto(v, video_scaled, casting="same_kind")
+        for dst, src in ((a, audio_scaled), (v, video_scaled)):
+            if isinstance(src, np.ndarray) and src.dtype == np.float32 and src.flags.c_contiguous:
+                host_copy(dst, src)
+            else:
+                np.copyto(dst, src, casting="same_kind")
         plans = [p for p in plans if p[2] > p[1]]
         arr = (Corridor * max(len(plans), 1))()
         for k, (idx, lo, hi, slope, offset) in enumerate(plans):
@@ -331,7 +351,7 @@ class Pair:
     def path2(self):
         rows = self._staging("path2", (self.n_path2, 5), np.float64)
         self.ctx.check(self.lib.dab_pair_get_path2(self.handle, _ptr(rows)))
-        return np.array(rows)
+        return copied(rows)
 
     def points2(self):
         n = self.n_points2

@@ -125,7 +125,7 @@ def gpu_runner(pair):
         job.close()
 
 
-def run_local(pairs, in_flight: int = 8, runner: Callable | None = None):
+def run_local(pairs, in_flight: int = 24, runner: Callable | None = None):
     """Run `pairs` on this process's GPU with up to `in_flight` pairs in progress at once.
     A pair that fails (e.g. RuntimeError("Alignment failed, ...")) yields its exception."""
     runner = gpu_runner if runner is None else runner
@@ -142,7 +142,7 @@ def run_local(pairs, in_flight: int = 8, runner: Callable | None = None):
         return list(ex.map(one, pairs))
 
 
-def align_batch(pairs, durations: Sequence[float] | None = None, in_flight: int = 8, group=None,
+def align_batch(pairs, durations: Sequence[float] | None = None, in_flight: int = 24, group=None,
                 runner: Callable | None = None):
     """Align a list of (video_pcm, description_pcm) pairs (or zero-argument loaders returning
     such a pair) over all ranks of the current process group.

@@ -35,6 +35,7 @@ static inline int64_t now_us() {
 // Device buffers only ever grow, and are freed with cudaFreeAsync on the pair's stream: a plain
 // cudaFree would wait for every other pair's kernels (the frontier DPs run for ~0.1 s).
 thread_local cudaStream_t dab_t_stream = nullptr;
+int64_t ApiTimer::now() { return now_us(); }
 
 int dab_ensure(dab_ctx *ctx, DevBuf &b, size_t bytes) {
   if (bytes <= b.cap && b.p) return DAB_OK;
@@ -99,6 +100,10 @@ void dab_free_pinned(void *p) {
   if (it == g_pin_live.end()) return;
   g_pin_free.emplace(it->second, p);
   g_pin_live.erase(it);
+}
+
+void dab_host_copy(void *dst, const void *src, size_t bytes) {
+  if (dst && src && bytes) memcpy(dst, src, bytes);
 }
 
 void dab_alloc_stats(int64_t out[4]) {
@@ -219,6 +224,7 @@ int dab_pair_set_pcm(dab_pair *pr, int track, const void *pcm, int64_t samples, 
   if (!pr) return DAB_E_ARG;
   dab_ctx *ctx = pr->ctx;
   StreamScope scope__(pr->stream);
+  ApiTimer timer__(&pr->api_us[0]);
   if (track < 0 || track > 1 || !pcm || samples < 0 || (channels != 1 && channels != 2) ||
       (format != DAB_PCM_S16 && format != DAB_PCM_F16)) {
     ctx->err = "dab_pair_set_pcm: invalid argument";
@@ -230,6 +236,7 @@ int dab_pair_set_pcm(dab_pair *pr, int track, const void *pcm, int64_t samples, 
   tk.ch = channels;
   tk.have_features = false;
   pr->matched = false;
+  if (track == DAB_TRACK_VIDEO) { pr->api_us[1] = pr->api_us[2] = pr->api_us[3] = 0; }
   const void *d_pcm = pcm;
   cudaEvent_t e0 = pr->ev[2 * track], e1 = pr->ev[2 * track + 1];
   if (!on_device) {
@@ -250,6 +257,7 @@ int dab_pair_set_features(dab_pair *pr, int track, const float *energy, int64_t 
   if (!pr) return DAB_E_ARG;
   dab_ctx *ctx = pr->ctx;
   StreamScope scope__(pr->stream);
+  ApiTimer timer__(&pr->api_us[0]);
   if (track < 0 || track > 1 || !energy || !zc || !band0 || !band1 || !band2 || n < 0 ||
       (n_energy != n && n_energy != n + 1)) {
     ctx->err = "dab_pair_set_features: invalid argument (len(energy) must be n or n + 1)";
@@ -290,6 +298,7 @@ int dab_pair_get_features(dab_pair *pr, int track, float *energy, float *zc, flo
                           double *band2) {
   if (!pr || track < 0 || track > 1) return DAB_E_ARG;
   dab_ctx *ctx = pr->ctx;
+  ApiTimer timer__(&pr->api_us[3]);
   Track &tk = pr->trk[track];
   if (!tk.have_features) { ctx->err = "no features computed for this track"; return DAB_E_STATE; }
   DAB_CUDA(cudaSetDevice(ctx->device));
@@ -309,6 +318,7 @@ int dab_pair_stage_a(dab_pair *pr, int64_t *n_points, int64_t *n_path) {
   if (!pr) return DAB_E_ARG;
   dab_ctx *ctx = pr->ctx;
   StreamScope scope__(pr->stream);
+  ApiTimer timer__(&pr->api_us[1]);
   for (int t = 0; t < 2; ++t) {
     if (!pr->trk[t].have_features) { ctx->err = "stage_a: features of both tracks are required first"; return DAB_E_STATE; }
     const int64_t lmin = pr->trk[t].Le < pr->trk[t].L ? pr->trk[t].Le : pr->trk[t].L;
@@ -325,6 +335,7 @@ int dab_pair_stage_a(dab_pair *pr, int64_t *n_points, int64_t *n_path) {
 int dab_pair_get_path1(dab_pair *pr, int32_t *x_audio, int32_t *y_video) {
   if (!pr) return DAB_E_ARG;
   dab_ctx *ctx = pr->ctx;
+  ApiTimer timer__(&pr->api_us[3]);
   DAB_CUDA(cudaSetDevice(ctx->device));
   const size_t bytes = sizeof(int32_t) * (size_t)pr->n_path1;
   if (bytes) {
@@ -349,6 +360,7 @@ extern "C" {
 static int export_points1(dab_pair *pr, int32_t *i_audio, int32_t *v_video, double *qual, int dst_on_device) {
   dab_ctx *ctx = pr->ctx;
   StreamScope scope__(pr->stream);
+  ApiTimer timer__(&pr->api_us[3]);
   DAB_CUDA(cudaSetDevice(ctx->device));
   const cudaMemcpyKind kind = dst_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
   const int64_t n = pr->n_points1;
@@ -393,6 +405,7 @@ int dab_pair_stage_a_match(dab_pair *pr, int64_t row_lo, int64_t row_hi, int64_t
   if (!pr) return DAB_E_ARG;
   dab_ctx *ctx = pr->ctx;
   StreamScope scope__(pr->stream);
+  ApiTimer timer__(&pr->api_us[1]);
   if (row_lo < 0 || row_hi < row_lo) { ctx->err = "dab_pair_stage_a_match: invalid row range"; return DAB_E_ARG; }
   DAB_TRY(check_stage_a_inputs(pr, "stage_a_match"));
   DAB_CUDA(cudaSetDevice(ctx->device));
@@ -417,6 +430,7 @@ int dab_pair_dp1(dab_pair *pr, int64_t *n_path) {
   if (!pr) return DAB_E_ARG;
   dab_ctx *ctx = pr->ctx;
   StreamScope scope__(pr->stream);
+  ApiTimer timer__(&pr->api_us[1]);
   if (!pr->matched) { ctx->err = "dp1: no match points (run stage_a_match / import_points1 first)"; return DAB_E_STATE; }
   DAB_CUDA(cudaSetDevice(ctx->device));
   DAB_TRY(dab_run_stage_a_dp(pr));
@@ -430,6 +444,7 @@ int dab_pair_stage_b(dab_pair *pr, const float *audio_scaled, int64_t n_audio, c
   if (!pr) return DAB_E_ARG;
   dab_ctx *ctx = pr->ctx;
   StreamScope scope__(pr->stream);
+  ApiTimer timer__(&pr->api_us[2]);
   if (!audio_scaled || !video_scaled || n_audio <= 0 || n_video <= 8 || n_corridors < 0 || n_clusters < 0 ||
       (n_corridors > 0 && !corridors)) {
     ctx->err = "dab_pair_stage_b: invalid argument";
@@ -482,6 +497,7 @@ int dab_pair_stage_b(dab_pair *pr, const float *audio_scaled, int64_t n_audio, c
 int dab_pair_get_path2(dab_pair *pr, double *rows) {
   if (!pr) return DAB_E_ARG;
   dab_ctx *ctx = pr->ctx;
+  ApiTimer timer__(&pr->api_us[3]);
   DAB_CUDA(cudaSetDevice(ctx->device));
   if (rows && pr->n_path2 > 0)
     DAB_CUDA(cudaMemcpyAsync(rows, pr->path2.p, sizeof(double) * 5 * (size_t)pr->n_path2, cudaMemcpyDeviceToHost, pr->stream));
@@ -492,6 +508,7 @@ int dab_pair_get_path2(dab_pair *pr, double *rows) {
 int dab_pair_get_points2(dab_pair *pr, int32_t *i_audio, double *j_video, int32_t *cluster, double *qual) {
   if (!pr) return DAB_E_ARG;
   dab_ctx *ctx = pr->ctx;
+  ApiTimer timer__(&pr->api_us[3]);
   DAB_CUDA(cudaSetDevice(ctx->device));
   const size_t n = (size_t)pr->n_points2;
   cudaStream_t st = pr->stream;
@@ -522,6 +539,7 @@ int dab_pair_get_timings(dab_pair *pr, float ms[16]) {
       float t = 0.0f;
       if (cudaEventElapsedTime(&t, pr->ev[2 * s], pr->ev[2 * s + 1]) == cudaSuccess) ms[s] = t;
     }
+    if (s >= 10 && s <= 13) ms[s] = (float)(pr->api_us[s - 10] / 1e3);
     if (s == 9 && pr->ev_used[8]) {
       float t = 0.0f;
       if (cudaEventElapsedTime(&t, pr->ev[16], pr->ev[18]) == cudaSuccess) ms[s] = t;

@@ -95,6 +95,17 @@ struct dab_pair {
   bool ev_used[16] = {};
   // pinned host mirror of small results
   int64_t *h_counters = nullptr;
+  // host time spent inside the library's calls for this pair since the last set_pcm (microseconds):
+  // [0] set_pcm / set_features, [1] stage A, [2] stage B, [3] get_* copies
+  int64_t api_us[4] = {0, 0, 0, 0};
+};
+
+struct ApiTimer {
+  int64_t *slot;
+  int64_t t0;
+  static int64_t now();
+  explicit ApiTimer(int64_t *s) : slot(s), t0(now()) {}
+  ~ApiTimer() { *slot += now() - t0; }
 };
 
 #define DAB_CUDA(call)                                                                     \

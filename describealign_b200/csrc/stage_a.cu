@@ -876,6 +876,7 @@ int dab_run_stage_a_dp(dab_pair *pr) {
     da.meta = pr->back1.as<int4>();
     da.result = pr->dpres.as<int32_t>();
     dp1_kernel<<<1, 32, 0, st>>>(da);
+    DAB_CUDA(cudaStreamSynchronize(st));   // keep dependents of the serial DP out of the hardware queues (see stage_b.cu)
     TraceArgs ta;
     ta.meta = da.meta; ta.result = da.result;
     ta.pt_i = pr->pt_i.as<int32_t>(); ta.pt_s = pr->pt_s.as<int32_t>(); ta.v_sel = V.nq_list.as<int32_t>();

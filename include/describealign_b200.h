@@ -98,6 +98,9 @@ int dab_device_count(void);
 void *dab_alloc_pinned(size_t bytes);
 void dab_free_pinned(void *p);
 void dab_trim_pinned(void);
+/* Plain host memcpy.  Exists so that a Python host can move results between its pinned staging
+ * buffers and ordinary arrays without holding the interpreter lock (ctypes releases it). */
+void dab_host_copy(void *dst, const void *src, size_t bytes);
 /* Allocator activity since load: out[0] device (re)allocations, out[1] microseconds spent in them,
  * out[2] page-locked allocations that missed the pool, out[3] microseconds spent in them.  A batch in
  * steady state should show no growth: both kinds of call synchronise the whole device. */
@@ -176,7 +179,9 @@ int dab_pair_get_stats(dab_pair *pair, dab_stats *out);
 /* Device-side time of the kernels of the last stage_a / stage_b / set_pcm call on this pair,
  * in milliseconds, measured with CUDA events on the pair's stream; slots:
  * 0 features(video) 1 features(audio) 2 prep+codes 3 tables 4 gate 5 score 6 dp1+traceback
- * 7 corridor scoring 8 dp2+traceback 9 dp2 alone.  Slots not run since creation are 0. */
+ * 7 corridor scoring 8 dp2+traceback 9 dp2 alone; and HOST wall time spent inside the library for
+ * this pair since its last video set_pcm: 10 set_pcm/set_features 11 stage A 12 stage B 13 get_*
+ * copies.  Slots not run since creation are 0. */
 int dab_pair_get_timings(dab_pair *pair, float ms[16]);
 /* number of kernel launches issued by this context since creation */
 int64_t dab_launch_count(const dab_ctx *ctx);

@@ -319,3 +319,45 @@ def test_long_pair_two_gpus():
                          capture_output=True, text=True, timeout=900)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     assert "long pair ok" in res.stdout
+
+
+@pytest.mark.parametrize("name,scale", [("C1", 1.0), ("C3", 0.12), ("C4", 0.05)])
+def test_baseline_config_shapes_vs_oracle(gpu_ctx, name, scale):
+    """BASELINE.json's other configurations (trimmed-media stand-in at full size; the stereo
+    --stretch_audio shape and a batch episode at reduced length) through the public API against
+    the oracle on identical PCM."""
+    from describealign_b200 import api, host_fit, synth
+    from oracle import align_oracle as ao, features as of
+    v, a = synth.config_pair(name, 3, scale)
+    nx, ny, sim, path, med = api.align_pcm(v, a)
+    V, A = of.all_features(v), of.all_features(a)
+    ox, oy, osim, opath, omed = ao.align(V, A, V[0], A[0], host_fit)
+    assert path.shape == opath.shape
+    assert np.array_equal(path[:, 1], opath[:, 1]) and np.array_equal(path[:, 2], opath[:, 2])
+    np.testing.assert_allclose(path[:, 0], opath[:, 0], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(nx, ox, rtol=0, atol=1e-9)
+    np.testing.assert_allclose(ny, oy, rtol=0, atol=1e-9)
+    assert abs(sim - osim) < 1e-9 and med == omed
+    # start offset as the reference's report prints it (describealign.py:211-214)
+    assert round(float(ny[0] - nx[0]), 4) == round(float(oy[0] - ox[0]), 4)
+
+
+def test_batch_run_local_matches_sequential(gpu_ctx):
+    """Several pairs in flight on one GPU (batch.run_local, one CUDA stream per pair) give the
+    results of running them one after the other; a mismatched pair yields its exception."""
+    from describealign_b200 import api, batch, synth
+    specs = [(45.0, 4.0, [(20.0, 1.5)], 11), (75.0, 6.0, [(30.0, 2.0)], 7), (40.0, 3.0, [], 12), (60.0, 2.0, [(25.0, -1.0)], 14)]
+    pairs = [synth.make_pair(vs, off, skips=sk, seed=sd) for vs, off, sk, sd in specs]
+    bad_v, _ = synth.make_pair(60.0, 1.0, seed=201)
+    _, bad_a = synth.make_pair(60.0, 1.0, seed=202)
+    pairs.append((bad_v, bad_a))
+    got = batch.run_local(pairs, in_flight=4)
+    assert isinstance(got[-1], RuntimeError) and "Alignment failed" in str(got[-1])
+    for pair, res in zip(pairs[:-1], got[:-1]):
+        assert not isinstance(res, Exception), res
+        want = api.align_pcm(*pair)
+        np.testing.assert_array_equal(res[0], want[0])
+        np.testing.assert_array_equal(res[1], want[1])
+        np.testing.assert_array_equal(res[3], want[3])
+        assert res[2] == want[2] and res[4] == want[4]
+    assert batch.align_batch(pairs[:2], in_flight=2)[1][2] == got[1][2]     # world size 1: no process group needed
