@@ -346,7 +346,9 @@ def run_ours(args, rank, world, local_rank):
         cpu_s, fit_s, o = cpu_pass(pairs[0], keep=True)
         # one more (untimed) pass of pair 0 through the public API, keeping its intermediates
         det = {}
-        nx, ny, sim, path, med = api.align_pcm(pairs[0][0], pairs[0][1], details=det)
+        import contextlib
+        with contextlib.redirect_stdout(sys.stderr):     # progress labels (describealign.py:604,635,726,860) stay off the JSON line
+            nx, ny, sim, path, med = api.align_pcm(pairs[0][0], pairs[0][1], details=det)
 
         class _J:
             video_features, audio_features = det["video_features"], det["audio_features"]
