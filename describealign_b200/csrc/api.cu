@@ -164,7 +164,7 @@ void dab_destroy(dab_ctx *ctx) { delete ctx; }
 int dab_set_option(dab_ctx *ctx, const char *name, int64_t value) {
   if (!ctx || !name) return DAB_E_ARG;
   if (strcmp(name, "dp2_generic") == 0) { ctx->opt_dp2_generic = value != 0; return DAB_OK; }
-  if (strcmp(name, "dp2_impl") == 0 && value >= 0 && value <= 2) { ctx->opt_dp2_impl = (int)value; return DAB_OK; }
+  if (strcmp(name, "dp2_impl") == 0 && value >= 0 && value <= 3) { ctx->opt_dp2_impl = (int)value; return DAB_OK; }
   ctx->err = std::string("dab_set_option: unknown option ") + name;
   return DAB_E_ARG;
 }

@@ -27,7 +27,7 @@ struct dab_ctx {
   int64_t launches = 0;
   int sm_count = 148;
   int opt_dp2_generic = 0;   // force the tree DP for pass 2 (testing)
-  int opt_dp2_impl = 0;      // 0 lane-per-corridor kernel, 1 corridor-state kernel, 2 tree DP (all exact)
+  int opt_dp2_impl = 0;      // 0 block kernel, 1 corridor-state kernel, 2 tree DP, 3 lane-per-corridor kernel (all exact)
 };
 
 // Features and prep data of one track, device resident.

@@ -1005,6 +1005,455 @@ __global__ void __launch_bounds__(32, 1) dp2_lane_kernel(Dp2LArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------
+// DP #2, block formulation (the product path).  State and one-point rules are those of
+// dp2_lane_kernel (lane l owns corridor l); what changes is that up to 32 consecutive points are
+// evaluated together instead of one after the other (tools/dp2_block_model.py is an executable
+// statement of the control flow, checked against the sequential rules on full-size inputs):
+//   * a corridor whose last cum lies well above the frontier's best value ("leader") cannot take a
+//     frontier jump: its owner lane walks ITS points of the block with the local rules only
+//     (cluster best, the corridor's previous two points) - all leaders at once, each in its lane;
+//   * the frontier's best entry before every point of the block is a prefix arg-max over the
+//     leaders' new entries (warp scan, lane = point);
+//   * the other corridors ("followers") need the frontier: its best entry when that lies at
+//     j' <= j, else F(j) = best entry with j' <= j, computed by the point's lane from the running-max
+//     rows written before the block (one L2 read per corridor that can matter) and the leaders'
+//     entries of the block; then their owner lanes walk their points with the full rules;
+//   * lane = point again: every assumption is checked (leaders: frontier best <= what they chose
+//     from; followers: their new entry stays below the frontier's best, and no follower entry of
+//     the block could have been a candidate of a queried point).  The points before the first
+//     failed check are committed - by induction they are exactly what the sequential rules give -
+//     and the failing point, like every point flagged NEAR or GAP, takes the one-point path.
+// Every cum is still "chosen predecessor value + qual" in the reference's order, so values and
+// decisions are bit-identical; only the evaluation schedule changed.
+// ------------------------------------------------------------------------------------------
+constexpr int MIN_BLOCK = 4;            // shortest range worth a block evaluation
+constexpr double LEAD_MARGIN = 500.0;   // leader: last cum >= frontier best + margin (a heuristic; checked per point)
+
+__global__ void __launch_bounds__(32, 1) dp2_block_kernel(Dp2LArgs a) {
+  __shared__ PmEntry s_ring[RING][32];          // [row & 15][corridor]: last 16 running-max rows
+  __shared__ PmEntry s_win[32][WAYS * WLEN];    // per-lane window cache of older rows
+  __shared__ P2Rec s_rec[2][32];
+  // per corridor: line, extent, running-max rows; and the state at the start of the current block
+  __shared__ double s_csl[32], s_cof[32], s_cinv[32], s_headv[32];
+  __shared__ int s_clo[32], s_crows[32], s_fill0[32], s_headi[32];
+  __shared__ PmEntry *s_pmbase[32];
+  __shared__ unsigned s_mask[32];               // points of each corridor in the current block
+  // per point of the current block (index = lane of the point)
+  __shared__ double s_best[32], s_m[32], s_cum[32], s_pmv[32], s_topv[32], s_topj[32], s_fv[32];
+  __shared__ int s_pred[32], s_pmi[32], s_topi[32], s_fi[32];
+
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x;
+  const int n = a.n_points;
+  const int n_cor = a.n_cor;
+  const double NEG = -INFINITY;
+
+  // ---- this lane's corridor -----------------------------------------------------------------
+  const bool have = lane < n_cor;
+  int lo = 0x7fffffff, rows = 0, cluster = -1;
+  double sl = 1.0, of = 0.0, inv = 1.0;
+  PmEntry *pm = a.pm;
+  if (have) {
+    const dab_corridor c = a.cor[lane];
+    lo = c.lo; rows = c.hi > c.lo ? c.hi - c.lo : 0; cluster = c.cluster;
+    sl = c.slope; of = c.offset; inv = 1.0 / c.slope;
+    pm = a.pm + a.pm_off[lane];
+  }
+  s_csl[lane] = sl; s_cof[lane] = of; s_cinv[lane] = inv;
+  s_clo[lane] = lo; s_crows[lane] = rows; s_pmbase[lane] = pm;
+  double c0 = NEG, c1 = NEG, c2 = NEG;          // cums of the corridor's last three points
+  int id0 = -2, id1 = -2, id2 = -2;
+  double cl_v = -1000.0; int cl_i = -1;          // clusters_best_so_far seed (describealign.py:948)
+  double pm_v = NEG; int pm_i = -2;              // head of the running maximum of cum - 1000
+  int filled = -1;                               // last running-max row written
+  int wbase[WAYS], wnext = 0;
+#pragma unroll
+  for (int w = 0; w < WAYS; ++w) wbase[w] = -0x40000000;
+  // frontier top: seed (0, 0, -1, 0, 0) (describealign.py:947); uniform across lanes
+  double top_v = 0.0, top_j = 0.0;
+  int top_i = -1;
+  unsigned n_query = 0, n_refill = 0, n_near = 0, n_blockpts = 0;
+
+  // F(j) seen from a point of corridor k on row i: lane c' contributes PM_c'[rows of c' with j' <= j]
+  auto frontier_query = [&](int i, double j, int k, double &fv_out, int &fi_out) {
+    double v = NEG;
+    int id = -2;
+    if (lane == k) { v = 0.0; id = -1; }          // the frontier's seed entry, j' = 0
+    else if (have && lo <= i) {
+      double est = floor((j - of) * inv) - (double)lo + 1.0;
+      int kk = est < 0.0 ? 0 : (est > (double)rows ? rows : (int)est);
+      while (kk < rows && __dadd_rn(__dmul_rn(sl, (double)(lo + kk)), of) <= j) ++kk;
+      while (kk > 0 && __dadd_rn(__dmul_rn(sl, (double)(lo + kk - 1)), of) > j) --kk;
+      const int done = (i + 1 < lo + rows ? i + 1 : lo + rows) - lo;   // rows <= i
+      const int idx = kk < done ? kk : done;
+      const int f = filled;
+      if (idx > 0 && f >= 0) {
+        const int x = idx - 1;
+        if (x >= f) { v = pm_v; id = pm_i; }
+        else if (x > f - RING) { const PmEntry e = s_ring[x & (RING - 1)][lane]; v = e.val; id = e.id; }
+        else {
+          int hit = -1;
+#pragma unroll
+          for (int w = 0; w < WAYS; ++w) if (x >= wbase[w] && x < wbase[w] + WLEN) hit = w;
+          if (hit < 0) {
+            hit = wnext; wnext = (wnext + 1) & (WAYS - 1);
+            ++n_refill;
+            const PmEntry *src = pm + x;                   // rows x .. x+15 < f are final
+#pragma unroll
+            for (int e = 0; e < WLEN; ++e) {
+              const int4 raw = __ldcg(reinterpret_cast<const int4 *>(src + e));
+              *reinterpret_cast<int4 *>(&s_win[lane][hit * WLEN + e]) = raw;
+            }
+#pragma unroll
+            for (int w = 0; w < WAYS; ++w) if (w == hit) wbase[w] = x;
+          }
+          int wb = 0;
+#pragma unroll
+          for (int w = 0; w < WAYS; ++w) if (w == hit) wb = wbase[w];
+          const PmEntry e = s_win[lane][hit * WLEN + (x - wb)];
+          v = e.val; id = e.id;
+        }
+      }
+    }
+    // warp arg-max on (val desc, j' asc, id asc)
+    const unsigned long long ob = order_bits(v);
+    const unsigned hi = (unsigned)(ob >> 32), lo32 = (unsigned)ob;
+    const unsigned mhi = __reduce_max_sync(FULL, hi);
+    bool alive = hi == mhi;
+    const unsigned mlo = __reduce_max_sync(FULL, alive ? lo32 : 0u);
+    alive = alive && lo32 == mlo;
+    unsigned bal = __ballot_sync(FULL, alive);
+    if (__popc(bal) > 1) {
+      const double jj = !alive ? INFINITY : (id < 0 ? 0.0 : a.p_j[id]);
+      const unsigned long long jb = (unsigned long long)__double_as_longlong(jj);   // jj >= 0
+      const unsigned jh = (unsigned)(jb >> 32), jl = (unsigned)jb;
+      const unsigned nh = __reduce_min_sync(FULL, alive ? jh : 0xffffffffu);
+      alive = alive && jh == nh;
+      const unsigned nl = __reduce_min_sync(FULL, alive ? jl : 0xffffffffu);
+      alive = alive && jl == nl;
+      const unsigned ni = __reduce_min_sync(FULL, alive ? (unsigned)(id + 2) : 0xffffffffu);
+      alive = alive && (unsigned)(id + 2) == ni;
+      bal = __ballot_sync(FULL, alive);
+    }
+    const int src = __ffs(bal) - 1;
+    fv_out = __shfl_sync(FULL, v, src);
+    fi_out = __shfl_sync(FULL, id, src);
+  };
+
+  P2Rec rr;
+  if (lane < n) rr = a.rec[lane];
+  for (int base = 0; base < n; base += 32) {
+    const int buf = (base >> 5) & 1;
+    s_rec[buf][lane] = rr;
+    __syncwarp();
+    if (base + 32 + lane < n) rr = a.rec[base + 32 + lane];
+    const int cnt = n - base < 32 ? n - base : 32;
+    const P2Rec own = s_rec[buf][lane];
+    const int own_k = own.kf & 0xff;
+    // points a block may not contain: NEAR / GAP points, and the lanes past the last point
+    const unsigned hard = __ballot_sync(FULL, lane >= cnt || (own.kf & (P2_NEAR | P2_GAP)) != 0);
+
+    // the owner lane's walk over its points `todo` of the block: local rules, plus the frontier
+    // candidate prepared per point (s_topv/j/i, s_fv/s_fi) when with_frontier.  No warp-level
+    // operation inside: lanes run it divergently.
+    auto own_pass = [&](unsigned todo, const bool with_frontier) {
+      while (todo) {
+        const int u = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const P2Rec r = s_rec[buf][u];
+        const int kf = r.kf;
+        double m = cl_v;
+        int mi = cl_i;
+        const bool t2 = (kf & P2_VIS2) && c1 >= m;
+        m = t2 ? c1 : m; mi = t2 ? id1 : mi;
+        const bool t1 = (kf & P2_VIS1) && c0 >= m;
+        m = t1 ? c0 : m; mi = t1 ? id0 : mi;
+        double best = m;
+        int pred = mi;
+        if (with_frontier) {
+          double fv = NEG;
+          int fi = -2;
+          if (s_topj[u] <= r.j) { fv = s_topv[u]; fi = s_topi[u]; }     // the top entry is F(j) itself
+          else if (kf & P2_MAYQ) { fv = s_fv[u]; fi = s_fi[u]; }
+          if (fv > m) { best = fv; pred = fi; }
+        }
+        const double cum = best + r.q;
+        const int p = base + u;
+        c2 = c1; id2 = id1; c1 = c0; id1 = id0; c0 = cum; id0 = p;
+        const double cj = cum - 50.0;
+        if (cl_v < cj) { cl_v = cj; cl_i = p; }
+        const double jump = cum - 1000.0;
+        if (jump > pm_v) { pm_v = jump; pm_i = p; }
+        filled = r.ro;
+        s_best[u] = best; s_pred[u] = pred; s_m[u] = m; s_cum[u] = cum; s_pmv[u] = pm_v; s_pmi[u] = pm_i;
+      }
+    };
+
+    int t = 0;
+    while (t < cnt) {
+      const unsigned stopbits = hard >> t;
+      const int e = stopbits ? t + __ffs(stopbits) - 1 : 32;       // block = points [t, e)
+      if (e - t >= MIN_BLOCK) {
+        const unsigned below_e = e >= 32 ? FULL : ((1u << e) - 1u);
+        const unsigned rmask = below_e & ~((1u << t) - 1u);
+        const bool inr = lane >= t && lane < e;
+        // ---- who owns which points; leaders and followers --------------------------------------
+        const unsigned grp = __match_any_sync(FULL, inr ? own_k : 32 + lane);
+        s_mask[lane] = 0u;
+        s_fill0[lane] = filled; s_headv[lane] = pm_v; s_headi[lane] = pm_i;
+        __syncwarp();
+        if (inr) s_mask[own_k] = grp;
+        __syncwarp();
+        const unsigned mine_mask = s_mask[lane];
+        const bool leader = have && c0 >= top_v + LEAD_MARGIN;
+        const unsigned leadlanes = __ballot_sync(FULL, leader);
+        const bool pt_leader = inr && ((leadlanes >> own_k) & 1u);
+        const unsigned lead_pts = __ballot_sync(FULL, pt_leader);
+        const unsigned foll_pts = rmask & ~lead_pts;
+        // the owner's registers at the start of the block (restored if only a prefix commits)
+        const double sv_c0 = c0, sv_c1 = c1, sv_c2 = c2, sv_clv = cl_v, sv_pmv = pm_v;
+        const int sv_id0 = id0, sv_id1 = id1, sv_id2 = id2, sv_cli = cl_i, sv_pmi = pm_i, sv_filled = filled;
+
+        // ---- A: leaders ------------------------------------------------------------------------
+        if (leader && mine_mask) own_pass(mine_mask, false);
+        __syncwarp();
+
+        // ---- B: the frontier's best entry before / after every point (leaders' entries only) ----
+        double sv = NEG, sj = INFINITY;
+        int si = -2;
+        if (pt_leader) { sv = s_cum[lane] - 1000.0; sj = own.j; si = base + lane; }
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const double ov = __shfl_up_sync(FULL, sv, d), oj = __shfl_up_sync(FULL, sj, d);
+          const int oi = __shfl_up_sync(FULL, si, d);
+          // the later entry replaces the earlier one only when strictly better (value, then smaller j)
+          const bool keep = lane < d || sv > ov || (sv == ov && sj < oj);
+          sv = keep ? sv : ov; sj = keep ? sj : oj; si = keep ? si : oi;
+        }
+        double xv = __shfl_up_sync(FULL, sv, 1), xj = __shfl_up_sync(FULL, sj, 1);
+        int xi = __shfl_up_sync(FULL, si, 1);
+        if (lane == 0) { xv = NEG; xj = INFINITY; xi = -2; }
+        const bool nb = xv > top_v || (xv == top_v && xj < top_j);
+        const double tv_l = nb ? xv : top_v, tj_l = nb ? xj : top_j;      // top before this lane's point
+        const int ti_l = nb ? xi : top_i;
+        const bool nb2 = sv > top_v || (sv == top_v && sj < top_j);
+        const double inc_v = nb2 ? sv : top_v, inc_j = nb2 ? sj : top_j;  // top after this lane's point
+        const int inc_i = nb2 ? si : top_i;
+        s_topv[lane] = tv_l; s_topj[lane] = tj_l; s_topi[lane] = ti_l;
+
+        // ---- Q: F(j) for follower points whose top entry lies to their right ----------------------
+        const bool needq = inr && !pt_leader && (own.kf & P2_MAYQ) && !(tj_l <= own.j);
+        if (__ballot_sync(FULL, needq)) {
+          const double clv0 = __shfl_sync(FULL, sv_clv, own_k);      // the point's m is at least this
+          if (needq) {
+            double bv = 0.0;                 // the frontier's seed entry (j' = 0, id -1)
+            int bi = -1;
+            auto consider = [&](double v, int id) {
+              if (v > bv) { bv = v; bi = id; }
+              else if (v == bv) {            // (value desc, j' asc, id asc)
+                const double ja = id < 0 ? 0.0 : a.p_j[id], jb = bi < 0 ? 0.0 : a.p_j[bi];
+                if (ja < jb || (ja == jb && id < bi)) bi = id;
+              }
+            };
+            const double j = own.j;
+            const int i = own.i;
+            for (int c = 0; c < n_cor; ++c) {
+              if (c == own_k) continue;
+              const int f0 = s_fill0[c], lo2 = s_clo[c], rows2 = s_crows[c];
+              const double hv = s_headv[c];
+              // rows written before the block; an entry that cannot beat the point's own cluster
+              // best can never be chosen (its value would have to exceed m >= clv0)
+              if (f0 < 0 || lo2 > i || !(hv > clv0)) continue;
+              const double sl2 = s_csl[c], of2 = s_cof[c];
+              double est = floor((j - of2) * s_cinv[c]) - (double)lo2 + 1.0;
+              int kk = est < 0.0 ? 0 : (est > (double)rows2 ? rows2 : (int)est);
+              while (kk < rows2 && __dadd_rn(__dmul_rn(sl2, (double)(lo2 + kk)), of2) <= j) ++kk;
+              while (kk > 0 && __dadd_rn(__dmul_rn(sl2, (double)(lo2 + kk - 1)), of2) > j) --kk;
+              const int done = (i + 1 < lo2 + rows2 ? i + 1 : lo2 + rows2) - lo2;
+              const int idx = kk < done ? kk : done;
+              if (idx <= 0) continue;
+              const int x = idx - 1;
+              if (x >= f0) consider(hv, s_headi[c]);
+              else {
+                const int4 raw = __ldcg(reinterpret_cast<const int4 *>(s_pmbase[c] + x));
+                consider(__hiloint2double(raw.y, raw.x), raw.z);
+              }
+            }
+            // the leaders' entries of this block
+            unsigned lm = lead_pts & ((1u << lane) - 1u);
+            while (lm) {
+              const int u = __ffs(lm) - 1;
+              lm &= lm - 1;
+              const P2Rec ru = s_rec[buf][u];
+              if ((ru.kf & 0xff) != own_k && ru.j <= j) consider(s_cum[u] - 1000.0, base + u);
+            }
+            s_fv[lane] = bv; s_fi[lane] = bi;
+          }
+        }
+        __syncwarp();
+
+        // ---- C: followers ----------------------------------------------------------------------
+        if (have && !leader && mine_mask) own_pass(mine_mask, true);
+        __syncwarp();
+
+        // ---- D: check the assumptions, commit the verified prefix ----------------------------------
+        bool ok = true;
+        if (inr) {
+          if (pt_leader) ok = tv_l <= s_m[lane];
+          else {
+            ok = (s_cum[lane] - 1000.0) < tv_l;
+            if (needq) {
+              const double mm = s_m[lane];
+              unsigned fm = foll_pts & ((1u << lane) - 1u);
+              while (fm) {
+                const int u = __ffs(fm) - 1;
+                fm &= fm - 1;
+                const P2Rec ru = s_rec[buf][u];
+                if ((ru.kf & 0xff) != own_k && ru.j <= own.j && !((s_cum[u] - 1000.0) <= mm)) ok = false;
+              }
+            }
+          }
+        }
+        const unsigned badm = __ballot_sync(FULL, inr && !ok);
+        const int stop_at = badm ? __ffs(badm) - 1 : e;
+        const int glen = stop_at - t;
+        if (stop_at < e) {
+          // only a prefix holds: put the owners' registers back and walk the prefix again
+          c0 = sv_c0; c1 = sv_c1; c2 = sv_c2; cl_v = sv_clv; pm_v = sv_pmv;
+          id0 = sv_id0; id1 = sv_id1; id2 = sv_id2; cl_i = sv_cli; pm_i = sv_pmi; filled = sv_filled;
+          const unsigned lim = mine_mask & ((1u << stop_at) - 1u);
+          if (lim) own_pass(lim, !leader);
+          __syncwarp();
+        }
+        if (glen > 0) {
+          if (lane >= t && lane < stop_at) {
+            BackRec b; b.best = s_best[lane]; b.pred = s_pred[lane]; b.pad = 0;
+            a.back[base + lane] = b;
+            PmEntry en; en.val = s_pmv[lane]; en.id = s_pmi[lane]; en.pad = 0;
+            s_pmbase[own_k][own.ro] = en;
+            // shared ring: the corridor's last RING committed rows
+            const unsigned same = s_mask[own_k] & ((stop_at >= 32 ? FULL : ((1u << stop_at) - 1u)));
+            const int last_ro = s_rec[buf][31 - __clz(same)].ro;
+            if (own.ro > last_ro - RING) s_ring[own.ro & (RING - 1)][own_k] = en;
+          }
+          top_v = __shfl_sync(FULL, inc_v, stop_at - 1);
+          top_j = __shfl_sync(FULL, inc_j, stop_at - 1);
+          top_i = __shfl_sync(FULL, inc_i, stop_at - 1);
+          n_blockpts += glen;
+          __syncwarp();
+        }
+        t = stop_at;
+        if (t >= cnt) break;
+      }
+      // ---- one point by the sequential rules (dp2_lane_kernel) -----------------------------------
+      const int p = base + t;
+      const P2Rec pt = s_rec[buf][t];
+      ++t;
+      const double j = pt.j, q = pt.q;
+      const int kf = pt.kf, k = kf & 0xff, ro = pt.ro;
+      const bool mine = lane == k;
+      double best;
+      int pred;
+      if (!(kf & P2_NEAR)) {
+        double m = cl_v;
+        int mi = cl_i;
+        const bool t2 = (kf & P2_VIS2) && c1 >= m;
+        m = t2 ? c1 : m; mi = t2 ? id1 : mi;
+        const bool t1 = (kf & P2_VIS1) && c0 >= m;
+        m = t1 ? c0 : m; mi = t1 ? id0 : mi;
+        const bool left = top_j <= j;              // the top entry is F(j) itself
+        const bool tt = left && top_v > m;
+        best = tt ? top_v : m; pred = tt ? top_i : mi;
+        if (kf & P2_MAYQ) {
+          // the top lies right of the point: F(j) <= top value, needed only if that beats m
+          if (__ballot_sync(FULL, mine && !left && m < top_v)) {
+            ++n_query;
+            double fv; int fi;
+            frontier_query(pt.i, j, k, fv, fi);
+            if (fv > m) { best = fv; pred = fi; }
+          }
+        }
+      } else {
+        // ---- a point of another corridor may sit in this point's prev_cache cells: generic
+        //      evaluation over the last three points of every corridor (uniform values)
+        ++n_near;
+        const int i = pt.i, cell = pt.cell;
+        double ub = NEG; int up = -2;
+        if (top_j <= j) { ub = top_v; up = top_i; }
+        else { ++n_query; frontier_query(i, j, k, ub, up); }
+        const double clk = __shfl_sync(FULL, cl_v, k);
+        const int cik = __shfl_sync(FULL, cl_i, k);
+        const int cluster_k = __shfl_sync(FULL, cluster, k);
+        if (clk >= ub) { ub = clk; up = cik; }
+        int hr0 = -100, hr1 = -100, hr2 = -100, hc0 = -100, hc1 = -100, hc2 = -100;
+        if (id0 >= 0) { const P2Rec r = a.rec[id0]; hr0 = r.i; hc0 = r.cell; }
+        if (id1 >= 0) { const P2Rec r = a.rec[id1]; hr1 = r.i; hc1 = r.cell; }
+        if (id2 >= 0) { const P2Rec r = a.rec[id2]; hr2 = r.i; hc2 = r.cell; }
+#pragma unroll 1
+        for (int x = cell - 2; x <= cell; ++x) {
+          int brow = -1, bh = 0;
+          if (hc0 == x && hr0 > brow) { brow = hr0; bh = 0; }
+          if (hc1 == x && hr1 > brow) { brow = hr1; bh = 1; }
+          if (hc2 == x && hr2 > brow) { brow = hr2; bh = 2; }
+          const int mrow = (int)__reduce_max_sync(FULL, (unsigned)(brow + 1)) - 1;
+          if (mrow < 0 || mrow < i - 2) continue;         // nothing written recently enough
+          const int src = __ffs(__ballot_sync(FULL, brow == mrow)) - 1;
+          const double myc = bh == 0 ? c0 : (bh == 1 ? c1 : c2);
+          const int myid = bh == 0 ? id0 : (bh == 1 ? id1 : id2);
+          double pc = __shfl_sync(FULL, myc, src);
+          const int pid = __shfl_sync(FULL, myid, src);
+          const double pj = __shfl_sync(FULL, __dadd_rn(__dmul_rn(sl, (double)mrow), of), src);
+          if (__shfl_sync(FULL, cluster, src) != cluster_k) {
+            const double d = (j - pj) - (double)(i - mrow);
+            pc = pc - (100.0 + 100.0 * (d * d));
+          }
+          if (pj <= j && pc >= ub) { ub = pc; up = pid; }
+        }
+        best = ub; pred = up;
+      }
+
+      // ---- commit (lane k) ---------------------------------------------------------------------
+      const double cum = best + q;
+      c2 = mine ? c1 : c2; id2 = mine ? id1 : id2;
+      c1 = mine ? c0 : c1; id1 = mine ? id0 : id1;
+      c0 = mine ? cum : c0; id0 = mine ? p : id0;
+      const double cj = cum - 50.0;
+      const bool ucl = mine && cl_v < cj;
+      cl_v = ucl ? cj : cl_v; cl_i = ucl ? p : cl_i;
+      const double jump = cum - 1000.0;
+      if (kf & P2_GAP) {
+        // rows without a point (their cell was claimed by an earlier cluster) repeat the head
+        if (mine) {
+          PmEntry e; e.val = pm_v; e.id = pm_i; e.pad = 0;
+          for (int r = filled + 1; r < ro; ++r) { pm[r] = e; s_ring[r & (RING - 1)][lane] = e; }
+        }
+        __syncwarp();
+      }
+      const bool upm = mine && jump > pm_v;
+      pm_v = upm ? jump : pm_v; pm_i = upm ? p : pm_i;
+      filled = mine ? ro : filled;
+      if (mine) {
+        PmEntry e; e.val = pm_v; e.id = pm_i; e.pad = 0;
+        s_ring[ro & (RING - 1)][lane] = e;
+        pm[ro] = e;
+        BackRec b; b.best = best; b.pred = pred; b.pad = 0;
+        a.back[p] = b;
+      }
+      const double jk = __shfl_sync(FULL, jump, k);
+      const bool ut = jk > top_v || (jk == top_v && j < top_j);
+      top_v = ut ? jk : top_v; top_j = ut ? j : top_j; top_i = ut ? p : top_i;
+    }
+    __syncwarp();
+  }
+  n_refill = __reduce_add_sync(FULL, n_refill);
+  if (lane == 0) {
+    a.result[0] = top_i;
+    *reinterpret_cast<double *>(a.result + 2) = top_v;
+    a.counters[0] = n_query; a.counters[1] = n_refill; a.counters[2] = n_near; a.counters[3] = n_blockpts;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // Traceback by pointer jumping (binary lifting): up[k][p] = 2^k-th predecessor, node n = root.
 // depth doubles alongside; the ancestors of the end point are marked level by level from the
 // top; each marked point writes its own path row at position depth - 1.
@@ -1151,7 +1600,8 @@ int dab_run_stage_b(dab_pair *pr, int32_t n_cor, int32_t n_clusters) {
     la.counters = reinterpret_cast<unsigned long long *>(pr->pmoff2.as<int64_t>() + 32);
     DAB_CUDA(cudaMemsetAsync(la.counters, 0, 4 * sizeof(unsigned long long), st));
     if (pr->ctx->opt_dp2_impl == 1) dp2_corridor_kernel<<<1, 32, 0, st>>>(la);
-    else dp2_lane_kernel<<<1, 32, 0, st>>>(la);
+    else if (pr->ctx->opt_dp2_impl == 3) dp2_lane_kernel<<<1, 32, 0, st>>>(la);
+    else dp2_block_kernel<<<1, 32, 0, st>>>(la);
     DAB_CUDA(cudaEventRecord(pr->ev[18], st));
     // The DP runs for ~0.1 s on one warp.  Nothing that depends on it is enqueued until it is done:
     // streams share the GPU's 32 hardware queues, and a dependent kernel waiting at the head of a

@@ -84,7 +84,7 @@ typedef struct {
   int64_t n_dp2_queries;      /* pass-2 points that needed a real frontier query */
   int64_t n_dp2_refills;      /* 16-row refills of the per-corridor running-max windows */
   int64_t n_dp2_neighbour;    /* pass-2 points with another corridor within 2 cells / 2 rows */
-  int64_t n_dp2_run_points;   /* pass-2 points committed by the lane-parallel run path */
+  int64_t n_dp2_run_points;   /* pass-2 points committed by block evaluation (dp2_block_kernel) */
 } dab_stats;
 
 int dab_abi_version(void);
