@@ -47,12 +47,13 @@ def parse_args():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--pairs", type=int, default=56, help="pairs per GPU per step")
-    ap.add_argument("--workers", type=int, default=28, help="pairs in flight per GPU (one CUDA stream each)")
+    ap.add_argument("--pairs", type=int, default=256, help="pairs per GPU per step")
+    ap.add_argument("--workers", type=int, default=64, help="pairs in flight per GPU (one CUDA stream and one host thread each)")
     ap.add_argument("--distinct", type=int, default=8, help="distinct synthetic pairs per GPU; a step cycles over them")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the C2 durations (debugging only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--spin-wait", action="store_true", help="leave the CUDA default (spinning) host wait")
     return ap.parse_args()
 
 
@@ -215,6 +216,8 @@ def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
     from describealign_b200 import api, build
     build.build()
+    # W host threads wait on W pair streams: they must sleep, not spin (16 host cores, W >> 16)
+    sched = api._cabi.set_host_wait(local_rank, blocking=not args.spin_wait)
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -236,10 +239,25 @@ def run_ours(args, rank, world, local_rank):
            for v, a in base_pairs]
     pinned = [(torch.from_numpy(np.ascontiguousarray(v)).pin_memory(), torch.from_numpy(np.ascontiguousarray(a)).pin_memory())
               for v, a in base_pairs]
+    # what the PCIe link gives a single large pinned copy (the bound of the end-to-end number)
+    h2d_gbs = None
+    try:
+        src = pinned[0][1]
+        dst = torch.empty_like(src, device="cuda")
+        best = 0.0
+        for _ in range(4):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); dst.copy_(src, non_blocking=True); e1.record(); e1.synchronize()
+            best = max(best, src.numel() * src.element_size() / (e0.elapsed_time(e1) * 1e-3) / 1e9)
+        h2d_gbs = best
+        del dst
+    except Exception:
+        pass
     ctx = api.context()
     # W pairs in flight: one dab_pair (device buffers + CUDA stream) per worker slot.  The frontier DPs
-    # are one warp per pair and ~0.1 s long, so throughput comes from keeping W of them running while
-    # the data-parallel kernels of other pairs fill the SMs; W stays below the 32 hardware queues.
+    # are one warp per pair and tens of milliseconds long, so throughput comes from keeping W of them
+    # running while the data-parallel kernels of other pairs fill the SMs.  A step ends with a tail in
+    # which only the last DPs run, so a step is several rounds of W pairs (B = 4 W by default).
     W = max(1, min(B, args.workers))
     slot_pairs = [api._cabi.Pair(ctx) for _ in range(W)]
     streams = [torch.cuda.ExternalStream(p.stream) for p in slot_pairs]
@@ -336,6 +354,9 @@ def run_ours(args, rank, world, local_rank):
     ms_e2e, _, jobs_e = run_steps(True)
     h2d = sum(j.h2d_bytes for j in jobs_e)
     d2h = sum(j.d2h_bytes for j in jobs_e)
+    host_calls_e2e = {k: {"mean": float(np.mean([j.host_ms.get(k, 0.0) for j in jobs_e])),
+                          "max": float(np.max([j.host_ms.get(k, 0.0) for j in jobs_e]))}
+                      for k in sorted(set().union(*[j.host_ms.keys() for j in jobs_e]))}
 
     # parity inside the run: rank 0 checks its first pair against the oracle
     parity = None
@@ -413,7 +434,12 @@ def run_ours(args, rank, world, local_rank):
                 v["frac"] = v["achieved"] / v["peak"]
         dom_key = dominant if dominant in roof else ("features" if dominant.startswith("features") else None)
         main_roof = dict(roof[dom_key]) if dom_key else dict(roof["features"])
-        main_roof.update({"kernel": dom_key or dominant, "peak_source": peak_src, "traffic": None})
+        # DRAM bytes per launch of that kernel from the committed ncu --set full captures of the same
+        # workload (seed 0 pair): profiles/r1_v6_dp2_block_full.txt, profiles/r1_v8_features_full.txt
+        ncu_traffic = {"dp2_trace": 12.902912e6 + 256, "features": (116.465152e6 + 5.258240e6 + 143.008e6 + 9.717248e6) / 2}
+        main_roof.update({"kernel": dom_key or dominant, "peak_source": peak_src,
+                          "traffic": ncu_traffic.get(dom_key) if args.scale == 1.0 else None,
+                          "traffic_note": "bytes per launch (dram read + write), ncu --set full of one C2 pair, see profiles/"})
         line = {
             "metric": METRIC, "value": hours / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak",
@@ -426,12 +452,17 @@ def run_ours(args, rank, world, local_rank):
             "ms_per_pair": ms_dev / B,
             "pairs_in_flight": W,
             "e2e": {"value": hours / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
-                    "h2d_bytes_per_step": h2d_all, "d2h_bytes_per_step": d2h_all},
+                    "h2d_bytes_per_step": h2d_all, "d2h_bytes_per_step": d2h_all,
+                    "h2d_gbs_achieved": h2d_all / world / (ms_e2e * 1e-3) / 1e9,
+                    "h2d_gbs_single_copy": h2d_gbs,
+                    "note": "PCM is 2 bytes per sample per channel; the end-to-end rate is bounded by the host-to-device link"},
+            "host_wait": {"cuda_schedule_flags": sched, "mode": "spin (CUDA default)" if args.spin_wait else "blocking"},
             "gpu_launches": int(launches_all),
             "roofline": main_roof,
             "roofline_by_kernel": roof,
             "kernel_ms_last_step": agg,
             "host_call_ms_last_step": host_calls,
+            "host_call_ms_last_step_e2e": host_calls_e2e,
             "host_ms_inside_library_per_pair": lib_host,
             "allocator_activity_in_timed_steps": alloc_timed,
             "work": {k: sum(s[k] for s in stats) for k in stats[0]},

@@ -24,6 +24,7 @@ EXPORTS = [
     "dab_pair_get_points2", "dab_pair_get_stats", "dab_pair_get_timings", "dab_launch_count",
     "dab_pair_stage_a_match", "dab_pair_export_points1", "dab_pair_import_points1", "dab_pair_dp1",
     "dab_alloc_pinned", "dab_free_pinned", "dab_trim_pinned", "dab_alloc_stats", "dab_host_copy",
+    "dab_set_host_wait",
 ]
 
 
@@ -75,6 +76,8 @@ def load() -> ctypes.CDLL:
     lib.dab_alloc_stats.argtypes = [ctypes.POINTER(ctypes.c_int64 * 4)]
     lib.dab_alloc_stats.restype = None
     lib.dab_device_count.restype = i32
+    lib.dab_set_host_wait.argtypes = [i32, i32]
+    lib.dab_set_host_wait.restype = i32
     lib.dab_create.argtypes = [i32, ctypes.POINTER(vp)]
     lib.dab_destroy.argtypes = [vp]
     lib.dab_destroy.restype = None
@@ -166,6 +169,15 @@ def pinned_empty(shape, dtype) -> np.ndarray:
     buf = (ctypes.c_char * max(nbytes, 1)).from_address(block.ptr)
     buf._block = block          # the ctypes array (kept alive as the numpy base) keeps the block
     return np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
+
+
+def set_host_wait(device: int = -1, blocking: bool = True) -> int:
+    """Host threads sleep (True) or spin (False, the CUDA default) while waiting for the device; call
+    it before the first pair is created.  Returns the device's schedule flags after the call."""
+    rc = load().dab_set_host_wait(int(device), 1 if blocking else 0)
+    if rc < 0:
+        raise DabError(f"dab_set_host_wait failed ({rc})")
+    return rc
 
 
 class Context:

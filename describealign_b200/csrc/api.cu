@@ -128,6 +128,17 @@ int dab_device_count(void) {
 
 const char *dab_last_error(const dab_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
 
+int dab_set_host_wait(int device, int blocking) {
+  if (device >= 0 && cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return -DAB_E_CUDA; }
+  unsigned flags = 0;
+  if (cudaGetDeviceFlags(&flags) != cudaSuccess) { cudaGetLastError(); return -DAB_E_CUDA; }
+  flags = (flags & ~(unsigned)cudaDeviceScheduleMask) |
+          (blocking ? (unsigned)cudaDeviceScheduleBlockingSync : (unsigned)cudaDeviceScheduleAuto);
+  if (cudaSetDeviceFlags(flags) != cudaSuccess) { cudaGetLastError(); return -DAB_E_CUDA; }
+  if (cudaGetDeviceFlags(&flags) != cudaSuccess) { cudaGetLastError(); return -DAB_E_CUDA; }
+  return (int)(flags & (unsigned)cudaDeviceScheduleMask);
+}
+
 int dab_create(int device, dab_ctx **out) {
   if (!out) return DAB_E_ARG;
   *out = nullptr;
@@ -224,6 +235,7 @@ int dab_pair_set_pcm(dab_pair *pr, int track, const void *pcm, int64_t samples, 
   if (!pr) return DAB_E_ARG;
   dab_ctx *ctx = pr->ctx;
   StreamScope scope__(pr->stream);
+  if (track == DAB_TRACK_VIDEO) pr->api_us[0] = 0;     // a new pair starts with its video track
   ApiTimer timer__(&pr->api_us[0]);
   if (track < 0 || track > 1 || !pcm || samples < 0 || (channels != 1 && channels != 2) ||
       (format != DAB_PCM_S16 && format != DAB_PCM_F16)) {

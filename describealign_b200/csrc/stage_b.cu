@@ -1602,11 +1602,12 @@ int dab_run_stage_b(dab_pair *pr, int32_t n_cor, int32_t n_clusters) {
     if (pr->ctx->opt_dp2_impl == 1) dp2_corridor_kernel<<<1, 32, 0, st>>>(la);
     else if (pr->ctx->opt_dp2_impl == 3) dp2_lane_kernel<<<1, 32, 0, st>>>(la);
     else dp2_block_kernel<<<1, 32, 0, st>>>(la);
-    DAB_CUDA(cudaEventRecord(pr->ev[18], st));
-    // The DP runs for ~0.1 s on one warp.  Nothing that depends on it is enqueued until it is done:
-    // streams share the GPU's 32 hardware queues, and a dependent kernel waiting at the head of a
-    // queue would stall the other pairs' work mapped to that queue.
+    // The DP runs for tens of milliseconds on one warp.  Nothing that depends on it - not even an
+    // event record - is enqueued until it is done: streams share the GPU's 32 hardware queues, and a
+    // dependent command waiting at the head of a queue stalls the other pairs' work mapped to that
+    // queue (with more pairs in flight than queues that costs all the concurrency beyond 32).
     DAB_CUDA(cudaStreamSynchronize(st));
+    DAB_CUDA(cudaEventRecord(pr->ev[18], st));
     int32_t *up = pr->lift_up.as<int32_t>();
     int32_t *dep0 = pr->lift_dep.as<int32_t>(), *dep1 = dep0 + np1, *mark = dep1 + np1;
     const unsigned gl = (unsigned)cdiv(np1, 256);

@@ -106,6 +106,14 @@ void dab_host_copy(void *dst, const void *src, size_t bytes);
  * steady state should show no growth: both kinds of call synchronise the whole device. */
 void dab_alloc_stats(int64_t out[4]);
 
+/* How host threads wait for the device (cudaStreamSynchronize inside the stage calls).  blocking = 1:
+ * the thread sleeps until the device signals (cudaDeviceScheduleBlockingSync); 0: the CUDA default,
+ * which spins when the process has fewer contexts than the host has cores.  A batch driver that
+ * keeps more pairs in flight (one host thread each) than there are host cores must use 1, or the
+ * spinning waiters starve the threads that have kernels to launch.  Returns the device's schedule
+ * flags after the call (>= 0) or a negative DAB_E_* code.  device < 0: current device. */
+int dab_set_host_wait(int device, int blocking);
+
 /* device < 0: current device. */
 int dab_create(int device, dab_ctx **out);
 void dab_destroy(dab_ctx *ctx);
