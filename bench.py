@@ -53,6 +53,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the C2 durations (debugging only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--timeline", default=None, help="write the device timeline of the last step (per pair and stage) to this JSON file")
     ap.add_argument("--spin-wait", action="store_true", help="leave the CUDA default (spinning) host wait")
     return ap.parse_args()
 
@@ -290,6 +291,8 @@ def run_ours(args, rank, world, local_rank):
         for pr in slot_pairs:
             slots.put(pr)
 
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
         def work(k):
             pr = slots.get()
             t_in = time.perf_counter()
@@ -307,12 +310,15 @@ def run_ours(args, rank, world, local_rank):
                 job.device_stage_b()
                 job.kernel_ms = pr.timings()
                 job.work = pr.stats()
+                if args.timeline:
+                    job.timeline = pr.timeline(start.cuda_event)
+                    job.host_span = (t_in, time.perf_counter())
                 job.host_ms["whole_pair"] = 1e3 * (time.perf_counter() - t_in)
             finally:
                 slots.put(pr)
 
-        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         start.record(cur)
+        t_step = time.perf_counter()
         for st in streams:
             st.wait_event(start)
         list(pool.map(work, range(B)))
@@ -322,6 +328,11 @@ def run_ours(args, rank, world, local_rank):
             cur.wait_event(e)
         stop.record(cur)
         stop.synchronize()
+        if args.timeline:
+            tl = [{"pair": k, "slot_host_ms": [1e3 * (j.host_span[0] - t_step), 1e3 * (j.host_span[1] - t_step)], **j.timeline}
+                  for k, j in enumerate(jobs)]
+            with open(args.timeline, "w") as f:
+                json.dump({"step_ms": start.elapsed_time(stop), "host_input": host_input, "pairs": tl}, f)
         return start.elapsed_time(stop), jobs
 
     alloc0 = {}

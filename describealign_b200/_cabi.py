@@ -24,7 +24,7 @@ EXPORTS = [
     "dab_pair_get_points2", "dab_pair_get_stats", "dab_pair_get_timings", "dab_launch_count",
     "dab_pair_stage_a_match", "dab_pair_export_points1", "dab_pair_import_points1", "dab_pair_dp1",
     "dab_alloc_pinned", "dab_free_pinned", "dab_trim_pinned", "dab_alloc_stats", "dab_host_copy",
-    "dab_set_host_wait",
+    "dab_set_host_wait", "dab_pair_get_timeline",
 ]
 
 
@@ -381,6 +381,14 @@ class Pair:
         ms = (ctypes.c_float * 16)()
         self.ctx.check(self.lib.dab_pair_get_timings(self.handle, ctypes.byref(ms)))
         return {name: float(ms[k]) for k, name in enumerate(TIMING_SLOTS)}
+
+    def timeline(self, ref_event: int) -> dict:
+        """(start, end) of the device stages in ms after `ref_event` (a cudaEvent_t handle)."""
+        t0, t1 = (ctypes.c_float * 9)(), (ctypes.c_float * 9)()
+        self.lib.dab_pair_get_timeline.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_float * 9),
+                                                   ctypes.POINTER(ctypes.c_float * 9)]
+        self.ctx.check(self.lib.dab_pair_get_timeline(self.handle, ctypes.c_void_p(ref_event), ctypes.byref(t0), ctypes.byref(t1)))
+        return {name: (float(t0[k]), float(t1[k])) for k, name in enumerate(TIMING_SLOTS[:9]) if t0[k] >= 0}
 
     def sync(self):
         self.ctx.check(self.lib.dab_pair_sync(self.handle))

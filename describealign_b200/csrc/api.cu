@@ -560,4 +560,21 @@ int dab_pair_get_timings(dab_pair *pr, float ms[16]) {
   return DAB_OK;
 }
 
+int dab_pair_get_timeline(dab_pair *pr, void *ref_event, float start_ms[9], float end_ms[9]) {
+  if (!pr || !ref_event || !start_ms || !end_ms) return DAB_E_ARG;
+  dab_ctx *ctx = pr->ctx;
+  DAB_CUDA(cudaSetDevice(ctx->device));
+  DAB_CUDA(cudaStreamSynchronize(pr->stream));
+  cudaEvent_t ref = reinterpret_cast<cudaEvent_t>(ref_event);
+  for (int s = 0; s < 9; ++s) {
+    start_ms[s] = end_ms[s] = -1.0f;
+    if (!pr->ev_used[s]) continue;
+    float t0 = 0.0f, t1 = 0.0f;
+    if (cudaEventElapsedTime(&t0, ref, pr->ev[2 * s]) == cudaSuccess &&
+        cudaEventElapsedTime(&t1, ref, pr->ev[2 * s + 1]) == cudaSuccess) { start_ms[s] = t0; end_ms[s] = t1; }
+    cudaGetLastError();
+  }
+  return DAB_OK;
+}
+
 }  // extern "C"

@@ -191,6 +191,10 @@ int dab_pair_get_stats(dab_pair *pair, dab_stats *out);
  * this pair since its last video set_pcm: 10 set_pcm/set_features 11 stage A 12 stage B 13 get_*
  * copies.  Slots not run since creation are 0. */
 int dab_pair_get_timings(dab_pair *pair, float ms[16]);
+/* Where on the device's clock the stages 0-8 above started and ended, in milliseconds after
+ * `ref_event` (a cudaEvent_t recorded with timing by the caller, e.g. at the start of a batch);
+ * -1 for stages not run.  With many pairs in flight this is the timeline of the batch. */
+int dab_pair_get_timeline(dab_pair *pair, void *ref_event, float start_ms[9], float end_ms[9]);
 /* number of kernel launches issued by this context since creation */
 int64_t dab_launch_count(const dab_ctx *ctx);
 
