@@ -53,7 +53,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the C2 durations (debugging only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--timeline", default=None, help="write the device timeline of the last step (per pair and stage) to this JSON file")
+    ap.add_argument("--timeline", default=None, help="write the device timeline of the last step of each arm (per pair and stage) to <name>_dev.json / <name>_e2e.json")
     ap.add_argument("--spin-wait", action="store_true", help="leave the CUDA default (spinning) host wait")
     return ap.parse_args()
 
@@ -275,12 +275,12 @@ def run_ours(args, rank, world, local_rank):
         stage A keeps returning that same path.  Inside the timed region it is a dictionary lookup."""
         c = host_cache.get(k % distinct)
         if c is not None and np.array_equal(c["x"], job.x) and np.array_equal(c["y"], job.y):
-            for name in ("kept_x", "kept_y", "audio_scaled", "video_scaled", "fit", "clusters", "plans"):
+            for name in ("kept_x", "kept_y", "audio_scaled", "video_scaled", "fit", "clusters", "plans", "gains"):
                 setattr(job, name, c[name])
             return
         job.host_stage()
         host_cache[k % distinct] = {"x": job.x, "y": job.y, **{name: getattr(job, name) for name in
-                                    ("kept_x", "kept_y", "audio_scaled", "video_scaled", "fit", "clusters", "plans")}}
+                                    ("kept_x", "kept_y", "audio_scaled", "video_scaled", "fit", "clusters", "plans", "gains")}}
 
     def one_step(host_input: bool):
         """All B pairs through stage A -> (cached) host fit -> stage B, W at a time.  Returns the
@@ -331,7 +331,8 @@ def run_ours(args, rank, world, local_rank):
         if args.timeline:
             tl = [{"pair": k, "slot_host_ms": [1e3 * (j.host_span[0] - t_step), 1e3 * (j.host_span[1] - t_step)], **j.timeline}
                   for k, j in enumerate(jobs)]
-            with open(args.timeline, "w") as f:
+            name = args.timeline.replace(".json", "") + ("_e2e.json" if host_input else "_dev.json")
+            with open(name, "w") as f:
                 json.dump({"step_ms": start.elapsed_time(stop), "host_input": host_input, "pairs": tl}, f)
         return start.elapsed_time(stop), jobs
 

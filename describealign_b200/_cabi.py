@@ -24,7 +24,7 @@ EXPORTS = [
     "dab_pair_get_points2", "dab_pair_get_stats", "dab_pair_get_timings", "dab_launch_count",
     "dab_pair_stage_a_match", "dab_pair_export_points1", "dab_pair_import_points1", "dab_pair_dp1",
     "dab_alloc_pinned", "dab_free_pinned", "dab_trim_pinned", "dab_alloc_stats", "dab_host_copy",
-    "dab_set_host_wait", "dab_pair_get_timeline",
+    "dab_set_host_wait", "dab_pair_get_timeline", "dab_pair_stage_b_gains",
 ]
 
 
@@ -357,6 +357,27 @@ class Pair:
         self.ctx.check(self.lib.dab_pair_stage_b(self.handle, _ptr(a), a.shape[0], _ptr(v), v.shape[0],
                                                  ctypes.cast(arr, ctypes.c_void_p), len(plans), int(n_clusters),
                                                  ctypes.byref(npts), ctypes.byref(npath)))
+        self.n_points2, self.n_path2 = npts.value, npath.value
+        return npts.value, npath.value
+
+    def stage_b_gains(self, gains, audio_stds, audio_scaled: np.ndarray, video_scaled: np.ndarray, plans, n_clusters: int):
+        """Stage B for a pair that holds its features on the device: the scaled arrays are rebuilt
+        there from the six scalars; the host copies only provide lengths and energy maxima."""
+        g = (ctypes.c_float * 3)(*[float(x) for x in gains])
+        sd = (ctypes.c_float * 3)(*[float(x) for x in audio_stds])
+        plans = [p for p in plans if p[2] > p[1]]
+        arr = (Corridor * max(len(plans), 1))()
+        for k, (idx, lo, hi, slope, offset) in enumerate(plans):
+            arr[k] = Corridor(int(idx), int(lo), int(hi), 0, float(slope), float(offset))
+        npts, npath = ctypes.c_int64(), ctypes.c_int64()
+        fn = self.lib.dab_pair_stage_b_gains
+        fn.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float * 3), ctypes.POINTER(ctypes.c_float * 3),
+                       ctypes.c_int64, ctypes.c_int64, ctypes.c_float, ctypes.c_float, ctypes.c_void_p, ctypes.c_int32,
+                       ctypes.c_int32, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]
+        self.ctx.check(fn(self.handle, ctypes.byref(g), ctypes.byref(sd), audio_scaled.shape[0], video_scaled.shape[0],
+                          float(audio_scaled[:, 0].max()), float(video_scaled[:, 0].max()),
+                          ctypes.cast(arr, ctypes.c_void_p), len(plans), int(n_clusters),
+                          ctypes.byref(npts), ctypes.byref(npath)))
         self.n_points2, self.n_path2 = npts.value, npath.value
         return npts.value, npath.value
 

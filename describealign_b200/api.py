@@ -118,6 +118,8 @@ class AlignJob:
         self._own = pair is None
         self.video_features = self.audio_features = None
         self.want_all_features = False
+        self.device_scaling = True   # stage B scales the pair's device-resident features itself (6 floats up)
+        self.gains = None
         self.h2d_bytes = self.d2h_bytes = 0
         self.host_ms = {}        # wall time of each host-side call of this job (diagnostics)
 
@@ -185,16 +187,22 @@ class AlignJob:
         """The untimed "rate-change fit" on the host (describealign.py:702-893)."""
         keep = host_fit.continuity_error(self.x, self.y) < 3
         self.kept_x, self.kept_y = self.x[keep], self.y[keep]
-        self.audio_scaled, self.video_scaled = host_fit.scale_features(
-            self.video_features, self.audio_features, self.kept_x, self.kept_y)
+        self.audio_scaled, self.video_scaled, self.gains = host_fit.scale_features(
+            self.video_features, self.audio_features, self.kept_x, self.kept_y, return_gains=True)
         fit_x, fit_y = host_fit.compress_path(self.kept_x, self.kept_y)
         self.fit = host_fit.rate_change_fit(fit_x, fit_y)
         self.clusters = host_fit.line_clusters(self.fit)
         self.plans = host_fit.plan_corridors(self.clusters, self.audio_scaled, self.video_scaled)
 
     def device_stage_b(self):
-        self._timed("stage_b", self.pair.stage_b, self.audio_scaled, self.video_scaled, self.plans, len(self.clusters))
-        self.h2d_bytes += self.audio_scaled.nbytes + self.video_scaled.nbytes
+        if getattr(self, "gains", None) is not None and self.device_scaling:
+            # the pair still holds the features: the device redoes describealign.py:737-741 from six scalars
+            self._timed("stage_b", self.pair.stage_b_gains, self.gains[0], self.gains[1], self.audio_scaled,
+                        self.video_scaled, self.plans, len(self.clusters))
+            self.h2d_bytes += 24
+        else:
+            self._timed("stage_b", self.pair.stage_b, self.audio_scaled, self.video_scaled, self.plans, len(self.clusters))
+            self.h2d_bytes += self.audio_scaled.nbytes + self.video_scaled.nbytes
         self.path = self._timed("path2", self.pair.path2)
         self.d2h_bytes += self.path.nbytes
         if len(self.path) < self.min_len:

@@ -182,6 +182,29 @@ int dab_set_option(dab_ctx *ctx, const char *name, int64_t value) {
 
 int64_t dab_launch_count(const dab_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
+}  // extern "C"
+
+// A few words from device memory into the pair's mapped host block, written by a one-warp kernel.
+// A cudaMemcpyAsync of 4 bytes would do the same, but copies share the copy engines' queues with
+// the bulk PCM uploads of the other pairs in flight, and a 4-byte read-back was seen to wait
+// 100-200 ms behind them (profiles/r1_v10_timeline_e2e.txt); a store over PCIe does not queue.
+__global__ void readback_kernel(uint32_t *dst, const uint32_t *src, int n_words) {
+  if ((int)threadIdx.x < n_words) dst[threadIdx.x] = src[threadIdx.x];
+  __threadfence_system();
+}
+
+cudaError_t dab_readback(dab_pair *pr, void *host_dst, const void *dev_src, size_t bytes) {
+  const ptrdiff_t off = reinterpret_cast<const char *>(host_dst) - reinterpret_cast<const char *>(pr->h_counters);
+  if (off < 0 || off + (ptrdiff_t)bytes > (ptrdiff_t)(sizeof(int64_t) * 32) || bytes % 4 != 0 || bytes > 128)
+    return cudaErrorInvalidValue;
+  pr->ctx->launches++;
+  readback_kernel<<<1, 32, 0, pr->stream>>>(reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(pr->d_counters_map) + off),
+                                            reinterpret_cast<const uint32_t *>(dev_src), (int)(bytes / 4));
+  return cudaGetLastError();
+}
+
+extern "C" {
+
 int dab_pair_create(dab_ctx *ctx, dab_pair **out) {
   if (!ctx || !out) return DAB_E_ARG;
   *out = nullptr;
@@ -191,8 +214,11 @@ int dab_pair_create(dab_ctx *ctx, dab_pair **out) {
   pr->ctx = ctx;
   DAB_CUDA(cudaStreamCreateWithFlags(&pr->stream, cudaStreamNonBlocking));
   for (int k = 0; k < 32; ++k) DAB_CUDA(cudaEventCreate(&pr->ev[k]));
-  DAB_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&pr->h_counters), sizeof(int64_t) * 32, cudaHostAllocDefault));
+  // mapped: kernels write the counts the host waits for straight into this block (dab_readback)
+  DAB_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&pr->h_counters), sizeof(int64_t) * 32,
+                         cudaHostAllocMapped | cudaHostAllocPortable));
   memset(pr->h_counters, 0, sizeof(int64_t) * 32);
+  DAB_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void **>(&pr->d_counters_map), pr->h_counters, 0));
   *out = pr;
   return DAB_OK;
 }
@@ -450,18 +476,12 @@ int dab_pair_dp1(dab_pair *pr, int64_t *n_path) {
   return DAB_OK;
 }
 
-int dab_pair_stage_b(dab_pair *pr, const float *audio_scaled, int64_t n_audio, const float *video_scaled,
-                     int64_t n_video, const dab_corridor *corridors, int32_t n_corridors, int32_t n_clusters,
-                     int64_t *n_points, int64_t *n_path) {
-  if (!pr) return DAB_E_ARG;
+// shared by the two stage-B entry points: corridor checks, corridor upload, the run itself
+static int stage_b_common(dab_pair *pr, int64_t n_audio, int64_t n_video, const dab_corridor *corridors,
+                          int32_t n_corridors, int32_t n_clusters, float amax, float vmax, int64_t *n_points,
+                          int64_t *n_path) {
   dab_ctx *ctx = pr->ctx;
-  StreamScope scope__(pr->stream);
-  ApiTimer timer__(&pr->api_us[2]);
-  if (!audio_scaled || !video_scaled || n_audio <= 0 || n_video <= 8 || n_corridors < 0 || n_clusters < 0 ||
-      (n_corridors > 0 && !corridors)) {
-    ctx->err = "dab_pair_stage_b: invalid argument";
-    return DAB_E_ARG;
-  }
+  cudaStream_t st = pr->stream;
   int64_t rows = 0;
   for (int k = 0; k < n_corridors; ++k) {
     const dab_corridor &c = corridors[k];
@@ -481,20 +501,10 @@ int dab_pair_stage_b(dab_pair *pr, const float *audio_scaled, int64_t n_audio, c
       rows += c.hi - c.lo;
     }
   }
-  DAB_CUDA(cudaSetDevice(ctx->device));
-  cudaStream_t st = pr->stream;
   pr->h_cor.assign(corridors, corridors + n_corridors);
-  DAB_TRY(dab_ensure(ctx, pr->a_scaled, sizeof(float) * 3 * (size_t)n_audio));
-  DAB_TRY(dab_ensure(ctx, pr->v_scaled, sizeof(float) * 3 * (size_t)n_video));
   DAB_TRY(dab_ensure(ctx, pr->corridors, sizeof(dab_corridor) * (size_t)(n_corridors + 1)));
-  DAB_CUDA(cudaMemcpyAsync(pr->a_scaled.p, audio_scaled, sizeof(float) * 3 * (size_t)n_audio, cudaMemcpyHostToDevice, st));
-  DAB_CUDA(cudaMemcpyAsync(pr->v_scaled.p, video_scaled, sizeof(float) * 3 * (size_t)n_video, cudaMemcpyHostToDevice, st));
   if (n_corridors > 0)
     DAB_CUDA(cudaMemcpyAsync(pr->corridors.p, corridors, sizeof(dab_corridor) * (size_t)n_corridors, cudaMemcpyHostToDevice, st));
-  // np.max of the energy columns (:908-909)
-  float amax = audio_scaled[0], vmax = video_scaled[0];
-  for (int64_t k = 1; k < n_audio; ++k) amax = audio_scaled[3 * k] > amax ? audio_scaled[3 * k] : amax;
-  for (int64_t k = 1; k < n_video; ++k) vmax = video_scaled[3 * k] > vmax ? video_scaled[3 * k] : vmax;
   reinterpret_cast<float *>(pr->h_counters + 8)[0] = amax;
   reinterpret_cast<float *>(pr->h_counters + 8)[1] = vmax;
   pr->h_counters[11] = rows;
@@ -504,6 +514,81 @@ int dab_pair_stage_b(dab_pair *pr, const float *audio_scaled, int64_t n_audio, c
   if (n_points) *n_points = pr->n_points2;
   if (n_path) *n_path = pr->n_path2;
   return DAB_OK;
+}
+
+int dab_pair_stage_b(dab_pair *pr, const float *audio_scaled, int64_t n_audio, const float *video_scaled,
+                     int64_t n_video, const dab_corridor *corridors, int32_t n_corridors, int32_t n_clusters,
+                     int64_t *n_points, int64_t *n_path) {
+  if (!pr) return DAB_E_ARG;
+  dab_ctx *ctx = pr->ctx;
+  StreamScope scope__(pr->stream);
+  ApiTimer timer__(&pr->api_us[2]);
+  if (!audio_scaled || !video_scaled || n_audio <= 0 || n_video <= 8 || n_corridors < 0 || n_clusters < 0 ||
+      (n_corridors > 0 && !corridors)) {
+    ctx->err = "dab_pair_stage_b: invalid argument";
+    return DAB_E_ARG;
+  }
+  DAB_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = pr->stream;
+  DAB_TRY(dab_ensure(ctx, pr->a_scaled, sizeof(float) * 3 * (size_t)n_audio));
+  DAB_TRY(dab_ensure(ctx, pr->v_scaled, sizeof(float) * 3 * (size_t)n_video));
+  DAB_CUDA(cudaMemcpyAsync(pr->a_scaled.p, audio_scaled, sizeof(float) * 3 * (size_t)n_audio, cudaMemcpyHostToDevice, st));
+  DAB_CUDA(cudaMemcpyAsync(pr->v_scaled.p, video_scaled, sizeof(float) * 3 * (size_t)n_video, cudaMemcpyHostToDevice, st));
+  // np.max of the energy columns (:908-909)
+  float amax = audio_scaled[0], vmax = video_scaled[0];
+  for (int64_t k = 1; k < n_audio; ++k) amax = audio_scaled[3 * k] > amax ? audio_scaled[3 * k] : amax;
+  for (int64_t k = 1; k < n_video; ++k) vmax = video_scaled[3 * k] > vmax ? video_scaled[3 * k] : vmax;
+  return stage_b_common(pr, n_audio, n_video, corridors, n_corridors, n_clusters, amax, vmax, n_points, n_path);
+}
+
+}  // extern "C"
+
+// describealign.py:737-741 on the device: audio_scaled = audio / std(audio), video_scaled =
+// video * gain / std(audio), float32 with numpy's roundings (one division; one multiply then one
+// division), stacked as (n, 3).  The feature vectors are the pair's own device copies.
+__global__ void scale_features_kernel(const float *f0, const float *f1, const float *f2, int64_t n, float g0, float g1,
+                                      float g2, float s0, float s1, float s2, int with_gain, float *out) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  float x0 = f0[k], x1 = f1[k], x2 = f2[k];
+  if (with_gain) { x0 = __fmul_rn(x0, g0); x1 = __fmul_rn(x1, g1); x2 = __fmul_rn(x2, g2); }
+  out[3 * k + 0] = __fdiv_rn(x0, s0);
+  out[3 * k + 1] = __fdiv_rn(x1, s1);
+  out[3 * k + 2] = __fdiv_rn(x2, s2);
+}
+
+extern "C" {
+
+int dab_pair_stage_b_gains(dab_pair *pr, const float gain[3], const float audio_std[3], int64_t n_audio,
+                           int64_t n_video, float audio_energy_max, float video_energy_max,
+                           const dab_corridor *corridors, int32_t n_corridors, int32_t n_clusters,
+                           int64_t *n_points, int64_t *n_path) {
+  if (!pr) return DAB_E_ARG;
+  dab_ctx *ctx = pr->ctx;
+  StreamScope scope__(pr->stream);
+  ApiTimer timer__(&pr->api_us[2]);
+  if (!gain || !audio_std || n_audio <= 0 || n_video <= 8 || n_corridors < 0 || n_clusters < 0 ||
+      (n_corridors > 0 && !corridors)) {
+    ctx->err = "dab_pair_stage_b_gains: invalid argument";
+    return DAB_E_ARG;
+  }
+  Track &V = pr->trk[DAB_TRACK_VIDEO], &A = pr->trk[DAB_TRACK_AUDIO];
+  if (!V.have_features || !A.have_features) { ctx->err = "dab_pair_stage_b_gains: the pair holds no features"; return DAB_E_STATE; }
+  // np.stack truncates to the shortest of the three vectors (energy may be one longer)
+  const int64_t na = A.L < A.Le ? A.L : A.Le, nv = V.L < V.Le ? V.L : V.Le;
+  if (n_audio != na || n_video != nv) { ctx->err = "dab_pair_stage_b_gains: lengths differ from the pair's features"; return DAB_E_ARG; }
+  DAB_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = pr->stream;
+  DAB_TRY(dab_ensure(ctx, pr->a_scaled, sizeof(float) * 3 * (size_t)n_audio));
+  DAB_TRY(dab_ensure(ctx, pr->v_scaled, sizeof(float) * 3 * (size_t)n_video));
+  scale_features_kernel<<<(unsigned)cdiv(n_audio, 256), 256, 0, st>>>(A.energy.as<float>(), A.zc.as<float>(), A.b0.as<float>(),
+      n_audio, 1.f, 1.f, 1.f, audio_std[0], audio_std[1], audio_std[2], 0, pr->a_scaled.as<float>());
+  scale_features_kernel<<<(unsigned)cdiv(n_video, 256), 256, 0, st>>>(V.energy.as<float>(), V.zc.as<float>(), V.b0.as<float>(),
+      n_video, gain[0], gain[1], gain[2], audio_std[0], audio_std[1], audio_std[2], 1, pr->v_scaled.as<float>());
+  ctx->launches += 2;
+  DAB_CUDA(cudaGetLastError());
+  return stage_b_common(pr, n_audio, n_video, corridors, n_corridors, n_clusters, audio_energy_max, video_energy_max,
+                        n_points, n_path);
 }
 
 int dab_pair_get_path2(dab_pair *pr, double *rows) {

@@ -94,7 +94,8 @@ struct dab_pair {
   cudaEvent_t ev[32] = {};
   bool ev_used[16] = {};
   // pinned host mirror of small results
-  int64_t *h_counters = nullptr;
+  int64_t *h_counters = nullptr;       // pinned + mapped host block
+  int64_t *d_counters_map = nullptr;   // its device-side address
   // host time spent inside the library's calls for this pair since the last set_pcm (microseconds):
   // [0] set_pcm / set_features, [1] stage A, [2] stage B, [3] get_* copies
   int64_t api_us[4] = {0, 0, 0, 0};
@@ -135,6 +136,7 @@ struct StreamScope {
   ~StreamScope() { dab_t_stream = prev; }
 };
 int dab_ensure(dab_ctx *ctx, DevBuf &b, size_t bytes);
+cudaError_t dab_readback(dab_pair *pr, void *host_dst, const void *dev_src, size_t bytes);
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // exclusive scan of n int32 values; out[n] receives the total (out has n + 1 entries).

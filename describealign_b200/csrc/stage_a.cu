@@ -696,12 +696,12 @@ static int prep_track(dab_pair *pr, int track, int64_t row_lo = 0, int64_t row_h
   compact_kernel<<<(unsigned)cdiv(nqn, 256), 256, 0, pr->stream>>>(flag, off, nqn, track == DAB_TRACK_VIDEO ? 4 : 1,
                                                                   tk.nq_list.as<int32_t>());
   ctx->launches += 1;
-  DAB_CUDA(cudaMemcpyAsync(&pr->h_counters[track], off + nqn, sizeof(int32_t), cudaMemcpyDeviceToHost, pr->stream));
+  DAB_CUDA(dab_readback(pr, &pr->h_counters[track], off + nqn, sizeof(int32_t)));
   if (track == DAB_TRACK_AUDIO) {
     // list positions of the first not-quiet frame >= row_lo / >= row_hi (row-sharded match stage)
     const int64_t lo = row_lo < 0 ? 0 : (row_lo > nqn ? nqn : row_lo), hi = row_hi < lo ? lo : (row_hi > nqn ? nqn : row_hi);
-    DAB_CUDA(cudaMemcpyAsync(&pr->h_counters[20], off + lo, sizeof(int32_t), cudaMemcpyDeviceToHost, pr->stream));
-    DAB_CUDA(cudaMemcpyAsync(&pr->h_counters[21], off + hi, sizeof(int32_t), cudaMemcpyDeviceToHost, pr->stream));
+    DAB_CUDA(dab_readback(pr, &pr->h_counters[20], off + lo, sizeof(int32_t)));
+    DAB_CUDA(dab_readback(pr, &pr->h_counters[21], off + hi, sizeof(int32_t)));
   }
   DAB_CUDA(cudaGetLastError());
   return DAB_OK;
@@ -754,8 +754,7 @@ int dab_run_stage_a_match(dab_pair *pr, int64_t row_lo, int64_t row_hi) {
     ctx->launches += 1;
   }
   DAB_TRY(dab_exclusive_scan(pr, pr->tbl_count.as<int32_t>(), pr->tbl_start.as<int32_t>(), nslots));
-  DAB_CUDA(cudaMemcpyAsync(&pr->h_counters[2], pr->tbl_start.as<int32_t>() + nslots, sizeof(int32_t),
-                           cudaMemcpyDeviceToHost, st));
+  DAB_CUDA(dab_readback(pr, &pr->h_counters[2], pr->tbl_start.as<int32_t>() + nslots, sizeof(int32_t)));
   DAB_CUDA(cudaStreamSynchronize(st));
   const int64_t n_entries = (int32_t)pr->h_counters[2];
   pr->stats.n_table_entries = n_entries;
@@ -787,10 +786,8 @@ int dab_run_stage_a_match(dab_pair *pr, int64_t row_lo, int64_t row_hi) {
     gate_kernel<false><<<gb, 256, 0, st>>>(ga);
     ctx->launches += 1;
     DAB_TRY(dab_exclusive_scan(pr, pr->row_count.as<int32_t>(), pr->row_off.as<int32_t>(), n_q));
-    DAB_CUDA(cudaMemcpyAsync(&pr->h_counters[4], pr->row_off.as<int32_t>() + n_q, sizeof(int32_t),
-                             cudaMemcpyDeviceToHost, st));
-    DAB_CUDA(cudaMemcpyAsync(&pr->h_counters[3], pr->counters.as<int64_t>() + 3, sizeof(int64_t),
-                             cudaMemcpyDeviceToHost, st));
+    DAB_CUDA(dab_readback(pr, &pr->h_counters[4], pr->row_off.as<int32_t>() + n_q, sizeof(int32_t)));
+    DAB_CUDA(dab_readback(pr, &pr->h_counters[3], pr->counters.as<int64_t>() + 3, sizeof(int64_t)));
     DAB_CUDA(cudaStreamSynchronize(st));
     n_cand = (int32_t)pr->h_counters[4];
     pr->stats.n_enumerated = pr->h_counters[3];
@@ -825,8 +822,7 @@ int dab_run_stage_a_match(dab_pair *pr, int64_t row_lo, int64_t row_hi) {
     score_kernel<<<(unsigned)cdiv(n_cand, 128), 128, 0, st>>>(sa);
     ctx->launches += 1;
     DAB_TRY(dab_exclusive_scan(pr, pr->keep_flag.as<int32_t>(), pr->keep_off.as<int32_t>(), n_cand));
-    DAB_CUDA(cudaMemcpyAsync(&pr->h_counters[5], pr->keep_off.as<int32_t>() + n_cand, sizeof(int32_t),
-                             cudaMemcpyDeviceToHost, st));
+    DAB_CUDA(dab_readback(pr, &pr->h_counters[5], pr->keep_off.as<int32_t>() + n_cand, sizeof(int32_t)));
     DAB_CUDA(cudaStreamSynchronize(st));
     n_pts = (int32_t)pr->h_counters[5];
     DAB_TRY(dab_ensure(ctx, pr->pt_i, sizeof(int32_t) * (size_t)(n_pts + 1)));
@@ -883,7 +879,7 @@ int dab_run_stage_a_dp(dab_pair *pr) {
     ta.seg = pr->seglist.as<int32_t>(); ta.path_x = pr->path1_x.as<int32_t>(); ta.path_y = pr->path1_y.as<int32_t>();
     trace1_kernel<<<1, 256, 0, st>>>(ta);
     ctx->launches += 3;
-    DAB_CUDA(cudaMemcpyAsync(&pr->h_counters[6], pr->dpres.as<int32_t>(), 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    DAB_CUDA(dab_readback(pr, &pr->h_counters[6], pr->dpres.as<int32_t>(), 2 * sizeof(int32_t)));
     DAB_CUDA(cudaEventRecord(pr->ev[13], st));
     DAB_CUDA(cudaStreamSynchronize(st));
     n_path = reinterpret_cast<int32_t *>(&pr->h_counters[6])[1];
@@ -940,7 +936,7 @@ int dab_run_import_points1(dab_pair *pr, const int32_t *i_audio, const int32_t *
                                                                     (int32_t)V.n_list, pr->pt_s.as<int32_t>(),
                                                                     pr->dpres.as<int32_t>() + 8);
     ctx->launches += 1;
-    DAB_CUDA(cudaMemcpyAsync(&pr->h_counters[22], pr->dpres.as<int32_t>() + 8, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    DAB_CUDA(dab_readback(pr, &pr->h_counters[22], pr->dpres.as<int32_t>() + 8, sizeof(int32_t)));
     DAB_CUDA(cudaStreamSynchronize(st));
     if ((int32_t)pr->h_counters[22] != 0) {
       ctx->err = "import_points1: a point's video frame is not one of this pair's hashed video frames";

@@ -1551,8 +1551,8 @@ int dab_run_stage_b(dab_pair *pr, int32_t n_cor, int32_t n_clusters) {
     corridor_kernel<false><<<gb, 128, 0, st>>>(sb);
     ctx->launches += 1;
     DAB_TRY(dab_exclusive_scan(pr, sb.row_count, pr->row2_off.as<int32_t>(), n_a));
-    DAB_CUDA(cudaMemcpyAsync(&pr->h_counters[9], pr->row2_off.as<int32_t>() + n_a, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    DAB_CUDA(cudaMemcpyAsync(&pr->h_counters[10], pr->dpres.as<int32_t>() + 6, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    DAB_CUDA(dab_readback(pr, &pr->h_counters[9], pr->row2_off.as<int32_t>() + n_a, sizeof(int32_t)));
+    DAB_CUDA(dab_readback(pr, &pr->h_counters[10], pr->dpres.as<int32_t>() + 6, sizeof(int32_t)));
     DAB_CUDA(cudaStreamSynchronize(st));
     if ((int32_t)pr->h_counters[10] != 0) { ctx->err = "more than 32 corridors overlap one audio row"; return DAB_E_CAPACITY; }
     n_pts = (int32_t)pr->h_counters[9];
@@ -1624,8 +1624,8 @@ int dab_run_stage_b(dab_pair *pr, int32_t n_cor, int32_t n_clusters) {
     ea.n = (int32_t)n_pts; ea.rows = pr->path2.as<double>(); ea.n_path = pr->dpres.as<int32_t>() + 1;
     lift_emit_kernel<<<gl, 256, 0, st>>>(ea);
     ctx->launches += 2 + 2 * levels;
-    DAB_CUDA(cudaMemcpyAsync(&pr->h_counters[12], pr->dpres.as<int32_t>(), 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    DAB_CUDA(cudaMemcpyAsync(&pr->h_counters[16], la.counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    DAB_CUDA(dab_readback(pr, &pr->h_counters[12], pr->dpres.as<int32_t>(), 2 * sizeof(int32_t)));
+    DAB_CUDA(dab_readback(pr, &pr->h_counters[16], la.counters, 4 * sizeof(unsigned long long)));
     DAB_CUDA(cudaEventRecord(pr->ev[17], st));
     DAB_CUDA(cudaStreamSynchronize(st));
     n_path = reinterpret_cast<int32_t *>(&pr->h_counters[12])[1];
@@ -1679,7 +1679,7 @@ int dab_run_stage_b(dab_pair *pr, int32_t n_cor, int32_t n_clusters) {
     ta.seg = pr->seglist.as<int32_t>(); ta.rows = pr->path2.as<double>();
     trace2_kernel<<<1, 256, 0, st>>>(ta);
     ctx->launches += 3;
-    DAB_CUDA(cudaMemcpyAsync(&pr->h_counters[12], pr->dpres.as<int32_t>(), 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    DAB_CUDA(dab_readback(pr, &pr->h_counters[12], pr->dpres.as<int32_t>(), 2 * sizeof(int32_t)));
     DAB_CUDA(cudaEventRecord(pr->ev[17], st));
     DAB_CUDA(cudaStreamSynchronize(st));
     n_path = reinterpret_cast<int32_t *>(&pr->h_counters[12])[1];

@@ -176,6 +176,16 @@ int dab_pair_dp1(dab_pair *pair, int64_t *n_path);
 int dab_pair_stage_b(dab_pair *pair, const float *audio_scaled, int64_t n_audio,
                      const float *video_scaled, int64_t n_video, const dab_corridor *corridors,
                      int32_t n_corridors, int32_t n_clusters, int64_t *n_points, int64_t *n_path);
+/* The same stage for a pair that still holds its feature vectors on the device (after dab_pair_set_pcm
+ * or dab_pair_set_features): the scaled arrays of describealign.py:737-741 are produced on the device
+ * from the least-squares gains and the audio standard deviations of the first three features (numpy
+ * float32 roundings: audio / std ; video * gain / std), so only 6 floats travel instead of
+ * 12 (n_audio + n_video) bytes.  n_audio / n_video: lengths of the scaled arrays (the shortest of the
+ * three vectors of each track); *_energy_max: np.max of column 0 of each scaled array (:908-909). */
+int dab_pair_stage_b_gains(dab_pair *pair, const float gain[3], const float audio_std[3], int64_t n_audio,
+                           int64_t n_video, float audio_energy_max, float video_energy_max,
+                           const dab_corridor *corridors, int32_t n_corridors, int32_t n_clusters,
+                           int64_t *n_points, int64_t *n_path);
 /* final path rows (video j, audio i, cluster, qual, cum), float64 row-major (n_path, 5),
  * in frames (the /210 scaling of :1026 is the caller's). */
 int dab_pair_get_path2(dab_pair *pair, double *rows);

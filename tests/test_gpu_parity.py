@@ -277,6 +277,32 @@ def test_stage_b_block_dp_many_corridors(gpu_ctx, seed, n_cor):
     assert stats["n_dp2_run_points"] > 0.05 * stats["n_points2"], stats
 
 
+def test_stage_b_device_scaling_equals_uploaded_arrays(gpu_ctx, golden_align):
+    """dab_pair_stage_b_gains (scaled features rebuilt on the device from 6 scalars, describealign.py:737-741)
+    against dab_pair_stage_b with the host's numpy arrays: identical points, quals and path."""
+    from describealign_b200 import api
+    _, meta = golden_align
+    v, a = golden_pair_pcm(meta, "pair_warp")
+    res = []
+    for device_scaling in (True, False):
+        job = api.AlignJob()
+        try:
+            job.device_scaling = device_scaling
+            job.load_pcm(v, a)
+            job.device_stage_a()
+            job.host_stage()
+            assert job.gains is not None
+            job.device_stage_b()
+            res.append((job.pair.points2(), job.path.copy(), job.h2d_bytes))
+        finally:
+            job.close()
+    (p0, path0, up0), (p1, path1, up1) = res
+    for x, y in zip(p0, p1):
+        np.testing.assert_array_equal(x, y)
+    np.testing.assert_array_equal(path0, path1)
+    assert up0 < up1
+
+
 def test_end_to_end_dp2_variants_agree(gpu_ctx, golden_align):
     """Same pair through the four pass-2 DPs: identical paths (the block DP is the product path;
     the tree DP is the generic fallback)."""
