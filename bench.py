@@ -54,7 +54,9 @@ def parse_args():
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the C2 durations (debugging only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--timeline", default=None, help="write the device timeline of the last step of each arm (per pair and stage) to <name>_dev.json / <name>_e2e.json")
-    ap.add_argument("--spin-wait", action="store_true", help="leave the CUDA default (spinning) host wait")
+    ap.add_argument("--dp-reserve-kb", type=int, default=0, help="see dab_set_option: keeps other pairs' big CTAs off the DP's SM")
+    ap.add_argument("--switch-interval", type=float, default=0.005, help="Python thread switch interval (s)")
+    ap.add_argument("--host-wait", type=int, default=2, help="dab_set_host_wait mode: 0 spin (CUDA default), 1 blocking sync, 2 query + sleep")
     return ap.parse_args()
 
 
@@ -218,7 +220,7 @@ def run_ours(args, rank, world, local_rank):
     from describealign_b200 import api, build
     build.build()
     # W host threads wait on W pair streams: they must sleep, not spin (16 host cores, W >> 16)
-    sched = api._cabi.set_host_wait(local_rank, blocking=not args.spin_wait)
+    sched = api._cabi.set_host_wait(local_rank, args.host_wait)
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -255,6 +257,9 @@ def run_ours(args, rank, world, local_rank):
     except Exception:
         pass
     ctx = api.context()
+    if args.dp_reserve_kb:
+        ctx.set_option("dp_reserve_kb", args.dp_reserve_kb)
+    sys.setswitchinterval(args.switch_interval)
     # W pairs in flight: one dab_pair (device buffers + CUDA stream) per worker slot.  The frontier DPs
     # are one warp per pair and tens of milliseconds long, so throughput comes from keeping W of them
     # running while the data-parallel kernels of other pairs fill the SMs.  A step ends with a tail in
@@ -468,7 +473,7 @@ def run_ours(args, rank, world, local_rank):
                     "h2d_gbs_achieved": h2d_all / world / (ms_e2e * 1e-3) / 1e9,
                     "h2d_gbs_single_copy": h2d_gbs,
                     "note": "PCM is 2 bytes per sample per channel; the end-to-end rate is bounded by the host-to-device link"},
-            "host_wait": {"cuda_schedule_flags": sched, "mode": "spin (CUDA default)" if args.spin_wait else "blocking"},
+            "host_wait": {"cuda_schedule_flags": sched, "mode": ["spin (CUDA default)", "blocking sync", "query + sleep polling"][args.host_wait]},
             "gpu_launches": int(launches_all),
             "roofline": main_roof,
             "roofline_by_kernel": roof,

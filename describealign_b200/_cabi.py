@@ -171,10 +171,10 @@ def pinned_empty(shape, dtype) -> np.ndarray:
     return np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
 
 
-def set_host_wait(device: int = -1, blocking: bool = True) -> int:
-    """Host threads sleep (True) or spin (False, the CUDA default) while waiting for the device; call
-    it before the first pair is created.  Returns the device's schedule flags after the call."""
-    rc = load().dab_set_host_wait(int(device), 1 if blocking else 0)
+def set_host_wait(device: int = -1, mode: int = 2) -> int:
+    """How host threads wait for the device: 0 CUDA default (spin), 1 blocking sync, 2 query + sleep
+    polling.  Call it before the first pair is created.  Returns the device's schedule flags."""
+    rc = load().dab_set_host_wait(int(device), int(mode))
     if rc < 0:
         raise DabError(f"dab_set_host_wait failed ({rc})")
     return rc

@@ -3,9 +3,26 @@
 
 #include <new>
 
+#include <time.h>
+
 #include "common.cuh"
 
 static std::string g_create_err;
+
+int dab_g_wait_mode = 0;
+
+cudaError_t dab_wait_stream(cudaStream_t st) {
+  if (dab_g_wait_mode != 2) return cudaStreamSynchronize(st);
+  // poll and sleep: 20 us at first, backing off to 400 us (a DP kernel runs for tens of milliseconds)
+  long ns = 20000;
+  for (;;) {
+    const cudaError_t e = cudaStreamQuery(st);
+    if (e != cudaErrorNotReady) return e;
+    struct timespec ts = {0, ns};
+    nanosleep(&ts, nullptr);
+    if (ns < 400000) ns += ns / 2;
+  }
+}
 
 // ---- pinned host memory pool ----------------------------------------------------------------
 // Results (features, paths) are copied device -> host asynchronously; with pageable destinations
@@ -128,14 +145,16 @@ int dab_device_count(void) {
 
 const char *dab_last_error(const dab_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
 
-int dab_set_host_wait(int device, int blocking) {
+int dab_set_host_wait(int device, int mode) {
+  if (mode < 0 || mode > 2) return -DAB_E_ARG;
   if (device >= 0 && cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return -DAB_E_CUDA; }
   unsigned flags = 0;
   if (cudaGetDeviceFlags(&flags) != cudaSuccess) { cudaGetLastError(); return -DAB_E_CUDA; }
   flags = (flags & ~(unsigned)cudaDeviceScheduleMask) |
-          (blocking ? (unsigned)cudaDeviceScheduleBlockingSync : (unsigned)cudaDeviceScheduleAuto);
+          (mode == 1 ? (unsigned)cudaDeviceScheduleBlockingSync : (unsigned)cudaDeviceScheduleAuto);
   if (cudaSetDeviceFlags(flags) != cudaSuccess) { cudaGetLastError(); return -DAB_E_CUDA; }
   if (cudaGetDeviceFlags(&flags) != cudaSuccess) { cudaGetLastError(); return -DAB_E_CUDA; }
+  dab_g_wait_mode = mode;
   return (int)(flags & (unsigned)cudaDeviceScheduleMask);
 }
 
@@ -175,6 +194,7 @@ void dab_destroy(dab_ctx *ctx) { delete ctx; }
 int dab_set_option(dab_ctx *ctx, const char *name, int64_t value) {
   if (!ctx || !name) return DAB_E_ARG;
   if (strcmp(name, "dp2_generic") == 0) { ctx->opt_dp2_generic = value != 0; return DAB_OK; }
+  if (strcmp(name, "dp_reserve_kb") == 0 && value >= 0 && value <= 176) { ctx->opt_dp_reserve_kb = (int)value; return DAB_OK; }
   if (strcmp(name, "dp2_impl") == 0 && value >= 0 && value <= 3) { ctx->opt_dp2_impl = (int)value; return DAB_OK; }
   ctx->err = std::string("dab_set_option: unknown option ") + name;
   return DAB_E_ARG;
@@ -226,7 +246,7 @@ int dab_pair_create(dab_ctx *ctx, dab_pair **out) {
 void dab_pair_destroy(dab_pair *pr) {
   if (!pr) return;
   cudaSetDevice(pr->ctx->device);
-  if (pr->stream) cudaStreamSynchronize(pr->stream);
+  if (pr->stream) dab_wait_stream(pr->stream);
   for (int t = 0; t < 2; ++t) {
     Track &k = pr->trk[t];
     DevBuf *bs[] = {&k.pcm, &k.energy, &k.zc, &k.b0, &k.b1, &k.b2, &k.ms, &k.nrm, &k.pack, &k.code, &k.nq_flag, &k.nq_list};
@@ -250,7 +270,7 @@ void dab_pair_destroy(dab_pair *pr) {
 int dab_pair_sync(dab_pair *pr) {
   if (!pr) return DAB_E_ARG;
   dab_ctx *ctx = pr->ctx;
-  DAB_CUDA(cudaStreamSynchronize(pr->stream));
+  DAB_CUDA(dab_wait_stream(pr->stream));
   return DAB_OK;
 }
 
@@ -318,7 +338,7 @@ int dab_pair_set_features(dab_pair *pr, int track, const float *energy, int64_t 
   DAB_CUDA(cudaMemcpyAsync(tk.b0.p, band0, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, st));
   DAB_CUDA(cudaMemcpyAsync(tk.b1.p, band1, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, st));
   DAB_CUDA(cudaMemcpyAsync(tk.b2.p, band2, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, st));
-  DAB_CUDA(cudaStreamSynchronize(st));   // the caller may free its arrays right after (describealign.py:1107)
+  DAB_CUDA(dab_wait_stream(st));   // the caller may free its arrays right after (describealign.py:1107)
   tk.have_features = true;
   return DAB_OK;
 }
@@ -348,7 +368,7 @@ int dab_pair_get_features(dab_pair *pr, int track, float *energy, float *zc, flo
     if (band1) DAB_CUDA(cudaMemcpyAsync(band1, tk.b1.p, sizeof(float) * (size_t)tk.L, cudaMemcpyDeviceToHost, st));
     if (band2) DAB_CUDA(cudaMemcpyAsync(band2, tk.b2.p, sizeof(double) * (size_t)tk.L, cudaMemcpyDeviceToHost, st));
   }
-  DAB_CUDA(cudaStreamSynchronize(st));
+  DAB_CUDA(dab_wait_stream(st));
   return DAB_OK;
 }
 
@@ -380,7 +400,7 @@ int dab_pair_get_path1(dab_pair *pr, int32_t *x_audio, int32_t *y_video) {
     if (x_audio) DAB_CUDA(cudaMemcpyAsync(x_audio, pr->path1_x.p, bytes, cudaMemcpyDeviceToHost, pr->stream));
     if (y_video) DAB_CUDA(cudaMemcpyAsync(y_video, pr->path1_y.p, bytes, cudaMemcpyDeviceToHost, pr->stream));
   }
-  DAB_CUDA(cudaStreamSynchronize(pr->stream));
+  DAB_CUDA(dab_wait_stream(pr->stream));
   return DAB_OK;
 }
 
@@ -415,7 +435,7 @@ static int export_points1(dab_pair *pr, int32_t *i_audio, int32_t *v_video, doub
       DAB_CUDA(cudaMemcpyAsync(v_video, pr->cand_tmp.p, sizeof(int32_t) * (size_t)n, kind, st));
     }
   }
-  DAB_CUDA(cudaStreamSynchronize(pr->stream));
+  DAB_CUDA(dab_wait_stream(pr->stream));
   return DAB_OK;
 }
 
@@ -598,7 +618,7 @@ int dab_pair_get_path2(dab_pair *pr, double *rows) {
   DAB_CUDA(cudaSetDevice(ctx->device));
   if (rows && pr->n_path2 > 0)
     DAB_CUDA(cudaMemcpyAsync(rows, pr->path2.p, sizeof(double) * 5 * (size_t)pr->n_path2, cudaMemcpyDeviceToHost, pr->stream));
-  DAB_CUDA(cudaStreamSynchronize(pr->stream));
+  DAB_CUDA(dab_wait_stream(pr->stream));
   return DAB_OK;
 }
 
@@ -615,7 +635,7 @@ int dab_pair_get_points2(dab_pair *pr, int32_t *i_audio, double *j_video, int32_
     if (cluster) DAB_CUDA(cudaMemcpyAsync(cluster, pr->p2_c.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
     if (qual) DAB_CUDA(cudaMemcpyAsync(qual, pr->p2_q.p, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
   }
-  DAB_CUDA(cudaStreamSynchronize(st));
+  DAB_CUDA(dab_wait_stream(st));
   return DAB_OK;
 }
 
@@ -629,7 +649,7 @@ int dab_pair_get_timings(dab_pair *pr, float ms[16]) {
   if (!pr || !ms) return DAB_E_ARG;
   dab_ctx *ctx = pr->ctx;
   DAB_CUDA(cudaSetDevice(ctx->device));
-  DAB_CUDA(cudaStreamSynchronize(pr->stream));
+  DAB_CUDA(dab_wait_stream(pr->stream));
   for (int s = 0; s < 16; ++s) {
     ms[s] = 0.0f;
     if (s < 9 && pr->ev_used[s]) {
@@ -649,7 +669,7 @@ int dab_pair_get_timeline(dab_pair *pr, void *ref_event, float start_ms[9], floa
   if (!pr || !ref_event || !start_ms || !end_ms) return DAB_E_ARG;
   dab_ctx *ctx = pr->ctx;
   DAB_CUDA(cudaSetDevice(ctx->device));
-  DAB_CUDA(cudaStreamSynchronize(pr->stream));
+  DAB_CUDA(dab_wait_stream(pr->stream));
   cudaEvent_t ref = reinterpret_cast<cudaEvent_t>(ref_event);
   for (int s = 0; s < 9; ++s) {
     start_ms[s] = end_ms[s] = -1.0f;

@@ -27,6 +27,7 @@ struct dab_ctx {
   int64_t launches = 0;
   int sm_count = 148;
   int opt_dp2_generic = 0;   // force the tree DP for pass 2 (testing)
+  int opt_dp_reserve_kb = 0; // dynamic shared memory the pass-2 DP kernel asks for without using it (see dab_set_option)
   int opt_dp2_impl = 0;      // 0 block kernel, 1 corridor-state kernel, 2 tree DP, 3 lane-per-corridor kernel (all exact)
 };
 
@@ -136,6 +137,11 @@ struct StreamScope {
   ~StreamScope() { dab_t_stream = prev; }
 };
 int dab_ensure(dab_ctx *ctx, DevBuf &b, size_t bytes);
+// Host thread waits for everything queued in `st`.  Mode 0/1: cudaStreamSynchronize (spinning or
+// blocking, as the device's schedule flags say); mode 2: cudaStreamQuery + short sleeps with back-off
+// (see dab_set_host_wait).
+extern int dab_g_wait_mode;
+cudaError_t dab_wait_stream(cudaStream_t st);
 cudaError_t dab_readback(dab_pair *pr, void *host_dst, const void *dev_src, size_t bytes);
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -726,7 +726,7 @@ int dab_run_stage_a_match(dab_pair *pr, int64_t row_lo, int64_t row_hi) {
   DAB_TRY(prep_track(pr, DAB_TRACK_VIDEO));
   DAB_TRY(prep_track(pr, DAB_TRACK_AUDIO, row_lo, row_hi));
   DAB_CUDA(cudaEventRecord(pr->ev[5], st));
-  DAB_CUDA(cudaStreamSynchronize(st));
+  DAB_CUDA(dab_wait_stream(st));
   const int64_t n_vnq = (int32_t)pr->h_counters[0];
   const int64_t n_vsel = (n_vnq + 3) / 4;
   const int64_t n_q_all = (int32_t)pr->h_counters[1];
@@ -755,7 +755,7 @@ int dab_run_stage_a_match(dab_pair *pr, int64_t row_lo, int64_t row_hi) {
   }
   DAB_TRY(dab_exclusive_scan(pr, pr->tbl_count.as<int32_t>(), pr->tbl_start.as<int32_t>(), nslots));
   DAB_CUDA(dab_readback(pr, &pr->h_counters[2], pr->tbl_start.as<int32_t>() + nslots, sizeof(int32_t)));
-  DAB_CUDA(cudaStreamSynchronize(st));
+  DAB_CUDA(dab_wait_stream(st));
   const int64_t n_entries = (int32_t)pr->h_counters[2];
   pr->stats.n_table_entries = n_entries;
   DAB_TRY(dab_ensure(ctx, pr->tbl_items, sizeof(int32_t) * (size_t)(n_entries + 1)));
@@ -788,7 +788,7 @@ int dab_run_stage_a_match(dab_pair *pr, int64_t row_lo, int64_t row_hi) {
     DAB_TRY(dab_exclusive_scan(pr, pr->row_count.as<int32_t>(), pr->row_off.as<int32_t>(), n_q));
     DAB_CUDA(dab_readback(pr, &pr->h_counters[4], pr->row_off.as<int32_t>() + n_q, sizeof(int32_t)));
     DAB_CUDA(dab_readback(pr, &pr->h_counters[3], pr->counters.as<int64_t>() + 3, sizeof(int64_t)));
-    DAB_CUDA(cudaStreamSynchronize(st));
+    DAB_CUDA(dab_wait_stream(st));
     n_cand = (int32_t)pr->h_counters[4];
     pr->stats.n_enumerated = pr->h_counters[3];
     DAB_TRY(dab_ensure(ctx, pr->cand_tmp, sizeof(int32_t) * (size_t)(n_cand + 1)));
@@ -823,7 +823,7 @@ int dab_run_stage_a_match(dab_pair *pr, int64_t row_lo, int64_t row_hi) {
     ctx->launches += 1;
     DAB_TRY(dab_exclusive_scan(pr, pr->keep_flag.as<int32_t>(), pr->keep_off.as<int32_t>(), n_cand));
     DAB_CUDA(dab_readback(pr, &pr->h_counters[5], pr->keep_off.as<int32_t>() + n_cand, sizeof(int32_t)));
-    DAB_CUDA(cudaStreamSynchronize(st));
+    DAB_CUDA(dab_wait_stream(st));
     n_pts = (int32_t)pr->h_counters[5];
     DAB_TRY(dab_ensure(ctx, pr->pt_i, sizeof(int32_t) * (size_t)(n_pts + 1)));
     DAB_TRY(dab_ensure(ctx, pr->pt_s, sizeof(int32_t) * (size_t)(n_pts + 1)));
@@ -872,7 +872,7 @@ int dab_run_stage_a_dp(dab_pair *pr) {
     da.meta = pr->back1.as<int4>();
     da.result = pr->dpres.as<int32_t>();
     dp1_kernel<<<1, 32, 0, st>>>(da);
-    DAB_CUDA(cudaStreamSynchronize(st));   // keep dependents of the serial DP out of the hardware queues (see stage_b.cu)
+    DAB_CUDA(dab_wait_stream(st));   // keep dependents of the serial DP out of the hardware queues (see stage_b.cu)
     TraceArgs ta;
     ta.meta = da.meta; ta.result = da.result;
     ta.pt_i = pr->pt_i.as<int32_t>(); ta.pt_s = pr->pt_s.as<int32_t>(); ta.v_sel = V.nq_list.as<int32_t>();
@@ -881,7 +881,7 @@ int dab_run_stage_a_dp(dab_pair *pr) {
     ctx->launches += 3;
     DAB_CUDA(dab_readback(pr, &pr->h_counters[6], pr->dpres.as<int32_t>(), 2 * sizeof(int32_t)));
     DAB_CUDA(cudaEventRecord(pr->ev[13], st));
-    DAB_CUDA(cudaStreamSynchronize(st));
+    DAB_CUDA(dab_wait_stream(st));
     n_path = reinterpret_cast<int32_t *>(&pr->h_counters[6])[1];
   } else {
     DAB_CUDA(cudaEventRecord(pr->ev[13], st));
@@ -937,7 +937,7 @@ int dab_run_import_points1(dab_pair *pr, const int32_t *i_audio, const int32_t *
                                                                     pr->dpres.as<int32_t>() + 8);
     ctx->launches += 1;
     DAB_CUDA(dab_readback(pr, &pr->h_counters[22], pr->dpres.as<int32_t>() + 8, sizeof(int32_t)));
-    DAB_CUDA(cudaStreamSynchronize(st));
+    DAB_CUDA(dab_wait_stream(st));
     if ((int32_t)pr->h_counters[22] != 0) {
       ctx->err = "import_points1: a point's video frame is not one of this pair's hashed video frames";
       return DAB_E_ARG;

@@ -1189,7 +1189,97 @@ __global__ void __launch_bounds__(32, 1) dp2_block_kernel(Dp2LArgs a) {
       }
     };
 
-    int t = 0;
+    // ---- fast path: a full group whose 32 points all lie on ONE leader corridor and all see the
+    //      corridor's previous two points.  If the cluster best is never the choice, cum is the chain
+    //      max(c0, c1) + q - the only serial part, 6 instructions per point, every lane runs it - and
+    //      predecessor, checks, running maxima and the new state are per-point work plus three warp
+    //      scans.  All or nothing: a failed check leaves everything to the general path below.
+    bool fast_done = false;
+    if (hard == 0u) {
+      const int k0 = __shfl_sync(FULL, own_k, 0);
+      const int both = P2_VIS1 | P2_VIS2;
+      const bool uniform = __all_sync(FULL, own_k == k0 && (own.kf & both) == both);
+      const double k_c0 = __shfl_sync(FULL, c0, k0), k_c1 = __shfl_sync(FULL, c1, k0);
+      if (uniform && k_c0 >= top_v + LEAD_MARGIN) {
+        double ca = k_c0, cb = k_c1;
+#pragma unroll
+        for (int u = 0; u < 32; ++u) {
+          const double m = ca >= cb ? ca : cb;
+          const double cum = m + s_rec[buf][u].q;
+          cb = ca; ca = cum;
+          s_cum[u] = cum;                        // same value from every lane
+        }
+        __syncwarp();
+        const double my_cum = s_cum[lane];
+        const int k_id0 = __shfl_sync(FULL, id0, k0), k_id1 = __shfl_sync(FULL, id1, k0);
+        const double k_clv = __shfl_sync(FULL, cl_v, k0), k_pmv = __shfl_sync(FULL, pm_v, k0);
+        const int k_pmi = __shfl_sync(FULL, pm_i, k0);
+        double c0u = __shfl_up_sync(FULL, my_cum, 1), c1u = __shfl_up_sync(FULL, my_cum, 2);
+        if (lane == 0) { c0u = k_c0; c1u = k_c1; }
+        if (lane == 1) c1u = k_c0;
+        const int id0u = lane == 0 ? k_id0 : base + lane - 1;
+        const int id1u = lane == 0 ? k_id1 : (lane == 1 ? k_id0 : base + lane - 2);
+        const bool take0 = c0u >= c1u;             // the later candidate wins ties (describealign.py:966-973)
+        const double m_u = take0 ? c0u : c1u;
+        const int pred_u = take0 ? id0u : id1u;
+        // cluster best before this point: running maximum of cum - 50 over the earlier points
+        const double cj = my_cum - 50.0;
+        double pcj = cj;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const double o = __shfl_up_sync(FULL, pcj, d);
+          if (lane >= d && o > pcj) pcj = o;
+        }
+        const double xcj = __shfl_up_sync(FULL, pcj, 1);
+        const double clv_u = (lane > 0 && xcj > k_clv) ? xcj : k_clv;
+        // frontier entries of the block: running arg-max of cum - 1000, first occurrence on ties
+        // (inside one corridor the earlier point also has the smaller j)
+        double sv = my_cum - 1000.0;
+        int sl_ = lane;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const double ov = __shfl_up_sync(FULL, sv, d);
+          const int ol = __shfl_up_sync(FULL, sl_, d);
+          if (lane >= d && !(sv > ov)) { sv = ov; sl_ = ol; }
+        }
+        const double xv = __shfl_up_sync(FULL, sv, 1);
+        const double tv_u = (lane > 0 && xv > top_v) ? xv : top_v;     // value of the frontier's best entry before this point
+        const bool ok = m_u >= clv_u && tv_u <= m_u;
+        if (__all_sync(FULL, ok)) {
+          BackRec b; b.best = m_u; b.pred = pred_u; b.pad = 0;
+          a.back[base + lane] = b;
+          const bool newhead = sv > k_pmv;
+          PmEntry en; en.val = newhead ? sv : k_pmv; en.id = newhead ? base + sl_ : k_pmi; en.pad = 0;
+          s_pmbase[k0][own.ro] = en;
+          if (lane >= 32 - RING) s_ring[own.ro & (RING - 1)][k0] = en;
+          // the owner lane's new state
+          const double n_c0 = __shfl_sync(FULL, my_cum, 31), n_c1 = __shfl_sync(FULL, my_cum, 30);
+          const double n_c2 = __shfl_sync(FULL, my_cum, 29);
+          const double maxcj = __shfl_sync(FULL, pcj, 31);
+          const int first_cj = __ffs(__ballot_sync(FULL, cj == maxcj)) - 1;
+          const double h_v = __shfl_sync(FULL, en.val, 31);
+          const int h_i = __shfl_sync(FULL, en.id, 31);
+          const int n_ro = __shfl_sync(FULL, own.ro, 31);
+          if (lane == k0) {
+            c0 = n_c0; c1 = n_c1; c2 = n_c2;
+            id0 = base + 31; id1 = base + 30; id2 = base + 29;
+            if (maxcj > cl_v) { cl_v = maxcj; cl_i = base + first_cj; }
+            pm_v = h_v; pm_i = h_i;
+            filled = n_ro;
+          }
+          // the frontier's best entry after the block
+          const double e_v = __shfl_sync(FULL, sv, 31);
+          const int e_l = __shfl_sync(FULL, sl_, 31);
+          const double e_j = __shfl_sync(FULL, own.j, e_l);
+          if (e_v > top_v || (e_v == top_v && e_j < top_j)) { top_v = e_v; top_j = e_j; top_i = base + e_l; }
+          n_blockpts += 32;
+          fast_done = true;
+          __syncwarp();
+        }
+      }
+    }
+
+    int t = fast_done ? cnt : 0;
     while (t < cnt) {
       const unsigned stopbits = hard >> t;
       const int e = stopbits ? t + __ffs(stopbits) - 1 : 32;       // block = points [t, e)
@@ -1553,7 +1643,7 @@ int dab_run_stage_b(dab_pair *pr, int32_t n_cor, int32_t n_clusters) {
     DAB_TRY(dab_exclusive_scan(pr, sb.row_count, pr->row2_off.as<int32_t>(), n_a));
     DAB_CUDA(dab_readback(pr, &pr->h_counters[9], pr->row2_off.as<int32_t>() + n_a, sizeof(int32_t)));
     DAB_CUDA(dab_readback(pr, &pr->h_counters[10], pr->dpres.as<int32_t>() + 6, sizeof(int32_t)));
-    DAB_CUDA(cudaStreamSynchronize(st));
+    DAB_CUDA(dab_wait_stream(st));
     if ((int32_t)pr->h_counters[10] != 0) { ctx->err = "more than 32 corridors overlap one audio row"; return DAB_E_CAPACITY; }
     n_pts = (int32_t)pr->h_counters[9];
     DAB_TRY(dab_ensure(ctx, pr->p2_i, sizeof(int32_t) * (size_t)(n_pts + 1)));
@@ -1601,12 +1691,19 @@ int dab_run_stage_b(dab_pair *pr, int32_t n_cor, int32_t n_clusters) {
     DAB_CUDA(cudaMemsetAsync(la.counters, 0, 4 * sizeof(unsigned long long), st));
     if (pr->ctx->opt_dp2_impl == 1) dp2_corridor_kernel<<<1, 32, 0, st>>>(la);
     else if (pr->ctx->opt_dp2_impl == 3) dp2_lane_kernel<<<1, 32, 0, st>>>(la);
-    else dp2_block_kernel<<<1, 32, 0, st>>>(la);
+    else {
+      // "dp_reserve_kb": unused dynamic shared memory that keeps the feature kernel's 105 KB CTAs (and a
+      // second DP) off the SM this one-warp kernel runs on, so that its dependent chain does not share
+      // issue slots with 32 busy warps
+      const size_t reserve = (size_t)ctx->opt_dp_reserve_kb * 1024;
+      if (reserve) DAB_CUDA(cudaFuncSetAttribute(dp2_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)reserve));
+      dp2_block_kernel<<<1, 32, reserve, st>>>(la);
+    }
     // The DP runs for tens of milliseconds on one warp.  Nothing that depends on it - not even an
     // event record - is enqueued until it is done: streams share the GPU's 32 hardware queues, and a
     // dependent command waiting at the head of a queue stalls the other pairs' work mapped to that
     // queue (with more pairs in flight than queues that costs all the concurrency beyond 32).
-    DAB_CUDA(cudaStreamSynchronize(st));
+    DAB_CUDA(dab_wait_stream(st));
     DAB_CUDA(cudaEventRecord(pr->ev[18], st));
     int32_t *up = pr->lift_up.as<int32_t>();
     int32_t *dep0 = pr->lift_dep.as<int32_t>(), *dep1 = dep0 + np1, *mark = dep1 + np1;
@@ -1627,7 +1724,7 @@ int dab_run_stage_b(dab_pair *pr, int32_t n_cor, int32_t n_clusters) {
     DAB_CUDA(dab_readback(pr, &pr->h_counters[12], pr->dpres.as<int32_t>(), 2 * sizeof(int32_t)));
     DAB_CUDA(dab_readback(pr, &pr->h_counters[16], la.counters, 4 * sizeof(unsigned long long)));
     DAB_CUDA(cudaEventRecord(pr->ev[17], st));
-    DAB_CUDA(cudaStreamSynchronize(st));
+    DAB_CUDA(dab_wait_stream(st));
     n_path = reinterpret_cast<int32_t *>(&pr->h_counters[12])[1];
     pr->stats.n_dp2_queries = pr->h_counters[16];
     pr->stats.n_dp2_refills = pr->h_counters[17];
@@ -1681,7 +1778,7 @@ int dab_run_stage_b(dab_pair *pr, int32_t n_cor, int32_t n_clusters) {
     ctx->launches += 3;
     DAB_CUDA(dab_readback(pr, &pr->h_counters[12], pr->dpres.as<int32_t>(), 2 * sizeof(int32_t)));
     DAB_CUDA(cudaEventRecord(pr->ev[17], st));
-    DAB_CUDA(cudaStreamSynchronize(st));
+    DAB_CUDA(dab_wait_stream(st));
     n_path = reinterpret_cast<int32_t *>(&pr->h_counters[12])[1];
   } else {
     DAB_CUDA(cudaEventRecord(pr->ev[18], st));

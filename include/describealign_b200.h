@@ -106,19 +106,26 @@ void dab_host_copy(void *dst, const void *src, size_t bytes);
  * steady state should show no growth: both kinds of call synchronise the whole device. */
 void dab_alloc_stats(int64_t out[4]);
 
-/* How host threads wait for the device (cudaStreamSynchronize inside the stage calls).  blocking = 1:
- * the thread sleeps until the device signals (cudaDeviceScheduleBlockingSync); 0: the CUDA default,
- * which spins when the process has fewer contexts than the host has cores.  A batch driver that
- * keeps more pairs in flight (one host thread each) than there are host cores must use 1, or the
- * spinning waiters starve the threads that have kernels to launch.  Returns the device's schedule
- * flags after the call (>= 0) or a negative DAB_E_* code.  device < 0: current device. */
-int dab_set_host_wait(int device, int blocking);
+/* How host threads wait for the device inside the stage calls.  mode 0: cudaStreamSynchronize with the
+ * CUDA default, which spins when the process has fewer contexts than the host has cores; 1: the same call
+ * with cudaDeviceScheduleBlockingSync (the thread sleeps until the driver wakes it); 2: cudaStreamQuery
+ * polling with 20-400 us sleeps in between.  A batch driver that keeps more pairs in flight (one host
+ * thread each) than there are host cores must not use 0: the spinning waiters starve the threads that
+ * have kernels to launch.  Measured with 64 pairs in flight on 16 cores (profiles/r1_v9_pairs_in_flight.txt):
+ * mode 1 wakes a thread only milliseconds after its stream drained, mode 2 within the sleep it was in.
+ * Returns the device's schedule flags after the call (>= 0) or a negative DAB_E_* code.  device < 0:
+ * current device. */
+int dab_set_host_wait(int device, int mode);
 
 /* device < 0: current device. */
 int dab_create(int device, dab_ctx **out);
 void dab_destroy(dab_ctx *ctx);
 /* Tuning / testing switches.  "dp2_generic" = 1 forces the tree-based pass-2 DP instead of the
- * corridor-state DP (both are exact; the tests compare them).  Unknown names return DAB_E_ARG. */
+ * corridor-state DP (both are exact; the tests compare them).  "dp2_impl" = 0..3 selects among the
+ * exact pass-2 DP kernels (0 = block kernel, the default).  "dp_reserve_kb" = 0..176: dynamic shared
+ * memory the one-warp pass-2 DP kernel requests without using it, which keeps large-shared-memory CTAs of
+ * other pairs (the feature kernel) off its SM when many pairs are in flight.  Unknown names return
+ * DAB_E_ARG. */
 int dab_set_option(dab_ctx *ctx, const char *name, int64_t value);
 const char *dab_last_error(const dab_ctx *ctx);   /* ctx may be NULL for dab_create failures */
 

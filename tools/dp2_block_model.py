@@ -193,6 +193,8 @@ def run_blocks(plans, pi, pj, pq, pk, ro, flags, min_block=2):
     for base in range(0, n, 32):
         gcnt = min(32, n - base)
         t = 0
+        if gcnt == 32 and fast_block(st, base, pi, pj, pq, pk, ro, flags, back, cnt):
+            continue
         while t < gcnt:
             e = t
             while e < gcnt and not (int(flags[base + e]) & (P2_NEAR | P2_GAP)):
@@ -208,6 +210,55 @@ def run_blocks(plans, pi, pj, pq, pk, ro, flags, min_block=2):
             cnt["scalar_points"] += 1
             t += 1
     return back, st, cnt
+
+
+def fast_block(st, base, pi, pj, pq, pk, ro, flags, back, cnt):
+    """A full group of 32 points that all belong to ONE leader corridor and all see the corridor's
+    previous two points: under the assumption that the cluster best is never chosen, cum is the
+    chain max(c0, c1) + q (the only serial part); everything else is decided per point afterwards
+    and the assumption checked.  All or nothing: returns False (nothing committed) when a check fails."""
+    pts = list(range(base, base + 32))
+    k = int(pk[base])
+    both = P2_VIS1 | P2_VIS2
+    if any(int(pk[p]) != k or (int(flags[p]) & both) != both or (int(flags[p]) & (P2_NEAR | P2_GAP)) for p in pts):
+        return False
+    if not (st.c[k][0] >= st.top[0] + LEAD_MARGIN):
+        return False
+    cnt["fast_tried"] = cnt.get("fast_tried", 0) + 1
+    a, b = st.c[k][0], st.c[k][1]
+    cums = []
+    for p in pts:
+        m = a if a >= b else b
+        cum = m + float(pq[p])
+        cums.append(cum)
+        b, a = a, cum
+    # per point, in parallel
+    pre_c = [st.c[k][1], st.c[k][0]]          # cums two and one before the block
+    pre_id = [st.id[k][1], st.id[k][0]]
+    allc = pre_c + cums
+    allid = pre_id + pts
+    clv = st.cl[k][0]
+    top = st.top
+    outs = []
+    for u, p in enumerate(pts):
+        c0, c1 = allc[u + 1], allc[u]
+        m, pred = (c0, allid[u + 1]) if c0 >= c1 else (c1, allid[u])
+        if not (m >= clv):
+            return False                      # the cluster best would have been chosen
+        if not (top[0] <= m):
+            return False                      # the frontier could have been chosen
+        outs.append((m, pred))
+        cum = cums[u]
+        clv = max(clv, cum - 50.0)
+        jump = cum - 1000.0
+        if jump > top[0] or (jump == top[0] and float(pj[p]) < top[1]):
+            top = (jump, float(pj[p]), p)
+    for u, p in enumerate(pts):
+        commit(st, k, p, float(pj[p]), int(ro[p]), int(flags[p]), outs[u][0], outs[u][1], float(pq[p]), back)
+        assert st.c[k][0] == cums[u]
+    assert st.top == top
+    cnt["fast_points"] = cnt.get("fast_points", 0) + 32
+    return True
 
 
 def block(st, base, t0, t1, pi, pj, pq, pk, ro, flags, back, cnt, nc):
