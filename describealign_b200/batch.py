@@ -125,7 +125,7 @@ def gpu_runner(pair):
         job.close()
 
 
-def run_local(pairs, in_flight: int = 24, runner: Callable | None = None):
+def run_local(pairs, in_flight: int = 64, runner: Callable | None = None):
     """Run `pairs` on this process's GPU with up to `in_flight` pairs in progress at once.
     A pair that fails (e.g. RuntimeError("Alignment failed, ...")) yields its exception."""
     runner = gpu_runner if runner is None else runner
@@ -138,11 +138,15 @@ def run_local(pairs, in_flight: int = 24, runner: Callable | None = None):
 
     if in_flight <= 1 or len(pairs) <= 1:
         return [one(p) for p in pairs]
+    if runner is gpu_runner:
+        # one host thread per pair in flight: they must sleep, not spin, while their streams drain
+        from . import _cabi
+        _cabi.set_host_wait(-1, 2)
     with ThreadPoolExecutor(max_workers=in_flight) as ex:
         return list(ex.map(one, pairs))
 
 
-def align_batch(pairs, durations: Sequence[float] | None = None, in_flight: int = 24, group=None,
+def align_batch(pairs, durations: Sequence[float] | None = None, in_flight: int = 64, group=None,
                 runner: Callable | None = None):
     """Align a list of (video_pcm, description_pcm) pairs (or zero-argument loaders returning
     such a pair) over all ranks of the current process group.
