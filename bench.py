@@ -449,6 +449,14 @@ def run_ours(args, rank, world, local_rank):
         for v in roof.values():
             if v.get("frac") is None and v.get("achieved") is not None:
                 v["frac"] = v["achieved"] / v["peak"]
+        # what bounds the DPs is the dependent chain, not bytes: per point at least one f64 compare, one
+        # select and one f64 add that depend on the previous point (about 20 SM cycles)
+        clk_hz = 1e6 * float(peaks.get("sm_max_mhz", 1965.0))
+        for key, pts in (("dp1_trace", dp_pts[0]), ("dp2_trace", dp_pts[1])):
+            r = roof[key]
+            if r["ms"] > 0:
+                r["serial_chain_floor_ms"] = 1e3 * 20.0 * pts / clk_hz
+                r["frac_of_serial_chain_floor"] = r["serial_chain_floor_ms"] / r["ms"]
         dom_key = dominant if dominant in roof else ("features" if dominant.startswith("features") else None)
         main_roof = dict(roof[dom_key]) if dom_key else dict(roof["features"])
         # DRAM bytes per launch of that kernel from the committed ncu --set full captures of the same
