@@ -1041,6 +1041,9 @@ __global__ void __launch_bounds__(32, 1) dp2_block_kernel(Dp2LArgs a) {
   // per point of the current block (index = lane of the point)
   __shared__ double s_best[32], s_m[32], s_cum[32], s_pmv[32], s_topv[32], s_topj[32], s_fv[32];
   __shared__ int s_pred[32], s_pmi[32], s_topi[32], s_fi[32];
+  __shared__ double s_clvb[32];                 // lite walk: the corridor's cluster best before the point ...
+  __shared__ int s_clib[32];                    // ... and its id
+  __shared__ double s_bmax[32];                 // per corridor: largest new frontier entry of the current block
 
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x;
@@ -1157,6 +1160,7 @@ __global__ void __launch_bounds__(32, 1) dp2_block_kernel(Dp2LArgs a) {
     // candidate prepared per point (s_topv/j/i, s_fv/s_fi) when with_frontier.  No warp-level
     // operation inside: lanes run it divergently.
     auto own_pass = [&](unsigned todo, const bool with_frontier) {
+      double bmax = NEG;
       while (todo) {
         const int u = __ffs(todo) - 1;
         todo &= todo - 1;
@@ -1184,9 +1188,11 @@ __global__ void __launch_bounds__(32, 1) dp2_block_kernel(Dp2LArgs a) {
         if (cl_v < cj) { cl_v = cj; cl_i = p; }
         const double jump = cum - 1000.0;
         if (jump > pm_v) { pm_v = jump; pm_i = p; }
+        bmax = jump > bmax ? jump : bmax;
         filled = r.ro;
         s_best[u] = best; s_pred[u] = pred; s_m[u] = m; s_cum[u] = cum; s_pmv[u] = pm_v; s_pmi[u] = pm_i;
       }
+      s_bmax[lane] = bmax;
     };
 
     // ---- fast path: a full group whose 32 points all lie on ONE leader corridor and all see the
@@ -1201,11 +1207,14 @@ __global__ void __launch_bounds__(32, 1) dp2_block_kernel(Dp2LArgs a) {
       const bool uniform = __all_sync(FULL, own_k == k0 && (own.kf & both) == both);
       const double k_c0 = __shfl_sync(FULL, c0, k0), k_c1 = __shfl_sync(FULL, c1, k0);
       if (uniform && k_c0 >= top_v + LEAD_MARGIN) {
+        // max(ca, cb) + q == (ca >= cb ? ca + q : cb + q) bit for bit (rounding is monotone), and in
+        // this form the add and the compare both start from ca: one f64 latency per point, not two
         double ca = k_c0, cb = k_c1;
 #pragma unroll
         for (int u = 0; u < 32; ++u) {
-          const double m = ca >= cb ? ca : cb;
-          const double cum = m + s_rec[buf][u].q;
+          const double q = s_rec[buf][u].q;
+          const double x = ca + q, y = cb + q;
+          const double cum = ca >= cb ? x : y;
           cb = ca; ca = cum;
           s_cum[u] = cum;                        // same value from every lane
         }
@@ -1304,102 +1313,214 @@ __global__ void __launch_bounds__(32, 1) dp2_block_kernel(Dp2LArgs a) {
         const double sv_c0 = c0, sv_c1 = c1, sv_c2 = c2, sv_clv = cl_v, sv_pmv = pm_v;
         const int sv_id0 = id0, sv_id1 = id1, sv_id2 = id2, sv_cli = cl_i, sv_pmi = pm_i, sv_filled = filled;
 
-        // ---- A: leaders ------------------------------------------------------------------------
-        if (leader && mine_mask) own_pass(mine_mask, false);
-        __syncwarp();
-
-        // ---- B: the frontier's best entry before / after every point (leaders' entries only) ----
-        double sv = NEG, sj = INFINITY;
-        int si = -2;
-        if (pt_leader) { sv = s_cum[lane] - 1000.0; sj = own.j; si = base + lane; }
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          const double ov = __shfl_up_sync(FULL, sv, d), oj = __shfl_up_sync(FULL, sj, d);
-          const int oi = __shfl_up_sync(FULL, si, d);
-          // the later entry replaces the earlier one only when strictly better (value, then smaller j)
-          const bool keep = lane < d || sv > ov || (sv == ov && sj < oj);
-          sv = keep ? sv : ov; sj = keep ? sj : oj; si = keep ? si : oi;
-        }
-        double xv = __shfl_up_sync(FULL, sv, 1), xj = __shfl_up_sync(FULL, sj, 1);
-        int xi = __shfl_up_sync(FULL, si, 1);
-        if (lane == 0) { xv = NEG; xj = INFINITY; xi = -2; }
-        const bool nb = xv > top_v || (xv == top_v && xj < top_j);
-        const double tv_l = nb ? xv : top_v, tj_l = nb ? xj : top_j;      // top before this lane's point
-        const int ti_l = nb ? xi : top_i;
-        const bool nb2 = sv > top_v || (sv == top_v && sj < top_j);
-        const double inc_v = nb2 ? sv : top_v, inc_j = nb2 ? sj : top_j;  // top after this lane's point
-        const int inc_i = nb2 ? si : top_i;
-        s_topv[lane] = tv_l; s_topj[lane] = tj_l; s_topi[lane] = ti_l;
-
-        // ---- Q: F(j) for follower points whose top entry lies to their right ----------------------
-        const bool needq = inr && !pt_leader && (own.kf & P2_MAYQ) && !(tj_l <= own.j);
-        if (__ballot_sync(FULL, needq)) {
-          const double clv0 = __shfl_sync(FULL, sv_clv, own_k);      // the point's m is at least this
-          if (needq) {
-            double bv = 0.0;                 // the frontier's seed entry (j' = 0, id -1)
-            int bi = -1;
-            auto consider = [&](double v, int id) {
-              if (v > bv) { bv = v; bi = id; }
-              else if (v == bv) {            // (value desc, j' asc, id asc)
-                const double ja = id < 0 ? 0.0 : a.p_j[id], jb = bi < 0 ? 0.0 : a.p_j[bi];
-                if (ja < jb || (ja == jb && id < bi)) bi = id;
-              }
-            };
-            const double j = own.j;
-            const int i = own.i;
-            for (int c = 0; c < n_cor; ++c) {
-              if (c == own_k) continue;
-              const int f0 = s_fill0[c], lo2 = s_clo[c], rows2 = s_crows[c];
-              const double hv = s_headv[c];
-              // rows written before the block; an entry that cannot beat the point's own cluster
-              // best can never be chosen (its value would have to exceed m >= clv0)
-              if (f0 < 0 || lo2 > i || !(hv > clv0)) continue;
-              const double sl2 = s_csl[c], of2 = s_cof[c];
-              double est = floor((j - of2) * s_cinv[c]) - (double)lo2 + 1.0;
-              int kk = est < 0.0 ? 0 : (est > (double)rows2 ? rows2 : (int)est);
-              while (kk < rows2 && __dadd_rn(__dmul_rn(sl2, (double)(lo2 + kk)), of2) <= j) ++kk;
-              while (kk > 0 && __dadd_rn(__dmul_rn(sl2, (double)(lo2 + kk - 1)), of2) > j) --kk;
-              const int done = (i + 1 < lo2 + rows2 ? i + 1 : lo2 + rows2) - lo2;
-              const int idx = kk < done ? kk : done;
-              if (idx <= 0) continue;
-              const int x = idx - 1;
-              if (x >= f0) consider(hv, s_headi[c]);
-              else {
-                const int4 raw = __ldcg(reinterpret_cast<const int4 *>(s_pmbase[c] + x));
-                consider(__hiloint2double(raw.y, raw.x), raw.z);
-              }
+        // The owner lanes' walks come in two forms.  The LITE walk assumes that a point never restarts
+        // from its cluster's best (true for 98.6 % of the points of a C2 pair): then cum is just
+        // max(c0, c1, frontier candidate) + q, 14-18 instructions per point, and predecessor ids,
+        // running maxima and the assumption itself are worked out afterwards by the points' own lanes.
+        // It needs every point of the block to see the corridor's previous two points.  If a point
+        // violates the assumption the block is evaluated again with the exact walk (own_pass).
+        const int both = P2_VIS1 | P2_VIS2;
+        bool use_lite = __all_sync(FULL, !inr || (own.kf & both) == both) != 0;
+        auto lite_pass = [&](unsigned todo, const bool with_frontier) {
+          // cum = max(la, lb, f) + q, written so that the adds and the compares all start from la (see
+          // the fast path): (f > la && f > lb) ? f + q : (la >= lb ? la + q : lb + q); the next point's
+          // index and inputs are fetched before the dependent arithmetic of this one.  The cluster best
+          // and the running-max head ride along as their own short chains (nothing in the cum chain
+          // waits for them); the owner's registers stay untouched.
+          double la = c0, lb = c1, clv = cl_v, pmv = pm_v, bmax = NEG;
+          int cli = cl_i, pmi = pm_i;
+          int u = __ffs(todo) - 1;
+          todo &= todo - 1;
+          double q = s_rec[buf][u].q, f = with_frontier ? s_fv[u] : NEG;
+          for (;;) {
+            int un = -1;
+            double qn = 0.0, fn = NEG;
+            if (todo) {
+              un = __ffs(todo) - 1;
+              todo &= todo - 1;
+              qn = s_rec[buf][un].q;
+              if (with_frontier) fn = s_fv[un];
             }
-            // the leaders' entries of this block
-            unsigned lm = lead_pts & ((1u << lane) - 1u);
-            while (lm) {
-              const int u = __ffs(lm) - 1;
-              lm &= lm - 1;
-              const P2Rec ru = s_rec[buf][u];
-              if ((ru.kf & 0xff) != own_k && ru.j <= j) consider(s_cum[u] - 1000.0, base + u);
-            }
-            s_fv[lane] = bv; s_fi[lane] = bi;
+            const double x = la + q, y = lb + q, z = f + q;
+            const bool pf = f > la && f > lb;
+            const double cum = pf ? z : (la >= lb ? x : y);
+            lb = la; la = cum;
+            s_cum[u] = cum; s_clvb[u] = clv; s_clib[u] = cli;
+            const double cj = cum - 50.0, jump = cum - 1000.0;
+            if (clv < cj) { clv = cj; cli = base + u; }
+            if (jump > pmv) { pmv = jump; pmi = base + u; }
+            bmax = jump > bmax ? jump : bmax;
+            s_pmv[u] = pmv; s_pmi[u] = pmi;
+            if (un < 0) break;
+            u = un; q = qn; f = fn;
           }
-        }
-        __syncwarp();
+          s_bmax[lane] = bmax;
+        };
+        // pre-block state of each point's corridor, for the lite walk's per-point work
+        const int ksrc = own_k & 31;
+        const double K_c0 = __shfl_sync(FULL, c0, ksrc), K_c1 = __shfl_sync(FULL, c1, ksrc);
+        const int K_id0 = __shfl_sync(FULL, id0, ksrc), K_id1 = __shfl_sync(FULL, id1, ksrc);
+        const unsigned present = __ballot_sync(FULL, mine_mask != 0u);    // corridors with points in the block
+        double sv, sj, tv_l, tj_l, inc_v, inc_j;
+        int si, ti_l, inc_i;
+        bool needq;
+        double r_m = NEG, r_best = NEG, r_pmv = NEG;   // this lane's point: chosen-from value, best, head after it
+        int r_pred = -2, r_pmi = -2;
+        for (;;) {
+          // ---- A: leaders ----------------------------------------------------------------------
+          if (leader && mine_mask) { if (use_lite) lite_pass(mine_mask, false); else own_pass(mine_mask, false); }
+          __syncwarp();
 
-        // ---- C: followers ----------------------------------------------------------------------
-        if (have && !leader && mine_mask) own_pass(mine_mask, true);
-        __syncwarp();
+          // ---- B: the frontier's best entry before / after every point (leaders' entries only) ----
+          sv = NEG; sj = INFINITY; si = -2;
+          if (pt_leader) { sv = s_cum[lane] - 1000.0; sj = own.j; si = base + lane; }
+  #pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            const double ov = __shfl_up_sync(FULL, sv, d), oj = __shfl_up_sync(FULL, sj, d);
+            const int oi = __shfl_up_sync(FULL, si, d);
+            // the later entry replaces the earlier one only when strictly better (value, then smaller j)
+            const bool keep = lane < d || sv > ov || (sv == ov && sj < oj);
+            sv = keep ? sv : ov; sj = keep ? sj : oj; si = keep ? si : oi;
+          }
+          double xv = __shfl_up_sync(FULL, sv, 1), xj = __shfl_up_sync(FULL, sj, 1);
+          int xi = __shfl_up_sync(FULL, si, 1);
+          if (lane == 0) { xv = NEG; xj = INFINITY; xi = -2; }
+          const bool nb = xv > top_v || (xv == top_v && xj < top_j);
+          tv_l = nb ? xv : top_v; tj_l = nb ? xj : top_j;      // top before this lane's point
+          ti_l = nb ? xi : top_i;
+          const bool nb2 = sv > top_v || (sv == top_v && sj < top_j);
+          inc_v = nb2 ? sv : top_v; inc_j = nb2 ? sj : top_j;  // top after this lane's point
+          inc_i = nb2 ? si : top_i;
+          s_topv[lane] = tv_l; s_topj[lane] = tj_l; s_topi[lane] = ti_l;
+
+
+          // ---- Q: F(j) for follower points whose top entry lies to their right ----------------------
+          needq = inr && !pt_leader && (own.kf & P2_MAYQ) && !(tj_l <= own.j);
+          if (__ballot_sync(FULL, needq)) {
+            const double clv0 = __shfl_sync(FULL, sv_clv, own_k);      // the point's m is at least this
+            if (needq) {
+              double bv = 0.0;                 // the frontier's seed entry (j' = 0, id -1)
+              int bi = -1;
+              auto consider = [&](double v, int id) {
+                if (v > bv) { bv = v; bi = id; }
+                else if (v == bv) {            // (value desc, j' asc, id asc)
+                  const double ja = id < 0 ? 0.0 : a.p_j[id], jb = bi < 0 ? 0.0 : a.p_j[bi];
+                  if (ja < jb || (ja == jb && id < bi)) bi = id;
+                }
+              };
+              const double j = own.j;
+              const int i = own.i;
+              for (int c = 0; c < n_cor; ++c) {
+                if (c == own_k) continue;
+                // a leader's points of this block: the corridor's coordinate grows with the row, so the
+                // qualifying ones (j' <= j) are a prefix; the running-max head recorded at the last of them
+                // is the corridor's best entry with j' <= j, rows before the block included
+                if ((leadlanes >> c) & 1u) {
+                  unsigned mc = s_mask[c] & ((1u << lane) - 1u);
+                  int ustar = -1;
+                  while (mc) {
+                    const int uh = 31 - __clz(mc);
+                    if (s_rec[buf][uh].j <= j) { ustar = uh; break; }
+                    mc &= ~(1u << uh);
+                    if (mc && s_rec[buf][__ffs(mc) - 1].j > j) break;      // none qualifies
+                  }
+                  if (ustar >= 0) { consider(s_pmv[ustar], s_pmi[ustar]); continue; }
+                }
+                const int f0 = s_fill0[c], lo2 = s_clo[c], rows2 = s_crows[c];
+                const double hv = s_headv[c];
+                // rows written before the block; an entry that cannot beat the point's own cluster
+                // best can never be chosen (its value would have to exceed m >= clv0)
+                if (f0 < 0 || lo2 > i || !(hv > clv0)) continue;
+                const double sl2 = s_csl[c], of2 = s_cof[c];
+                double est = floor((j - of2) * s_cinv[c]) - (double)lo2 + 1.0;
+                int kk = est < 0.0 ? 0 : (est > (double)rows2 ? rows2 : (int)est);
+                while (kk < rows2 && __dadd_rn(__dmul_rn(sl2, (double)(lo2 + kk)), of2) <= j) ++kk;
+                while (kk > 0 && __dadd_rn(__dmul_rn(sl2, (double)(lo2 + kk - 1)), of2) > j) --kk;
+                const int done = (i + 1 < lo2 + rows2 ? i + 1 : lo2 + rows2) - lo2;
+                const int idx = kk < done ? kk : done;
+                if (idx <= 0) continue;
+                const int x = idx - 1;
+                if (x >= f0) consider(hv, s_headi[c]);
+                else {
+                  const int4 raw = __ldcg(reinterpret_cast<const int4 *>(s_pmbase[c] + x));
+                  consider(__hiloint2double(raw.y, raw.x), raw.z);
+                }
+              }
+              s_fv[lane] = bv; s_fi[lane] = bi;
+            }
+          }
+          __syncwarp();
+
+
+          if (use_lite) {
+            // the one frontier candidate of every follower point
+            if (inr && !pt_leader) {
+              double fc = NEG;
+              int fci = -2;
+              if (tj_l <= own.j) { fc = tv_l; fci = ti_l; }
+              else if (own.kf & P2_MAYQ) { fc = s_fv[lane]; fci = s_fi[lane]; }
+              s_fv[lane] = fc; s_fi[lane] = fci;
+            }
+            __syncwarp();
+          }
+
+          // ---- C: followers --------------------------------------------------------------------
+          if (have && !leader && mine_mask) { if (use_lite) lite_pass(mine_mask, true); else own_pass(mine_mask, true); }
+          __syncwarp();
+          if (!use_lite) break;
+
+          // ---- lite: each point's lane works out what the exact walk would have recorded -----------
+          bool hyp = true;
+          if (inr) {
+            const unsigned prevm = grp & ((1u << lane) - 1u);     // the corridor's earlier points of the block
+            int p1 = -1, p2 = -1;
+            if (prevm) {
+              p1 = 31 - __clz(prevm);
+              const unsigned r = prevm & ~(1u << p1);
+              if (r) p2 = 31 - __clz(r);
+            }
+            const double c0u = p1 >= 0 ? s_cum[p1] : K_c0;
+            const int id0u = p1 >= 0 ? base + p1 : K_id0;
+            const double c1u = p2 >= 0 ? s_cum[p2] : (p1 >= 0 ? K_c0 : K_c1);
+            const int id1u = p2 >= 0 ? base + p2 : (p1 >= 0 ? K_id0 : K_id1);
+            const bool take0 = c0u >= c1u;                        // the later candidate wins ties
+            const double mm = take0 ? c0u : c1u;
+            const int mid = take0 ? id0u : id1u;
+            double fc = NEG;
+            int fci = -2;
+            if (!pt_leader) { fc = s_fv[lane]; fci = s_fi[lane]; }
+            const bool tf = fc > mm;
+            const double clvb = s_clvb[lane];
+            hyp = mm >= clvb || fc > clvb;                        // else the cluster best would have been chosen
+            r_m = mm; r_best = tf ? fc : mm; r_pred = tf ? fci : mid;
+            r_pmv = s_pmv[lane]; r_pmi = s_pmi[lane];
+          }
+          if (__any_sync(FULL, inr && !hyp)) { use_lite = false; __syncwarp(); continue; }
+          break;
+        }
+        if (!use_lite && inr) {
+          r_m = s_m[lane]; r_best = s_best[lane]; r_pred = s_pred[lane]; r_pmv = s_pmv[lane]; r_pmi = s_pmi[lane];
+        }
 
         // ---- D: check the assumptions, commit the verified prefix ----------------------------------
         bool ok = true;
         if (inr) {
-          if (pt_leader) ok = tv_l <= s_m[lane];
+          if (pt_leader) ok = tv_l <= r_m;
           else {
             ok = (s_cum[lane] - 1000.0) < tv_l;
             if (needq) {
-              const double mm = s_m[lane];
-              unsigned fm = foll_pts & ((1u << lane) - 1u);
-              while (fm) {
-                const int u = __ffs(fm) - 1;
-                fm &= fm - 1;
-                const P2Rec ru = s_rec[buf][u];
-                if ((ru.kf & 0xff) != own_k && ru.j <= own.j && !((s_cum[u] - 1000.0) <= mm)) ok = false;
+              // follower corridors whose largest new entry could matter at all (rarely any)
+              unsigned fcs = present & ~leadlanes & ~(1u << own_k);
+              while (fcs) {
+                const int c = __ffs(fcs) - 1;
+                fcs &= fcs - 1;
+                if (s_bmax[c] <= r_m) continue;
+                unsigned fm = s_mask[c] & ((1u << lane) - 1u);
+                while (fm) {
+                  const int u = __ffs(fm) - 1;
+                  fm &= fm - 1;
+                  if (s_rec[buf][u].j <= own.j && !((s_cum[u] - 1000.0) <= r_m)) ok = false;
+                }
               }
             }
           }
@@ -1407,7 +1528,30 @@ __global__ void __launch_bounds__(32, 1) dp2_block_kernel(Dp2LArgs a) {
         const unsigned badm = __ballot_sync(FULL, inr && !ok);
         const int stop_at = badm ? __ffs(badm) - 1 : e;
         const int glen = stop_at - t;
-        if (stop_at < e) {
+        if (use_lite) {
+          // the lite walk left the owners' registers alone: take the new state from the committed points
+          const unsigned mc = mine_mask & (stop_at >= 32 ? FULL : ((1u << stop_at) - 1u));
+          const int nmc = __popc(mc);
+          if (nmc >= 1) {
+            const int l1 = 31 - __clz(mc);
+            const unsigned m2 = mc & ~(1u << l1);
+            const int l2 = m2 ? 31 - __clz(m2) : l1;
+            const unsigned m3 = m2 ? (m2 & ~(1u << l2)) : 0u;
+            const int l3 = m3 ? 31 - __clz(m3) : l1;
+            const double oc0 = c0, oc1 = c1;
+            const int oi0 = id0, oi1 = id1;
+            const double x1 = s_cum[l1];
+            c0 = x1; id0 = base + l1;
+            c1 = nmc >= 2 ? s_cum[l2] : oc0; id1 = nmc >= 2 ? base + l2 : oi0;
+            c2 = nmc >= 3 ? s_cum[l3] : (nmc == 2 ? oc0 : oc1);
+            id2 = nmc >= 3 ? base + l3 : (nmc == 2 ? oi0 : oi1);
+            const double cb = s_clvb[l1], cj1 = x1 - 50.0;
+            const bool up = cb < cj1;
+            cl_v = up ? cj1 : cb; cl_i = up ? base + l1 : s_clib[l1];
+            pm_v = s_pmv[l1]; pm_i = s_pmi[l1];
+            filled = s_rec[buf][l1].ro;
+          }
+        } else if (stop_at < e) {
           // only a prefix holds: put the owners' registers back and walk the prefix again
           c0 = sv_c0; c1 = sv_c1; c2 = sv_c2; cl_v = sv_clv; pm_v = sv_pmv;
           id0 = sv_id0; id1 = sv_id1; id2 = sv_id2; cl_i = sv_cli; pm_i = sv_pmi; filled = sv_filled;
@@ -1417,9 +1561,9 @@ __global__ void __launch_bounds__(32, 1) dp2_block_kernel(Dp2LArgs a) {
         }
         if (glen > 0) {
           if (lane >= t && lane < stop_at) {
-            BackRec b; b.best = s_best[lane]; b.pred = s_pred[lane]; b.pad = 0;
+            BackRec b; b.best = r_best; b.pred = r_pred; b.pad = 0;
             a.back[base + lane] = b;
-            PmEntry en; en.val = s_pmv[lane]; en.id = s_pmi[lane]; en.pad = 0;
+            PmEntry en; en.val = r_pmv; en.id = r_pmi; en.pad = 0;
             s_pmbase[own_k][own.ro] = en;
             // shared ring: the corridor's last RING committed rows
             const unsigned same = s_mask[own_k] & ((stop_at >= 32 ? FULL : ((1u << stop_at) - 1u)));

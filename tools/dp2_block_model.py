@@ -277,6 +277,7 @@ def block(st, base, t0, t1, pi, pj, pq, pk, ro, flags, back, cnt, nc):
 
     def own_step(p, frontier):
         k, fl, q = int(pk[p]), int(flags[p]), float(pq[p])
+        c_before, cl_before = (wc[k][0], wc[k][1]), wcl[k][0]
         m, mi = wcl[k]
         if (fl & P2_VIS2) and wc[k][1] >= m:
             m, mi = wc[k][1], wid[k][1]
@@ -293,7 +294,11 @@ def block(st, base, t0, t1, pi, pj, pq, pk, ro, flags, back, cnt, nc):
         jump = cum - 1000.0
         if jump > wpm[k][0]:
             wpm[k] = (jump, p)
-        out[p] = {"best": best, "pred": pred, "m": m, "cum": cum, "jump": jump, "pm": wpm[k]}
+        # the kernel's LITE walk computes cum as max(c0, c1, frontier candidate) + q; that is what the
+        # exact rules give unless the cluster best is the choice
+        lite_ok = (fl & (P2_VIS1 | P2_VIS2)) == (P2_VIS1 | P2_VIS2) and \
+            (max(c_before[0], c_before[1]) >= cl_before or (frontier is not None and frontier[0] > cl_before))
+        out[p] = {"best": best, "pred": pred, "m": m, "cum": cum, "jump": jump, "pm": wpm[k], "lite_ok": lite_ok}
 
     # phase A: leaders, frontier ignored
     for p in pts:
@@ -344,6 +349,12 @@ def block(st, base, t0, t1, pi, pj, pq, pk, ro, flags, back, cnt, nc):
             ku = int(pk[u])
             if not leader[ku] and ku != k and float(pj[u]) <= float(pj[p]) and not (out[u]["jump"] <= out[p]["m"]):
                 qfail.add(p)
+    # (kernel: if every point qualified for the lite walk the block was evaluated that way, otherwise -
+    # or when a point turns out to restart from its cluster best - with the exact walk; same results)
+    if all(out[p]["lite_ok"] for p in pts if p in out):
+        cnt["lite_blocks"] = cnt.get("lite_blocks", 0) + 1
+    else:
+        cnt["exact_blocks"] = cnt.get("exact_blocks", 0) + 1
     # phase D: verification, first failure
     glen = 0
     for p in pts:
