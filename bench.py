@@ -375,6 +375,21 @@ def run_ours(args, rank, world, local_rank):
                           "max": float(np.max([j.host_ms.get(k, 0.0) for j in jobs_e]))}
                       for k in sorted(set().union(*[j.host_ms.keys() for j in jobs_e]))}
 
+    # one pair alone on the GPU (device-resident PCM, three passes, the last one is kept): kernel
+    # durations without the other 63 pairs' work in the way
+    solo_ms = solo_work = None
+    if rank == 0:
+        pr0 = slot_pairs[0]
+        for _ in range(3):
+            job = api.AlignJob(pr0)
+            v0, a0 = dev[0]
+            job.load_pcm_device((v0.data_ptr(), v0.shape[0], v0.shape[1]), (a0.data_ptr(), a0.shape[0], a0.shape[1]))
+            job.device_stage_a()
+            host_stage(0, job)
+            job.device_stage_b()
+            solo_ms = {k: v for k, v in pr0.timings().items() if not k.startswith("host_in_")}
+            solo_work = pr0.stats()
+
     # parity inside the run: rank 0 checks its first pair against the oracle
     parity = None
     cpu = None
@@ -423,46 +438,46 @@ def run_ours(args, rank, world, local_rank):
 
     if rank == 0:
         peaks, peak_src = measured_peaks()
-        # per-kernel device times of the last timed step, summed over this rank's pairs
+        # per-kernel device times of the last timed step, summed over this rank's pairs (64 in flight: the
+        # events around a kernel then also count the time it waited for SMs), and of one pair alone
         agg = {k: sum(tm[k] for tm in timings) for k in timings[0] if not k.startswith("host_in_")}
         lib_host = {k: float(np.mean([tm[k] for tm in timings])) for k in timings[0] if k.startswith("host_in_")}
-        dominant = max((k for k in agg if k != "dp2"), key=agg.get)
-        # feature kernel roofline: algorithmic bytes = PCM read once + 24 B per output frame
-        feat_ms = agg["features_video"] + agg["features_audio"]
-        feat_bytes = sum(2 * (v.shape[0] * v.shape[1] + a.shape[0] * a.shape[1]) + 24 * (v.shape[0] // 210 + a.shape[0] // 210)
-                         for v, a in pairs)
-        feat_gbs = feat_bytes / (feat_ms * 1e-3) / 1e9 if feat_ms > 0 else None
-        # DP kernels: 24 B per point (i, v, qual in; back pointer out), SURVEY.md 8(d)
-        dp_pts = sum(s["n_points1"] for s in stats), sum(s["n_points2"] for s in stats)
-        dp_ms = agg["dp1_trace"], agg["dp2_trace"]
-        roof = {"features": {"bound": "hbm", "achieved": feat_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                             "frac": feat_gbs / peaks["hbm_gbs"] if feat_gbs else None, "ms": feat_ms,
-                             "algorithmic_bytes": feat_bytes},
-                "dp1_trace": {"bound": "hbm", "achieved": 24 * dp_pts[0] / (dp_ms[0] * 1e-3) / 1e9 if dp_ms[0] > 0 else None,
-                              "peak": peaks["hbm_gbs"], "unit": "GB/s", "ms": dp_ms[0], "points": dp_pts[0],
-                              "points_per_s": dp_pts[0] / (dp_ms[0] * 1e-3) if dp_ms[0] > 0 else None,
-                              "note": "latency-bound serial dependency, not bandwidth-bound"},
-                "dp2_trace": {"bound": "hbm", "achieved": 24 * dp_pts[1] / (dp_ms[1] * 1e-3) / 1e9 if dp_ms[1] > 0 else None,
-                              "peak": peaks["hbm_gbs"], "unit": "GB/s", "ms": dp_ms[1], "points": dp_pts[1],
-                              "points_per_s": dp_pts[1] / (dp_ms[1] * 1e-3) if dp_ms[1] > 0 else None,
-                              "note": "latency-bound serial dependency, not bandwidth-bound"}}
-        for v in roof.values():
-            if v.get("frac") is None and v.get("achieved") is not None:
-                v["frac"] = v["achieved"] / v["peak"]
-        # what bounds the DPs is the dependent chain, not bytes: per point at least one f64 compare, one
-        # select and one f64 add that depend on the previous point (about 20 SM cycles)
         clk_hz = 1e6 * float(peaks.get("sm_max_mhz", 1965.0))
-        for key, pts in (("dp1_trace", dp_pts[0]), ("dp2_trace", dp_pts[1])):
-            r = roof[key]
-            if r["ms"] > 0:
-                r["serial_chain_floor_ms"] = 1e3 * 20.0 * pts / clk_hz
-                r["frac_of_serial_chain_floor"] = r["serial_chain_floor_ms"] / r["ms"]
-        dom_key = dominant if dominant in roof else ("features" if dominant.startswith("features") else None)
-        main_roof = dict(roof[dom_key]) if dom_key else dict(roof["features"])
+
+        def rooflines(kernel_ms, work, pair_list):
+            feat_ms = kernel_ms["features_video"] + kernel_ms["features_audio"]
+            # feature kernel: algorithmic bytes = PCM read once + 24 B per output frame
+            feat_bytes = sum(2 * (v.shape[0] * v.shape[1] + a.shape[0] * a.shape[1]) + 24 * (v.shape[0] // 210 + a.shape[0] // 210)
+                             for v, a in pair_list)
+            out = {"features": {"bound": "hbm", "achieved": feat_bytes / (feat_ms * 1e-3) / 1e9 if feat_ms > 0 else None,
+                                "peak": peaks["hbm_gbs"], "unit": "GB/s", "ms": feat_ms, "launches": 2 * len(pair_list),
+                                "algorithmic_bytes": feat_bytes}}
+            # DP kernels: 24 B per point (i, v, qual in; back pointer out); what bounds them is
+            # the dependent chain: one f64 add + select per point, measured at 52 SM cycles on this chip
+            # (profiles/r1_v18_dp2_block_hot_loops.txt)
+            for key, npts in (("dp1_trace", work["n_points1"]), ("dp2_trace", work["n_points2"])):
+                ms = kernel_ms[key]
+                out[key] = {"bound": "hbm", "achieved": 24 * npts / (ms * 1e-3) / 1e9 if ms > 0 else None,
+                            "peak": peaks["hbm_gbs"], "unit": "GB/s", "ms": ms, "launches": len(pair_list), "points": npts,
+                            "points_per_s": npts / (ms * 1e-3) if ms > 0 else None,
+                            "note": "latency-bound serial dependency, not bandwidth-bound",
+                            "serial_chain_floor_ms": 1e3 * 52.0 * npts / clk_hz,
+                            "frac_of_serial_chain_floor": (1e3 * 52.0 * npts / clk_hz) / ms if ms > 0 else None}
+            for v in out.values():
+                v["frac"] = v["achieved"] / v["peak"] if v.get("achieved") is not None else None
+            return out
+
+        work_all = {k: sum(st[k] for st in stats) for k in stats[0]}
+        roof_load = rooflines(agg, work_all, pairs)
+        roof = rooflines(solo_ms, solo_work, pairs[:1])
+        dominant = max((k for k in solo_ms if k in roof or k.startswith("features")), key=lambda k: solo_ms[k])
+        dom_key = dominant if dominant in roof else "features"
+        main_roof = dict(roof[dom_key])
         # DRAM bytes per launch of that kernel from the committed ncu --set full captures of the same
-        # workload (seed 0 pair): profiles/r1_v6_dp2_block_full.txt, profiles/r1_v8_features_full.txt
-        ncu_traffic = {"dp2_trace": 12.902912e6 + 256, "features": (116.465152e6 + 5.258240e6 + 143.008e6 + 9.717248e6) / 2}
-        main_roof.update({"kernel": dom_key or dominant, "peak_source": peak_src,
+        # workload (seed 0 pair): profiles/r1_v18_dp2_block_full.txt, profiles/r1_v8_features_full.txt
+        ncu_traffic = {"dp2_trace": 12.918784e6 + 2048, "features": (116.465152e6 + 5.258240e6 + 143.008e6 + 9.717248e6) / 2}
+        main_roof.update({"kernel": dom_key, "peak_source": peak_src,
+                          "measured": "CUDA events on the pair's stream, one C2 pair alone on the GPU right after the timed steps",
                           "traffic": ncu_traffic.get(dom_key) if args.scale == 1.0 else None,
                           "traffic_note": "bytes per launch (dram read + write), ncu --set full of one C2 pair, see profiles/"})
         line = {
@@ -485,12 +500,14 @@ def run_ours(args, rank, world, local_rank):
             "gpu_launches": int(launches_all),
             "roofline": main_roof,
             "roofline_by_kernel": roof,
+            "roofline_by_kernel_under_load": roof_load,
+            "kernel_ms_one_pair_alone": solo_ms,
             "kernel_ms_last_step": agg,
             "host_call_ms_last_step": host_calls,
             "host_call_ms_last_step_e2e": host_calls_e2e,
             "host_ms_inside_library_per_pair": lib_host,
             "allocator_activity_in_timed_steps": alloc_timed,
-            "work": {k: sum(s[k] for s in stats) for k in stats[0]},
+            "work": work_all,
             "clocks": clocks,
             "cpu_baseline": cpu,
             "parity": parity,

@@ -1332,11 +1332,6 @@ __global__ void __launch_bounds__(32, 1) dp2_block_kernel(Dp2LArgs a) {
           int u = __ffs(todo) - 1;
           todo &= todo - 1;
           double q = s_rec[buf][u].q, f = with_frontier ? s_fv[u] : NEG;
-          // The warp issues in order and an f64 add or compare takes ~45 cycles, so the bookkeeping of
-          // point t-1 (cum - 50, cum - 1000 and their compares) is issued together with the adds of
-          // point t instead of behind the select that produces cum(t-1).
-          int up = -1;             // previous point of the walk, bookkeeping still to do
-          double cp = NEG;
           for (;;) {
             int un = -1;
             double qn = 0.0, fn = NEG;
@@ -1347,28 +1342,17 @@ __global__ void __launch_bounds__(32, 1) dp2_block_kernel(Dp2LArgs a) {
               if (with_frontier) fn = s_fv[un];
             }
             const double x = la + q, y = lb + q, z = f + q;
-            const double cjp = cp - 50.0, jp = cp - 1000.0;      // previous point (NEG - c stays NEG)
             const bool pf = f > la && f > lb;
-            const bool ge = la >= lb;
-            const double cum = pf ? z : (ge ? x : y);
+            const double cum = pf ? z : (la >= lb ? x : y);
             lb = la; la = cum;
-            s_cum[u] = cum;
-            if (up >= 0) {
-              if (clv < cjp) { clv = cjp; cli = base + up; }
-              if (jp > pmv) { pmv = jp; pmi = base + up; }
-              bmax = jp > bmax ? jp : bmax;
-              s_pmv[up] = pmv; s_pmi[up] = pmi;
-            }
-            s_clvb[u] = clv; s_clib[u] = cli;
-            up = u; cp = cum;
+            s_cum[u] = cum; s_clvb[u] = clv; s_clib[u] = cli;
+            const double cj = cum - 50.0, jump = cum - 1000.0;
+            if (clv < cj) { clv = cj; cli = base + u; }
+            if (jump > pmv) { pmv = jump; pmi = base + u; }
+            bmax = jump > bmax ? jump : bmax;
+            s_pmv[u] = pmv; s_pmi[u] = pmi;
             if (un < 0) break;
             u = un; q = qn; f = fn;
-          }
-          {
-            const double jp = cp - 1000.0;
-            if (jp > pmv) { pmv = jp; pmi = base + up; }
-            bmax = jp > bmax ? jp : bmax;
-            s_pmv[up] = pmv; s_pmi[up] = pmi;
           }
           s_bmax[lane] = bmax;
         };
