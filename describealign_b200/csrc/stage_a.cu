@@ -289,6 +289,8 @@ __global__ void gate_kernel(GateArgs g) {
   const int lane = threadIdx.x & 31;
   const int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (q >= g.n_queries) return;
+  // second pass: only the rows that have candidates (one row in six at the Ask-Dad shape) enumerate again
+  if (FILL && g.row_off[q + 1] == g.row_off[q]) return;
   const int32_t i = g.a_list[q];
   uint32_t ap[5];
   int32_t st[5], en[5];
