@@ -49,7 +49,9 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--pairs", type=int, default=256, help="pairs per GPU per step")
     ap.add_argument("--workers", type=int, default=64, help="pairs in flight per GPU (one CUDA stream and one host thread each)")
-    ap.add_argument("--distinct", type=int, default=8, help="distinct synthetic pairs per GPU; a step cycles over them")
+    ap.add_argument("--distinct", type=int, default=0,
+                    help="distinct synthetic pairs per GPU, a step cycles over them (default: 8, or 4 per GPU when more than two ranks "
+                         "share the host's cores for generating them; 4 pairs are 1 GB of PCM, still 8x the L2)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the C2 durations (debugging only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -60,14 +62,15 @@ def parse_args():
     return ap.parse_args()
 
 
-def make_pairs(n, first_seed, scale):
-    """n C2 pairs with distinct seeds, generated in parallel worker processes."""
+def make_pairs(n, first_seed, scale, world=1):
+    """n C2 pairs with distinct seeds, generated in parallel worker processes (the host's cores are
+    shared by the `world` ranks of the node)."""
     from concurrent.futures import ProcessPoolExecutor
     from describealign_b200 import synth
     seeds = [first_seed + k for k in range(n)]
     if n == 1:
         return [synth.config_pair("C2", seeds[0], scale)]
-    with ProcessPoolExecutor(max_workers=min(n, os.cpu_count() or 1)) as ex:
+    with ProcessPoolExecutor(max_workers=max(1, min(n, (os.cpu_count() or 1) // max(1, world)))) as ex:
         return list(ex.map(_make_one, [(s, scale) for s in seeds]))
 
 
@@ -232,8 +235,8 @@ def run_ours(args, rank, world, local_rank):
 
     # B pairs per step, cycling over a few distinct synthetic pairs (generating one takes ~35 s of CPU)
     B = args.pairs
-    distinct = max(1, min(B, args.distinct))
-    base_pairs = make_pairs(distinct, rank * distinct, args.scale)
+    distinct = max(1, min(B, args.distinct if args.distinct > 0 else (8 if world <= 2 else 4)))
+    base_pairs = make_pairs(distinct, rank * distinct, args.scale, world)
     pairs = [base_pairs[k % distinct] for k in range(B)]
     hours_rank = audio_hours(pairs)
 
