@@ -1026,6 +1026,13 @@ __global__ void __launch_bounds__(32, 1) dp2_lane_kernel(Dp2LArgs a) {
 // Every cum is still "chosen predecessor value + qual" in the reference's order, so values and
 // decisions are bit-identical; only the evaluation schedule changed.
 // ------------------------------------------------------------------------------------------
+// order-preserving integer image of a double (no NaNs here): a > b  <=>  dkey(a) > dkey(b), except that
+// -0.0 sorts below +0.0 (callers treat "key says greater but the values compare equal" as ambiguous)
+__device__ __forceinline__ long long dkey(double x) {
+  const long long b = __double_as_longlong(x);
+  return b ^ ((b >> 63) & 0x7fffffffffffffffLL);
+}
+
 constexpr int MIN_BLOCK = 4;            // shortest range worth a block evaluation
 constexpr double LEAD_MARGIN = 500.0;   // leader: last cum >= frontier best + margin (a heuristic; checked per point)
 
@@ -1041,8 +1048,8 @@ __global__ void __launch_bounds__(32, 1) dp2_block_kernel(Dp2LArgs a) {
   // per point of the current block (index = lane of the point)
   __shared__ double s_best[32], s_m[32], s_cum[32], s_pmv[32], s_topv[32], s_topj[32], s_fv[32];
   __shared__ int s_pred[32], s_pmi[32], s_topi[32], s_fi[32];
-  __shared__ double s_clvb[32];                 // lite walk: the corridor's cluster best before the point ...
-  __shared__ int s_clib[32];                    // ... and its id
+  __shared__ double s_mb[32];                   // lite walk: largest cum among the corridor's earlier points of the block ...
+  __shared__ int s_mbi[32];                     // ... and the lane of that point (-1: none yet)
   __shared__ double s_bmax[32];                 // per corridor: largest new frontier entry of the current block
 
   const unsigned FULL = 0xffffffffu;
@@ -1324,11 +1331,15 @@ __global__ void __launch_bounds__(32, 1) dp2_block_kernel(Dp2LArgs a) {
         auto lite_pass = [&](unsigned todo, const bool with_frontier) {
           // cum = max(la, lb, f) + q, written so that the adds and the compares all start from la (see
           // the fast path): (f > la && f > lb) ? f + q : (la >= lb ? la + q : lb + q); the next point's
-          // index and inputs are fetched before the dependent arithmetic of this one.  The cluster best
-          // and the running-max head ride along as their own short chains (nothing in the cum chain
-          // waits for them); the owner's registers stay untouched.
-          double la = c0, lb = c1, clv = cl_v, pmv = pm_v, bmax = NEG;
-          int cli = cl_i, pmi = pm_i;
+          // index and inputs are fetched before the dependent arithmetic of this one.  The warp issues
+          // in order and an f64 add or compare takes ~45 cycles, so nothing else in the loop may use
+          // the f64 pipe: the only bookkeeping is the running maximum of cum (first occurrence), kept
+          // by INTEGER compares of order-preserving keys.  Cluster best and running-max head follow
+          // from it per point afterwards (point_head), because rounding is monotone:
+          // max fl(cum - c) = fl(max cum - c).  The owner's registers stay untouched.
+          double la = c0, lb = c1, mval = NEG;
+          long long mkey = dkey(NEG);
+          int midx = -1;
           int u = __ffs(todo) - 1;
           todo &= todo - 1;
           double q = s_rec[buf][u].q, f = with_frontier ? s_fv[u] : NEG;
@@ -1345,22 +1356,42 @@ __global__ void __launch_bounds__(32, 1) dp2_block_kernel(Dp2LArgs a) {
             const bool pf = f > la && f > lb;
             const double cum = pf ? z : (la >= lb ? x : y);
             lb = la; la = cum;
-            s_cum[u] = cum; s_clvb[u] = clv; s_clib[u] = cli;
-            const double cj = cum - 50.0, jump = cum - 1000.0;
-            if (clv < cj) { clv = cj; cli = base + u; }
-            if (jump > pmv) { pmv = jump; pmi = base + u; }
-            bmax = jump > bmax ? jump : bmax;
-            s_pmv[u] = pmv; s_pmi[u] = pmi;
+            s_cum[u] = cum; s_mb[u] = mval; s_mbi[u] = midx;
+            const long long k = dkey(cum);
+            if (k > mkey) { mkey = k; mval = cum; midx = u; }
             if (un < 0) break;
             u = un; q = qn; f = fn;
           }
-          s_bmax[lane] = bmax;
+          s_bmax[lane] = mval - 1000.0;          // the corridor's largest new frontier entry of the block
         };
         // pre-block state of each point's corridor, for the lite walk's per-point work
         const int ksrc = own_k & 31;
         const double K_c0 = __shfl_sync(FULL, c0, ksrc), K_c1 = __shfl_sync(FULL, c1, ksrc);
         const int K_id0 = __shfl_sync(FULL, id0, ksrc), K_id1 = __shfl_sync(FULL, id1, ksrc);
+        const double K_clv = __shfl_sync(FULL, cl_v, ksrc), K_pmv = __shfl_sync(FULL, pm_v, ksrc);
+        const int K_pmi = __shfl_sync(FULL, pm_i, ksrc);
         const unsigned present = __ballot_sync(FULL, mine_mask != 0u);    // corridors with points in the block
+        // lite: what the exact walk would have recorded as running-max head after this lane's point, and
+        // the cluster best before it, from the running maximum of cum the walk left in s_mb / s_mbi.
+        // "ambiguous": a new maximum whose rounded cum - 50 or cum - 1000 equals that of the previous
+        // maximum - the exact walk keeps the earlier id there (strict compares), so it has to decide.
+        double h_clvb = NEG;
+        bool h_amb = false;
+        auto point_head = [&](double &pmv_out, int &pmi_out) {
+          const double mb = s_mb[lane], cum = s_cum[lane];
+          const int mbi = s_mbi[lane];
+          const bool newmax = dkey(cum) > dkey(mb);
+          const double cjm = mb - 50.0, jm = mb - 1000.0;              // -inf stays -inf
+          h_clvb = cjm > K_clv ? cjm : K_clv;
+          const double ma = newmax ? cum : mb;
+          const int mai = newmax ? lane : mbi;
+          const double ja = ma - 1000.0;
+          const bool hp = ja > K_pmv;
+          pmv_out = hp ? ja : K_pmv;
+          pmi_out = hp ? base + mai : K_pmi;
+          h_amb = newmax && mbi >= 0 && (!(cum > mb) || (cum - 50.0) == cjm || (cum - 1000.0) == jm);
+          s_pmv[lane] = pmv_out; s_pmi[lane] = pmi_out;
+        };
         double sv, sj, tv_l, tj_l, inc_v, inc_j;
         int si, ti_l, inc_i;
         bool needq;
@@ -1370,6 +1401,10 @@ __global__ void __launch_bounds__(32, 1) dp2_block_kernel(Dp2LArgs a) {
           // ---- A: leaders ----------------------------------------------------------------------
           if (leader && mine_mask) { if (use_lite) lite_pass(mine_mask, false); else own_pass(mine_mask, false); }
           __syncwarp();
+          if (use_lite) {
+            if (pt_leader) point_head(r_pmv, r_pmi);       // the frontier look-ups below read the leaders' heads
+            __syncwarp();
+          }
 
           // ---- B: the frontier's best entry before / after every point (leaders' entries only) ----
           sv = NEG; sj = INFINITY; si = -2;
@@ -1490,10 +1525,9 @@ __global__ void __launch_bounds__(32, 1) dp2_block_kernel(Dp2LArgs a) {
             int fci = -2;
             if (!pt_leader) { fc = s_fv[lane]; fci = s_fi[lane]; }
             const bool tf = fc > mm;
-            const double clvb = s_clvb[lane];
-            hyp = mm >= clvb || fc > clvb;                        // else the cluster best would have been chosen
+            if (!pt_leader) point_head(r_pmv, r_pmi);
+            hyp = (mm >= h_clvb || fc > h_clvb) && !h_amb;         // else the exact walk has to decide
             r_m = mm; r_best = tf ? fc : mm; r_pred = tf ? fci : mid;
-            r_pmv = s_pmv[lane]; r_pmi = s_pmi[lane];
           }
           if (__any_sync(FULL, inr && !hyp)) { use_lite = false; __syncwarp(); continue; }
           break;
@@ -1545,9 +1579,13 @@ __global__ void __launch_bounds__(32, 1) dp2_block_kernel(Dp2LArgs a) {
             c1 = nmc >= 2 ? s_cum[l2] : oc0; id1 = nmc >= 2 ? base + l2 : oi0;
             c2 = nmc >= 3 ? s_cum[l3] : (nmc == 2 ? oc0 : oc1);
             id2 = nmc >= 3 ? base + l3 : (nmc == 2 ? oi0 : oi1);
-            const double cb = s_clvb[l1], cj1 = x1 - 50.0;
-            const bool up = cb < cj1;
-            cl_v = up ? cj1 : cb; cl_i = up ? base + l1 : s_clib[l1];
+            // running maximum of the committed own points (inclusive of l1), then cluster best and head
+            const double mb1 = s_mb[l1];
+            const bool nm = dkey(x1) > dkey(mb1);
+            const double ma = nm ? x1 : mb1;
+            const int mai = nm ? l1 : s_mbi[l1];
+            const double cja = ma - 50.0;
+            if (cl_v < cja) { cl_v = cja; cl_i = base + mai; }
             pm_v = s_pmv[l1]; pm_i = s_pmi[l1];
             filled = s_rec[buf][l1].ro;
           }
