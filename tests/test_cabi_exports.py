@@ -103,3 +103,38 @@ def test_launcher_patches_a_module():
     broken = types.ModuleType("describealign")
     with pytest.raises(AttributeError):
         launcher.patch(broken)
+
+
+def test_host_wait_mode_is_validated(lib):
+    lib.dab_set_host_wait.argtypes = [ctypes.c_int, ctypes.c_int]
+    lib.dab_set_host_wait.restype = ctypes.c_int
+    assert lib.dab_set_host_wait(-1, 7) < 0          # unknown mode
+    # without a device the call reports the CUDA failure instead of pretending
+    from describealign_b200 import _cabi
+    if lib.dab_device_count() == 0:
+        assert lib.dab_set_host_wait(-1, 2) < 0
+        with pytest.raises(_cabi.DabError):
+            _cabi.set_host_wait(-1, 2)
+
+
+def test_scaled_features_follow_from_six_scalars():
+    """host_fit.scale_features(return_gains=True): the scaled arrays are exactly audio / std and
+    video * gain / std in float32 - what dab_pair_stage_b_gains redoes on the device."""
+    from describealign_b200 import host_fit
+    rng = np.random.default_rng(5)
+    n_v, n_a = 5000, 5600
+    video = [rng.standard_normal(n_v + (k == 0)).astype(np.float32) for k in range(5)]
+    audio = [rng.standard_normal(n_a + (k == 0)).astype(np.float32) for k in range(5)]
+    y = np.sort(rng.integers(0, n_v, 900)); x = np.sort(rng.integers(0, n_a, 900))
+    a_s, v_s, gains = host_fit.scale_features(video, audio, x, y, return_gains=True)
+    a_ref, v_ref = host_fit.scale_features(video, audio, x, y)
+    np.testing.assert_array_equal(a_s, a_ref); np.testing.assert_array_equal(v_s, v_ref)
+    assert gains is not None and a_s.shape == (n_a, 3) and v_s.shape == (n_v, 3)
+    g, sd = gains
+    assert g.dtype == np.float32 and sd.dtype == np.float32
+    for k in range(3):
+        np.testing.assert_array_equal(a_s[:, k], (audio[k][:n_a] / sd[k]).astype(np.float32))
+        np.testing.assert_array_equal(v_s[:, k], ((video[k][:n_v] * g[k]).astype(np.float32) / sd[k]).astype(np.float32))
+    # float64 features: the device cannot redo numpy's arithmetic from float32 scalars
+    video64 = [f.astype(np.float64) for f in video]
+    assert host_fit.scale_features(video64, audio, x, y, return_gains=True)[2] is None

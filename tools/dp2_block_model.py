@@ -295,7 +295,9 @@ def block(st, base, t0, t1, pi, pj, pq, pk, ro, flags, back, cnt, nc):
         if jump > wpm[k][0]:
             wpm[k] = (jump, p)
         # the kernel's LITE walk computes cum as max(c0, c1, frontier candidate) + q; that is what the
-        # exact rules give unless the cluster best is the choice
+        # exact rules give unless the cluster best is the choice (the kernel also falls back to the exact
+        # walk when two successive running maxima of cum round to the same cum - 50 or cum - 1000: a pure
+        # id tie, which the exact rules resolve in favour of the earlier point)
         lite_ok = (fl & (P2_VIS1 | P2_VIS2)) == (P2_VIS1 | P2_VIS2) and \
             (max(c_before[0], c_before[1]) >= cl_before or (frontier is not None and frontier[0] > cl_before))
         out[p] = {"best": best, "pred": pred, "m": m, "cum": cum, "jump": jump, "pm": wpm[k], "lite_ok": lite_ok}
