@@ -391,6 +391,31 @@ def test_baseline_config_shapes_vs_oracle(gpu_ctx, name, scale):
     assert round(float(ny[0] - nx[0]), 4) == round(float(oy[0] - ox[0]), 4)
 
 
+def test_full_size_pair_properties_and_concurrency(gpu_ctx):
+    """BASELINE.json's headline shape (C2, 22-min video / 27-min description) at full size: size-independent
+    properties of the result (the oracle takes too long here; bench.py compares one such pair with it in every
+    run) and 12 copies of the pair in flight at once - own streams, polling host waits, mapped count
+    read-backs - returning bit-identical results."""
+    from describealign_b200 import api, batch, synth
+    v, a = synth.config_pair("C2", 5, 1.0)
+    nx, ny, sim, path, med = api.align_pcm(v, a)
+    n_a, n_v = a.shape[0] // 210, v.shape[0] // 210
+    assert len(path) >= max(min(n_a, n_v) / 500, 1050)                    # describealign.py:991-992
+    assert np.all(np.diff(path[:, 1]) >= 0) and np.all(np.diff(path[:, 0]) >= 0)   # the chain never goes back
+    assert path[:, 1].min() >= 0 and path[:, 1].max() * 210 < n_a and path[:, 0].max() * 210 < n_v
+    assert np.all(np.diff(nx) >= 0) and 0 < sim <= 100
+    assert abs((ny[0] - nx[0]) + 202.0) < 1.0                             # the 202 s start offset of the shape
+    again = api.align_pcm(v, a)                                           # idempotent, buffers reused
+    for x, y in zip((nx, ny, path), (again[0], again[1], again[3])):
+        np.testing.assert_array_equal(x, y)
+    res = batch.run_local([(v, a)] * 12, in_flight=12)
+    for r in res:
+        assert not isinstance(r, Exception), r
+        np.testing.assert_array_equal(r[0], nx); np.testing.assert_array_equal(r[1], ny)
+        np.testing.assert_array_equal(r[3], path)
+        assert r[2] == sim and r[4] == med
+
+
 def test_batch_run_local_matches_sequential(gpu_ctx):
     """Several pairs in flight on one GPU (batch.run_local, one CUDA stream per pair) give the
     results of running them one after the other; a mismatched pair yields its exception."""
