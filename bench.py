@@ -47,8 +47,10 @@ def parse_args():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--pairs", type=int, default=256, help="pairs per GPU per step")
-    ap.add_argument("--workers", type=int, default=64, help="pairs in flight per GPU (one CUDA stream and one host thread each)")
+    ap.add_argument("--pairs", type=int, default=0, help="pairs per GPU per step (default: 4 x workers)")
+    ap.add_argument("--workers", type=int, default=0,
+                    help="pairs in flight per GPU, one CUDA stream and one host thread each (default: 128, 96 with 4 ranks "
+                         "and 64 with 8 ranks sharing the host's cores)")
     ap.add_argument("--distinct", type=int, default=0,
                     help="distinct synthetic pairs per GPU, a step cycles over them (default: 8, or 4 per GPU when more than two ranks "
                          "share the host's cores for generating them; 4 pairs are 1 GB of PCM, still 8x the L2)")
@@ -234,6 +236,10 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     # B pairs per step, cycling over a few distinct synthetic pairs (generating one takes ~35 s of CPU)
+    if args.workers <= 0:
+        args.workers = 128 if world <= 2 else (96 if world <= 4 else 64)
+    if args.pairs <= 0:
+        args.pairs = 4 * args.workers
     B = args.pairs
     distinct = max(1, min(B, args.distinct if args.distinct > 0 else (8 if world <= 2 else 4)))
     base_pairs = make_pairs(distinct, rank * distinct, args.scale, world)
