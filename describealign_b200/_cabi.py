@@ -176,7 +176,7 @@ def set_host_wait(device: int = -1, mode: int = 2) -> int:
     polling.  Call it before the first pair is created.  Returns the device's schedule flags."""
     rc = load().dab_set_host_wait(int(device), int(mode))
     if rc < 0:
-        raise DabError(f"dab_set_host_wait failed ({rc})")
+        raise DabError(f"dab_set_host_wait failed ({rc}): no usable CUDA device? (describealign_b200 has no CPU fallback)")
     return rc
 
 
