@@ -25,7 +25,10 @@ import oracle
 oracle.build()
 da = load_reference()
 seed, ch = %(seed)d, %(ch)d
-v, a = synth.make_pair(%(video_s)f, %(offset_s)f, skips=%(skips)r, seed=seed, ch=ch)
+if %(config)r:
+    v, a = synth.config_pair(%(config)r, seed, 1.0)
+else:
+    v, a = synth.make_pair(%(video_s)f, %(offset_s)f, skips=%(skips)r, seed=seed, ch=ch)
 out = {}
 feats = {}
 for name, pcm in (("video", v), ("audio", a)):
@@ -57,15 +60,16 @@ def _reference_present():
 
 
 @pytest.mark.skipif(not _reference_present(), reason="the reference is only mounted in the authoring container")
-@pytest.mark.parametrize("seed,ch,video_s,offset_s,skips", [
-    (301, 1, 70.0, 5.0, [(25.0, 2.0), (50.0, -1.0)]),
-    (302, 2, 64.0, 3.0, [(30.0, 1.5)]),
+@pytest.mark.parametrize("seed,ch,video_s,offset_s,skips,config", [
+    (301, 1, 70.0, 5.0, [(25.0, 2.0), (50.0, -1.0)], ""),
+    (302, 2, 64.0, 3.0, [(30.0, 1.5)], ""),
+    (303, 1, 0.0, 0.0, [], "C1"),        # BASELINE.json config 1 stand-in at full size: 179 s video, 378 s description
 ])
-def test_oracle_equals_reference_on_fresh_pairs(seed, ch, video_s, offset_s, skips):
+def test_oracle_equals_reference_on_fresh_pairs(seed, ch, video_s, offset_s, skips, config):
     env = dict(os.environ)
     env["NPY_DISABLE_CPU_FEATURES"] = "AVX512F AVX512CD AVX512_SKX AVX512_CLX AVX512_CNL AVX512_ICL AVX512_SPR"
     env["OMP_NUM_THREADS"] = "1"
-    code = CHILD % dict(root=ROOT, seed=seed, ch=ch, video_s=video_s, offset_s=offset_s, skips=skips)
+    code = CHILD % dict(root=ROOT, seed=seed, ch=ch, video_s=video_s, offset_s=offset_s, skips=skips, config=config)
     res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=900)
     assert res.returncode == 0, res.stdout[-1500:] + res.stderr[-3000:]
     line = [ln for ln in res.stdout.splitlines() if ln.startswith("RESULT ")][-1]
