@@ -1300,8 +1300,6 @@ __global__ void __launch_bounds__(32, 1) dp2_block_kernel(Dp2LArgs a) {
       const unsigned stopbits = hard >> t;
       const int e = stopbits ? t + __ffs(stopbits) - 1 : 32;       // block = points [t, e)
       if (e - t >= MIN_BLOCK) {
-        const unsigned below_e = e >= 32 ? FULL : ((1u << e) - 1u);
-        const unsigned rmask = below_e & ~((1u << t) - 1u);
         const bool inr = lane >= t && lane < e;
         // ---- who owns which points; leaders and followers --------------------------------------
         const unsigned grp = __match_any_sync(FULL, inr ? own_k : 32 + lane);
@@ -1315,14 +1313,13 @@ __global__ void __launch_bounds__(32, 1) dp2_block_kernel(Dp2LArgs a) {
         const unsigned leadlanes = __ballot_sync(FULL, leader);
         const bool pt_leader = inr && ((leadlanes >> own_k) & 1u);
         const unsigned lead_pts = __ballot_sync(FULL, pt_leader);
-        const unsigned foll_pts = rmask & ~lead_pts;
         // the owner's registers at the start of the block (restored if only a prefix commits)
         const double sv_c0 = c0, sv_c1 = c1, sv_c2 = c2, sv_clv = cl_v, sv_pmv = pm_v;
         const int sv_id0 = id0, sv_id1 = id1, sv_id2 = id2, sv_cli = cl_i, sv_pmi = pm_i, sv_filled = filled;
 
         // The owner lanes' walks come in two forms.  The LITE walk assumes that a point never restarts
         // from its cluster's best (true for 98.6 % of the points of a C2 pair): then cum is just
-        // max(c0, c1, frontier candidate) + q, 14-18 instructions per point, and predecessor ids,
+        // max(c0, c1, frontier candidate) + q, 42-56 instructions per point (ncu), and predecessor ids,
         // running maxima and the assumption itself are worked out afterwards by the points' own lanes.
         // It needs every point of the block to see the corridor's previous two points.  If a point
         // violates the assumption the block is evaluated again with the exact walk (own_pass).
