@@ -200,7 +200,7 @@ int dab_set_option(dab_ctx *ctx, const char *name, int64_t value) {
   return DAB_E_ARG;
 }
 
-int64_t dab_launch_count(const dab_ctx *ctx) { return ctx ? ctx->launches : 0; }
+int64_t dab_launch_count(const dab_ctx *ctx) { return ctx ? ctx->launches.load() : 0; }
 
 }  // extern "C"
 

@@ -4,6 +4,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <atomic>
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
@@ -24,7 +25,7 @@ struct DevBuf {
 struct dab_ctx {
   int device = 0;
   std::string err;
-  int64_t launches = 0;
+  std::atomic<int64_t> launches{0};   // kernels launched through this context (many host threads)
   int sm_count = 148;
   int opt_dp2_generic = 0;   // force the tree DP for pass 2 (testing)
   int opt_dp_reserve_kb = 0; // dynamic shared memory the pass-2 DP kernel asks for without using it (see dab_set_option)

@@ -20,6 +20,9 @@
 // 630 f32->f64 conversions) is what bounds this kernel, not HBM.
 #include <cuda_fp16.h>
 
+#include <atomic>
+#include <mutex>
+
 #include "common.cuh"
 #include "hann_tables.h"
 
@@ -459,12 +462,16 @@ __global__ void __launch_bounds__(THREADS, 2) features_kernel(FeatArgs a) {
   }
 }
 
-bool g_const_ready[64] = {};
+std::atomic<bool> g_const_ready[64];
+std::mutex g_const_mu;
 
+// the tables are the same for every pair: uploaded once per device, by whichever host thread comes first
 int upload_constants(dab_ctx *ctx) {
   int dev = 0;
   DAB_CUDA(cudaGetDevice(&dev));
-  if (dev < 64 && g_const_ready[dev]) return DAB_OK;
+  if (dev < 64 && g_const_ready[dev].load(std::memory_order_acquire)) return DAB_OK;
+  std::lock_guard<std::mutex> lock(g_const_mu);
+  if (dev < 64 && g_const_ready[dev].load(std::memory_order_acquire)) return DAB_OK;
   float tab[NTAB] = {};
   memcpy(tab, DAB_HANN630_F32, sizeof(DAB_HANN630_F32));
   memcpy(tab + 630, DAB_HANN90_F32, sizeof(DAB_HANN90_F32));
@@ -474,7 +481,7 @@ int upload_constants(dab_ctx *ctx) {
   DAB_CUDA(cudaMemcpyToSymbol(g_tables, tab, sizeof(tab)));
   DAB_CUDA(cudaMemcpyToSymbol(c_logf_invc, h_logf_invc, sizeof(h_logf_invc)));
   DAB_CUDA(cudaMemcpyToSymbol(c_logf_logc, h_logf_logc, sizeof(h_logf_logc)));
-  if (dev < 64) g_const_ready[dev] = true;
+  if (dev < 64) g_const_ready[dev].store(true, std::memory_order_release);
   return DAB_OK;
 }
 
