@@ -1,0 +1,74 @@
+"""bench.py's output contract (the keys the driver and the judge read), checked on the CPU:
+the committed B200 line under profiles/ has every required key with sane values, and the
+reference arm (`--impl reference`, the oracle port on the host cores) runs here and prints a
+conforming line."""
+import glob
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+BASE_KEYS = ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+             "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches"]
+
+
+def _check_common(line):
+    for k in BASE_KEYS:
+        assert k in line, k
+    base = json.load(open(os.path.join(ROOT, "BASELINE.json")))
+    assert line["metric"] == "audio_hours_aligned_per_second" and "audio-hours" in base["metric"]
+    assert line["unit"] == "audio-hours/s" and line["higher_is_better"] is True and line["scaling"] == "weak"
+    assert line["vs_baseline"] is None and base["published"] == {}          # nothing published to divide by
+    assert line["data"] == "synthetic" and "workload" in line["config"] and "model" not in line["config"]
+    for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"):
+        assert k in line["e2e"], k
+
+
+def test_committed_b200_line_has_the_contract_keys():
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r1_v*_bench*.json")),
+                   key=lambda p: int(os.path.basename(p).split("_")[1][1:]))
+    newest_full = [p for p in files if "gpu" not in os.path.basename(p) and "reference" not in os.path.basename(p)][-1]
+    text = open(newest_full).read()
+    line = json.loads(text[text.index("{"):])
+    _check_common(line)
+    assert line["n_gpus"] == 1 and line["warmup"] >= 3 and line["value"] > 0 and line["gpu_launches"] > 0
+    assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0
+    assert 0 < line["e2e"]["value"] < line["value"]                           # the copies cost something
+    roof = line["roofline"]
+    for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert k in roof, k
+    assert roof["bound"] in ("hbm", "tensor") and abs(roof["frac"] - roof["achieved"] / roof["peak"]) < 1e-12
+    cpu = line["cpu_baseline"]
+    for k in ("value", "unit", "cores", "kind", "sample"):
+        assert k in cpu, k
+    assert cpu["kind"] in ("port", "reference") and cpu["cores"] >= 1
+    clocks = line["clocks"]
+    assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(clocks)
+    assert not ({"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(clocks["reasons"]))
+    par = line["parity"]
+    assert par["features_f32_identical"] and par["path1_identical"] and par["path2_int_identical"]
+    assert par["nodes_max_abs_diff_s"] <= 1e-9
+
+
+def test_reference_arm_runs_on_the_host_cores():
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0", "--scale", "0.03"], capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1                                                    # ONE JSON line on stdout
+    line = json.loads(lines[0])
+    _check_common(line)
+    assert line["impl"] == "reference" and line["gpu_launches"] == 0
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert line["e2e"]["value"] == line["value"] == line["cpu_baseline"]["value"]
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+
+
+def test_reference_arm_other_ranks_stay_silent():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
+                          "--steps", "1", "--warmup", "0", "--scale", "0.03"], capture_output=True, text=True,
+                         timeout=300, cwd=ROOT, env=env)
+    assert res.returncode == 0 and res.stdout.strip() == ""
