@@ -226,6 +226,7 @@ def run_ours(args, rank, world, local_rank):
     build.build()
     # W host threads wait on W pair streams: they must sleep, not spin (16 host cores, W >> 16)
     sched = api._cabi.set_host_wait(local_rank, args.host_wait)
+    api.set_device(local_rank)
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))

@@ -29,13 +29,24 @@ FAILED_MSG = host_fit.FAILED_MSG
 _tls = threading.local()
 
 
+_device = -1     # GPU index of this process (-1: whatever device is current in the calling thread)
+
+
+def set_device(index: int):
+    """The GPU this process works on (one process per GPU).  Needed when host threads other than the
+    main one call into the library - CUDA's "current device" is per thread and starts at 0 - e.g. the
+    worker threads of batch.run_local under torchrun."""
+    global _device
+    _device = int(index)
+
+
 def context() -> _cabi.Context:
     """Per-thread CUDA context handle, created on first use (never at import time, so that
     a GUI parent process that only imports this module does not initialise CUDA before it
     forks its worker; reference describealign.py:1432)."""
     ctx = getattr(_tls, "ctx", None)
     if ctx is None:
-        ctx = _cabi.Context(-1)
+        ctx = _cabi.Context(_device)
         _tls.ctx = ctx
         _tls.pairs = []
     return ctx

@@ -140,8 +140,8 @@ def run_local(pairs, in_flight: int = 64, runner: Callable | None = None):
         return [one(p) for p in pairs]
     if runner is gpu_runner:
         # one host thread per pair in flight: they must sleep, not spin, while their streams drain
-        from . import _cabi
-        _cabi.set_host_wait(-1, 2)
+        from . import _cabi, api
+        _cabi.set_host_wait(api._device, 2)
     with ThreadPoolExecutor(max_workers=in_flight) as ex:
         return list(ex.map(one, pairs))
 
@@ -225,6 +225,8 @@ def init_from_env(backend: str = "nccl"):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if backend == "nccl":
         torch.cuda.set_device(local)
+        from . import api
+        api.set_device(local)      # the library's worker threads must not fall back to device 0
     if world > 1 and not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29511")

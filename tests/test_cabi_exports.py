@@ -138,3 +138,22 @@ def test_scaled_features_follow_from_six_scalars():
     # float64 features: the device cannot redo numpy's arithmetic from float32 scalars
     video64 = [f.astype(np.float64) for f in video]
     assert host_fit.scale_features(video64, audio, x, y, return_gains=True)[2] is None
+
+
+def test_worker_threads_use_the_process_device(monkeypatch):
+    """api.set_device: contexts created lazily in worker threads (CUDA's current device is per thread and
+    starts at 0) must be opened on the process's GPU, e.g. LOCAL_RANK under torchrun."""
+    import threading
+    from describealign_b200 import _cabi, api
+    seen = []
+
+    class FakeContext:
+        def __init__(self, device=-1):
+            seen.append(device)
+
+    monkeypatch.setattr(_cabi, "Context", FakeContext)
+    monkeypatch.setattr(api, "_device", -1)
+    t = threading.Thread(target=api.context); t.start(); t.join()
+    api.set_device(3)
+    t = threading.Thread(target=api.context); t.start(); t.join()
+    assert seen == [-1, 3]
