@@ -64,6 +64,7 @@ def _reference_present():
     (301, 1, 70.0, 5.0, [(25.0, 2.0), (50.0, -1.0)], ""),
     (302, 2, 64.0, 3.0, [(30.0, 1.5)], ""),
     (303, 1, 0.0, 0.0, [], "C1"),        # BASELINE.json config 1 stand-in at full size: 179 s video, 378 s description
+    (0, 1, 0.0, 0.0, [], "C2"),          # the bench workload itself at full size (22-min video, 27-min description)
 ])
 def test_oracle_equals_reference_on_fresh_pairs(seed, ch, video_s, offset_s, skips, config):
     env = dict(os.environ)
