@@ -442,568 +442,6 @@ struct Dp2LArgs {
   unsigned long long *counters;   // [0] frontier queries, [1] window refills, [2] neighbour points
 };
 
-__global__ void __launch_bounds__(32, 1) dp2_corridor_kernel(Dp2LArgs a) {
-  __shared__ CorState s_st[32];
-  __shared__ double s_pmv[32];                 // SoA mirrors of what the query lanes read
-  __shared__ int s_pmi[32], s_filled[32];
-  __shared__ int s_lo[32], s_hi[32], s_cluster[32];
-  __shared__ double s_slope[32], s_off[32], s_inv[32];
-  __shared__ PmEntry s_ring[32][RING];
-  __shared__ PmEntry s_win[32][WAYS * WLEN];
-  __shared__ P2Rec s_rec[2][32];
-
-  const int lane = threadIdx.x;
-  const int n = a.n_points;
-  const int n_cor = a.n_cor;
-  const double NEG = -INFINITY;
-  {
-    const bool v = lane < n_cor;
-    dab_corridor c;
-    if (v) c = a.cor[lane];
-    s_lo[lane] = v ? c.lo : 0x7fffffff;
-    s_hi[lane] = v ? c.hi : 0x7fffffff;
-    s_cluster[lane] = v ? c.cluster : -1;
-    s_slope[lane] = v ? c.slope : 1.0;
-    s_off[lane] = v ? c.offset : 0.0;
-    s_inv[lane] = v ? 1.0 / c.slope : 1.0;
-    CorState z;
-    z.h_cum0 = z.h_cum1 = z.h_cum2 = NEG;
-    z.h_row0 = z.h_row1 = z.h_row2 = -100;
-    z.h_cell0 = z.h_cell1 = z.h_cell2 = -100;
-    z.h_id0 = z.h_id1 = z.h_id2 = -2;
-    z.filled = -1;
-    z.cl_v = -1000.0; z.cl_i = -1;               // clusters_best_so_far seed (describealign.py:948)
-    z.pm_v = NEG; z.pm_i = -2;
-    z.pm_base = v ? a.pm_off[lane] : 0;
-    s_st[lane] = z;
-    s_pmv[lane] = NEG; s_pmi[lane] = -2; s_filled[lane] = -1;
-  }
-  __syncwarp();
-  // lane-private window tags (lane l caches older PM rows of corridor l)
-  int wbase[WAYS], wnext = 0;
-#pragma unroll
-  for (int w = 0; w < WAYS; ++w) wbase[w] = -0x40000000;
-  unsigned n_query = 0, n_refill = 0, n_near = 0;
-
-  // state of the current corridor (uniform registers)
-  int cur = 0;
-  CorState st = s_st[0];
-  int c_cluster = s_cluster[0];
-  // frontier top: seed (0, 0, -1, 0, 0) (describealign.py:947)
-  double top_v = 0.0, top_j = 0.0;
-  int top_i = -1;
-
-  // every lane writes the same values to the same addresses: no divergence, and each lane's later
-  // reads see at least its own writes, so no barrier is needed
-  auto spill = [&]() {
-    s_st[cur] = st;
-    s_pmv[cur] = st.pm_v; s_pmi[cur] = st.pm_i; s_filled[cur] = st.filled;
-  };
-
-  // F(j) for a point of corridor k at row i: lane c' contributes PM_c'[rows of c' with j' <= j]
-  auto frontier_query = [&](int i, double j, int k, double &fv_out, int &fi_out) {
-        spill();                        // the other lanes' view of every corridor but `cur` is current
-        double v = NEG;
-        int id = -2;
-        if (lane == k) { v = 0.0; id = -1; }          // the frontier's seed entry, j' = 0
-        else if (lane < n_cor && s_lo[lane] <= i) {
-          const int lo = s_lo[lane], rows = s_hi[lane] - lo;
-          const double sl = s_slope[lane], of = s_off[lane];
-          // rows of this corridor whose coordinate is <= j
-          double est = floor((j - of) * s_inv[lane]) - (double)lo + 1.0;
-          int kk = est < 0.0 ? 0 : (est > (double)rows ? rows : (int)est);
-          while (kk < rows && __dadd_rn(__dmul_rn(sl, (double)(lo + kk)), of) <= j) ++kk;
-          while (kk > 0 && __dadd_rn(__dmul_rn(sl, (double)(lo + kk - 1)), of) > j) --kk;
-          const int done = (i + 1 < lo + rows ? i + 1 : lo + rows) - lo;   // rows <= i
-          const int idx = kk < done ? kk : done;
-          const int f = s_filled[lane];
-          if (idx > 0 && f >= 0) {
-            const int x = idx - 1;
-            if (x >= f) { v = s_pmv[lane]; id = s_pmi[lane]; }
-            else if (x > f - RING) { const PmEntry e = s_ring[lane][x & (RING - 1)]; v = e.val; id = e.id; }
-            else {
-              int hit = -1;
-#pragma unroll
-              for (int w = 0; w < WAYS; ++w) if (x >= wbase[w] && x < wbase[w] + WLEN) hit = w;
-              if (hit < 0) {
-                hit = wnext; wnext = (wnext + 1) & (WAYS - 1);
-                ++n_refill;
-                const PmEntry *src = a.pm + s_st[lane].pm_base + x;      // rows x .. x+15 < f are final
-#pragma unroll
-                for (int e = 0; e < WLEN; ++e) {
-                  const int4 raw = __ldcg(reinterpret_cast<const int4 *>(src + e));
-                  *reinterpret_cast<int4 *>(&s_win[lane][hit * WLEN + e]) = raw;
-                }
-#pragma unroll
-                for (int w = 0; w < WAYS; ++w) if (w == hit) wbase[w] = x;
-              }
-              int wb = 0;
-#pragma unroll
-              for (int w = 0; w < WAYS; ++w) if (w == hit) wb = wbase[w];
-              const PmEntry e = s_win[lane][hit * WLEN + (x - wb)];
-              v = e.val; id = e.id;
-            }
-          }
-        }
-        // warp arg-max on (val desc, j' asc, id asc)
-        const unsigned long long ob = order_bits(v);
-        const unsigned hi = (unsigned)(ob >> 32), lo32 = (unsigned)ob;
-        const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
-        bool alive = hi == mhi;
-        const unsigned mlo = __reduce_max_sync(0xffffffffu, alive ? lo32 : 0u);
-        alive = alive && lo32 == mlo;
-        unsigned bal = __ballot_sync(0xffffffffu, alive);
-        if (__popc(bal) > 1) {
-          // equal values (flat stretches that started from the same jump): smallest j', then id
-          const double jj = !alive ? INFINITY : (id < 0 ? 0.0 : a.p_j[id]);
-          const unsigned long long jb = (unsigned long long)__double_as_longlong(jj);   // jj >= 0
-          const unsigned jh = (unsigned)(jb >> 32), jl = (unsigned)jb;
-          const unsigned nh = __reduce_min_sync(0xffffffffu, alive ? jh : 0xffffffffu);
-          alive = alive && jh == nh;
-          const unsigned nl = __reduce_min_sync(0xffffffffu, alive ? jl : 0xffffffffu);
-          alive = alive && jl == nl;
-          const unsigned ni = __reduce_min_sync(0xffffffffu, alive ? (unsigned)(id + 2) : 0xffffffffu);
-          alive = alive && (unsigned)(id + 2) == ni;
-          bal = __ballot_sync(0xffffffffu, alive);
-        }
-        const int src = __ffs(bal) - 1;
-        const double fv = __shfl_sync(0xffffffffu, v, src);
-        const int fi = __shfl_sync(0xffffffffu, id, src);
-        fv_out = fv; fi_out = fi;
-  };
-
-  P2Rec rr;
-  if (lane < n) rr = a.rec[lane];
-  for (int base = 0; base < n; base += 32) {
-    const int buf = (base >> 5) & 1;
-    s_rec[buf][lane] = rr;
-    __syncwarp();
-    if (base + 32 + lane < n) rr = a.rec[base + 32 + lane];
-    const int cnt = n - base < 32 ? n - base : 32;
-    P2Rec nx = s_rec[buf][0];
-    for (int t = 0; t < cnt; ++t) {
-      const int p = base + t;
-      const P2Rec pt = nx;
-      if (t + 1 < cnt) nx = s_rec[buf][t + 1];
-      const int i = pt.i, cell = pt.cell, ro = pt.ro;
-      const double j = pt.j, q = pt.q;
-      const int k = pt.kf & 0xff;
-      const bool near = (pt.kf & P2_NEAR) != 0;
-      if (k != cur) {
-        spill();
-        cur = k;
-        st = s_st[k];
-        c_cluster = s_cluster[k];
-      }
-      double best;
-      int pred;
-      if (!near) {
-        // own-corridor prev_cache candidates: rows i-1 / i-2 of this line, latest write per cell
-        const bool vis1 = st.h_row0 >= i - 2 && st.h_cell0 >= cell - 2;
-        const bool vis2 = st.h_row1 >= i - 2 && st.h_cell1 >= cell - 2 && st.h_cell1 != st.h_cell0;
-        // candidates in the reference's order [frontier, cluster best, cell(s)]: the LAST one that
-        // attains the maximum wins (every test is ">=", describealign.py:960-973)
-        double m = st.cl_v;
-        int mi = st.cl_i;
-        if (vis2 && st.h_cum1 >= m) { m = st.h_cum1; mi = st.h_id1; }
-        if (vis1 && st.h_cum0 >= m) { m = st.h_cum0; mi = st.h_id0; }
-        best = m; pred = mi;
-        if (top_j <= j) {
-          if (top_v > m) { best = top_v; pred = top_i; }     // the top entry is F(j) itself
-        } else if (m < top_v) {                               // else F(j) <= top value <= m
-          ++n_query;
-          double fv; int fi;
-          frontier_query(i, j, k, fv, fi);
-          if (fv > m) { best = fv; pred = fi; }
-        }
-      } else {
-        ++n_near;
-        best = NEG; pred = -2;
-        if (top_j <= j) { best = top_v; pred = top_i; }
-        else { ++n_query; frontier_query(i, j, k, best, pred); }
-      }
-      if (near) {
-        // generic prev_cache evaluation over the histories of all corridors
-        if (st.cl_v >= best) { best = st.cl_v; pred = st.cl_i; }
-        spill();
-#pragma unroll 1
-        for (int x = cell - 2; x <= cell; ++x) {
-          int brow = -1, bh = 0;
-          if (lane < n_cor) {
-            const CorState *o = &s_st[lane];
-            if (o->h_cell0 == x && o->h_row0 > brow) { brow = o->h_row0; bh = 0; }
-            if (o->h_cell1 == x && o->h_row1 > brow) { brow = o->h_row1; bh = 1; }
-            if (o->h_cell2 == x && o->h_row2 > brow) { brow = o->h_row2; bh = 2; }
-          }
-          const int mrow = (int)__reduce_max_sync(0xffffffffu, (unsigned)(brow + 1)) - 1;
-          if (mrow < 0 || mrow < i - 2) continue;         // nothing written recently enough
-          const int src = __ffs(__ballot_sync(0xffffffffu, brow == mrow)) - 1;
-          const int sh = __shfl_sync(0xffffffffu, bh, src);
-          const CorState *o = &s_st[src];
-          double pc = sh == 0 ? o->h_cum0 : (sh == 1 ? o->h_cum1 : o->h_cum2);
-          const int pid = sh == 0 ? o->h_id0 : (sh == 1 ? o->h_id1 : o->h_id2);
-          const double pj = __dadd_rn(__dmul_rn(s_slope[src], (double)mrow), s_off[src]);
-          if (s_cluster[src] != c_cluster) {
-            const double d = (j - pj) - (double)(i - mrow);
-            pc = pc - (100.0 + 100.0 * (d * d));
-          }
-          if (pj <= j && pc >= best) { best = pc; pred = pid; }
-        }
-      }
-      {
-        const double cum = best + q;
-        // ---- updates ---------------------------------------------------------------------
-        st.h_row2 = st.h_row1; st.h_cell2 = st.h_cell1; st.h_id2 = st.h_id1; st.h_cum2 = st.h_cum1;
-        st.h_row1 = st.h_row0; st.h_cell1 = st.h_cell0; st.h_id1 = st.h_id0; st.h_cum1 = st.h_cum0;
-        st.h_row0 = i; st.h_cell0 = cell; st.h_id0 = p; st.h_cum0 = cum;
-        const double cj = cum - 50.0;
-        if (st.cl_v < cj) { st.cl_v = cj; st.cl_i = p; }
-        const double jump = cum - 1000.0;
-        if (ro - st.filled > 1) {
-          // rows without a point (their cell was claimed by an earlier cluster) repeat the head
-          PmEntry e; e.val = st.pm_v; e.id = st.pm_i; e.pad = 0;
-          for (int r = st.filled + 1; r < ro; ++r) {
-            if (lane == 0) a.pm[st.pm_base + r] = e;
-            s_ring[k][r & (RING - 1)] = e;
-          }
-        }
-        if (jump > st.pm_v) { st.pm_v = jump; st.pm_i = p; }
-        st.filled = ro;
-        PmEntry e; e.val = st.pm_v; e.id = st.pm_i; e.pad = 0;
-        s_ring[k][ro & (RING - 1)] = e;
-        // lane 0 appends the PM row, lane 1 the back record: one predicated 16-byte store
-        int4 *dst = lane == 0 ? reinterpret_cast<int4 *>(a.pm + st.pm_base + ro) : reinterpret_cast<int4 *>(a.back + p);
-        int4 val;
-        if (lane == 0) { val.x = __double2loint(e.val); val.y = __double2hiint(e.val); val.z = e.id; val.w = 0; }
-        else { val.x = __double2loint(best); val.y = __double2hiint(best); val.z = pred; val.w = 0; }
-        if (lane < 2) *dst = val;
-        if (jump > top_v || (jump == top_v && j < top_j)) { top_v = jump; top_j = j; top_i = p; }
-      }
-    }
-    __syncwarp();
-  }
-  if (lane == 0) {
-    a.result[0] = top_i;
-    *reinterpret_cast<double *>(a.result + 2) = top_v;
-    a.counters[0] = n_query; a.counters[1] = n_refill; a.counters[2] = n_near;
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// DP #2, lane-per-corridor formulation (the product path).  Same mathematics as
-// dp2_corridor_kernel above, but lane l of the walking warp OWNS corridor l: its last cums, its
-// cluster best, its running-max head and its line live in that lane's registers, so there is no
-// state to spill when consecutive points alternate between overlapping corridors, and the
-// per-point code is one branch-free instruction stream: every lane evaluates "its" candidates,
-// only the lane that owns the point's corridor commits (selects, predicated stores).  The facts
-// that do not depend on cum values - which earlier points are prev_cache candidates, whether rows
-// of the corridor were skipped, whether the frontier's best entry can lie right of the point -
-// were worked out by corridor_kernel (P2_* flags).  Cross-lane traffic per point: one 64-bit
-// shuffle (the committed cum - 1000 for the frontier top).
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32, 1) dp2_lane_kernel(Dp2LArgs a) {
-  __shared__ PmEntry s_ring[RING][32];          // [row & 15][corridor]: last 16 running-max rows
-  __shared__ PmEntry s_win[32][WAYS * WLEN];    // per-lane window cache of older rows
-  __shared__ P2Rec s_rec[2][32];
-
-  const unsigned FULL = 0xffffffffu;
-  const int lane = threadIdx.x;
-  const int n = a.n_points;
-  const int n_cor = a.n_cor;
-  const double NEG = -INFINITY;
-
-  // ---- this lane's corridor -----------------------------------------------------------------
-  const bool have = lane < n_cor;
-  int lo = 0x7fffffff, rows = 0, cluster = -1;
-  double sl = 1.0, of = 0.0, inv = 1.0;
-  PmEntry *pm = a.pm;
-  if (have) {
-    const dab_corridor c = a.cor[lane];
-    lo = c.lo; rows = c.hi > c.lo ? c.hi - c.lo : 0; cluster = c.cluster;
-    sl = c.slope; of = c.offset; inv = 1.0 / c.slope;
-    pm = a.pm + a.pm_off[lane];
-  }
-  double c0 = NEG, c1 = NEG, c2 = NEG;          // cums of the corridor's last three points
-  int id0 = -2, id1 = -2, id2 = -2;
-  double cl_v = -1000.0; int cl_i = -1;          // clusters_best_so_far seed (describealign.py:948)
-  double pm_v = NEG; int pm_i = -2;              // head of the running maximum of cum - 1000
-  int filled = -1;                               // last running-max row written
-  int wbase[WAYS], wnext = 0;
-#pragma unroll
-  for (int w = 0; w < WAYS; ++w) wbase[w] = -0x40000000;
-  // frontier top: seed (0, 0, -1, 0, 0) (describealign.py:947); uniform across lanes
-  double top_v = 0.0, top_j = 0.0;
-  int top_i = -1;
-  unsigned n_query = 0, n_refill = 0, n_near = 0, n_runpts = 0;
-
-  // F(j) seen from a point of corridor k on row i: lane c' contributes PM_c'[rows of c' with j' <= j]
-  auto frontier_query = [&](int i, double j, int k, double &fv_out, int &fi_out) {
-    double v = NEG;
-    int id = -2;
-    if (lane == k) { v = 0.0; id = -1; }          // the frontier's seed entry, j' = 0
-    else if (have && lo <= i) {
-      double est = floor((j - of) * inv) - (double)lo + 1.0;
-      int kk = est < 0.0 ? 0 : (est > (double)rows ? rows : (int)est);
-      while (kk < rows && __dadd_rn(__dmul_rn(sl, (double)(lo + kk)), of) <= j) ++kk;
-      while (kk > 0 && __dadd_rn(__dmul_rn(sl, (double)(lo + kk - 1)), of) > j) --kk;
-      const int done = (i + 1 < lo + rows ? i + 1 : lo + rows) - lo;   // rows <= i
-      const int idx = kk < done ? kk : done;
-      const int f = filled;
-      if (idx > 0 && f >= 0) {
-        const int x = idx - 1;
-        if (x >= f) { v = pm_v; id = pm_i; }
-        else if (x > f - RING) { const PmEntry e = s_ring[x & (RING - 1)][lane]; v = e.val; id = e.id; }
-        else {
-          int hit = -1;
-#pragma unroll
-          for (int w = 0; w < WAYS; ++w) if (x >= wbase[w] && x < wbase[w] + WLEN) hit = w;
-          if (hit < 0) {
-            hit = wnext; wnext = (wnext + 1) & (WAYS - 1);
-            ++n_refill;
-            const PmEntry *src = pm + x;                   // rows x .. x+15 < f are final
-#pragma unroll
-            for (int e = 0; e < WLEN; ++e) {
-              const int4 raw = __ldcg(reinterpret_cast<const int4 *>(src + e));
-              *reinterpret_cast<int4 *>(&s_win[lane][hit * WLEN + e]) = raw;
-            }
-#pragma unroll
-            for (int w = 0; w < WAYS; ++w) if (w == hit) wbase[w] = x;
-          }
-          int wb = 0;
-#pragma unroll
-          for (int w = 0; w < WAYS; ++w) if (w == hit) wb = wbase[w];
-          const PmEntry e = s_win[lane][hit * WLEN + (x - wb)];
-          v = e.val; id = e.id;
-        }
-      }
-    }
-    // warp arg-max on (val desc, j' asc, id asc)
-    const unsigned long long ob = order_bits(v);
-    const unsigned hi = (unsigned)(ob >> 32), lo32 = (unsigned)ob;
-    const unsigned mhi = __reduce_max_sync(FULL, hi);
-    bool alive = hi == mhi;
-    const unsigned mlo = __reduce_max_sync(FULL, alive ? lo32 : 0u);
-    alive = alive && lo32 == mlo;
-    unsigned bal = __ballot_sync(FULL, alive);
-    if (__popc(bal) > 1) {
-      const double jj = !alive ? INFINITY : (id < 0 ? 0.0 : a.p_j[id]);
-      const unsigned long long jb = (unsigned long long)__double_as_longlong(jj);   // jj >= 0
-      const unsigned jh = (unsigned)(jb >> 32), jl = (unsigned)jb;
-      const unsigned nh = __reduce_min_sync(FULL, alive ? jh : 0xffffffffu);
-      alive = alive && jh == nh;
-      const unsigned nl = __reduce_min_sync(FULL, alive ? jl : 0xffffffffu);
-      alive = alive && jl == nl;
-      const unsigned ni = __reduce_min_sync(FULL, alive ? (unsigned)(id + 2) : 0xffffffffu);
-      alive = alive && (unsigned)(id + 2) == ni;
-      bal = __ballot_sync(FULL, alive);
-    }
-    const int src = __ffs(bal) - 1;
-    fv_out = __shfl_sync(FULL, v, src);
-    fi_out = __shfl_sync(FULL, id, src);
-  };
-
-  P2Rec rr;
-  if (lane < n) rr = a.rec[lane];
-  for (int base = 0; base < n; base += 32) {
-    const int buf = (base >> 5) & 1;
-    s_rec[buf][lane] = rr;
-    __syncwarp();
-    if (base + 32 + lane < n) rr = a.rec[base + 32 + lane];
-    const int cnt = n - base < 32 ? n - base : 32;
-    // ---- runs: consecutive points of ONE corridor that each extend that corridor's best chain,
-    //      while the corridor's last point is also the frontier's top.  Then every point's best
-    //      predecessor is the point before it (cluster best = c0 - 50 < c0, c1 <= c0, frontier top =
-    //      c0 - 1000 < c0), so the cums are one sequential chain of f64 adds - exactly the
-    //      reference's order - and the rest (back records, running-max rows) is lane-parallel. ----
-    const P2Rec own = s_rec[buf][lane];
-    const int own_k = own.kf & 0xff;
-    const int prev_k = lane > 0 ? (s_rec[buf][lane - 1].kf & 0xff) : -1;
-    const bool simple = lane < cnt && (own.kf & (P2_NEAR | P2_GAP | P2_VIS1)) == P2_VIS1 && own.q > 0.0;
-    const unsigned simplemask = __ballot_sync(FULL, simple);
-    const unsigned contmask = __ballot_sync(FULL, simple && own_k == prev_k);
-    int t = 0, no_run_at = -1;       // no_run_at: the point that just ended a run takes the scalar path
-    while (t < cnt) {
-      if (((simplemask >> t) & 1u) && t != no_run_at) {
-        int len = 1;
-        if (t + 1 < 32) {
-          const unsigned stop = (~contmask) >> (t + 1);
-          len += stop ? __ffs(stop) - 1 : 31 - t;
-        }
-        if (len > cnt - t) len = cnt - t;
-        const int k = s_rec[buf][t].kf & 0xff;
-        const bool rising = id0 >= 0 && cl_i == id0 && pm_i == id0 && top_i == id0;
-        if (len >= RUN_MIN && __shfl_sync(FULL, (int)rising, k)) {
-          // state of the corridor's owner lane
-          const double k_c0 = __shfl_sync(FULL, c0, k), k_c1 = __shfl_sync(FULL, c1, k);
-          const double k_cl = __shfl_sync(FULL, cl_v, k), k_pm = __shfl_sync(FULL, pm_v, k);
-          const int k_id0 = __shfl_sync(FULL, id0, k), k_id1 = __shfl_sync(FULL, id1, k);
-          PmEntry *const k_pmrow = reinterpret_cast<PmEntry *>(
-              __shfl_sync(FULL, (unsigned long long)reinterpret_cast<uintptr_t>(pm), k));
-          double c = k_c0, my_cum = 0.0;
-          for (int u = 0; u < len; ++u) {
-            c = c + s_rec[buf][t + u].q;
-            if (lane == t + u) my_cum = c;
-          }
-          const bool in_run = lane >= t && lane < t + len;
-          const bool first = lane == t;
-          double prev_cum = __shfl_up_sync(FULL, my_cum, 1);
-          if (first) prev_cum = k_c0;
-          const int prev_id = first ? k_id0 : base + lane - 1;
-          const double cj = my_cum - 50.0, jump = my_cum - 1000.0;
-          double prev_cj = __shfl_up_sync(FULL, cj, 1), prev_jump = __shfl_up_sync(FULL, jump, 1);
-          if (first) { prev_cj = k_cl; prev_jump = k_pm > top_v ? k_pm : top_v; }
-          // strictly rising in all three derived values, else the scalar rules decide
-          const bool good = in_run && my_cum > prev_cum && cj > prev_cj && jump > prev_jump;
-          const unsigned bad = (~__ballot_sync(FULL, good)) >> t;
-          int glen = bad ? __ffs(bad) - 1 : 32 - t;
-          if (glen > len) glen = len;
-          if (glen > 0) {
-            const int last = t + glen - 1;
-            if (lane >= t && lane <= last) {
-              BackRec b; b.best = prev_cum; b.pred = prev_id; b.pad = 0;
-              a.back[base + lane] = b;
-              PmEntry e; e.val = jump; e.id = base + lane; e.pad = 0;
-              k_pmrow[own.ro] = e;
-              if (lane > last - RING) s_ring[own.ro & (RING - 1)][k] = e;
-            }
-            // new state of the owner lane and the frontier top
-            const int l1 = last - 1 >= t ? last - 1 : t, l2 = last - 2 >= t ? last - 2 : t;
-            const double n_c0 = __shfl_sync(FULL, my_cum, last);
-            const double s1 = __shfl_sync(FULL, my_cum, l1), s2 = __shfl_sync(FULL, my_cum, l2);
-            const double n_cj = __shfl_sync(FULL, cj, last), n_jump = __shfl_sync(FULL, jump, last);
-            const int n_ro = __shfl_sync(FULL, own.ro, last);
-            const double n_j = __shfl_sync(FULL, own.j, last);
-            if (lane == k) {
-              c2 = glen >= 3 ? s2 : (glen == 2 ? k_c0 : k_c1);
-              id2 = glen >= 3 ? base + last - 2 : (glen == 2 ? k_id0 : k_id1);
-              c1 = glen >= 2 ? s1 : k_c0;
-              id1 = glen >= 2 ? base + last - 1 : k_id0;
-              c0 = n_c0; id0 = base + last;
-              cl_v = n_cj; cl_i = base + last;
-              pm_v = n_jump; pm_i = base + last;
-              filled = n_ro;
-            }
-            top_v = n_jump; top_j = n_j; top_i = base + last;
-            n_runpts += glen;
-            __syncwarp();
-            t += glen;
-            no_run_at = t;
-            continue;
-          }
-          no_run_at = t;
-        }
-      }
-      const int p = base + t;
-      const P2Rec pt = s_rec[buf][t];
-      ++t;
-      const double j = pt.j, q = pt.q;
-      const int kf = pt.kf, k = kf & 0xff, ro = pt.ro;
-      const bool mine = lane == k;
-
-      // ---- candidates in the reference's order [frontier, cluster best, cells]; every test is
-      //      ">=", so the LAST candidate attaining the maximum wins (describealign.py:960-973)
-      double best;
-      int pred;
-      if (!(kf & P2_NEAR)) {
-        double m = cl_v;
-        int mi = cl_i;
-        const bool t2 = (kf & P2_VIS2) && c1 >= m;
-        m = t2 ? c1 : m; mi = t2 ? id1 : mi;
-        const bool t1 = (kf & P2_VIS1) && c0 >= m;
-        m = t1 ? c0 : m; mi = t1 ? id0 : mi;
-        const bool left = top_j <= j;              // the top entry is F(j) itself
-        const bool tt = left && top_v > m;
-        best = tt ? top_v : m; pred = tt ? top_i : mi;
-        if (kf & P2_MAYQ) {
-          // the top lies right of the point: F(j) <= top value, needed only if that beats m
-          if (__ballot_sync(FULL, mine && !left && m < top_v)) {
-            ++n_query;
-            double fv; int fi;
-            frontier_query(pt.i, j, k, fv, fi);
-            if (fv > m) { best = fv; pred = fi; }
-          }
-        }
-      } else {
-        // ---- a point of another corridor may sit in this point's prev_cache cells: generic
-        //      evaluation over the last three points of every corridor (uniform values)
-        ++n_near;
-        const int i = pt.i, cell = pt.cell;
-        double ub = NEG; int up = -2;
-        if (top_j <= j) { ub = top_v; up = top_i; }
-        else { ++n_query; frontier_query(i, j, k, ub, up); }
-        const double clk = __shfl_sync(FULL, cl_v, k);
-        const int cik = __shfl_sync(FULL, cl_i, k);
-        const int cluster_k = __shfl_sync(FULL, cluster, k);
-        if (clk >= ub) { ub = clk; up = cik; }
-        // rows / cells of this lane's last three points
-        int hr0 = -100, hr1 = -100, hr2 = -100, hc0 = -100, hc1 = -100, hc2 = -100;
-        if (id0 >= 0) { const P2Rec r = a.rec[id0]; hr0 = r.i; hc0 = r.cell; }
-        if (id1 >= 0) { const P2Rec r = a.rec[id1]; hr1 = r.i; hc1 = r.cell; }
-        if (id2 >= 0) { const P2Rec r = a.rec[id2]; hr2 = r.i; hc2 = r.cell; }
-#pragma unroll 1
-        for (int x = cell - 2; x <= cell; ++x) {
-          int brow = -1, bh = 0;
-          if (hc0 == x && hr0 > brow) { brow = hr0; bh = 0; }
-          if (hc1 == x && hr1 > brow) { brow = hr1; bh = 1; }
-          if (hc2 == x && hr2 > brow) { brow = hr2; bh = 2; }
-          const int mrow = (int)__reduce_max_sync(FULL, (unsigned)(brow + 1)) - 1;
-          if (mrow < 0 || mrow < i - 2) continue;         // nothing written recently enough
-          const int src = __ffs(__ballot_sync(FULL, brow == mrow)) - 1;
-          const double myc = bh == 0 ? c0 : (bh == 1 ? c1 : c2);
-          const int myid = bh == 0 ? id0 : (bh == 1 ? id1 : id2);
-          double pc = __shfl_sync(FULL, myc, src);
-          const int pid = __shfl_sync(FULL, myid, src);
-          const double pj = __shfl_sync(FULL, __dadd_rn(__dmul_rn(sl, (double)mrow), of), src);
-          if (__shfl_sync(FULL, cluster, src) != cluster_k) {
-            const double d = (j - pj) - (double)(i - mrow);
-            pc = pc - (100.0 + 100.0 * (d * d));
-          }
-          if (pj <= j && pc >= ub) { ub = pc; up = pid; }
-        }
-        best = ub; pred = up;
-      }
-
-      // ---- commit (lane k) ---------------------------------------------------------------------
-      const double cum = best + q;
-      c2 = mine ? c1 : c2; id2 = mine ? id1 : id2;
-      c1 = mine ? c0 : c1; id1 = mine ? id0 : id1;
-      c0 = mine ? cum : c0; id0 = mine ? p : id0;
-      const double cj = cum - 50.0;
-      const bool ucl = mine && cl_v < cj;
-      cl_v = ucl ? cj : cl_v; cl_i = ucl ? p : cl_i;
-      const double jump = cum - 1000.0;
-      if (kf & P2_GAP) {
-        // rows without a point (their cell was claimed by an earlier cluster) repeat the head
-        if (mine) {
-          PmEntry e; e.val = pm_v; e.id = pm_i; e.pad = 0;
-          for (int r = filled + 1; r < ro; ++r) { pm[r] = e; s_ring[r & (RING - 1)][lane] = e; }
-        }
-        __syncwarp();
-      }
-      const bool upm = mine && jump > pm_v;
-      pm_v = upm ? jump : pm_v; pm_i = upm ? p : pm_i;
-      filled = mine ? ro : filled;
-      if (mine) {
-        PmEntry e; e.val = pm_v; e.id = pm_i; e.pad = 0;
-        s_ring[ro & (RING - 1)][lane] = e;
-        pm[ro] = e;
-        BackRec b; b.best = best; b.pred = pred; b.pad = 0;
-        a.back[p] = b;
-      }
-      const double jk = __shfl_sync(FULL, jump, k);
-      const bool ut = jk > top_v || (jk == top_v && j < top_j);
-      top_v = ut ? jk : top_v; top_j = ut ? j : top_j; top_i = ut ? p : top_i;
-    }
-    __syncwarp();
-  }
-  n_refill = __reduce_add_sync(FULL, n_refill);
-  if (lane == 0) {
-    a.result[0] = top_i;
-    *reinterpret_cast<double *>(a.result + 2) = top_v;
-    a.counters[0] = n_query; a.counters[1] = n_refill; a.counters[2] = n_near; a.counters[3] = n_runpts;
-  }
-}
-
 // ------------------------------------------------------------------------------------------
 // DP #2, block formulation (the product path).  State and one-point rules are those of
 // dp2_lane_kernel (lane l owns corridor l); what changes is that up to 32 consecutive points are
@@ -1722,6 +1160,8 @@ __global__ void __launch_bounds__(32, 1) dp2_block_kernel(Dp2LArgs a) {
   }
 }
 
+#include "dp2_scan.cuh"
+
 // ------------------------------------------------------------------------------------------
 // Traceback by pointer jumping (binary lifting): up[k][p] = 2^k-th predecessor, node n = root.
 // depth doubles alongside; the ancestors of the end point are marked level by level from the
@@ -1868,15 +1308,16 @@ int dab_run_stage_b(dab_pair *pr, int32_t n_cor, int32_t n_clusters) {
     la.result = pr->dpres.as<int32_t>();
     la.counters = reinterpret_cast<unsigned long long *>(pr->pmoff2.as<int64_t>() + 32);
     DAB_CUDA(cudaMemsetAsync(la.counters, 0, 4 * sizeof(unsigned long long), st));
-    if (pr->ctx->opt_dp2_impl == 1) dp2_corridor_kernel<<<1, 32, 0, st>>>(la);
-    else if (pr->ctx->opt_dp2_impl == 3) dp2_lane_kernel<<<1, 32, 0, st>>>(la);
-    else {
-      // "dp_reserve_kb": unused dynamic shared memory that keeps the feature kernel's 105 KB CTAs (and a
-      // second DP) off the SM this one-warp kernel runs on, so that its dependent chain does not share
-      // issue slots with 32 busy warps
-      const size_t reserve = (size_t)ctx->opt_dp_reserve_kb * 1024;
-      if (reserve) DAB_CUDA(cudaFuncSetAttribute(dp2_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)reserve));
-      dp2_block_kernel<<<1, 32, reserve, st>>>(la);
+    if (pr->ctx->opt_dp2_impl == 1) {
+      // the one-warp block kernel of round 1 (kept for cross-checks)
+      dp2_block_kernel<<<1, 32, 0, st>>>(la);
+    } else {
+      static std::atomic<int> attr_set[64];
+      if (ctx->device < 64 && !attr_set[ctx->device].load()) {
+        DAB_CUDA(cudaFuncSetAttribute(dp2_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanShared)));
+        attr_set[ctx->device].store(1);
+      }
+      dp2_scan_kernel<<<1, SC_T, sizeof(ScanShared), st>>>(la);
     }
     // The DP runs for tens of milliseconds on one warp.  Nothing that depends on it - not even an
     // event record - is enqueued until it is done: streams share the GPU's 32 hardware queues, and a
