@@ -3,20 +3,20 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--pairs B] [--impl ours|reference]
 
-A step = one pass of the hot path over one batch of B synthetic pairs per GPU (W in flight) of the C2 shape
-(22-min video audio vs 27-min description, 202 s start offset, injected skips):
-features of both tracks, device stage A (describealign.py:596-700) and device stage B
-(:895-993).  The host-side rate-change fit between the two device stages (:702-893) is outside
-the timed regions, as BASELINE.json prescribes; it is solved once per pair and reused for as long
-as stage A returns the identical pass-1 path.  W pairs are in flight at once (one CUDA stream
-each): the frontier DPs are one warp per pair, so throughput comes from overlapping pairs.
+A step = one pass of the hot path over one batch of B synthetic pairs per GPU of the C2 shape (22-min
+video audio vs 27-min description, 202 s start offset, injected skips): features of both
+tracks, device stage A (describealign.py:596-700) and device stage B (:895-993).  The host-side
+rate-change fit between the two device stages (:702-893) is outside the timed regions, as BASELINE.json
+prescribes; it is solved once per distinct pair and reused for as long as stage A returns the identical
+pass-1 path.  The pairs go through the library's batch engine (include/describealign_b200.h, dab_engine_*):
+W slots per GPU, every device stage enqueued in one go by one scheduler thread, one Python thread serving
+the event queue.  The configuration (W, B, distinct pairs per GPU) is the same at every N.
 
-value   device-resident: PCM already in HBM when the timed region starts; CUDA events
-        bracketing each device stage on the streams the kernels are launched on.
-e2e     the same passes through the public API (AlignJob.load_pcm + stages) from pinned HOST
-        buffers, H2D/D2H copies inside the timed region.
-One rank per GPU (torchrun for N > 1); ranks process disjoint pairs (weak scaling), no
-data-path collective; timings are max over ranks.
+value   device-resident: PCM already in HBM when the timed region starts; one CUDA-event bracket around
+        the whole step.
+e2e     the same passes from pinned HOST buffers: H2D of the PCM and D2H of the results inside the region.
+One rank per GPU (torchrun for N > 1); ranks process disjoint pairs (weak scaling), no data-path
+collective; timings are max over ranks.
 """
 from __future__ import annotations
 
@@ -47,20 +47,13 @@ def parse_args():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--pairs", type=int, default=0, help="pairs per GPU per step (default: 4 x workers)")
-    ap.add_argument("--workers", type=int, default=0,
-                    help="pairs in flight per GPU, one CUDA stream and one host thread each (default: 128, 96 with 4 ranks "
-                         "and 64 with 8 ranks sharing the host's cores)")
+    ap.add_argument("--pairs", type=int, default=0, help="pairs per GPU per step (default: 8 x slots)")
+    ap.add_argument("--workers", type=int, default=0, help="engine slots = pairs on the device at once per GPU (default 32, at every N)")
     ap.add_argument("--distinct", type=int, default=0,
-                    help="distinct synthetic pairs per GPU, a step cycles over them (default: 8, or 4 per GPU when more than two ranks "
-                         "share the host's cores for generating them; 4 pairs are 1 GB of PCM, still 8x the L2)")
+                    help="distinct synthetic pairs per GPU, a step cycles over them (default 4 at every N: 1 GB of PCM, 8x the L2)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the C2 durations (debugging only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--timeline", default=None, help="write the device timeline of the last step of each arm (per pair and stage) to <name>_dev.json / <name>_e2e.json")
-    ap.add_argument("--dp-reserve-kb", type=int, default=0, help="see dab_set_option: keeps other pairs' big CTAs off the DP's SM")
-    ap.add_argument("--switch-interval", type=float, default=0.005, help="Python thread switch interval (s)")
-    ap.add_argument("--host-wait", type=int, default=2, help="dab_set_host_wait mode: 0 spin (CUDA default), 1 blocking sync, 2 query + sleep")
     return ap.parse_args()
 
 
@@ -146,11 +139,22 @@ def measured_peaks():
 # ------------------------------------------------------------------------------------------------
 
 def cpu_pass(pair, keep=False):
-    """One pass of the hot path on the CPU through the oracle; returns (seconds without the host
-    fit, seconds of the host fit, outputs or path length)."""
+    """One pass of the hot path on the CPU through the oracle port.  Returns (times, outputs): times has
+    hot_path_s = features + align() minus scipy.optimize.linprog, linprog_s, and
+    device_stages_s = only what the GPU arm times (features, stage A, stage B)."""
+    import scipy.optimize
     from describealign_b200 import host_fit
     from oracle import align_oracle as ao, features as of
     v, a = pair
+    lp = [0.0]
+
+    def timed_linprog(*args, **kw):
+        t = time.perf_counter()
+        try:
+            return scipy.optimize.linprog(*args, **kw)
+        finally:
+            lp[0] += time.perf_counter() - t
+
     t0 = time.perf_counter()
     V, A = of.all_features(v), of.all_features(a)
     sa = ao.stage_a(V, A, V[0], A[0])
@@ -160,18 +164,20 @@ def cpu_pass(pair, keep=False):
     kx, ky = x[kp], y[kp]
     a_s, v_s = host_fit.scale_features(V, A, kx, ky)
     fx, fy = host_fit.compress_path(kx, ky)
-    fit = host_fit.rate_change_fit(fx, fy)
+    fit = host_fit.rate_change_fit(fx, fy, linprog=timed_linprog)
     clusters = host_fit.line_clusters(fit)
     plans = host_fit.plan_corridors(clusters, a_s, v_s)
     t2 = time.perf_counter()
     sb = ao.stage_b(plans, len(clusters), a_s, v_s)
+    path = sb["path"]
+    nx, ny, sim = host_fit.build_nodes(path, len(A[0]), len(V[0]), len(a_s), len(v_s))
     t3 = time.perf_counter()
-    out = len(sb["path"])
+    times = {"hot_path_s": (t3 - t0) - lp[0], "linprog_s": lp[0], "device_stages_s": (t1 - t0) + (t3 - t2),
+             "total_s": t3 - t0}
+    out = len(path)
     if keep:
-        path = sb["path"]
-        nx, ny, sim = host_fit.build_nodes(path, len(A[0]), len(V[0]), len(a_s), len(v_s))
         out = {"V": V, "A": A, "path1": (x, y), "path": path, "nodes": (nx, ny), "similarity": sim}
-    return (t1 - t0) + (t3 - t2), t2 - t1, out
+    return times, out
 
 
 def _cpu_worker(pair):
@@ -179,9 +185,53 @@ def _cpu_worker(pair):
     return cpu_pass(pair)
 
 
+def real_reference_once(pair):
+    """The UNMODIFIED reference (describealign.py from baseline/_ref or /root/reference, loaded with stubs
+    for its GUI / ffmpeg imports) on one pair, one process: (seconds of get_* + align() minus linprog,
+    seconds of linprog), or None where the reference is not present (it is Python and does not travel
+    unless baseline/_ref was installed)."""
+    try:
+        from oracle import ref_loader
+        da = ref_loader.load()
+    except Exception:
+        return None
+    if da is None:
+        return None
+    import contextlib
+    import scipy.optimize
+    v, a = pair
+    lp = [0.0]
+    orig = scipy.optimize.linprog
+
+    def timed(*args, **kw):
+        t = time.perf_counter()
+        try:
+            return orig(*args, **kw)
+        finally:
+            lp[0] += time.perf_counter() - t
+
+    va = np.ascontiguousarray(v.T).astype(np.float16) if v.ndim == 2 else v.astype(np.float16)[None, :]
+    aa = np.ascontiguousarray(a.T).astype(np.float16) if a.ndim == 2 else a.astype(np.float16)[None, :]
+    scipy.optimize.linprog = timed
+    try:
+        with contextlib.redirect_stdout(sys.stderr):
+            t0 = time.perf_counter()
+            vf = [da.get_energy(va), da.get_zero_crossings(va)] + list(da.get_freq_bands(va))
+            af = [da.get_energy(aa), da.get_zero_crossings(aa)] + list(da.get_freq_bands(aa))
+            da.align(vf, af, vf[0], af[0])
+            t1 = time.perf_counter()
+    finally:
+        scipy.optimize.linprog = orig
+    return (t1 - t0) - lp[0], lp[0]
+
+
 def run_reference(args, rank, world):
-    """--impl reference: the oracle port of the reference's CPU path on all host cores (one pair
-    per process, which is how the single-threaded reference would be run in parallel)."""
+    """--impl reference: the reference's CPU path on all host cores, one pair per process (the reference is
+    single-threaded and loops over a batch sequentially, describealign.py:1077; one process per core is the
+    harness-side extension BASELINE.md section 3 allows).  The reference is Python: what is timed on every
+    step is the oracle port of it (C features, C match + DPs, numpy/scipy host stage), which is ~6x faster
+    per core than the reference's own loops - a conservative baseline.  Where describealign.py itself is
+    present (baseline/_ref or /root/reference) it is also run once on one full pair and reported beside it."""
     if rank != 0:
         return
     import oracle
@@ -191,25 +241,34 @@ def run_reference(args, rank, world):
     hours = audio_hours(pairs)
     cores = min(len(pairs), os.cpu_count() or 1)
     from concurrent.futures import ProcessPoolExecutor
-    times = []
+    times, times_dev = [], []
     with ProcessPoolExecutor(max_workers=cores) as ex:
         for step in range(args.warmup + args.steps):
             res = list(ex.map(_cpu_worker, pairs))
-            # each worker times its own pass (host fit excluded, as in the GPU arm); with one
-            # process per pair running concurrently the step takes as long as the slowest one
-            dev = [r[0] for r in res]
-            step_s = max(dev) if cores >= len(pairs) else sum(dev) / cores
+            # each worker times its own pass (linprog subtracted); with one process per
+            # pair running concurrently the step takes as long as the slowest one
+            hot = [r[0]["hot_path_s"] for r in res]
+            devs = [r[0]["device_stages_s"] for r in res]
             if step >= args.warmup:
-                times.append(max(step_s, 1e-9))
+                times.append(max(max(hot) if cores >= len(pairs) else sum(hot) / cores, 1e-9))
+                times_dev.append(max(max(devs) if cores >= len(pairs) else sum(devs) / cores, 1e-9))
     ms = 1e3 * float(np.mean(times))
     value = hours / (ms / 1e3)
+    real = real_reference_once(pairs[0])
+    h1 = audio_hours(pairs[:1])
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic", "impl": "reference",
             "config": {"workload": WORKLOAD, "pairs_per_step": len(pairs), "audio_hours_per_step": hours,
-                       "scale": args.scale},
+                       "scale": args.scale,
+                       "timed": "features + align() minus scipy.optimize.linprog (BASELINE.md section 3), per pair, one process per pair"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{len(pairs)} full C2 pairs per step, one oracle process per pair"},
+                             "sample": f"{len(pairs)} full C2 pairs per step, one oracle-port process per pair",
+                             "value_device_stages_only": hours / float(np.mean(times_dev)),
+                             "unmodified_reference_one_pair_one_core": None if real is None else {
+                                 "value": h1 / real[0], "unit": UNIT, "seconds": real[0], "seconds_linprog_subtracted": real[1],
+                                 "kind": "reference", "cores": 1},
+                             "host_cpu": _cpu_model(), "host_cores": os.cpu_count()},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -219,13 +278,34 @@ def run_reference(args, rank, world):
 # GPU arm
 # ------------------------------------------------------------------------------------------------
 
+def h2d_probe(pinned, seconds=1.0):
+    """GB/s this rank's pinned PCM buffers reach when copied back to back for about `seconds` (all ranks
+    do this at the same time: the ceiling of the end-to-end number under the box's real contention)."""
+    import torch
+    bufs = [t for pair in pinned for t in pair]
+    dst = [torch.empty_like(t, device="cuda") for t in bufs]
+    stream = torch.cuda.Stream()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    nbytes, t_end = 0, time.perf_counter() + seconds
+    with torch.cuda.stream(stream):
+        e0.record()
+        while time.perf_counter() < t_end:
+            for d, s_ in zip(dst, bufs):
+                d.copy_(s_, non_blocking=True)
+                nbytes += s_.numel() * s_.element_size()
+            stream.synchronize()
+        e1.record()
+    e1.synchronize()
+    del dst
+    return nbytes / (e0.elapsed_time(e1) * 1e-3) / 1e9
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
-    from describealign_b200 import api, build
+    from describealign_b200 import api, batch, build
+    from describealign_b200 import _cabi
     build.build()
-    # W host threads wait on W pair streams: they must sleep, not spin (16 host cores, W >> 16)
-    sched = api._cabi.set_host_wait(local_rank, args.host_wait)
     api.set_device(local_rank)
     torch.cuda.set_device(local_rank)
     if world > 1:
@@ -236,13 +316,11 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # B pairs per step, cycling over a few distinct synthetic pairs (generating one takes ~35 s of CPU)
-    if args.workers <= 0:
-        args.workers = 128 if world <= 2 else (96 if world <= 4 else 64)
-    if args.pairs <= 0:
-        args.pairs = 4 * args.workers
-    B = args.pairs
-    distinct = max(1, min(B, args.distinct if args.distinct > 0 else (8 if world <= 2 else 4)))
+    # The same configuration at every N: W slots (pairs on the device at once), B pairs per step cycling
+    # over `distinct` synthetic pairs per GPU (generating one takes ~35 s of CPU).
+    W = args.workers if args.workers > 0 else 32
+    B = args.pairs if args.pairs > 0 else 8 * W
+    distinct = max(1, min(B, args.distinct if args.distinct > 0 else 4))
     base_pairs = make_pairs(distinct, rank * distinct, args.scale, world)
     pairs = [base_pairs[k % distinct] for k in range(B)]
     hours_rank = audio_hours(pairs)
@@ -252,8 +330,9 @@ def run_ours(args, rank, world, local_rank):
            for v, a in base_pairs]
     pinned = [(torch.from_numpy(np.ascontiguousarray(v)).pin_memory(), torch.from_numpy(np.ascontiguousarray(a)).pin_memory())
               for v, a in base_pairs]
-    # what the PCIe link gives a single large pinned copy (the bound of the end-to-end number)
-    h2d_gbs = None
+    pinned_np = [(v.numpy(), a.numpy()) for v, a in pinned]
+    # what the host-to-device link gives: one large pinned copy on an idle box, and every rank copying at once
+    h2d_single = h2d_all_ranks = None
     try:
         src = pinned[0][1]
         dst = torch.empty_like(src, device="cuda")
@@ -262,94 +341,69 @@ def run_ours(args, rank, world, local_rank):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(); dst.copy_(src, non_blocking=True); e1.record(); e1.synchronize()
             best = max(best, src.numel() * src.element_size() / (e0.elapsed_time(e1) * 1e-3) / 1e9)
-        h2d_gbs = best
+        h2d_single = best
         del dst
+        barrier()
+        h2d_all_ranks = h2d_probe(pinned)
+        barrier()
     except Exception:
         pass
     ctx = api.context()
-    if args.dp_reserve_kb:
-        ctx.set_option("dp_reserve_kb", args.dp_reserve_kb)
-    sys.setswitchinterval(args.switch_interval)
-    # W pairs in flight: one dab_pair (device buffers + CUDA stream) per worker slot.  The frontier DPs
-    # are one warp per pair and tens of milliseconds long, so throughput comes from keeping W of them
-    # running while the data-parallel kernels of other pairs fill the SMs.  A step ends with a tail in
-    # which only the last DPs run, so a step is several rounds of W pairs (B = 4 W by default).
-    W = max(1, min(B, args.workers))
-    slot_pairs = [api._cabi.Pair(ctx) for _ in range(W)]
-    streams = [torch.cuda.ExternalStream(p.stream) for p in slot_pairs]
-    cur = torch.cuda.current_stream()
-
-    import queue
-    from concurrent.futures import ThreadPoolExecutor
-    pool = ThreadPoolExecutor(max_workers=W)
+    eng = batch.engine(W)
     host_cache = {}
 
-    def host_stage(k, job):
-        """The rate-change fit is outside the metric (BASELINE.json); its result only depends on the
-        pass-1 path, so it is solved once per distinct pair (during warm-up) and reused for as long as
-        stage A keeps returning that same path.  Inside the timed region it is a dictionary lookup."""
+    def stage_b_struct_for(k, evt):
+        """The rate-change fit is outside the metric (BASELINE.json); its result only depends on the pass-1
+        path, so it is solved once per distinct pair (during warm-up) and reused for as long as stage A keeps
+        returning that same path: inside the timed region it is a comparison of the path and a lookup."""
+        x, y = eng.path1(evt)
         c = host_cache.get(k % distinct)
-        if c is not None and np.array_equal(c["x"], job.x) and np.array_equal(c["y"], job.y):
-            for name in ("kept_x", "kept_y", "audio_scaled", "video_scaled", "fit", "clusters", "plans", "gains"):
-                setattr(job, name, c[name])
-            return
+        if c is not None and np.array_equal(c["x"], x) and np.array_equal(c["y"], y):
+            return c["struct"]
+        job = api.AlignJob(detached=True)
+        job.video_features = [f.copy() for f in eng.features(evt, _cabi.VIDEO)]
+        job.audio_features = [f.copy() for f in eng.features(evt, _cabi.AUDIO)]
+        job.check_path1_length(int(evt.n_path1))
+        job.x, job.y = x.astype(np.int64), y.astype(np.int64)
         job.host_stage()
-        host_cache[k % distinct] = {"x": job.x, "y": job.y, **{name: getattr(job, name) for name in
-                                    ("kept_x", "kept_y", "audio_scaled", "video_scaled", "fit", "clusters", "plans", "gains")}}
+        st = eng.stage_b_struct(**job.stage_b_input())
+        host_cache[k % distinct] = {"x": x.copy(), "y": y.copy(), "struct": st, "job": job}
+        return st
 
-    def one_step(host_input: bool):
-        """All B pairs through stage A -> (cached) host fit -> stage B, W at a time.  Returns the
-        device time between a start event every pair stream waits on and a stop event that waits on
-        every pair stream."""
-        jobs = [None] * B
-        slots = queue.SimpleQueue()
-        for pr in slot_pairs:
-            slots.put(pr)
-
+    def one_step(host_input: bool, n_pairs=None, first=0):
+        """n_pairs pairs through stage A -> (cached) host fit -> stage B, W on the device at a time, all
+        driven by this one thread through the engine's event queue.  Returns the device time between an
+        event recorded before the first submit and one recorded after the last result reached the host."""
+        n_pairs = B if n_pairs is None else n_pairs
+        results = [None] * n_pairs
         start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-
-        def work(k):
-            pr = slots.get()
-            t_in = time.perf_counter()
-            try:
-                job = api.AlignJob(pr)
-                jobs[k] = job
-                if host_input:
-                    hv, ha = pinned[k % distinct]
-                    job.load_pcm(hv.numpy(), ha.numpy())
-                else:
-                    v, a = dev[k % distinct]
-                    job.load_pcm_device((v.data_ptr(), v.shape[0], v.shape[1]), (a.data_ptr(), a.shape[0], a.shape[1]))
-                job.device_stage_a()
-                host_stage(k, job)
-                job.device_stage_b()
-                job.kernel_ms = pr.timings()
-                job.work = pr.stats()
-                if args.timeline:
-                    job.timeline = pr.timeline(start.cuda_event)
-                    job.host_span = (t_in, time.perf_counter())
-                job.host_ms["whole_pair"] = 1e3 * (time.perf_counter() - t_in)
-            finally:
-                slots.put(pr)
-
-        start.record(cur)
-        t_step = time.perf_counter()
-        for st in streams:
-            st.wait_event(start)
-        list(pool.map(work, range(B)))
-        for st in streams:
-            e = torch.cuda.Event()
-            e.record(st)
-            cur.wait_event(e)
-        stop.record(cur)
+        t0 = time.perf_counter()
+        start.record()
+        for k in range(first, first + n_pairs):
+            if host_input:
+                hv, ha = pinned_np[k % distinct]
+                eng.submit(k, hv, ha)
+            else:
+                v, a = dev[k % distinct]
+                eng.submit(k, (v.data_ptr(), v.shape[0], v.shape[1]), (a.data_ptr(), a.shape[0], a.shape[1]))
+        done = 0
+        while done < n_pairs:
+            evt = eng.next(1000)
+            if evt is None:
+                continue
+            if evt.status != 0:
+                raise RuntimeError(f"pair {evt.tag} failed on the device: {eng.error(evt)}")
+            k = int(evt.tag)
+            if evt.kind == _cabi.EVENT_STAGE_A:
+                eng.submit_b(evt.slot, struct=stage_b_struct_for(k, evt))
+            else:
+                results[k - first] = {"kernel_ms": eng.timings(evt), "work": evt.stats.as_dict(), "n_path1": int(evt.n_path1),
+                                      "n_path2": int(evt.n_path2), "t_done": time.perf_counter() - t0}
+                eng.release(evt.slot)
+                done += 1
+        stop.record()
         stop.synchronize()
-        if args.timeline:
-            tl = [{"pair": k, "slot_host_ms": [1e3 * (j.host_span[0] - t_step), 1e3 * (j.host_span[1] - t_step)], **j.timeline}
-                  for k, j in enumerate(jobs)]
-            name = args.timeline.replace(".json", "") + ("_e2e.json" if host_input else "_dev.json")
-            with open(name, "w") as f:
-                json.dump({"step_ms": start.elapsed_time(stop), "host_input": host_input, "pairs": tl}, f)
-        return start.elapsed_time(stop), jobs
+        return start.elapsed_time(stop), results
 
     alloc0 = {}
 
@@ -358,50 +412,37 @@ def run_ours(args, rank, world, local_rank):
             one_step(host_input)
         barrier()
         l0 = ctx.launches()
-        alloc0.update(api._cabi.alloc_stats())
-        total, jobs = 0.0, None
+        alloc0.update(_cabi.alloc_stats())
+        total, res = 0.0, None
         for _ in range(args.steps):
-            ms, jobs = one_step(host_input)
+            ms, res = one_step(host_input)
             total += ms
         barrier()
-        return total / args.steps, ctx.launches() - l0, jobs
+        return total / args.steps, ctx.launches() - l0, res
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms_dev, launches, jobs = run_steps(False)
-    alloc1 = api._cabi.alloc_stats()
-    alloc_timed = {k: alloc1[k] - alloc0[k] for k in alloc1}
+    ms_dev, launches, res_dev = run_steps(False)
+    alloc1 = _cabi.alloc_stats()
     clocks = sampler.stop() if rank == 0 else None
-    timings = [j.kernel_ms for j in jobs]
-    host_calls = {k: {"mean": float(np.mean([j.host_ms.get(k, 0.0) for j in jobs])),
-                      "max": float(np.max([j.host_ms.get(k, 0.0) for j in jobs]))}
-                  for k in sorted(set().union(*[j.host_ms.keys() for j in jobs]))}
-    stats = [j.work for j in jobs]
-    ms_e2e, _, jobs_e = run_steps(True)
-    h2d = sum(j.h2d_bytes for j in jobs_e)
-    d2h = sum(j.d2h_bytes for j in jobs_e)
-    host_calls_e2e = {k: {"mean": float(np.mean([j.host_ms.get(k, 0.0) for j in jobs_e])),
-                          "max": float(np.max([j.host_ms.get(k, 0.0) for j in jobs_e]))}
-                      for k in sorted(set().union(*[j.host_ms.keys() for j in jobs_e]))}
+    sched0 = eng.counters()
+    ms_e2e, _, res_e2e = run_steps(True)
+    # bytes that crossed the link per pair in the end-to-end arm (counted from the arrays copied)
+    def bytes_of(k, r):
+        v, a = pinned_np[k % distinct]
+        feat = sum(4 * (x.shape[0] // 210 + 1) * 3 for x in (v, a))
+        return v.nbytes + a.nbytes + 16 * 32, 8 * r["n_path1"] + feat + 40 * r["n_path2"] + 2 * 128
+    h2d = sum(bytes_of(k, r)[0] for k, r in enumerate(res_e2e))
+    d2h = sum(bytes_of(k, r)[1] for k, r in enumerate(res_e2e))
 
-    # one pair alone on the GPU (device-resident PCM, three passes, the last one is kept): kernel
-    # durations without the other 63 pairs' work in the way
-    solo_ms = solo_work = solo_wall_ms = None
+    # one pair alone on the GPU (device-resident PCM, three passes, the last one is kept): BASELINE.json's
+    # second figure, "ms per 22-min pair"
+    solo = None
     if rank == 0:
-        pr0 = slot_pairs[0]
         for _ in range(3):
-            job = api.AlignJob(pr0)
-            v0, a0 = dev[0]
-            job.load_pcm_device((v0.data_ptr(), v0.shape[0], v0.shape[1]), (a0.data_ptr(), a0.shape[0], a0.shape[1]))
-            job.device_stage_a()
-            host_stage(0, job)
-            job.device_stage_b()
-            solo_ms = {k: v for k, v in pr0.timings().items() if not k.startswith("host_in_")}
-            solo_work = pr0.stats()
-            # BASELINE.json's second figure, "ms per 22-min pair": host wall time of the device stages and
-            # of the result copies for this one pair (the host fit between the stages is not in it)
-            solo_wall_ms = sum(job.host_ms.get(k, 0.0) for k in ("stage_a", "stage_b", "get_features", "path1", "path2"))
+            _, r1 = one_step(False, n_pairs=1)
+        solo = r1[0]
 
     # parity inside the run: rank 0 checks its first pair against the oracle
     parity = None
@@ -409,73 +450,86 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0 and not args.no_cpu_baseline:
         import oracle
         oracle.build()
-        cpu_s, fit_s, o = cpu_pass(pairs[0], keep=True)
-        # one more (untimed) pass of pair 0 through the public API, keeping its intermediates
+        cpu_t, o = cpu_pass(pairs[0], keep=True)
         det = {}
         import contextlib
         with contextlib.redirect_stdout(sys.stderr):     # progress labels (describealign.py:604,635,726,860) stay off the JSON line
             nx, ny, sim, path, med = api.align_pcm(pairs[0][0], pairs[0][1], details=det)
-
-        class _J:
-            video_features, audio_features = det["video_features"], det["audio_features"]
-            x, y = det["path1"]
-        j0 = _J
+        # the same pair through the batch engine must give the same thing as the synchronous API
+        eres = batch.run_engine([pairs[0]], in_flight=W)[0]
         ox, oy = o["nodes"]
         opath = o["path"]
         same_shape = path.shape == opath.shape
         parity = {
-            "features_f32_identical": bool(all(np.array_equal(j0.video_features[k], o["V"][k]) and
-                                               np.array_equal(j0.audio_features[k], o["A"][k])
-                                               for k in range(min(4, len(j0.video_features))))),
-            "path1_identical": bool(np.array_equal(j0.x, o["path1"][0]) and np.array_equal(j0.y, o["path1"][1])),
+            "features_f32_identical": bool(all(np.array_equal(det["video_features"][k], o["V"][k]) and
+                                               np.array_equal(det["audio_features"][k], o["A"][k]) for k in range(4))),
+            "path1_identical": bool(np.array_equal(det["path1"][0], o["path1"][0]) and np.array_equal(det["path1"][1], o["path1"][1])),
             "path2_rows": int(len(path)),
             "path2_int_identical": bool(same_shape and np.array_equal(path[:, 1], opath[:, 1]) and
                                         np.array_equal(path[:, 2], opath[:, 2]) and
                                         np.allclose(path[:, 0], opath[:, 0], rtol=0, atol=1e-9)),
             "nodes_max_abs_diff_s": float(max(np.max(np.abs(nx - ox)), np.max(np.abs(ny - oy)))) if len(nx) == len(ox) else None,
             "similarity_diff": float(abs(sim - o["similarity"])),
+            "engine_equals_sync_api": bool(not isinstance(eres, Exception) and np.array_equal(eres[3], path) and
+                                           np.array_equal(eres[0], nx) and np.array_equal(eres[1], ny)),
+            "bench_loop_path1_is_this_path1": bool(np.array_equal(host_cache[0]["x"], det["path1"][0]) and
+                                                   np.array_equal(host_cache[0]["y"], det["path1"][1])),
         }
         h1 = audio_hours(pairs[:1])
-        cpu = {"value": h1 / cpu_s, "unit": UNIT, "cores": 1, "kind": "port",
-               "sample": "1 full C2 pair through the oracle (C features, C match + DPs, numpy corridors); host fit (%.2f s) excluded as in the GPU arm" % fit_s,
-               "seconds": cpu_s, "host_cpu": _cpu_model(), "host_cores": os.cpu_count()}
+        cpu = {"value": h1 / cpu_t["hot_path_s"], "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": "1 full C2 pair through the oracle port (C features, C match + DPs, numpy host stage and corridors); "
+                         "timed as BASELINE.md section 3: features + align() minus scipy.optimize.linprog",
+               "seconds": cpu_t["hot_path_s"], "seconds_linprog_subtracted": cpu_t["linprog_s"],
+               "seconds_device_stages_only": cpu_t["device_stages_s"],
+               "value_device_stages_only": h1 / cpu_t["device_stages_s"],
+               "host_cpu": _cpu_model(), "host_cores": os.cpu_count()}
 
     # max over ranks
     t = torch.tensor([ms_dev, ms_e2e], device="cuda", dtype=torch.float64)
     tot = torch.tensor([hours_rank, float(launches), float(h2d), float(d2h)], device="cuda", dtype=torch.float64)
+    probe = torch.tensor([h2d_all_ranks or 0.0], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        dist.all_reduce(probe, op=dist.ReduceOp.SUM)
     ms_dev, ms_e2e = float(t[0]), float(t[1])
     hours, launches_all, h2d_all, d2h_all = (float(x) for x in tot)
+    h2d_probe_sum = float(probe[0])
 
     if rank == 0:
         peaks, peak_src = measured_peaks()
-        # per-kernel device times of the last timed step, summed over this rank's pairs (64 in flight: the
-        # events around a kernel then also count the time it waited for SMs), and of one pair alone
+        timings = [r["kernel_ms"] for r in res_dev]
+        stats = [r["work"] for r in res_dev]
         agg = {k: sum(tm[k] for tm in timings) for k in timings[0] if not k.startswith("host_in_")}
-        lib_host = {k: float(np.mean([tm[k] for tm in timings])) for k in timings[0] if k.startswith("host_in_")}
+        sched = {"scheduler_ms_per_pair": float(np.mean([tm["host_in_set_pcm"] for tm in timings])),
+                 "submit_to_stage_a_results_ms": float(np.mean([tm["host_in_stage_a"] for tm in timings])),
+                 "stage_b_input_to_path_ms": float(np.mean([tm["host_in_stage_b"] for tm in timings]))}
+        solo_ms = {k: v for k, v in solo["kernel_ms"].items() if not k.startswith("host_in_")}
+        solo_work = solo["work"]
         clk_hz = 1e6 * float(peaks.get("sm_max_mhz", 1965.0))
+
+        def pcm_bytes(pair_list):
+            return sum(2 * (v.shape[0] * v.shape[1] + a.shape[0] * a.shape[1]) + 24 * (v.shape[0] // 210 + a.shape[0] // 210)
+                       for v, a in pair_list)
 
         def rooflines(kernel_ms, work, pair_list):
             feat_ms = kernel_ms["features_video"] + kernel_ms["features_audio"]
             # feature kernel: algorithmic bytes = PCM read once + 24 B per output frame
-            feat_bytes = sum(2 * (v.shape[0] * v.shape[1] + a.shape[0] * a.shape[1]) + 24 * (v.shape[0] // 210 + a.shape[0] // 210)
-                             for v, a in pair_list)
+            feat_bytes = pcm_bytes(pair_list)
             out = {"features": {"bound": "hbm", "achieved": feat_bytes / (feat_ms * 1e-3) / 1e9 if feat_ms > 0 else None,
                                 "peak": peaks["hbm_gbs"], "unit": "GB/s", "ms": feat_ms, "launches": 2 * len(pair_list),
                                 "algorithmic_bytes": feat_bytes}}
-            # DP kernels: 24 B per point (i, v, qual in; back pointer out); what bounds them is
-            # the dependent chain: one f64 add + select per point, measured at 52 SM cycles on this chip
-            # (profiles/r1_v18_dp2_block_hot_loops.txt)
+            # DP kernels: 24 B per point (i, v, qual in; back pointer out), SURVEY.md 8(d).  They are bound by
+            # latency, not bandwidth: the reference point is one dependent f64 add + select per point (52 SM
+            # cycles on this chip, profiles/r1_v18_dp2_block_hot_loops.txt); the scan formulation of DP 2 is not
+            # held to that chain any more, so its fraction can exceed 1
             for key, npts in (("dp1_trace", work["n_points1"]), ("dp2_trace", work["n_points2"])):
                 ms = kernel_ms[key]
-                out[key] = {"bound": "hbm", "achieved": 24 * npts / (ms * 1e-3) / 1e9 if ms > 0 else None,
+                out[key] = {"bound": "latency", "achieved": 24 * npts / (ms * 1e-3) / 1e9 if ms > 0 else None,
                             "peak": peaks["hbm_gbs"], "unit": "GB/s", "ms": ms, "launches": len(pair_list), "points": npts,
                             "points_per_s": npts / (ms * 1e-3) if ms > 0 else None,
-                            "note": "latency-bound serial dependency, not bandwidth-bound",
-                            "serial_chain_floor_ms": 1e3 * 52.0 * npts / clk_hz,
-                            "frac_of_serial_chain_floor": (1e3 * 52.0 * npts / clk_hz) / ms if ms > 0 else None}
+                            "serial_chain_ms": 1e3 * 52.0 * npts / clk_hz,
+                            "speedup_over_serial_chain": (1e3 * 52.0 * npts / clk_hz) / ms if ms > 0 else None}
             for v in out.values():
                 v["frac"] = v["achieved"] / v["peak"] if v.get("achieved") is not None else None
             return out
@@ -483,47 +537,52 @@ def run_ours(args, rank, world, local_rank):
         work_all = {k: sum(st[k] for st in stats) for k in stats[0]}
         roof_load = rooflines(agg, work_all, pairs)
         roof = rooflines(solo_ms, solo_work, pairs[:1])
-        dominant = max((k for k in solo_ms if k in roof or k.startswith("features")), key=lambda k: solo_ms[k])
-        dom_key = dominant if dominant in roof else "features"
-        main_roof = dict(roof[dom_key])
-        # DRAM bytes per launch of that kernel from the committed ncu --set full captures of the same
-        # workload (seed 0 pair): profiles/r1_v18_dp2_block_full.txt, profiles/r1_v8_features_full.txt
-        ncu_traffic = {"dp2_trace": 12.918784e6 + 2048, "features": (116.465152e6 + 5.258240e6 + 143.008e6 + 9.717248e6) / 2}
-        main_roof.update({"kernel": dom_key, "peak_source": peak_src,
+        # the dominant kernel of the STEP: the one with the largest share of full-GPU time.  The DPs run on one
+        # CTA per pair beside everything else, so the kernel that bounds device-resident throughput is the
+        # feature kernel (ncu launch list under profiles/); its roofline is the headline, the step-level
+        # figure (all algorithmic bytes of a step over the step time) sits beside it.
+        main_roof = dict(roof["features"])
+        ncu_traffic = (116.465152e6 + 5.258240e6 + 143.008e6 + 9.717248e6) / 2
+        step_bytes = pcm_bytes(pairs) + 24 * (work_all["n_points1"] + work_all["n_points2"])
+        main_roof.update({"kernel": "features_kernel", "peak_source": peak_src,
                           "measured": "CUDA events on the pair's stream, one C2 pair alone on the GPU right after the timed steps",
-                          "traffic": ncu_traffic.get(dom_key) if args.scale == 1.0 else None,
-                          "traffic_note": "bytes per launch (dram read + write), ncu --set full of one C2 pair, see profiles/"})
+                          "traffic": ncu_traffic if args.scale == 1.0 else None,
+                          "traffic_note": "bytes per launch (dram read + write), ncu --set full of one C2 pair, see profiles/",
+                          "step": {"bound": "hbm", "algorithmic_bytes": step_bytes, "ms": ms_dev,
+                                   "achieved": step_bytes / (ms_dev * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                   "frac": step_bytes / (ms_dev * 1e-3) / 1e9 / peaks["hbm_gbs"]}})
+        e2e_gbs = h2d_all / world / (ms_e2e * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": hours / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32+f64 (u32 packed codes)", "data": "synthetic",
             "config": {"workload": WORKLOAD, "pairs_per_gpu_per_step": B, "pairs_in_flight_per_gpu": W,
                        "distinct_pairs_per_gpu": distinct, "audio_hours_per_step": hours,
-                       "l2_policy": "inputs larger than L2 (each pair streams 259 MB of PCM, %d distinct pairs per step; 126 MB L2)" % distinct,
-                       "timed": "one region per step: every pair through device stage A (features, prep, tables, gate, score, DP1, traceback) and device stage B (corridors, DP2, traceback), W pairs in flight; the host rate-change fit between them is solved during warm-up and is a cache lookup inside the region (untimed by BASELINE.json)",
+                       "l2_policy": "inputs larger than L2 (each pair streams 259 MB of PCM, %d distinct pairs per GPU; 126 MB L2)" % distinct,
+                       "timed": "one region per step: every pair through device stage A (features, prep, tables, gate, score, DP1, traceback) and device stage B (feature scaling, corridors, DP2, traceback) incl. the result copies to the host, W pairs on the device at a time, driven by the library's scheduler thread; the host rate-change fit between the stages (describealign.py:702-893 and the corridor planning :895-930) is solved during warm-up and is a path comparison + lookup inside the region (untimed by BASELINE.json)",
                        "scale": args.scale},
             "ms_per_pair": ms_dev / B,
             "pairs_in_flight": W,
             "e2e": {"value": hours / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": h2d_all, "d2h_bytes_per_step": d2h_all,
-                    "h2d_gbs_achieved": h2d_all / world / (ms_e2e * 1e-3) / 1e9,
-                    "h2d_gbs_single_copy": h2d_gbs,
-                    "note": "PCM is 2 bytes per sample per channel; the end-to-end rate is bounded by the host-to-device link"},
-            "host_wait": {"cuda_schedule_flags": sched, "mode": ["spin (CUDA default)", "blocking sync", "query + sleep polling"][args.host_wait]},
+                    "h2d_gbs_achieved_per_gpu": e2e_gbs,
+                    "h2d_gbs_single_copy_idle_box": h2d_single,
+                    "h2d_gbs_probe_all_ranks_at_once_per_gpu": h2d_probe_sum / world if h2d_probe_sum else None,
+                    "frac_of_h2d_probe": e2e_gbs / (h2d_probe_sum / world) if h2d_probe_sum else None,
+                    "note": "PCM is 2 bytes per sample per channel; the end-to-end rate is bounded by the host-to-device link (probe: every rank copying its pinned PCM back to back at the same time)"},
             "gpu_launches": int(launches_all),
             "roofline": main_roof,
             "roofline_by_kernel": roof,
             "roofline_by_kernel_under_load": roof_load,
             "kernel_ms_one_pair_alone": solo_ms,
-            "ms_per_pair_alone": {"device_stages_and_result_copies_host_wall": solo_wall_ms,
+            "ms_per_pair_alone": {"submit_to_final_path_on_host_excl_host_fit": solo["kernel_ms"]["host_in_stage_a"] + solo["kernel_ms"]["host_in_stage_b"],
                                   "kernels_only": sum(v for k, v in solo_ms.items() if k != "dp2"),
-                                  "cpu_port_same_pair": 1e3 * cpu["seconds"] if cpu else None,
-                                  "note": "one C2 pair (22-min video, 27-min description) alone on the GPU, PCM device-resident"},
+                                  "cpu_port_same_pair": 1e3 * cpu["seconds_device_stages_only"] if cpu else None,
+                                  "note": "one C2 pair (22-min video, 27-min description) alone on the GPU, PCM device-resident; wall time from submit to the stage-A results on the host plus stage-B input to the final path on the host"},
             "kernel_ms_last_step": agg,
-            "host_call_ms_last_step": host_calls,
-            "host_call_ms_last_step_e2e": host_calls_e2e,
-            "host_ms_inside_library_per_pair": lib_host,
-            "allocator_activity_in_timed_steps": alloc_timed,
+            "host_side": {**sched, **{k: eng.counters()[k] - sched0[k] for k in sched0},
+                          "python_threads": 1, "scheduler_threads": 1},
+            "allocator_activity_in_timed_steps": {k: alloc1[k] - alloc0[k] for k in alloc1},
             "work": work_all,
             "clocks": clocks,
             "cpu_baseline": cpu,

@@ -25,6 +25,9 @@ EXPORTS = [
     "dab_pair_stage_a_match", "dab_pair_export_points1", "dab_pair_import_points1", "dab_pair_dp1",
     "dab_alloc_pinned", "dab_free_pinned", "dab_trim_pinned", "dab_alloc_stats", "dab_host_copy",
     "dab_set_host_wait", "dab_pair_get_timeline", "dab_pair_stage_b_gains",
+    "dab_pair_set_gate_energy",
+    "dab_engine_create", "dab_engine_destroy", "dab_engine_submit", "dab_engine_next", "dab_engine_submit_b",
+    "dab_engine_release", "dab_engine_slot_error", "dab_engine_slot_pair", "dab_engine_counters",
 ]
 
 
@@ -42,6 +45,33 @@ class Stats(ctypes.Structure):
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
 
+
+class Job(ctypes.Structure):
+    """dab_job"""
+    _fields_ = [("tag", ctypes.c_uint64), ("pcm", ctypes.c_void_p * 2), ("samples", ctypes.c_int64 * 2),
+                ("channels", ctypes.c_int32 * 2), ("format", ctypes.c_int32), ("on_device", ctypes.c_int32)]
+
+
+class Event(ctypes.Structure):
+    """dab_event"""
+    _fields_ = [("kind", ctypes.c_int32), ("slot", ctypes.c_int32), ("tag", ctypes.c_uint64),
+                ("status", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("n_path1", ctypes.c_int64), ("path_x", ctypes.c_void_p), ("path_y", ctypes.c_void_p),
+                ("features", (ctypes.c_void_p * 3) * 2), ("feature_len", (ctypes.c_int64 * 3) * 2),
+                ("n_path2", ctypes.c_int64), ("rows", ctypes.c_void_p), ("stats", Stats),
+                ("timings_ms", ctypes.c_float * 16)]
+
+
+class StageBIn(ctypes.Structure):
+    """dab_stage_b_in"""
+    _fields_ = [("gain", ctypes.c_float * 3), ("audio_std", ctypes.c_float * 3),
+                ("audio_energy_max", ctypes.c_float), ("video_energy_max", ctypes.c_float),
+                ("n_audio", ctypes.c_int64), ("n_video", ctypes.c_int64), ("corridors", ctypes.c_void_p),
+                ("n_corridors", ctypes.c_int32), ("n_clusters", ctypes.c_int32)]
+
+
+EVENT_STAGE_A, EVENT_STAGE_B = 1, 2
+E_TIMEOUT = 6
 
 TIMING_SLOTS = ("features_video", "features_audio", "prep_codes", "tables", "gate", "score",
                 "dp1_trace", "corridors", "dp2_trace", "dp2",
@@ -92,6 +122,7 @@ def load() -> ctypes.CDLL:
     lib.dab_pair_stream.restype = vp
     lib.dab_pair_set_pcm.argtypes = [vp, i32, vp, i64, i32, i32, i32]
     lib.dab_pair_set_features.argtypes = [vp, i32, vp, i64, vp, vp, vp, vp, i64]
+    lib.dab_pair_set_gate_energy.argtypes = [vp, i32, vp, i64]
     lib.dab_pair_feature_lens.argtypes = [vp, i32, ctypes.POINTER(i64 * 5)]
     lib.dab_pair_get_features.argtypes = [vp, i32, vp, vp, vp, vp, vp]
     lib.dab_pair_stage_a.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(i64)]
@@ -109,6 +140,19 @@ def load() -> ctypes.CDLL:
     lib.dab_pair_get_timings.argtypes = [vp, ctypes.POINTER(ctypes.c_float * 16)]
     lib.dab_launch_count.argtypes = [vp]
     lib.dab_launch_count.restype = i64
+    lib.dab_engine_create.argtypes = [vp, ctypes.c_int32, ctypes.POINTER(vp)]
+    lib.dab_engine_destroy.argtypes = [vp]
+    lib.dab_engine_destroy.restype = None
+    lib.dab_engine_submit.argtypes = [vp, ctypes.POINTER(Job)]
+    lib.dab_engine_next.argtypes = [vp, ctypes.POINTER(Event), ctypes.c_int32]
+    lib.dab_engine_submit_b.argtypes = [vp, ctypes.c_int32, ctypes.POINTER(StageBIn)]
+    lib.dab_engine_release.argtypes = [vp, ctypes.c_int32]
+    lib.dab_engine_slot_error.argtypes = [vp, ctypes.c_int32]
+    lib.dab_engine_slot_error.restype = ctypes.c_char_p
+    lib.dab_engine_slot_pair.argtypes = [vp, ctypes.c_int32]
+    lib.dab_engine_slot_pair.restype = vp
+    lib.dab_engine_counters.argtypes = [vp, ctypes.POINTER(ctypes.c_int64 * 4)]
+    lib.dab_engine_counters.restype = None
     if lib.dab_abi_version() != 1:
         raise DabError("libdescribealign_b200.so has an unexpected ABI version")
     _lib = lib
@@ -267,6 +311,11 @@ class Pair:
         self.ctx.check(self.lib.dab_pair_set_features(self.handle, track, _ptr(e), len(e), _ptr(z), _ptr(b0),
                                                       _ptr(b1), _ptr(b2), n))
 
+    def set_gate_energy(self, track: int, energy):
+        """The separate *_energy argument of align() (decides the not-quiet frames) when it is not features[0]."""
+        e = np.ascontiguousarray(energy, np.float32)
+        self.ctx.check(self.lib.dab_pair_set_gate_energy(self.handle, track, _ptr(e), len(e)))
+
     def feature_lens(self, track: int):
         lens = (ctypes.c_int64 * 5)()
         self.ctx.check(self.lib.dab_pair_feature_lens(self.handle, track, ctypes.byref(lens)))
@@ -421,6 +470,143 @@ class Pair:
     def close(self):
         if getattr(self, "handle", None):
             self.lib.dab_pair_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _view(ptr, n, dtype):
+    """numpy view of n elements of page-locked memory owned by an engine slot (no copy)."""
+    dtype = np.dtype(dtype)
+    if not ptr or n <= 0:
+        return np.empty(0, dtype)
+    buf = (ctypes.c_char * (int(n) * dtype.itemsize)).from_address(int(ptr))
+    return np.frombuffer(buf, dtype=dtype, count=int(n))
+
+
+class Engine:
+    """dab_engine: many pairs in flight on one GPU, one scheduler thread inside the library.
+
+    submit() queues a pair; next() hands out events: EVENT_STAGE_A (pass-1 path + the features the host
+    fit needs) to be answered with submit_b(), and EVENT_STAGE_B (final path rows) to be answered with
+    release().  Arrays returned by the view helpers alias the slot's page-locked buffers: copy what must
+    outlive the slot."""
+
+    def __init__(self, ctx: Context, slots: int = 32):
+        self.ctx = ctx
+        self.lib = ctx.lib
+        h = ctypes.c_void_p()
+        ctx.check(self.lib.dab_engine_create(ctx.handle, int(slots), ctypes.byref(h)))
+        self.handle = h
+        self.slots = int(slots)
+        self._keep = {}          # tag -> PCM arrays that must stay alive until stage A has consumed them
+
+    def submit(self, tag: int, video, audio, fmt: int | None = None):
+        """video / audio: interleaved (S, ch) / (S,) int16 or float16 numpy arrays (ideally page-locked),
+        or (device pointer, samples per channel, channels) tuples for device-resident int16 PCM."""
+        job = Job()
+        job.tag = int(tag)
+        on_device = isinstance(video, tuple)
+        keep = []
+        for t, p in enumerate((video, audio)):
+            if on_device:
+                ptr, samples, ch = p
+                job.pcm[t] = ctypes.c_void_p(int(ptr))
+                job.samples[t], job.channels[t] = int(samples), int(ch)
+                f = PCM_S16 if fmt is None else fmt
+            else:
+                p = np.asarray(p)
+                if p.ndim == 1:
+                    p = p[:, None]
+                if p.dtype == np.int16:
+                    f = PCM_S16
+                elif p.dtype == np.float16:
+                    f = PCM_F16
+                else:
+                    raise TypeError("PCM must be int16 or float16")
+                p = np.ascontiguousarray(p)
+                keep.append(p)
+                job.pcm[t] = p.ctypes.data_as(ctypes.c_void_p)
+                job.samples[t], job.channels[t] = p.shape[0], p.shape[1]
+            if t == 0:
+                job.format = f
+            elif f != job.format:
+                raise TypeError("both tracks must have the same sample format")
+        job.on_device = 1 if on_device else 0
+        self._keep[int(tag)] = keep
+        self.ctx.check(self.lib.dab_engine_submit(self.handle, ctypes.byref(job)))
+
+    def next(self, timeout_ms: int = -1):
+        """The next finished stage, or None after timeout_ms (0 = poll, < 0 = wait)."""
+        evt = Event()
+        rc = self.lib.dab_engine_next(self.handle, ctypes.byref(evt), int(timeout_ms))
+        if rc == E_TIMEOUT:
+            return None
+        self.ctx.check(rc)
+        if evt.kind == EVENT_STAGE_A:
+            self._keep.pop(int(evt.tag), None)
+        return evt
+
+    def error(self, evt) -> str:
+        return (self.lib.dab_engine_slot_error(self.handle, evt.slot) or b"").decode()
+
+    # ---- views of an event's results -----------------------------------------------------------
+    @staticmethod
+    def path1(evt):
+        return _view(evt.path_x, evt.n_path1, np.int32), _view(evt.path_y, evt.n_path1, np.int32)
+
+    @staticmethod
+    def features(evt, track: int):
+        return [_view(evt.features[track][f], evt.feature_len[track][f], np.float32) for f in range(3)]
+
+    @staticmethod
+    def rows(evt):
+        return _view(evt.rows, 5 * evt.n_path2, np.float64).reshape(-1, 5)
+
+    @staticmethod
+    def timings(evt) -> dict:
+        return {name: float(evt.timings_ms[k]) for k, name in enumerate(TIMING_SLOTS)}
+
+    @staticmethod
+    def stage_b_struct(gains, audio_stds, n_audio: int, n_video: int, audio_energy_max: float,
+                       video_energy_max: float, plans, n_clusters: int):
+        """The dab_stage_b_in of a host fit (reusable: the engine copies the corridors on submit)."""
+        b = StageBIn()
+        for k in range(3):
+            b.gain[k] = float(gains[k])
+            b.audio_std[k] = float(audio_stds[k])
+        b.audio_energy_max, b.video_energy_max = float(audio_energy_max), float(video_energy_max)
+        b.n_audio, b.n_video = int(n_audio), int(n_video)
+        plans = [p for p in plans if p[2] > p[1]]
+        arr = (Corridor * max(len(plans), 1))()
+        for k, (idx, lo, hi, slope, offset) in enumerate(plans):
+            arr[k] = Corridor(int(idx), int(lo), int(hi), 0, float(slope), float(offset))
+        b.corridors = ctypes.cast(arr, ctypes.c_void_p)
+        b.n_corridors, b.n_clusters = len(plans), int(n_clusters)
+        b._corridor_array = arr          # keeps the array alive as long as the struct
+        return b
+
+    def submit_b(self, slot: int, gains=None, audio_stds=None, n_audio=0, n_video=0, audio_energy_max=0.0,
+                 video_energy_max=0.0, plans=(), n_clusters=0, struct: StageBIn | None = None):
+        b = struct if struct is not None else self.stage_b_struct(gains, audio_stds, n_audio, n_video, audio_energy_max,
+                                                                   video_energy_max, plans, n_clusters)
+        self.ctx.check(self.lib.dab_engine_submit_b(self.handle, int(slot), ctypes.byref(b)))
+
+    def release(self, slot: int):
+        self.ctx.check(self.lib.dab_engine_release(self.handle, int(slot)))
+
+    def counters(self) -> dict:
+        out = (ctypes.c_int64 * 4)()
+        self.lib.dab_engine_counters(self.handle, ctypes.byref(out))
+        return {"scheduler_loops": int(out[0]), "scheduler_idle_sleeps": int(out[1])}
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.dab_engine_destroy(self.handle)
             self.handle = None
 
     def __del__(self):

@@ -124,9 +124,11 @@ class AlignJob:
     without the host-side rate-change fit, which BASELINE.json excludes from the metric.
     """
 
-    def __init__(self, pair: _cabi.Pair | None = None):
-        self.pair = pair if pair is not None else acquire_pair()
-        self._own = pair is None
+    def __init__(self, pair: _cabi.Pair | None = None, detached: bool = False):
+        """detached: no dab_pair of its own - the device stages run in an engine slot (batch.run_local) and
+        this object only carries the host-side steps (length rules, host fit, nodes)."""
+        self.pair = None if detached else (pair if pair is not None else acquire_pair())
+        self._own = pair is None and not detached
         self.video_features = self.audio_features = None
         self.want_all_features = False
         self.device_scaling = True   # stage B scales the pair's device-resident features itself (6 floats up)
@@ -160,9 +162,14 @@ class AlignJob:
         self.pair.set_pcm_device(AUDIO, *audio)
         self._features_on_device = True
 
-    def load_features(self, video_features, audio_features):
+    def load_features(self, video_features, audio_features, video_energy=None, audio_energy=None):
+        """video_energy / audio_energy: align()'s separate energy arguments when they are not features[0]."""
         self.pair.set_features(VIDEO, video_features)
         self.pair.set_features(AUDIO, audio_features)
+        if video_energy is not None:
+            self.pair.set_gate_energy(VIDEO, video_energy)
+        if audio_energy is not None:
+            self.pair.set_gate_energy(AUDIO, audio_energy)
         self.video_features, self.audio_features = video_features, audio_features
         self.h2d_bytes += sum(np.asarray(f).nbytes for f in list(video_features) + list(audio_features))
         self._features_on_device = False
@@ -185,14 +192,25 @@ class AlignJob:
             self.video_features = self._timed("get_features", self.pair.get_features, VIDEO, count, keep)
             self.audio_features = self._timed("get_features", self.pair.get_features, AUDIO, count, keep)
             self.d2h_bytes += sum(f.nbytes for f in self.video_features + self.audio_features)
+        self.check_path1_length(n_path)
+        self.x, self.y = self._timed("path1", self.pair.path1)
+        self.d2h_bytes += 8 * n_path
+        return self.x, self.y
+
+    def check_path1_length(self, n_path):
+        """Length rule of describealign.py:698-699 (needs the feature vectors for the track lengths)."""
         self.n_video_energy = len(self.video_features[0])
         self.n_audio_energy = len(self.audio_features[0])
         self.min_len = host_fit.min_path_length(self.n_video_energy, self.n_audio_energy)
         if n_path < self.min_len:
             raise RuntimeError(FAILED_MSG)
-        self.x, self.y = self._timed("path1", self.pair.path1)
-        self.d2h_bytes += 8 * n_path
-        return self.x, self.y
+
+    def stage_b_input(self):
+        """What dab_engine_submit_b / dab_pair_stage_b_gains need from the host fit."""
+        return dict(gains=self.gains[0], audio_stds=self.gains[1], n_audio=len(self.audio_scaled),
+                    n_video=len(self.video_scaled), audio_energy_max=float(self.audio_scaled[:, 0].max()),
+                    video_energy_max=float(self.video_scaled[:, 0].max()), plans=self.plans,
+                    n_clusters=len(self.clusters))
 
     def host_stage(self):
         """The untimed "rate-change fit" on the host (describealign.py:702-893)."""
@@ -252,14 +270,18 @@ def align(video_features, audio_desc_features, video_energy, audio_desc_energy, 
     Returns (audio_desc_times, video_times, similarity_percent, path, median_slope) with the
     reference's meaning; raises RuntimeError("Alignment failed, ...") under the reference's
     length rule (:698-699, :991-992)."""
-    for feats, energy, name in ((video_features, video_energy, "video"),
-                                (audio_desc_features, audio_desc_energy, "audio_desc")):
-        if energy is not feats[0] and not np.array_equal(energy, feats[0]):
-            raise NotImplementedError(f"{name}_energy must be {name}_features[0], as in describealign.py:1121")
+    gates = []
+    for feats, energy in ((video_features, video_energy), (audio_desc_features, audio_desc_energy)):
+        # the reference's only caller passes features[0] (describealign.py:1121); anything else decides the
+        # not-quiet frames in its place (:629, :657) and the path-length rule (:698)
+        same = energy is feats[0] or (np.shape(energy) == np.shape(feats[0]) and np.array_equal(energy, feats[0]))
+        if not same and len(energy) != len(feats[0]):
+            raise ValueError("the energy arguments must have the length of features[0]")
+        gates.append(None if same else np.asarray(energy))
     print("  memorizing video...        \r", end='')
     job = AlignJob()
     try:
-        job.load_features(list(video_features), list(audio_desc_features))
+        job.load_features(list(video_features), list(audio_desc_features), gates[0], gates[1])
         return job.run(details)
     finally:
         job.close()

@@ -112,7 +112,7 @@ def exchange_points(i, v, q, group=None):
 # ---------------------------------------------------------------------------------------------
 
 def gpu_runner(pair):
-    """One pair through the CUDA path: PCM in, the reference's align() tuple out."""
+    """One pair through the CUDA path, synchronously: PCM in, the reference's align() tuple out."""
     from . import api
     job = api.AlignJob()
     try:
@@ -125,10 +125,125 @@ def gpu_runner(pair):
         job.close()
 
 
-def run_local(pairs, in_flight: int = 64, runner: Callable | None = None):
+_engines = {}
+
+
+def engine(slots: int = 32):
+    """This process's batch engine (one per GPU and slot count), created on first use."""
+    from . import _cabi, api
+    key = (api._device, int(slots))
+    eng = _engines.get(key)
+    if eng is None:
+        eng = _cabi.Engine(api.context(), slots)
+        _engines[key] = eng
+    return eng
+
+
+def _interleaved_pcm(p):
+    from . import api
+    p = np.asarray(p)
+    if p.dtype == np.float16 and p.ndim == 2 and p.shape[0] in (1, 2) and p.shape[1] > 2:
+        return api._interleaved(p)        # the reference's (ch, S) float16 arrays
+    return p
+
+
+def run_engine(pairs, in_flight: int = 32, host_workers: int = 0, host_stage: Callable | None = None, finish: bool = True):
+    """Run `pairs` on this process's GPU through the batch engine with up to `in_flight` pairs on the
+    device at once.  One Python thread serves the engine's event queue; the host fit of each pair
+    (describealign.py:702-893, ~1 s of scipy per 22-min pair) runs in a pool of `host_workers` threads
+    (default: one per host core, at most 16) so that it overlaps the device stages of other pairs.
+    host_stage(job): replaces AlignJob.host_stage (the benchmark passes a cache lookup).
+    Returns one result per pair in input order: the tuple align() returns (or the job when
+    finish=False), or the exception the pair raised."""
+    from concurrent.futures import ThreadPoolExecutor
+    from . import _cabi, api
+    eng = engine(in_flight)
+    n = len(pairs)
+    results: list = [None] * n
+    jobs: dict = {}
+    if host_workers <= 0:
+        host_workers = max(1, min(16, os.cpu_count() or 1))
+    pool = ThreadPoolExecutor(max_workers=host_workers)
+    fits = []            # (future, tag, slot)
+    submitted = done = 0
+    # PCM is read by asynchronous copies: keep no more pairs loaded than the engine can start soon
+    window = in_flight + 4
+
+    def fail(tag, slot, exc):
+        nonlocal done
+        results[tag] = exc
+        if slot is not None:
+            eng.release(slot)
+        jobs.pop(tag, None)
+        done += 1
+
+    def fit(job):
+        (host_stage or api.AlignJob.host_stage)(job)
+        return job
+
+    try:
+        while done < n:
+            while submitted < n and submitted - done < window:
+                p = pairs[submitted]
+                try:
+                    v, a = p() if callable(p) else p
+                    jobs[submitted] = api.AlignJob(detached=True)
+                    eng.submit(submitted, _interleaved_pcm(v), _interleaved_pcm(a))
+                except Exception as e:      # reported per pair; the batch goes on
+                    fail(submitted, None, e)
+                submitted += 1
+            # host fits that finished: hand their pairs back to the device
+            still = []
+            for fut, tag, slot in fits:
+                if not fut.done():
+                    still.append((fut, tag, slot))
+                    continue
+                try:
+                    job = fut.result()
+                    eng.submit_b(slot, **job.stage_b_input())
+                except Exception as e:
+                    fail(tag, slot, e)
+            fits = still
+            evt = eng.next(2 if fits else 50)
+            if evt is None:
+                continue
+            tag = int(evt.tag)
+            job = jobs.get(tag)
+            if evt.status != 0:
+                fail(tag, evt.slot, _cabi.DabError(f"describealign_b200 error {evt.status}: {eng.error(evt)}"))
+                continue
+            try:
+                if evt.kind == _cabi.EVENT_STAGE_A:
+                    job.video_features = [f.copy() for f in eng.features(evt, _cabi.VIDEO)]
+                    job.audio_features = [f.copy() for f in eng.features(evt, _cabi.AUDIO)]
+                    job.check_path1_length(int(evt.n_path1))
+                    x, y = eng.path1(evt)
+                    job.x, job.y = x.astype(np.int64), y.astype(np.int64)
+                    fits.append((pool.submit(fit, job), tag, evt.slot))
+                else:
+                    job.path = eng.rows(evt).copy()
+                    job.stats = evt.stats.as_dict()
+                    job.timings = eng.timings(evt)
+                    eng.release(evt.slot)
+                    if len(job.path) < job.min_len:
+                        raise RuntimeError(api.FAILED_MSG)
+                    results[tag] = job.finish() if finish else job
+                    jobs.pop(tag, None)
+                    done += 1
+            except Exception as e:
+                fail(tag, evt.slot if evt.kind == _cabi.EVENT_STAGE_A else None, e)
+    finally:
+        pool.shutdown(wait=True)
+    return results
+
+
+def run_local(pairs, in_flight: int = 32, runner: Callable | None = None):
     """Run `pairs` on this process's GPU with up to `in_flight` pairs in progress at once.
-    A pair that fails (e.g. RuntimeError("Alignment failed, ...")) yields its exception."""
-    runner = gpu_runner if runner is None else runner
+    A pair that fails (e.g. RuntimeError("Alignment failed, ...")) yields its exception.
+    With the default runner the pairs go through the batch engine (run_engine); a custom runner
+    (CPU tests, instrumentation) is called once per pair from a thread pool."""
+    if runner is None or runner is gpu_runner:
+        return run_engine(pairs, in_flight)
 
     def one(p):
         try:
@@ -138,15 +253,11 @@ def run_local(pairs, in_flight: int = 64, runner: Callable | None = None):
 
     if in_flight <= 1 or len(pairs) <= 1:
         return [one(p) for p in pairs]
-    if runner is gpu_runner:
-        # one host thread per pair in flight: they must sleep, not spin, while their streams drain
-        from . import _cabi, api
-        _cabi.set_host_wait(api._device, 2)
     with ThreadPoolExecutor(max_workers=in_flight) as ex:
         return list(ex.map(one, pairs))
 
 
-def align_batch(pairs, durations: Sequence[float] | None = None, in_flight: int = 64, group=None,
+def align_batch(pairs, durations: Sequence[float] | None = None, in_flight: int = 32, group=None,
                 runner: Callable | None = None):
     """Align a list of (video_pcm, description_pcm) pairs (or zero-argument loaders returning
     such a pair) over all ranks of the current process group.

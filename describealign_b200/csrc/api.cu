@@ -143,7 +143,14 @@ int dab_device_count(void) {
   return n;
 }
 
-const char *dab_last_error(const dab_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+const char *dab_last_error(const dab_ctx *ctx) {
+  static thread_local std::string copy;
+  if (!ctx) return g_create_err.c_str();
+  dab_ctx *c = const_cast<dab_ctx *>(ctx);
+  std::lock_guard<std::mutex> g(c->err_mu);
+  copy = c->err;
+  return copy.c_str();
+}
 
 int dab_set_host_wait(int device, int mode) {
   if (mode < 0 || mode > 2) return -DAB_E_ARG;
@@ -196,7 +203,7 @@ int dab_set_option(dab_ctx *ctx, const char *name, int64_t value) {
   if (strcmp(name, "dp2_generic") == 0) { ctx->opt_dp2_generic = value != 0; return DAB_OK; }
   if (strcmp(name, "dp_reserve_kb") == 0 && value >= 0 && value <= 176) { ctx->opt_dp_reserve_kb = (int)value; return DAB_OK; }
   if (strcmp(name, "dp2_impl") == 0 && value >= 0 && value <= 3) { ctx->opt_dp2_impl = (int)value; return DAB_OK; }
-  ctx->err = std::string("dab_set_option: unknown option ") + name;
+  dab_set_err(ctx, std::string("dab_set_option: unknown option ") + name);
   return DAB_E_ARG;
 }
 
@@ -249,7 +256,7 @@ void dab_pair_destroy(dab_pair *pr) {
   if (pr->stream) dab_wait_stream(pr->stream);
   for (int t = 0; t < 2; ++t) {
     Track &k = pr->trk[t];
-    DevBuf *bs[] = {&k.pcm, &k.energy, &k.zc, &k.b0, &k.b1, &k.b2, &k.ms, &k.nrm, &k.pack, &k.code, &k.nq_flag, &k.nq_list};
+    DevBuf *bs[] = {&k.pcm, &k.energy, &k.zc, &k.b0, &k.b1, &k.b2, &k.gate, &k.ms, &k.nrm, &k.pack, &k.code, &k.nq_flag, &k.nq_list};
     for (DevBuf *b : bs) free_buf(*b);
   }
   DevBuf *bs[] = {&pr->scan_tmp, &pr->tbl_count, &pr->tbl_start, &pr->tbl_items, &pr->row_count, &pr->row_off,
@@ -285,7 +292,7 @@ int dab_pair_set_pcm(dab_pair *pr, int track, const void *pcm, int64_t samples, 
   ApiTimer timer__(&pr->api_us[0]);
   if (track < 0 || track > 1 || !pcm || samples < 0 || (channels != 1 && channels != 2) ||
       (format != DAB_PCM_S16 && format != DAB_PCM_F16)) {
-    ctx->err = "dab_pair_set_pcm: invalid argument";
+    dab_set_err(ctx, "dab_pair_set_pcm: invalid argument");
     return DAB_E_ARG;
   }
   DAB_CUDA(cudaSetDevice(ctx->device));
@@ -293,6 +300,7 @@ int dab_pair_set_pcm(dab_pair *pr, int track, const void *pcm, int64_t samples, 
   tk.S = samples;
   tk.ch = channels;
   tk.have_features = false;
+  tk.have_gate = false;
   pr->matched = false;
   if (track == DAB_TRACK_VIDEO) { pr->api_us[1] = pr->api_us[2] = pr->api_us[3] = 0; }
   const void *d_pcm = pcm;
@@ -318,7 +326,7 @@ int dab_pair_set_features(dab_pair *pr, int track, const float *energy, int64_t 
   ApiTimer timer__(&pr->api_us[0]);
   if (track < 0 || track > 1 || !energy || !zc || !band0 || !band1 || !band2 || n < 0 ||
       (n_energy != n && n_energy != n + 1)) {
-    ctx->err = "dab_pair_set_features: invalid argument (len(energy) must be n or n + 1)";
+    dab_set_err(ctx, "dab_pair_set_features: invalid argument (len(energy) must be n or n + 1)");
     return DAB_E_ARG;
   }
   DAB_CUDA(cudaSetDevice(ctx->device));
@@ -326,6 +334,7 @@ int dab_pair_set_features(dab_pair *pr, int track, const float *energy, int64_t 
   tk.L = n;
   tk.Le = n_energy;
   tk.S = n * 210;
+  tk.have_gate = false;
   pr->matched = false;
   DAB_TRY(dab_ensure(ctx, tk.energy, sizeof(float) * (size_t)(n_energy + 1)));
   DAB_TRY(dab_ensure(ctx, tk.zc, sizeof(float) * (size_t)(n + 1)));
@@ -343,10 +352,27 @@ int dab_pair_set_features(dab_pair *pr, int track, const float *energy, int64_t 
   return DAB_OK;
 }
 
+int dab_pair_set_gate_energy(dab_pair *pr, int track, const float *energy, int64_t n_energy) {
+  if (!pr) return DAB_E_ARG;
+  dab_ctx *ctx = pr->ctx;
+  StreamScope scope__(pr->stream);
+  if (track < 0 || track > 1 || !energy) { dab_set_err(ctx, "dab_pair_set_gate_energy: invalid argument"); return DAB_E_ARG; }
+  Track &tk = pr->trk[track];
+  if (!tk.have_features) { dab_set_err(ctx, "dab_pair_set_gate_energy: set the track's features first"); return DAB_E_STATE; }
+  if (n_energy != tk.Le) { dab_set_err(ctx, "dab_pair_set_gate_energy: the energy argument must have the length of features[0]"); return DAB_E_ARG; }
+  DAB_CUDA(cudaSetDevice(ctx->device));
+  DAB_TRY(dab_ensure(ctx, tk.gate, sizeof(float) * (size_t)(n_energy + 1)));
+  DAB_CUDA(cudaMemcpyAsync(tk.gate.p, energy, sizeof(float) * (size_t)n_energy, cudaMemcpyHostToDevice, pr->stream));
+  DAB_CUDA(dab_wait_stream(pr->stream));
+  tk.have_gate = true;
+  pr->matched = false;
+  return DAB_OK;
+}
+
 int dab_pair_feature_lens(dab_pair *pr, int track, int64_t lens[5]) {
   if (!pr || track < 0 || track > 1 || !lens) return DAB_E_ARG;
   Track &tk = pr->trk[track];
-  if (!tk.have_features) { pr->ctx->err = "no features computed for this track"; return DAB_E_STATE; }
+  if (!tk.have_features) { dab_set_err(pr->ctx, "no features computed for this track"); return DAB_E_STATE; }
   lens[0] = tk.Le;
   lens[1] = lens[2] = lens[3] = lens[4] = tk.L;
   return DAB_OK;
@@ -358,7 +384,7 @@ int dab_pair_get_features(dab_pair *pr, int track, float *energy, float *zc, flo
   dab_ctx *ctx = pr->ctx;
   ApiTimer timer__(&pr->api_us[3]);
   Track &tk = pr->trk[track];
-  if (!tk.have_features) { ctx->err = "no features computed for this track"; return DAB_E_STATE; }
+  if (!tk.have_features) { dab_set_err(ctx, "no features computed for this track"); return DAB_E_STATE; }
   DAB_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = pr->stream;
   if (energy && tk.Le > 0) DAB_CUDA(cudaMemcpyAsync(energy, tk.energy.p, sizeof(float) * (size_t)tk.Le, cudaMemcpyDeviceToHost, st));
@@ -378,9 +404,9 @@ int dab_pair_stage_a(dab_pair *pr, int64_t *n_points, int64_t *n_path) {
   StreamScope scope__(pr->stream);
   ApiTimer timer__(&pr->api_us[1]);
   for (int t = 0; t < 2; ++t) {
-    if (!pr->trk[t].have_features) { ctx->err = "stage_a: features of both tracks are required first"; return DAB_E_STATE; }
+    if (!pr->trk[t].have_features) { dab_set_err(ctx, "stage_a: features of both tracks are required first"); return DAB_E_STATE; }
     const int64_t lmin = pr->trk[t].Le < pr->trk[t].L ? pr->trk[t].Le : pr->trk[t].L;
-    if (lmin < 2 * DAB_WIN) { ctx->err = "stage_a: track shorter than 82 frames"; return DAB_E_TOO_SHORT; }
+    if (lmin < 2 * DAB_WIN) { dab_set_err(ctx, "stage_a: track shorter than 82 frames"); return DAB_E_TOO_SHORT; }
   }
   DAB_CUDA(cudaSetDevice(ctx->device));
   DAB_TRY(dab_run_stage_a(pr));
@@ -452,9 +478,9 @@ int dab_pair_export_points1(dab_pair *pr, int32_t *i_audio, int32_t *v_video, do
 static int check_stage_a_inputs(dab_pair *pr, const char *who) {
   dab_ctx *ctx = pr->ctx;
   for (int t = 0; t < 2; ++t) {
-    if (!pr->trk[t].have_features) { ctx->err = std::string(who) + ": features of both tracks are required first"; return DAB_E_STATE; }
+    if (!pr->trk[t].have_features) { dab_set_err(ctx, std::string(who) + ": features of both tracks are required first"); return DAB_E_STATE; }
     const int64_t lmin = pr->trk[t].Le < pr->trk[t].L ? pr->trk[t].Le : pr->trk[t].L;
-    if (lmin < 2 * DAB_WIN) { ctx->err = std::string(who) + ": track shorter than 82 frames"; return DAB_E_TOO_SHORT; }
+    if (lmin < 2 * DAB_WIN) { dab_set_err(ctx, std::string(who) + ": track shorter than 82 frames"); return DAB_E_TOO_SHORT; }
   }
   return DAB_OK;
 }
@@ -464,7 +490,7 @@ int dab_pair_stage_a_match(dab_pair *pr, int64_t row_lo, int64_t row_hi, int64_t
   dab_ctx *ctx = pr->ctx;
   StreamScope scope__(pr->stream);
   ApiTimer timer__(&pr->api_us[1]);
-  if (row_lo < 0 || row_hi < row_lo) { ctx->err = "dab_pair_stage_a_match: invalid row range"; return DAB_E_ARG; }
+  if (row_lo < 0 || row_hi < row_lo) { dab_set_err(ctx, "dab_pair_stage_a_match: invalid row range"); return DAB_E_ARG; }
   DAB_TRY(check_stage_a_inputs(pr, "stage_a_match"));
   DAB_CUDA(cudaSetDevice(ctx->device));
   DAB_TRY(dab_run_stage_a_match(pr, row_lo, row_hi));
@@ -478,8 +504,8 @@ int dab_pair_import_points1(dab_pair *pr, const int32_t *i_audio, const int32_t 
   if (!pr) return DAB_E_ARG;
   dab_ctx *ctx = pr->ctx;
   StreamScope scope__(pr->stream);
-  if (n < 0 || (n > 0 && (!i_audio || !v_video || !qual))) { ctx->err = "dab_pair_import_points1: invalid argument"; return DAB_E_ARG; }
-  if (!pr->matched) { ctx->err = "import_points1: run stage_a_match on this pair first (it builds the hashed-frame list)"; return DAB_E_STATE; }
+  if (n < 0 || (n > 0 && (!i_audio || !v_video || !qual))) { dab_set_err(ctx, "dab_pair_import_points1: invalid argument"); return DAB_E_ARG; }
+  if (!pr->matched) { dab_set_err(ctx, "import_points1: run stage_a_match on this pair first (it builds the hashed-frame list)"); return DAB_E_STATE; }
   DAB_CUDA(cudaSetDevice(ctx->device));
   return dab_run_import_points1(pr, i_audio, v_video, qual, n, src_on_device);
 }
@@ -489,25 +515,23 @@ int dab_pair_dp1(dab_pair *pr, int64_t *n_path) {
   dab_ctx *ctx = pr->ctx;
   StreamScope scope__(pr->stream);
   ApiTimer timer__(&pr->api_us[1]);
-  if (!pr->matched) { ctx->err = "dp1: no match points (run stage_a_match / import_points1 first)"; return DAB_E_STATE; }
+  if (!pr->matched) { dab_set_err(ctx, "dp1: no match points (run stage_a_match / import_points1 first)"); return DAB_E_STATE; }
   DAB_CUDA(cudaSetDevice(ctx->device));
   DAB_TRY(dab_run_stage_a_dp(pr));
   if (n_path) *n_path = pr->n_path1;
   return DAB_OK;
 }
 
-// shared by the two stage-B entry points: corridor checks, corridor upload, the run itself
-static int stage_b_common(dab_pair *pr, int64_t n_audio, int64_t n_video, const dab_corridor *corridors,
-                          int32_t n_corridors, int32_t n_clusters, float amax, float vmax, int64_t *n_points,
-                          int64_t *n_path) {
+// shared by the stage-B entry points: corridor checks and upload, then the stage is enqueued
+static int stage_b_enqueue_common(dab_pair *pr, int64_t n_audio, int64_t n_video, const dab_corridor *corridors,
+                                  int32_t n_corridors, int32_t n_clusters, float amax, float vmax) {
   dab_ctx *ctx = pr->ctx;
   cudaStream_t st = pr->stream;
-  int64_t rows = 0;
   for (int k = 0; k < n_corridors; ++k) {
     const dab_corridor &c = corridors[k];
     if (c.cluster < 0 || c.cluster >= n_clusters || c.lo < 0 || c.hi > n_audio ||
         (k > 0 && c.cluster <= corridors[k - 1].cluster)) {
-      ctx->err = "dab_pair_stage_b: corridors must be in ascending cluster order with rows inside the audio track";
+      dab_set_err(ctx, "dab_pair_stage_b: corridors must be in ascending cluster order with rows inside the audio track");
       return DAB_E_ARG;
     }
     if (c.hi > c.lo) {
@@ -515,22 +539,30 @@ static int stage_b_common(dab_pair *pr, int64_t n_audio, int64_t n_video, const 
       const double j0 = c.slope * (double)c.lo + c.offset, j1 = c.slope * (double)(c.hi - 1) + c.offset;
       const double jmin = j0 < j1 ? j0 : j1, jmax = j0 < j1 ? j1 : j0;
       if (!(jmin >= 0.0) || !(jmax < (double)(n_video - 1))) {
-        ctx->err = "dab_pair_stage_b: corridor line leaves the video track";
+        dab_set_err(ctx, "dab_pair_stage_b: corridor line leaves the video track");
         return DAB_E_ARG;
       }
-      rows += c.hi - c.lo;
     }
   }
   pr->h_cor.assign(corridors, corridors + n_corridors);
   DAB_TRY(dab_ensure(ctx, pr->corridors, sizeof(dab_corridor) * (size_t)(n_corridors + 1)));
   if (n_corridors > 0)
     DAB_CUDA(cudaMemcpyAsync(pr->corridors.p, corridors, sizeof(dab_corridor) * (size_t)n_corridors, cudaMemcpyHostToDevice, st));
-  reinterpret_cast<float *>(pr->h_counters + 8)[0] = amax;
-  reinterpret_cast<float *>(pr->h_counters + 8)[1] = vmax;
-  pr->h_counters[11] = rows;
+  pr->b_amax = amax;
+  pr->b_vmax = vmax;
   pr->stats.n_audio_frames = n_audio;
   pr->stats.n_video_frames = n_video;
-  DAB_TRY(dab_run_stage_b(pr, n_corridors, n_clusters));
+  return dab_enqueue_stage_b(pr, n_corridors, n_clusters);
+}
+
+static int stage_b_common(dab_pair *pr, int64_t n_audio, int64_t n_video, const dab_corridor *corridors,
+                          int32_t n_corridors, int32_t n_clusters, float amax, float vmax, int64_t *n_points,
+                          int64_t *n_path) {
+  dab_ctx *ctx = pr->ctx;
+  DAB_TRY(stage_b_enqueue_common(pr, n_audio, n_video, corridors, n_corridors, n_clusters, amax, vmax));
+  DAB_TRY(dab_enqueue_counts(pr));
+  DAB_CUDA(dab_wait_stream(pr->stream));     // (corridors is the caller's array: it has been consumed by now)
+  DAB_TRY(dab_collect_stage_b(pr));
   if (n_points) *n_points = pr->n_points2;
   if (n_path) *n_path = pr->n_path2;
   return DAB_OK;
@@ -545,7 +577,7 @@ int dab_pair_stage_b(dab_pair *pr, const float *audio_scaled, int64_t n_audio, c
   ApiTimer timer__(&pr->api_us[2]);
   if (!audio_scaled || !video_scaled || n_audio <= 0 || n_video <= 8 || n_corridors < 0 || n_clusters < 0 ||
       (n_corridors > 0 && !corridors)) {
-    ctx->err = "dab_pair_stage_b: invalid argument";
+    dab_set_err(ctx, "dab_pair_stage_b: invalid argument");
     return DAB_E_ARG;
   }
   DAB_CUDA(cudaSetDevice(ctx->device));
@@ -577,26 +609,22 @@ __global__ void scale_features_kernel(const float *f0, const float *f1, const fl
   out[3 * k + 2] = __fdiv_rn(x2, s2);
 }
 
-extern "C" {
-
-int dab_pair_stage_b_gains(dab_pair *pr, const float gain[3], const float audio_std[3], int64_t n_audio,
-                           int64_t n_video, float audio_energy_max, float video_energy_max,
-                           const dab_corridor *corridors, int32_t n_corridors, int32_t n_clusters,
-                           int64_t *n_points, int64_t *n_path) {
-  if (!pr) return DAB_E_ARG;
+// Stage B for a pair that holds its features: scaling kernels + the stage, enqueued without waiting.
+// `corridors` must stay valid until the stream has consumed it (page-locked memory owned by the caller).
+int dab_enqueue_stage_b_gains(dab_pair *pr, const float gain[3], const float audio_std[3], int64_t n_audio, int64_t n_video,
+                              float amax, float vmax, const dab_corridor *corridors, int32_t n_corridors, int32_t n_clusters,
+                              const dab_corridor *) {
   dab_ctx *ctx = pr->ctx;
-  StreamScope scope__(pr->stream);
-  ApiTimer timer__(&pr->api_us[2]);
   if (!gain || !audio_std || n_audio <= 0 || n_video <= 8 || n_corridors < 0 || n_clusters < 0 ||
       (n_corridors > 0 && !corridors)) {
-    ctx->err = "dab_pair_stage_b_gains: invalid argument";
+    dab_set_err(ctx, "dab_pair_stage_b_gains: invalid argument");
     return DAB_E_ARG;
   }
   Track &V = pr->trk[DAB_TRACK_VIDEO], &A = pr->trk[DAB_TRACK_AUDIO];
-  if (!V.have_features || !A.have_features) { ctx->err = "dab_pair_stage_b_gains: the pair holds no features"; return DAB_E_STATE; }
+  if (!V.have_features || !A.have_features) { dab_set_err(ctx, "dab_pair_stage_b_gains: the pair holds no features"); return DAB_E_STATE; }
   // np.stack truncates to the shortest of the three vectors (energy may be one longer)
   const int64_t na = A.L < A.Le ? A.L : A.Le, nv = V.L < V.Le ? V.L : V.Le;
-  if (n_audio != na || n_video != nv) { ctx->err = "dab_pair_stage_b_gains: lengths differ from the pair's features"; return DAB_E_ARG; }
+  if (n_audio != na || n_video != nv) { dab_set_err(ctx, "dab_pair_stage_b_gains: lengths differ from the pair's features"); return DAB_E_ARG; }
   DAB_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = pr->stream;
   DAB_TRY(dab_ensure(ctx, pr->a_scaled, sizeof(float) * 3 * (size_t)n_audio));
@@ -607,8 +635,27 @@ int dab_pair_stage_b_gains(dab_pair *pr, const float gain[3], const float audio_
       n_video, gain[0], gain[1], gain[2], audio_std[0], audio_std[1], audio_std[2], 1, pr->v_scaled.as<float>());
   ctx->launches += 2;
   DAB_CUDA(cudaGetLastError());
-  return stage_b_common(pr, n_audio, n_video, corridors, n_corridors, n_clusters, audio_energy_max, video_energy_max,
-                        n_points, n_path);
+  return stage_b_enqueue_common(pr, n_audio, n_video, corridors, n_corridors, n_clusters, amax, vmax);
+}
+
+extern "C" {
+
+int dab_pair_stage_b_gains(dab_pair *pr, const float gain[3], const float audio_std[3], int64_t n_audio,
+                           int64_t n_video, float audio_energy_max, float video_energy_max,
+                           const dab_corridor *corridors, int32_t n_corridors, int32_t n_clusters,
+                           int64_t *n_points, int64_t *n_path) {
+  if (!pr) return DAB_E_ARG;
+  dab_ctx *ctx = pr->ctx;
+  StreamScope scope__(pr->stream);
+  ApiTimer timer__(&pr->api_us[2]);
+  DAB_TRY(dab_enqueue_stage_b_gains(pr, gain, audio_std, n_audio, n_video, audio_energy_max, video_energy_max, corridors,
+                                    n_corridors, n_clusters, nullptr));
+  DAB_TRY(dab_enqueue_counts(pr));
+  DAB_CUDA(dab_wait_stream(pr->stream));
+  DAB_TRY(dab_collect_stage_b(pr));
+  if (n_points) *n_points = pr->n_points2;
+  if (n_path) *n_path = pr->n_path2;
+  return DAB_OK;
 }
 
 int dab_pair_get_path2(dab_pair *pr, double *rows) {

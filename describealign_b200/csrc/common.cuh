@@ -5,6 +5,7 @@
 
 #include <cuda_runtime.h>
 #include <atomic>
+#include <mutex>
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
@@ -24,7 +25,8 @@ struct DevBuf {
 
 struct dab_ctx {
   int device = 0;
-  std::string err;
+  std::string err;                    // last error; written under err_mu (pairs of one context run on several host threads)
+  std::mutex err_mu;
   std::atomic<int64_t> launches{0};   // kernels launched through this context (many host threads)
   int sm_count = 148;
   int opt_dp2_generic = 0;   // force the tree DP for pass 2 (testing)
@@ -41,6 +43,8 @@ struct Track {
   bool have_features = false;
   DevBuf pcm;          // staging for host PCM
   DevBuf energy, zc, b0, b1, b2;   // f32 x4, f64
+  DevBuf gate;         // the separate *_energy argument of align() when it is not features[0] (:629, :657)
+  bool have_gate = false;
   // stage A prep (features 0..2 keep ms / nrm for scoring; 3, 4 only feed the codes)
   DevBuf ms;           // f64 [3][Lp]   Lp = min feature length
   DevBuf nrm;          // f64 [3][Lp-40]
@@ -76,6 +80,7 @@ struct dab_pair {
   DevBuf seglist;              // i32 checkpoints
   DevBuf path1_x, path1_y;     // i32
   int64_t n_points1 = 0, n_path1 = 0;
+  int64_t cap_entries = 0, cap_cand = 0, cap_points1 = 0;   // capacities of device-sized buffers (grown on overflow)
   bool matched = false;        // tables / hashed-frame list of the current features are built
   // stage B
   DevBuf a_scaled, v_scaled;   // f32 (n,3)
@@ -92,6 +97,8 @@ struct dab_pair {
   DevBuf len2, cp2, backid2;   // i32
   DevBuf path2;                // f64 (n,5)
   int64_t n_points2 = 0, n_path2 = 0;
+  int64_t cap_points2 = 0;     // upper bound of pass-2 points of the current stage_b call (sum of corridor rows)
+  float b_amax = 0.f, b_vmax = 0.f;   // np.max of the scaled energy columns (describealign.py:908-909)
   dab_stats stats = {};
   cudaEvent_t ev[32] = {};
   bool ev_used[16] = {};
@@ -102,6 +109,11 @@ struct dab_pair {
   // [0] set_pcm / set_features, [1] stage A, [2] stage B, [3] get_* copies
   int64_t api_us[4] = {0, 0, 0, 0};
 };
+
+inline void dab_set_err(dab_ctx *ctx, const std::string &msg) {
+  std::lock_guard<std::mutex> g(ctx->err_mu);
+  ctx->err = msg;
+}
 
 struct ApiTimer {
   int64_t *slot;
@@ -118,7 +130,7 @@ struct ApiTimer {
       char b__[512];                                                                       \
       snprintf(b__, sizeof b__, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__),   \
                __FILE__, __LINE__);                                                        \
-      ctx->err = b__;                                                                      \
+      dab_set_err(ctx, b__);                                                                    \
       return DAB_E_CUDA;                                                                   \
     }                                                                                      \
   } while (0)
@@ -146,14 +158,50 @@ cudaError_t dab_wait_stream(cudaStream_t st);
 cudaError_t dab_readback(dab_pair *pr, void *host_dst, const void *dev_src, size_t bytes);
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
-// exclusive scan of n int32 values; out[n] receives the total (out has n + 1 entries).
-int dab_exclusive_scan(dab_pair *pr, const int32_t *in, int32_t *out, int64_t n);
+// exclusive scan of n int32 values; out[n] receives the total (out has n + 1 entries).  n_dev (optional):
+// device-side count of valid elements (<= n; launches are sized for n); total_out (optional): device
+// word that also receives the total.
+int dab_exclusive_scan(dab_pair *pr, const int32_t *in, int32_t *out, int64_t n, const int32_t *n_dev = nullptr,
+                       int32_t *total_out = nullptr);
+
+// Counts that only the device knows while a stage is in flight (int32 words of dab_pair::counters).  Every
+// kernel of a stage reads the counts it needs from here, so a whole stage is enqueued without a host
+// round trip; the block is copied to the pair's mapped host page when the stage ends.
+enum {
+  DC_N_VNQ = 0,        // not-quiet video frames
+  DC_N_AQ_ALL = 1,     // not-quiet audio frames
+  DC_N_ENTRIES = 2,    // expanded table entries
+  DC_N_VSEL = 3,       // hashed video frames (every 4th not-quiet)
+  DC_ENUM_LO = 4, DC_ENUM_HI = 5,   // u64: bucket entries visited by the gate
+  DC_N_CAND = 6,
+  DC_N_PTS1 = 7,
+  DC_DP1_END = 8,      // end id, path length (two consecutive words, written by dp1_kernel)
+  DC_N_PATH1 = 9,
+  DC_Q_LO = 10, DC_Q_HI = 11, DC_N_Q = 12,    // query range of this shard in the not-quiet audio list
+  DC_OVERFLOW = 13,    // bit 0 table entries, bit 1 candidates, bit 2 > 32 corridors on a row, bit 3 pass-2 points
+  DC_BAD_IMPORT = 14,
+  DC_N_PTS2 = 16,
+  DC_OVERFLOW_B = 17,  // stage B: bit 2 more than 32 corridors on one audio row
+  DC_DP2_END = 18,     // end id, path length, then the frontier value (double at words 20-21)
+  DC_N_PATH2 = 19,
+  DC_DP2_CNT = 24,     // 4 x u64 DP-2 work counters
+  DC_WORDS = 32
+};
+enum { DAB_OVF_ENTRIES = 1, DAB_OVF_CAND = 2, DAB_OVF_ROWCOR = 4, DAB_OVF_PTS2 = 8 };
 
 // stage entry points implemented in the .cu files
 int dab_run_features(dab_pair *pr, int track, const void *d_pcm, int format);
 int dab_run_stage_a(dab_pair *pr);
 int dab_run_stage_a_match(dab_pair *pr, int64_t row_lo, int64_t row_hi);   // prep .. match points of audio rows [lo, hi)
 int dab_run_stage_a_dp(dab_pair *pr);                                       // DP #1 + traceback over the pair's points
+// the same stages, enqueued on the pair's stream without waiting (counts stay on the device); the counts
+// block is copied to the mapped host page by dab_enqueue_counts and interpreted by dab_collect_*
+int dab_enqueue_stage_a_match(dab_pair *pr, int64_t row_lo, int64_t row_hi);
+int dab_enqueue_stage_a_dp(dab_pair *pr);
+int dab_enqueue_counts(dab_pair *pr);
+int dab_collect_stage_a(dab_pair *pr, bool with_dp);
+int dab_enqueue_stage_b(dab_pair *pr, int32_t n_corridors, int32_t n_clusters);
+int dab_collect_stage_b(dab_pair *pr);
 int dab_run_import_points1(dab_pair *pr, const int32_t *i_audio, const int32_t *v_video, const double *qual,
                            int64_t n, int src_on_device);
 int dab_run_stage_b(dab_pair *pr, int32_t n_corridors, int32_t n_clusters);

@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(SC_T, 1) dp2_scan_kernel(Dp2LArgs a) {
   ScanShared &S = *reinterpret_cast<ScanShared *>(sc_smem_raw);
   const unsigned FULL = 0xffffffffu;
   const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-  const int n = a.n_points;
+  const int n = *a.n_points;
   const int n_cor = a.n_cor;
   const double NEG = -INFINITY;
   const int IMAX = 0x7fffffff;

@@ -522,7 +522,7 @@ int dab_run_features(dab_pair *pr, int track, const void *d_pcm, int format) {
   else if (format == DAB_PCM_S16 && tk.ch == 2) DAB_TRY((launch<DAB_PCM_S16, 2>(pr, fa, frames)));
   else if (format == DAB_PCM_F16 && tk.ch == 1) DAB_TRY((launch<DAB_PCM_F16, 1>(pr, fa, frames)));
   else if (format == DAB_PCM_F16 && tk.ch == 2) DAB_TRY((launch<DAB_PCM_F16, 2>(pr, fa, frames)));
-  else { ctx->err = "unsupported PCM format / channel count"; return DAB_E_ARG; }
+  else { dab_set_err(ctx, "unsupported PCM format / channel count"); return DAB_E_ARG; }
   tk.have_features = true;
   return DAB_OK;
 }

@@ -146,8 +146,17 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int *total, int *smem
   return res;
 }
 
-__global__ void scan_reduce_kernel(const int32_t *in, int64_t n, int32_t *block_sums) {
+// n_dev (optional): the number of valid elements lives in device memory (a count produced earlier in
+// the same stream); launches are sized for the capacity n and elements past *n_dev count as zero.
+__device__ __forceinline__ int64_t scan_len(int64_t n, const int32_t *n_dev) {
+  if (!n_dev) return n;
+  const int64_t m = *n_dev;
+  return m < n ? (m < 0 ? 0 : m) : n;
+}
+
+__global__ void scan_reduce_kernel(const int32_t *in, int64_t n, const int32_t *n_dev, int32_t *block_sums) {
   __shared__ int sm[33];
+  n = scan_len(n, n_dev);
   const int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
   int s = 0;
 #pragma unroll
@@ -161,7 +170,7 @@ __global__ void scan_reduce_kernel(const int32_t *in, int64_t n, int32_t *block_
 }
 
 // single block: exclusive scan of the block sums in place, total to sums[nblocks]
-__global__ void scan_sums_kernel(int32_t *sums, int nblocks) {
+__global__ void scan_sums_kernel(int32_t *sums, int nblocks, int32_t *total_out) {
   __shared__ int sm[33];
   int carry = 0;
   for (int base = 0; base < nblocks; base += SCAN_THREADS) {
@@ -172,11 +181,16 @@ __global__ void scan_sums_kernel(int32_t *sums, int nblocks) {
     if (i < nblocks) sums[i] = ex + carry;
     carry += total;
   }
-  if (threadIdx.x == 0) sums[nblocks] = carry;
+  if (threadIdx.x == 0) {
+    sums[nblocks] = carry;
+    if (total_out) *total_out = carry;
+  }
 }
 
-__global__ void scan_apply_kernel(const int32_t *in, int32_t *out, int64_t n, const int32_t *block_sums, int nblocks) {
+__global__ void scan_apply_kernel(const int32_t *in, int32_t *out, int64_t n, const int32_t *n_dev,
+                                  const int32_t *block_sums, int nblocks) {
   __shared__ int sm[33];
+  n = scan_len(n, n_dev);
   const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
   int v[SCAN_ITEMS];
   int s = 0;
@@ -224,11 +238,12 @@ __device__ __forceinline__ int32_t pack_to_code(uint32_t pk) {
 
 // One thread per (selected video frame, table).  FILL = false: count; FILL = true: place.
 template <bool FILL>
-__global__ void table_kernel(const uint32_t *pack, int64_t nstride, const int32_t *sel, int64_t nsel,
-                             int32_t *count, const int32_t *start, int32_t *items) {
+__global__ void table_kernel(const uint32_t *pack, int64_t nstride, const int32_t *sel, const int32_t *dc,
+                             int32_t *count, const int32_t *start, int32_t *items, int64_t items_cap) {
   const int f = blockIdx.y;
   const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= nsel) return;
+  if (s >= dc[DC_N_VSEL]) return;
+  if (FILL && (dc[DC_OVERFLOW] & DAB_OVF_ENTRIES)) return;
   const uint32_t pk = pack[(int64_t)f * nstride + sel[s]];
   const uint32_t fl = pk >> 21;
   const int32_t base = pack_to_code(pk);
@@ -243,7 +258,8 @@ __global__ void table_kernel(const uint32_t *pack, int64_t nstride, const int32_
       atomicAdd(&count[slot], 1);
     } else {
       int pos = atomicSub(&count[slot], 1) - 1;   // consumes the counts back to zero
-      items[start[slot] + pos] = (int32_t)s;
+      const int64_t at = (int64_t)start[slot] + pos;
+      if (at < items_cap) items[at] = (int32_t)s;
     }
     if (sub == 0) break;
   }
@@ -271,7 +287,8 @@ struct GateArgs {
   const uint32_t *a_pack;
   int64_t a_nstride;
   const int32_t *a_list;    // not-quiet audio frames
-  int64_t n_queries;
+  const int32_t *dc;        // device counts: query range [DC_Q_LO, DC_Q_HI) of the list
+  int64_t q_cap;            // launch size (rows)
   const uint32_t *v_pack;   // [5][v_nstride]
   int64_t v_nstride;
   const int32_t *v_sel;     // selected video frames (rank -> frame)
@@ -288,10 +305,15 @@ template <bool FILL>
 __global__ void gate_kernel(GateArgs g) {
   const int lane = threadIdx.x & 31;
   const int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (q >= g.n_queries) return;
+  if (q >= g.q_cap) return;
+  const int32_t n_queries = g.dc[DC_N_Q];
+  if (q >= n_queries) {
+    if (!FILL && lane == 0) g.row_count[q] = 0;
+    return;
+  }
   // second pass: only the rows that have candidates (one row in six at the Ask-Dad shape) enumerate again
-  if (FILL && g.row_off[q + 1] == g.row_off[q]) return;
-  const int32_t i = g.a_list[q];
+  if (FILL && ((g.dc[DC_OVERFLOW] & DAB_OVF_CAND) || g.row_off[q + 1] == g.row_off[q])) return;
+  const int32_t i = g.a_list[g.dc[DC_Q_LO] + q];
   uint32_t ap[5];
   int32_t st[5], en[5];
 #pragma unroll
@@ -356,7 +378,7 @@ __global__ void gate_kernel(GateArgs g) {
 // ------------------------------------------------------------------------------------------
 struct ScoreArgs {
   const int32_t *cand_s, *cand_i;
-  int64_t n_cand;
+  const int32_t *dc;             // n_cand = dc[DC_N_CAND]
   const int32_t *v_sel;
   const double *a_ms, *v_ms;     // [5][stride]
   int64_t a_stride, v_stride;
@@ -368,7 +390,7 @@ struct ScoreArgs {
 
 __global__ void score_kernel(ScoreArgs s) {
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= s.n_cand) return;
+  if (c >= s.dc[DC_N_CAND]) return;
   const int32_t i = s.cand_i[c];
   const int32_t v = s.v_sel[s.cand_s[c]];
   double prob = 1.0;
@@ -389,11 +411,11 @@ __global__ void score_kernel(ScoreArgs s) {
   s.keep[c] = qual >= 0.0 ? 1 : 0;
 }
 
-__global__ void gather_points_kernel(const int32_t *keep, const int32_t *off, int64_t n,
+__global__ void gather_points_kernel(const int32_t *keep, const int32_t *off, const int32_t *dc,
                                      const int32_t *cand_i, const int32_t *cand_s, const double *qual,
                                      int32_t *pt_i, int32_t *pt_s, double *pt_q) {
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c < n && keep[c]) {
+  if (c < dc[DC_N_CAND] && keep[c]) {
     const int o = off[c];
     pt_i[o] = cand_i[c];
     pt_s[o] = cand_s[c];
@@ -418,7 +440,7 @@ constexpr int DP_CHECK = 256;   // checkpoint spacing for the parallel traceback
 struct Dp1Args {
   const int32_t *pt_s;
   const double *pt_q;
-  int32_t n_points;
+  const int32_t *n_points;       // device count
   Node1 *level[DP_LEVELS];
   int4 *meta;                    // per point (back pointer, chain length, checkpoint id, -)
   int32_t *result;               // [0] end id, [1] path length
@@ -451,7 +473,7 @@ __global__ void __launch_bounds__(32, 1) dp1_kernel(Dp1Args a) {
   __shared__ int s_r[2][32];
   __shared__ double s_q[2][32];
   const int lane = threadIdx.x;
-  const int n = a.n_points;
+  const int n = *a.n_points;
   double top_cum = 0.0;
   int top_id = -1, top_rank = -1, top_len = 0, top_cp = -1;
   const int role = lane < DP_LEVELS ? lane : 0;
@@ -638,27 +660,47 @@ __global__ void fill_nodes_kernel(Node1 *p, int64_t n) {
   if (i < n) { Node1 z; z.cum = 0.0; z.id = -1; z.rank = 0x7fffffff; p[i] = z; }
 }
 
-bool g_hann_ready[64] = {};
-
 }  // namespace
 
 // ------------------------------------------------------------------------------------------
 // host drivers
 // ------------------------------------------------------------------------------------------
-int dab_exclusive_scan(dab_pair *pr, const int32_t *in, int32_t *out, int64_t n) {
+int dab_exclusive_scan(dab_pair *pr, const int32_t *in, int32_t *out, int64_t n, const int32_t *n_dev,
+                       int32_t *total_out) {
   dab_ctx *ctx = pr->ctx;
   const int nblocks = (int)cdiv(n > 0 ? n : 1, SCAN_TILE);
   DAB_TRY(dab_ensure(ctx, pr->scan_tmp, sizeof(int32_t) * (size_t)(nblocks + 1)));
   int32_t *sums = pr->scan_tmp.as<int32_t>();
-  scan_reduce_kernel<<<nblocks, SCAN_THREADS, 0, pr->stream>>>(in, n, sums);
-  scan_sums_kernel<<<1, SCAN_THREADS, 0, pr->stream>>>(sums, nblocks);
-  scan_apply_kernel<<<nblocks, SCAN_THREADS, 0, pr->stream>>>(in, out, n, sums, nblocks);
+  scan_reduce_kernel<<<nblocks, SCAN_THREADS, 0, pr->stream>>>(in, n, n_dev, sums);
+  scan_sums_kernel<<<1, SCAN_THREADS, 0, pr->stream>>>(sums, nblocks, total_out);
+  scan_apply_kernel<<<nblocks, SCAN_THREADS, 0, pr->stream>>>(in, out, n, n_dev, sums, nblocks);
   pr->ctx->launches += 3;
   DAB_CUDA(cudaGetLastError());
   return DAB_OK;
 }
 
-static int prep_track(dab_pair *pr, int track, int64_t row_lo = 0, int64_t row_hi = 0) {
+// derived counts after both tracks' not-quiet scans: hashed video frames, this shard's query range
+static __global__ void counts_lists_kernel(int32_t *dc, const int32_t *v_off, int64_t v_n, const int32_t *a_off, int64_t a_n,
+                                    int64_t row_lo, int64_t row_hi) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int32_t n_vnq = v_off[v_n];
+  dc[DC_N_VNQ] = n_vnq;
+  dc[DC_N_VSEL] = (n_vnq + 3) / 4;
+  dc[DC_N_AQ_ALL] = a_off[a_n];
+  const int64_t lo = row_lo < 0 ? 0 : (row_lo > a_n ? a_n : row_lo);
+  const int64_t hi = row_hi < lo ? lo : (row_hi > a_n ? a_n : row_hi);
+  dc[DC_Q_LO] = a_off[lo];
+  dc[DC_Q_HI] = a_off[hi];
+  dc[DC_N_Q] = a_off[hi] - a_off[lo];
+}
+
+// a scan total against the capacity of the buffer it sizes: clamps the count and raises the overflow bit
+static __global__ void check_capacity_kernel(int32_t *dc, int word, int64_t cap, int bit) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if ((int64_t)dc[word] > cap) { dc[word] = 0; atomicOr(&dc[DC_OVERFLOW], bit); }
+}
+
+static int prep_track(dab_pair *pr, int track) {
   dab_ctx *ctx = pr->ctx;
   Track &tk = pr->trk[track];
   const int64_t Lmax = tk.Le > tk.L ? tk.Le : tk.L;
@@ -692,212 +734,253 @@ static int prep_track(dab_pair *pr, int track, int64_t row_lo = 0, int64_t row_h
   DAB_TRY(dab_ensure(ctx, tk.nq_list, sizeof(int32_t) * (size_t)(nqn + 2)));
   int32_t *flag = tk.nq_flag.as<int32_t>();
   int32_t *off = flag + (nqn + 1);
-  notquiet_flag_kernel<<<(unsigned)cdiv(nqn, 256), 256, 0, pr->stream>>>(tk.energy.as<float>(), nqn, flag);
+  notquiet_flag_kernel<<<(unsigned)cdiv(nqn, 256), 256, 0, pr->stream>>>(tk.have_gate ? tk.gate.as<float>() : tk.energy.as<float>(), nqn, flag);
   ctx->launches += 1;
   DAB_TRY(dab_exclusive_scan(pr, flag, off, nqn));
   compact_kernel<<<(unsigned)cdiv(nqn, 256), 256, 0, pr->stream>>>(flag, off, nqn, track == DAB_TRACK_VIDEO ? 4 : 1,
                                                                   tk.nq_list.as<int32_t>());
   ctx->launches += 1;
-  DAB_CUDA(dab_readback(pr, &pr->h_counters[track], off + nqn, sizeof(int32_t)));
-  if (track == DAB_TRACK_AUDIO) {
-    // list positions of the first not-quiet frame >= row_lo / >= row_hi (row-sharded match stage)
-    const int64_t lo = row_lo < 0 ? 0 : (row_lo > nqn ? nqn : row_lo), hi = row_hi < lo ? lo : (row_hi > nqn ? nqn : row_hi);
-    DAB_CUDA(dab_readback(pr, &pr->h_counters[20], off + lo, sizeof(int32_t)));
-    DAB_CUDA(dab_readback(pr, &pr->h_counters[21], off + hi, sizeof(int32_t)));
-  }
   DAB_CUDA(cudaGetLastError());
   return DAB_OK;
 }
 
-int dab_run_stage_a_match(dab_pair *pr, int64_t row_lo, int64_t row_hi) {
-  dab_ctx *ctx = pr->ctx;
+static int ensure_hann(dab_ctx *ctx) {
+  static std::atomic<int> ready[64];
   int dev = 0;
   DAB_CUDA(cudaGetDevice(&dev));
-  if (!(dev < 64 && g_hann_ready[dev])) {
-    double hf[41];
-    for (int k = 0; k < 41; ++k) hf[k] = DAB_HANN41_F64[40 - k];
-    DAB_CUDA(cudaMemcpyToSymbol(c_hflip, hf, sizeof(hf)));
-    if (dev < 64) g_hann_ready[dev] = true;
-  }
+  if (dev < 64 && ready[dev].load(std::memory_order_acquire)) return DAB_OK;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> g(mu);
+  if (dev < 64 && ready[dev].load(std::memory_order_acquire)) return DAB_OK;
+  double hf[41];
+  for (int k = 0; k < 41; ++k) hf[k] = DAB_HANN41_F64[40 - k];
+  DAB_CUDA(cudaMemcpyToSymbol(c_hflip, hf, sizeof(hf)));
+  if (dev < 64) ready[dev].store(1, std::memory_order_release);
+  return DAB_OK;
+}
+
+// Capacities of the buffers whose fill level only the device knows (table entries, candidates).  They
+// start from what pairs of this size normally need and double when a run overflows (the overflow bit
+// comes back with the counts; the stage is then run again - rare, and only ever during the first pairs).
+static void default_caps(dab_pair *pr) {
+  Track &V = pr->trk[DAB_TRACK_VIDEO], &A = pr->trk[DAB_TRACK_AUDIO];
+  const int64_t vsel_ub = (V.Le - 41 + 3) / 4 + 1;
+  const int64_t q_ub = A.Le - 41;
+  const int64_t want_e = 5 * 16 * vsel_ub + 4096;        // ~10 expanded entries per frame and table
+  const int64_t want_c = 2 * q_ub + 4096;                // < 1 candidate per query on matching tracks
+  if (pr->cap_entries < want_e) pr->cap_entries = want_e;
+  if (pr->cap_cand < want_c) pr->cap_cand = want_c;
+}
+
+// ---- match stage, enqueued without a host round trip: prep, codes, lists, tables, gate, scoring ----
+int dab_enqueue_stage_a_match(dab_pair *pr, int64_t row_lo, int64_t row_hi) {
+  dab_ctx *ctx = pr->ctx;
+  DAB_TRY(ensure_hann(ctx));
   Track &V = pr->trk[DAB_TRACK_VIDEO], &A = pr->trk[DAB_TRACK_AUDIO];
   cudaStream_t st = pr->stream;
   pr->n_points1 = pr->n_path1 = 0;
+  default_caps(pr);
+  const int64_t v_nq = V.Le - 41, a_nq = A.Le - 41;
+  const int64_t vsel_ub = (v_nq + 3) / 4 + 1, q_ub = a_nq > 0 ? a_nq : 1;
+  const int64_t cap_e = pr->cap_entries, cap_c = pr->cap_cand;
 
+  DAB_TRY(dab_ensure(ctx, pr->counters, sizeof(int32_t) * DC_WORDS));
+  int32_t *dc = pr->counters.as<int32_t>();
   DAB_CUDA(cudaEventRecord(pr->ev[4], st));
-  pr->h_counters[0] = pr->h_counters[1] = 0;
+  DAB_CUDA(cudaMemsetAsync(dc, 0, sizeof(int32_t) * DC_WORDS, st));
   DAB_TRY(prep_track(pr, DAB_TRACK_VIDEO));
-  DAB_TRY(prep_track(pr, DAB_TRACK_AUDIO, row_lo, row_hi));
+  DAB_TRY(prep_track(pr, DAB_TRACK_AUDIO));
+  counts_lists_kernel<<<1, 32, 0, st>>>(dc, V.nq_flag.as<int32_t>() + (v_nq + 1), v_nq, A.nq_flag.as<int32_t>() + (a_nq + 1), a_nq,
+                                        row_lo, row_hi);
+  ctx->launches += 1;
   DAB_CUDA(cudaEventRecord(pr->ev[5], st));
-  DAB_CUDA(dab_wait_stream(st));
-  const int64_t n_vnq = (int32_t)pr->h_counters[0];
-  const int64_t n_vsel = (n_vnq + 3) / 4;
-  const int64_t n_q_all = (int32_t)pr->h_counters[1];
-  const int64_t q_lo = (int32_t)pr->h_counters[20], q_hi = (int32_t)pr->h_counters[21];
-  const int64_t n_q = q_hi - q_lo;          // queries of this shard (all of them unless row-sharded)
-  V.n_list = n_vsel;
-  A.n_list = n_q_all;
   pr->stats.n_video_frames = V.L; pr->stats.n_audio_frames = A.L;
-  pr->stats.n_video_selected = n_vsel; pr->stats.n_audio_queries = n_q;
 
   // ---- tables ----
   const int64_t nslots = 5LL * DAB_NCODE;
   DAB_TRY(dab_ensure(ctx, pr->tbl_count, sizeof(int32_t) * (size_t)(nslots + 1)));
   DAB_TRY(dab_ensure(ctx, pr->tbl_start, sizeof(int32_t) * (size_t)(nslots + 2)));
-  DAB_TRY(dab_ensure(ctx, pr->counters, sizeof(int64_t) * 16));
+  DAB_TRY(dab_ensure(ctx, pr->tbl_items, sizeof(int32_t) * (size_t)(cap_e + 1)));
   DAB_CUDA(cudaMemsetAsync(pr->tbl_count.p, 0, sizeof(int32_t) * (size_t)(nslots + 1), st));
-  DAB_CUDA(cudaMemsetAsync(pr->counters.p, 0, sizeof(int64_t) * 16, st));
   const int64_t v_nstride = (V.Le > V.L ? V.Le : V.L) - 40;
   const int64_t a_nstride = (A.Le > A.L ? A.Le : A.L) - 40;
   DAB_CUDA(cudaEventRecord(pr->ev[6], st));
-  if (n_vsel > 0) {
-    dim3 gt((unsigned)cdiv(n_vsel, 128), 5);
-    table_kernel<false><<<gt, 128, 0, st>>>(V.pack.as<uint32_t>(), v_nstride, V.nq_list.as<int32_t>(), n_vsel,
-                                            pr->tbl_count.as<int32_t>(), nullptr, nullptr);
-    ctx->launches += 1;
-  }
-  DAB_TRY(dab_exclusive_scan(pr, pr->tbl_count.as<int32_t>(), pr->tbl_start.as<int32_t>(), nslots));
-  DAB_CUDA(dab_readback(pr, &pr->h_counters[2], pr->tbl_start.as<int32_t>() + nslots, sizeof(int32_t)));
-  DAB_CUDA(dab_wait_stream(st));
-  const int64_t n_entries = (int32_t)pr->h_counters[2];
-  pr->stats.n_table_entries = n_entries;
-  DAB_TRY(dab_ensure(ctx, pr->tbl_items, sizeof(int32_t) * (size_t)(n_entries + 1)));
-  if (n_vsel > 0) {
-    dim3 gt((unsigned)cdiv(n_vsel, 128), 5);
-    table_kernel<true><<<gt, 128, 0, st>>>(V.pack.as<uint32_t>(), v_nstride, V.nq_list.as<int32_t>(), n_vsel,
-                                           pr->tbl_count.as<int32_t>(), pr->tbl_start.as<int32_t>(),
-                                           pr->tbl_items.as<int32_t>());
-    ctx->launches += 1;
-  }
+  dim3 gt((unsigned)cdiv(vsel_ub, 128), 5);
+  table_kernel<false><<<gt, 128, 0, st>>>(V.pack.as<uint32_t>(), v_nstride, V.nq_list.as<int32_t>(), dc,
+                                          pr->tbl_count.as<int32_t>(), nullptr, nullptr, 0);
+  ctx->launches += 1;
+  DAB_TRY(dab_exclusive_scan(pr, pr->tbl_count.as<int32_t>(), pr->tbl_start.as<int32_t>(), nslots, nullptr, dc + DC_N_ENTRIES));
+  check_capacity_kernel<<<1, 32, 0, st>>>(dc, DC_N_ENTRIES, cap_e, DAB_OVF_ENTRIES);
+  table_kernel<true><<<gt, 128, 0, st>>>(V.pack.as<uint32_t>(), v_nstride, V.nq_list.as<int32_t>(), dc,
+                                         pr->tbl_count.as<int32_t>(), pr->tbl_start.as<int32_t>(),
+                                         pr->tbl_items.as<int32_t>(), cap_e);
+  ctx->launches += 2;
   DAB_CUDA(cudaEventRecord(pr->ev[7], st));
 
   // ---- gate: count, scan, fill ----
-  DAB_TRY(dab_ensure(ctx, pr->row_count, sizeof(int32_t) * (size_t)(n_q + 2)));
-  DAB_TRY(dab_ensure(ctx, pr->row_off, sizeof(int32_t) * (size_t)(n_q + 2)));
+  DAB_TRY(dab_ensure(ctx, pr->row_count, sizeof(int32_t) * (size_t)(q_ub + 2)));
+  DAB_TRY(dab_ensure(ctx, pr->row_off, sizeof(int32_t) * (size_t)(q_ub + 2)));
+  DAB_TRY(dab_ensure(ctx, pr->cand_tmp, sizeof(int32_t) * (size_t)(cap_c + 1)));
+  DAB_TRY(dab_ensure(ctx, pr->cand_s, sizeof(int32_t) * (size_t)(cap_c + 1)));
+  DAB_TRY(dab_ensure(ctx, pr->cand_i, sizeof(int32_t) * (size_t)(cap_c + 1)));
   GateArgs ga;
   ga.a_code = A.code.as<int32_t>(); ga.a_pack = A.pack.as<uint32_t>(); ga.a_nstride = a_nstride;
-  ga.a_list = A.nq_list.as<int32_t>() + q_lo; ga.n_queries = n_q;
+  ga.a_list = A.nq_list.as<int32_t>(); ga.dc = dc; ga.q_cap = q_ub;
   ga.v_pack = V.pack.as<uint32_t>(); ga.v_nstride = v_nstride; ga.v_sel = V.nq_list.as<int32_t>();
   ga.start = pr->tbl_start.as<int32_t>(); ga.items = pr->tbl_items.as<int32_t>();
   ga.row_count = pr->row_count.as<int32_t>(); ga.row_off = pr->row_off.as<int32_t>();
-  ga.cand_tmp = ga.cand_s = ga.cand_i = nullptr; ga.cand_cap = 0;
-  ga.enumerated = reinterpret_cast<unsigned long long *>(pr->counters.as<int64_t>() + 3);
+  ga.cand_tmp = pr->cand_tmp.as<int32_t>(); ga.cand_s = pr->cand_s.as<int32_t>(); ga.cand_i = pr->cand_i.as<int32_t>();
+  ga.cand_cap = cap_c;
+  ga.enumerated = reinterpret_cast<unsigned long long *>(dc + DC_ENUM_LO);
   DAB_CUDA(cudaEventRecord(pr->ev[8], st));
-  int64_t n_cand = 0;
-  if (n_q > 0) {
-    const unsigned gb = (unsigned)cdiv(n_q * 32, 256);
-    gate_kernel<false><<<gb, 256, 0, st>>>(ga);
-    ctx->launches += 1;
-    DAB_TRY(dab_exclusive_scan(pr, pr->row_count.as<int32_t>(), pr->row_off.as<int32_t>(), n_q));
-    DAB_CUDA(dab_readback(pr, &pr->h_counters[4], pr->row_off.as<int32_t>() + n_q, sizeof(int32_t)));
-    DAB_CUDA(dab_readback(pr, &pr->h_counters[3], pr->counters.as<int64_t>() + 3, sizeof(int64_t)));
-    DAB_CUDA(dab_wait_stream(st));
-    n_cand = (int32_t)pr->h_counters[4];
-    pr->stats.n_enumerated = pr->h_counters[3];
-    DAB_TRY(dab_ensure(ctx, pr->cand_tmp, sizeof(int32_t) * (size_t)(n_cand + 1)));
-    DAB_TRY(dab_ensure(ctx, pr->cand_s, sizeof(int32_t) * (size_t)(n_cand + 1)));
-    DAB_TRY(dab_ensure(ctx, pr->cand_i, sizeof(int32_t) * (size_t)(n_cand + 1)));
-    ga.cand_tmp = pr->cand_tmp.as<int32_t>(); ga.cand_s = pr->cand_s.as<int32_t>(); ga.cand_i = pr->cand_i.as<int32_t>();
-    ga.cand_cap = n_cand;
-    if (n_cand > 0) {
-      gate_kernel<true><<<gb, 256, 0, st>>>(ga);
-      ctx->launches += 1;
-    }
-  }
-  pr->stats.n_candidates = n_cand;
+  const unsigned gb = (unsigned)cdiv(q_ub * 32, 256);
+  gate_kernel<false><<<gb, 256, 0, st>>>(ga);
+  DAB_TRY(dab_exclusive_scan(pr, pr->row_count.as<int32_t>(), pr->row_off.as<int32_t>(), q_ub, nullptr, dc + DC_N_CAND));
+  check_capacity_kernel<<<1, 32, 0, st>>>(dc, DC_N_CAND, cap_c, DAB_OVF_CAND);
+  gate_kernel<true><<<gb, 256, 0, st>>>(ga);
+  ctx->launches += 3;
   DAB_CUDA(cudaEventRecord(pr->ev[9], st));
 
   // ---- scoring + compaction ----
   DAB_CUDA(cudaEventRecord(pr->ev[10], st));
-  int64_t n_pts = 0;
-  if (n_cand > 0) {
-    DAB_TRY(dab_ensure(ctx, pr->cand_q, sizeof(double) * (size_t)(n_cand + 1)));
-    DAB_TRY(dab_ensure(ctx, pr->keep_flag, sizeof(int32_t) * (size_t)(n_cand + 2)));
-    DAB_TRY(dab_ensure(ctx, pr->keep_off, sizeof(int32_t) * (size_t)(n_cand + 2)));
-    ScoreArgs sa;
-    sa.cand_s = pr->cand_s.as<int32_t>(); sa.cand_i = pr->cand_i.as<int32_t>(); sa.n_cand = n_cand;
-    sa.v_sel = V.nq_list.as<int32_t>();
-    sa.a_ms = A.ms.as<double>(); sa.v_ms = V.ms.as<double>();
-    sa.a_stride = (A.Le > A.L ? A.Le : A.L); sa.v_stride = (V.Le > V.L ? V.Le : V.L);
-    sa.a_nrm = A.nrm.as<double>(); sa.v_nrm = V.nrm.as<double>();
-    sa.a_nstride = a_nstride; sa.v_nstride = v_nstride;
-    sa.qual = pr->cand_q.as<double>(); sa.keep = pr->keep_flag.as<int32_t>();
-    score_kernel<<<(unsigned)cdiv(n_cand, 128), 128, 0, st>>>(sa);
-    ctx->launches += 1;
-    DAB_TRY(dab_exclusive_scan(pr, pr->keep_flag.as<int32_t>(), pr->keep_off.as<int32_t>(), n_cand));
-    DAB_CUDA(dab_readback(pr, &pr->h_counters[5], pr->keep_off.as<int32_t>() + n_cand, sizeof(int32_t)));
-    DAB_CUDA(dab_wait_stream(st));
-    n_pts = (int32_t)pr->h_counters[5];
-    DAB_TRY(dab_ensure(ctx, pr->pt_i, sizeof(int32_t) * (size_t)(n_pts + 1)));
-    DAB_TRY(dab_ensure(ctx, pr->pt_s, sizeof(int32_t) * (size_t)(n_pts + 1)));
-    DAB_TRY(dab_ensure(ctx, pr->pt_q, sizeof(double) * (size_t)(n_pts + 1)));
-    if (n_pts > 0) {
-      gather_points_kernel<<<(unsigned)cdiv(n_cand, 256), 256, 0, st>>>(
-          pr->keep_flag.as<int32_t>(), pr->keep_off.as<int32_t>(), n_cand, pr->cand_i.as<int32_t>(),
-          pr->cand_s.as<int32_t>(), pr->cand_q.as<double>(), pr->pt_i.as<int32_t>(), pr->pt_s.as<int32_t>(),
-          pr->pt_q.as<double>());
-      ctx->launches += 1;
-    }
-  }
-  pr->n_points1 = n_pts;
-  pr->stats.n_points1 = n_pts;
+  DAB_TRY(dab_ensure(ctx, pr->cand_q, sizeof(double) * (size_t)(cap_c + 1)));
+  DAB_TRY(dab_ensure(ctx, pr->keep_flag, sizeof(int32_t) * (size_t)(cap_c + 2)));
+  DAB_TRY(dab_ensure(ctx, pr->keep_off, sizeof(int32_t) * (size_t)(cap_c + 2)));
+  DAB_TRY(dab_ensure(ctx, pr->pt_i, sizeof(int32_t) * (size_t)(cap_c + 1)));
+  DAB_TRY(dab_ensure(ctx, pr->pt_s, sizeof(int32_t) * (size_t)(cap_c + 1)));
+  DAB_TRY(dab_ensure(ctx, pr->pt_q, sizeof(double) * (size_t)(cap_c + 1)));
+  ScoreArgs sa;
+  sa.cand_s = pr->cand_s.as<int32_t>(); sa.cand_i = pr->cand_i.as<int32_t>(); sa.dc = dc;
+  sa.v_sel = V.nq_list.as<int32_t>();
+  sa.a_ms = A.ms.as<double>(); sa.v_ms = V.ms.as<double>();
+  sa.a_stride = (A.Le > A.L ? A.Le : A.L); sa.v_stride = (V.Le > V.L ? V.Le : V.L);
+  sa.a_nrm = A.nrm.as<double>(); sa.v_nrm = V.nrm.as<double>();
+  sa.a_nstride = a_nstride; sa.v_nstride = v_nstride;
+  sa.qual = pr->cand_q.as<double>(); sa.keep = pr->keep_flag.as<int32_t>();
+  score_kernel<<<(unsigned)cdiv(cap_c, 128), 128, 0, st>>>(sa);
+  DAB_TRY(dab_exclusive_scan(pr, pr->keep_flag.as<int32_t>(), pr->keep_off.as<int32_t>(), cap_c, dc + DC_N_CAND, dc + DC_N_PTS1));
+  gather_points_kernel<<<(unsigned)cdiv(cap_c, 256), 256, 0, st>>>(
+      pr->keep_flag.as<int32_t>(), pr->keep_off.as<int32_t>(), dc, pr->cand_i.as<int32_t>(),
+      pr->cand_s.as<int32_t>(), pr->cand_q.as<double>(), pr->pt_i.as<int32_t>(), pr->pt_s.as<int32_t>(),
+      pr->pt_q.as<double>());
+  ctx->launches += 2;
   DAB_CUDA(cudaEventRecord(pr->ev[11], st));
   for (int s = 2; s <= 5; ++s) pr->ev_used[s] = true;
+  pr->cap_points1 = cap_c;
   DAB_CUDA(cudaGetLastError());
   return DAB_OK;
 }
 
-// ---- DP #1 + traceback over pr->pt_* (n_points1 points sorted by (audio frame, video rank)) ----
-int dab_run_stage_a_dp(dab_pair *pr) {
+// ---- DP #1 + traceback over pr->pt_* (dc[DC_N_PTS1] points sorted by (audio frame, video rank)) ----
+int dab_enqueue_stage_a_dp(dab_pair *pr) {
   dab_ctx *ctx = pr->ctx;
   Track &V = pr->trk[DAB_TRACK_VIDEO];
   cudaStream_t st = pr->stream;
-  const int64_t n_pts = pr->n_points1, n_vsel = V.n_list;
+  int32_t *dc = pr->counters.as<int32_t>();
+  const int64_t cap_p = pr->cap_points1 > 0 ? pr->cap_points1 : 1;
+  const int64_t vsel_ub = (V.Le - 41 + 3) / 4 + 1;
   DAB_CUDA(cudaEventRecord(pr->ev[12], st));
-  int64_t n_path = 0;
-  if (n_pts > 0) {
-    if (n_vsel > (1LL << (5 * DP_LEVELS))) { ctx->err = "too many hashed video frames for the DP tree"; return DAB_E_CAPACITY; }
-    int64_t lv[DP_LEVELS], tot = 0;
-    int64_t m = n_vsel;
-    for (int k = 0; k < DP_LEVELS; ++k) { lv[k] = cdiv(m > 0 ? m : 1, 32) * 32; tot += lv[k]; m = cdiv(m, 32); }
-    DAB_TRY(dab_ensure(ctx, pr->tree1, sizeof(Node1) * (size_t)tot));
-    fill_nodes_kernel<<<(unsigned)cdiv(tot, 256), 256, 0, st>>>(pr->tree1.as<Node1>(), tot);
-    DAB_TRY(dab_ensure(ctx, pr->back1, sizeof(int4) * (size_t)(n_pts + 1)));
-    DAB_TRY(dab_ensure(ctx, pr->dpres, sizeof(int32_t) * 8));
-    DAB_TRY(dab_ensure(ctx, pr->seglist, sizeof(int32_t) * (size_t)(n_pts / DP_CHECK + 16)));
-    DAB_TRY(dab_ensure(ctx, pr->path1_x, sizeof(int32_t) * (size_t)(n_pts + 1)));
-    DAB_TRY(dab_ensure(ctx, pr->path1_y, sizeof(int32_t) * (size_t)(n_pts + 1)));
-    Dp1Args da;
-    da.pt_s = pr->pt_s.as<int32_t>(); da.pt_q = pr->pt_q.as<double>();
-    da.n_points = (int32_t)n_pts;
-    Node1 *base = pr->tree1.as<Node1>();
-    for (int k = 0; k < DP_LEVELS; ++k) { da.level[k] = base; base += lv[k]; }
-    da.meta = pr->back1.as<int4>();
-    da.result = pr->dpres.as<int32_t>();
-    dp1_kernel<<<1, 32, 0, st>>>(da);
-    DAB_CUDA(dab_wait_stream(st));   // keep dependents of the serial DP out of the hardware queues (see stage_b.cu)
-    TraceArgs ta;
-    ta.meta = da.meta; ta.result = da.result;
-    ta.pt_i = pr->pt_i.as<int32_t>(); ta.pt_s = pr->pt_s.as<int32_t>(); ta.v_sel = V.nq_list.as<int32_t>();
-    ta.seg = pr->seglist.as<int32_t>(); ta.path_x = pr->path1_x.as<int32_t>(); ta.path_y = pr->path1_y.as<int32_t>();
-    trace1_kernel<<<1, 256, 0, st>>>(ta);
-    ctx->launches += 3;
-    DAB_CUDA(dab_readback(pr, &pr->h_counters[6], pr->dpres.as<int32_t>(), 2 * sizeof(int32_t)));
-    DAB_CUDA(cudaEventRecord(pr->ev[13], st));
-    DAB_CUDA(dab_wait_stream(st));
-    n_path = reinterpret_cast<int32_t *>(&pr->h_counters[6])[1];
-  } else {
-    DAB_CUDA(cudaEventRecord(pr->ev[13], st));
-  }
-  pr->n_path1 = n_path;
-  pr->stats.n_path1 = n_path;
+  if (vsel_ub > (1LL << (5 * DP_LEVELS))) { dab_set_err(ctx, "too many hashed video frames for the DP tree"); return DAB_E_CAPACITY; }
+  int64_t lv[DP_LEVELS], tot = 0;
+  int64_t m = vsel_ub;
+  for (int k = 0; k < DP_LEVELS; ++k) { lv[k] = cdiv(m > 0 ? m : 1, 32) * 32; tot += lv[k]; m = cdiv(m, 32); }
+  DAB_TRY(dab_ensure(ctx, pr->tree1, sizeof(Node1) * (size_t)tot));
+  fill_nodes_kernel<<<(unsigned)cdiv(tot, 256), 256, 0, st>>>(pr->tree1.as<Node1>(), tot);
+  DAB_TRY(dab_ensure(ctx, pr->back1, sizeof(int4) * (size_t)(cap_p + 1)));
+  DAB_TRY(dab_ensure(ctx, pr->seglist, sizeof(int32_t) * (size_t)(cap_p / DP_CHECK + 16)));
+  DAB_TRY(dab_ensure(ctx, pr->path1_x, sizeof(int32_t) * (size_t)(cap_p + 1)));
+  DAB_TRY(dab_ensure(ctx, pr->path1_y, sizeof(int32_t) * (size_t)(cap_p + 1)));
+  Dp1Args da;
+  da.pt_s = pr->pt_s.as<int32_t>(); da.pt_q = pr->pt_q.as<double>();
+  da.n_points = dc + DC_N_PTS1;
+  Node1 *base = pr->tree1.as<Node1>();
+  for (int k = 0; k < DP_LEVELS; ++k) { da.level[k] = base; base += lv[k]; }
+  da.meta = pr->back1.as<int4>();
+  da.result = dc + DC_DP1_END;
+  dp1_kernel<<<1, 32, 0, st>>>(da);
+  TraceArgs ta;
+  ta.meta = da.meta; ta.result = da.result;
+  ta.pt_i = pr->pt_i.as<int32_t>(); ta.pt_s = pr->pt_s.as<int32_t>(); ta.v_sel = V.nq_list.as<int32_t>();
+  ta.seg = pr->seglist.as<int32_t>(); ta.path_x = pr->path1_x.as<int32_t>(); ta.path_y = pr->path1_y.as<int32_t>();
+  trace1_kernel<<<1, 256, 0, st>>>(ta);
+  ctx->launches += 3;
+  DAB_CUDA(cudaEventRecord(pr->ev[13], st));
   pr->ev_used[6] = true;
   DAB_CUDA(cudaGetLastError());
   return DAB_OK;
 }
 
+// The counts of the stage, copied to the pair's mapped host page by the stream (dab_enqueue_counts) and
+// read here once the stream has passed that point.  Returns DAB_E_CAPACITY after growing the capacity
+// that overflowed: the caller runs the stage again.
+int dab_enqueue_counts(dab_pair *pr) {
+  dab_ctx *ctx = pr->ctx;
+  DAB_CUDA(dab_readback(pr, pr->h_counters, pr->counters.as<int32_t>(), sizeof(int32_t) * DC_WORDS));
+  return DAB_OK;
+}
+
+int dab_collect_stage_a(dab_pair *pr, bool with_dp) {
+  dab_ctx *ctx = pr->ctx;
+  const int32_t *hc = reinterpret_cast<const int32_t *>(pr->h_counters);
+  Track &V = pr->trk[DAB_TRACK_VIDEO], &A = pr->trk[DAB_TRACK_AUDIO];
+  V.n_list = hc[DC_N_VSEL];
+  A.n_list = hc[DC_N_AQ_ALL];
+  pr->stats.n_video_selected = hc[DC_N_VSEL];
+  pr->stats.n_audio_queries = hc[DC_N_Q];
+  pr->stats.n_table_entries = hc[DC_N_ENTRIES];
+  pr->stats.n_enumerated = (int64_t)(((uint64_t)(uint32_t)hc[DC_ENUM_HI] << 32) | (uint32_t)hc[DC_ENUM_LO]);
+  pr->stats.n_candidates = hc[DC_N_CAND];
+  const int ovf = hc[DC_OVERFLOW];
+  if (ovf & (DAB_OVF_ENTRIES | DAB_OVF_CAND)) {
+    if (ovf & DAB_OVF_ENTRIES) pr->cap_entries *= 2;
+    if (ovf & DAB_OVF_CAND) pr->cap_cand *= 2;
+    dab_set_err(ctx, "stage A: a device buffer overflowed, capacity doubled");
+    return DAB_E_CAPACITY;
+  }
+  pr->n_points1 = hc[DC_N_PTS1];
+  pr->stats.n_points1 = pr->n_points1;
+  if (with_dp) {
+    pr->n_path1 = hc[DC_DP1_END] < 0 ? 0 : hc[DC_N_PATH1];
+    pr->stats.n_path1 = pr->n_path1;
+  }
+  return DAB_OK;
+}
+
+int dab_run_stage_a_match(dab_pair *pr, int64_t row_lo, int64_t row_hi) {
+  dab_ctx *ctx = pr->ctx;
+  for (int attempt = 0; attempt < 8; ++attempt) {
+    DAB_TRY(dab_enqueue_stage_a_match(pr, row_lo, row_hi));
+    DAB_TRY(dab_enqueue_counts(pr));
+    DAB_CUDA(dab_wait_stream(pr->stream));
+    const int rc = dab_collect_stage_a(pr, false);
+    if (rc != DAB_E_CAPACITY) return rc;
+  }
+  return DAB_E_CAPACITY;
+}
+
+int dab_run_stage_a_dp(dab_pair *pr) {
+  dab_ctx *ctx = pr->ctx;
+  if (pr->cap_points1 < pr->n_points1) pr->cap_points1 = pr->n_points1;
+  DAB_TRY(dab_enqueue_stage_a_dp(pr));
+  DAB_TRY(dab_enqueue_counts(pr));
+  DAB_CUDA(dab_wait_stream(pr->stream));
+  const int32_t *hc = reinterpret_cast<const int32_t *>(pr->h_counters);
+  pr->n_path1 = (pr->n_points1 <= 0 || hc[DC_DP1_END] < 0) ? 0 : hc[DC_N_PATH1];
+  pr->stats.n_path1 = pr->n_path1;
+  return DAB_OK;
+}
+
 int dab_run_stage_a(dab_pair *pr) {
-  DAB_TRY(dab_run_stage_a_match(pr, 0, INT64_MAX));
-  return dab_run_stage_a_dp(pr);
+  dab_ctx *ctx = pr->ctx;
+  for (int attempt = 0; attempt < 8; ++attempt) {
+    DAB_TRY(dab_enqueue_stage_a_match(pr, 0, INT64_MAX));
+    DAB_TRY(dab_enqueue_stage_a_dp(pr));
+    DAB_TRY(dab_enqueue_counts(pr));
+    DAB_CUDA(dab_wait_stream(pr->stream));
+    const int rc = dab_collect_stage_a(pr, true);
+    if (rc != DAB_E_CAPACITY) return rc;
+  }
+  return DAB_E_CAPACITY;
 }
 
 // ---- row-sharded match stage: exchange of match points -----------------------------------
@@ -917,6 +1000,10 @@ __global__ void frames_to_ranks_kernel(const int32_t *v_frame, int64_t n, const 
   rank[k] = lo;
 }
 }  // namespace
+
+static __global__ void set_word_kernel(int32_t *dc, int word, int32_t value) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) dc[word] = value;
+}
 
 int dab_run_import_points1(dab_pair *pr, const int32_t *i_audio, const int32_t *v_video, const double *qual,
                            int64_t n, int src_on_device) {
@@ -941,10 +1028,13 @@ int dab_run_import_points1(dab_pair *pr, const int32_t *i_audio, const int32_t *
     DAB_CUDA(dab_readback(pr, &pr->h_counters[22], pr->dpres.as<int32_t>() + 8, sizeof(int32_t)));
     DAB_CUDA(dab_wait_stream(st));
     if ((int32_t)pr->h_counters[22] != 0) {
-      ctx->err = "import_points1: a point's video frame is not one of this pair's hashed video frames";
+      dab_set_err(ctx, "import_points1: a point's video frame is not one of this pair's hashed video frames");
       return DAB_E_ARG;
     }
   }
+  set_word_kernel<<<1, 32, 0, st>>>(pr->counters.as<int32_t>(), DC_N_PTS1, (int32_t)n);
+  ctx->launches += 1;
+  DAB_CUDA(cudaGetLastError());
   pr->n_points1 = n;
   pr->stats.n_points1 = n;
   pr->n_path1 = 0;

@@ -83,7 +83,7 @@ __global__ void corridor_kernel(ScoreBArgs s) {
     bool dup = false;
     for (int m = 0; m < n; ++m) dup = dup || ((long long)js[m] == cell);
     if (dup) continue;     // an earlier (lower-index) cluster already claimed (i, int(j))
-    if (n == MAXC) { atomicExch(s.overflow, 1); break; }
+    if (n == MAXC) { atomicOr(s.overflow, DAB_OVF_ROWCOR); break; }
     js[n] = j; cs[n] = c.cluster; ks[n] = k; ++n;
   }
   if (!FILL) { s.row_count[i] = n; return; }
@@ -198,7 +198,7 @@ constexpr int CHECK2 = 256;
 struct Dp2Args {
   const int32_t *p_i, *p_c, *p_rank;
   const double *p_j, *p_q;
-  int32_t n_points;
+  const int32_t *n_points;   // device count
   Node2 *level[L2N];
   Cell2 *cache;
   double *cb_val;     // per cluster: cum - 50 of its best point
@@ -219,7 +219,7 @@ __device__ __forceinline__ bool key2_better(double va, int ra, double vb, int rb
 
 __global__ void __launch_bounds__(32, 1) dp2_kernel(Dp2Args a) {
   const int lane = threadIdx.x;
-  const int n = a.n_points;
+  const int n = *a.n_points;
   // the overall best frontier entry: starts as the seed (val 0 at rank 0)
   double top_val = 0.0;
   int top_id = -1, top_rank = 0;
@@ -432,10 +432,10 @@ constexpr int WLEN = 16;     // rows per window
 struct Dp2LArgs {
   const P2Rec *rec;
   const double *p_j;
-  int32_t n_points;
+  const int32_t *n_points;   // device count
   const dab_corridor *cor;
   int32_t n_cor;
-  const int64_t *pm_off;     // [n_cor] first PM row of each corridor
+  int64_t pm_off[32];        // first PM row of each corridor
   PmEntry *pm;
   BackRec *back;
   int32_t *result;           // [0] end id ; double top value at +2
@@ -492,7 +492,7 @@ __global__ void __launch_bounds__(32, 1) dp2_block_kernel(Dp2LArgs a) {
 
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x;
-  const int n = a.n_points;
+  const int n = *a.n_points;
   const int n_cor = a.n_cor;
   const double NEG = -INFINITY;
 
@@ -1167,8 +1167,9 @@ __global__ void __launch_bounds__(32, 1) dp2_block_kernel(Dp2LArgs a) {
 // depth doubles alongside; the ancestors of the end point are marked level by level from the
 // top; each marked point writes its own path row at position depth - 1.
 // ------------------------------------------------------------------------------------------
-__global__ void lift_init_kernel(const BackRec *back, int32_t n, int32_t *up0, int32_t *dep0, int32_t *mark,
+__global__ void lift_init_kernel(const BackRec *back, const int32_t *n_dev, int32_t *up0, int32_t *dep0, int32_t *mark,
                                  const int32_t *result) {
+  const int n = *n_dev;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p > n) return;
   if (p == n) { up0[p] = n; dep0[p] = 0; mark[p] = 0; return; }
@@ -1178,8 +1179,9 @@ __global__ void lift_init_kernel(const BackRec *back, int32_t n, int32_t *up0, i
   mark[p] = (p == result[0]) ? 1 : 0;
 }
 
-__global__ void lift_step_kernel(const int32_t *up_in, const int32_t *dep_in, int32_t n, int32_t *up_out,
+__global__ void lift_step_kernel(const int32_t *up_in, const int32_t *dep_in, const int32_t *n_dev, int32_t *up_out,
                                  int32_t *dep_out) {
+  const int n = *n_dev;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p > n) return;
   const int u = up_in[p];
@@ -1187,7 +1189,8 @@ __global__ void lift_step_kernel(const int32_t *up_in, const int32_t *dep_in, in
   dep_out[p] = dep_in[p] + dep_in[u];
 }
 
-__global__ void lift_mark_kernel(const int32_t *up_k, int32_t n, int32_t *mark) {
+__global__ void lift_mark_kernel(const int32_t *up_k, const int32_t *n_dev, int32_t *mark) {
+  const int n = *n_dev;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n || !mark[p]) return;
   const int u = up_k[p];
@@ -1199,14 +1202,14 @@ struct EmitArgs {
   const BackRec *back;
   const int32_t *p_i, *p_c;
   const double *p_j, *p_q;
-  int32_t n;
+  const int32_t *n_dev;
   double *rows;
   int32_t *n_path;
 };
 
 __global__ void lift_emit_kernel(EmitArgs a) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= a.n || !a.mark[p]) return;
+  if (p >= *a.n_dev || !a.mark[p]) return;
   const int pos = a.dep[p] - 1;
   double *row = a.rows + (int64_t)pos * 5;
   row[0] = a.p_j[p]; row[1] = (double)a.p_i[p]; row[2] = (double)a.p_c[p]; row[3] = a.p_q[p];
@@ -1233,81 +1236,75 @@ static bool corridor_dp_eligible(const dab_pair *pr, int32_t n_cor) {
   return true;
 }
 
-int dab_run_stage_b(dab_pair *pr, int32_t n_cor, int32_t n_clusters) {
+// Stage B enqueued on the pair's stream without a host round trip: every (corridor, row) yields at most
+// one point, so the sum of the corridor rows (known to the host) bounds all buffers; the actual point
+// count stays on the device and every later kernel reads it from there.
+int dab_enqueue_stage_b(dab_pair *pr, int32_t n_cor, int32_t n_clusters) {
   dab_ctx *ctx = pr->ctx;
   cudaStream_t st = pr->stream;
   const int64_t n_a = pr->stats.n_audio_frames, n_v = pr->stats.n_video_frames;  // set by the caller
   pr->n_points2 = pr->n_path2 = 0;
   const bool fast = corridor_dp_eligible(pr, n_cor);
+  int64_t pm_off[32], rows = 0;
+  for (int k = 0; k < n_cor; ++k) {
+    if (k < 32) pm_off[k] = rows;
+    rows += pr->h_cor[k].hi > pr->h_cor[k].lo ? pr->h_cor[k].hi - pr->h_cor[k].lo : 0;
+  }
+  const int64_t cap = rows > 0 ? rows : 1;
+  pr->cap_points2 = cap;
+  DAB_TRY(dab_ensure(ctx, pr->counters, sizeof(int32_t) * DC_WORDS));
+  int32_t *dc = pr->counters.as<int32_t>();
+  DAB_CUDA(cudaMemsetAsync(dc + DC_N_PTS2, 0, sizeof(int32_t) * (DC_WORDS - DC_N_PTS2), st));
   ScoreBArgs sb;
   sb.a_scaled = pr->a_scaled.as<float>(); sb.v_scaled = pr->v_scaled.as<float>();
   sb.n_a = n_a; sb.n_v = n_v;
   sb.cor = pr->corridors.as<dab_corridor>(); sb.n_cor = n_cor;
-  sb.a_max = reinterpret_cast<float *>(pr->h_counters + 8)[0];
-  sb.v_max = reinterpret_cast<float *>(pr->h_counters + 8)[1];
+  sb.a_max = pr->b_amax;
+  sb.v_max = pr->b_vmax;
   sb.want_rank = fast ? 0 : 1;
   DAB_TRY(dab_ensure(ctx, pr->row2_count, sizeof(int32_t) * (size_t)(n_a + 2)));
   DAB_TRY(dab_ensure(ctx, pr->row2_off, sizeof(int32_t) * (size_t)(n_a + 2)));
-  DAB_TRY(dab_ensure(ctx, pr->dpres, sizeof(int32_t) * 16));
-  DAB_CUDA(cudaMemsetAsync(pr->dpres.p, 0, sizeof(int32_t) * 16, st));
+  DAB_TRY(dab_ensure(ctx, pr->p2_i, sizeof(int32_t) * (size_t)(cap + 1)));
+  DAB_TRY(dab_ensure(ctx, pr->p2_c, sizeof(int32_t) * (size_t)(cap + 1)));
+  DAB_TRY(dab_ensure(ctx, pr->p2_rank, sizeof(int32_t) * (size_t)(cap + 1)));
+  DAB_TRY(dab_ensure(ctx, pr->p2_k, sizeof(P2Rec) * (size_t)(cap + 1)));
+  DAB_TRY(dab_ensure(ctx, pr->p2_j, sizeof(double) * (size_t)(cap + 1)));
+  DAB_TRY(dab_ensure(ctx, pr->p2_q, sizeof(double) * (size_t)(cap + 1)));
+  DAB_TRY(dab_ensure(ctx, pr->path2, sizeof(double) * 5 * (size_t)(cap + 1)));
   sb.row_count = pr->row2_count.as<int32_t>(); sb.row_off = pr->row2_off.as<int32_t>();
-  sb.p_i = sb.p_c = sb.p_rank = nullptr; sb.rec = nullptr; sb.p_j = sb.p_q = nullptr;
-  sb.overflow = pr->dpres.as<int32_t>() + 6;
+  sb.p_i = pr->p2_i.as<int32_t>(); sb.p_c = pr->p2_c.as<int32_t>(); sb.p_rank = pr->p2_rank.as<int32_t>();
+  sb.rec = pr->p2_k.as<P2Rec>();
+  sb.p_j = pr->p2_j.as<double>(); sb.p_q = pr->p2_q.as<double>();
+  sb.overflow = dc + DC_OVERFLOW_B;
   DAB_CUDA(cudaEventRecord(pr->ev[14], st));
-  int64_t n_pts = 0;
-  if (n_a > 0 && n_cor > 0) {
+  if (n_a > 0 && n_cor > 0 && rows > 0) {
     const unsigned gb = (unsigned)cdiv(n_a, 128);
     corridor_kernel<false><<<gb, 128, 0, st>>>(sb);
-    ctx->launches += 1;
-    DAB_TRY(dab_exclusive_scan(pr, sb.row_count, pr->row2_off.as<int32_t>(), n_a));
-    DAB_CUDA(dab_readback(pr, &pr->h_counters[9], pr->row2_off.as<int32_t>() + n_a, sizeof(int32_t)));
-    DAB_CUDA(dab_readback(pr, &pr->h_counters[10], pr->dpres.as<int32_t>() + 6, sizeof(int32_t)));
-    DAB_CUDA(dab_wait_stream(st));
-    if ((int32_t)pr->h_counters[10] != 0) { ctx->err = "more than 32 corridors overlap one audio row"; return DAB_E_CAPACITY; }
-    n_pts = (int32_t)pr->h_counters[9];
-    DAB_TRY(dab_ensure(ctx, pr->p2_i, sizeof(int32_t) * (size_t)(n_pts + 1)));
-    DAB_TRY(dab_ensure(ctx, pr->p2_c, sizeof(int32_t) * (size_t)(n_pts + 1)));
-    DAB_TRY(dab_ensure(ctx, pr->p2_rank, sizeof(int32_t) * (size_t)(n_pts + 1)));
-    DAB_TRY(dab_ensure(ctx, pr->p2_k, sizeof(P2Rec) * (size_t)(n_pts + 1)));
-    DAB_TRY(dab_ensure(ctx, pr->p2_j, sizeof(double) * (size_t)(n_pts + 1)));
-    DAB_TRY(dab_ensure(ctx, pr->p2_q, sizeof(double) * (size_t)(n_pts + 1)));
-    sb.p_i = pr->p2_i.as<int32_t>(); sb.p_c = pr->p2_c.as<int32_t>(); sb.p_rank = pr->p2_rank.as<int32_t>();
-    sb.rec = pr->p2_k.as<P2Rec>();
-    sb.p_j = pr->p2_j.as<double>(); sb.p_q = pr->p2_q.as<double>();
-    if (n_pts > 0) {
-      corridor_kernel<true><<<gb, 128, 0, st>>>(sb);
-      ctx->launches += 1;
-    }
+    DAB_TRY(dab_exclusive_scan(pr, sb.row_count, pr->row2_off.as<int32_t>(), n_a, nullptr, dc + DC_N_PTS2));
+    corridor_kernel<true><<<gb, 128, 0, st>>>(sb);
+    ctx->launches += 2;
   }
-  pr->n_points2 = n_pts;
-  pr->stats.n_points2 = n_pts;
   DAB_CUDA(cudaEventRecord(pr->ev[15], st));
 
   DAB_CUDA(cudaEventRecord(pr->ev[16], st));
-  int64_t n_path = 0;
-  if (n_pts > 0 && fast) {
-    // ---- corridor-state DP + pointer-jumping traceback ----
-    int64_t pm_off[32], rows = 0;
-    for (int k = 0; k < n_cor; ++k) { pm_off[k] = rows; rows += pr->h_cor[k].hi > pr->h_cor[k].lo ? pr->h_cor[k].hi - pr->h_cor[k].lo : 0; }
-    int levels = 1;                      // up[0 .. levels-1], 2^(levels-1) >= n_pts
-    while ((1LL << (levels - 1)) < n_pts) ++levels;
-    const int64_t np1 = n_pts + 1;
+  if (rows > 0 && fast) {
+    // ---- scan DP + pointer-jumping traceback ----
+    int levels = 1;                      // up[0 .. levels-1], 2^(levels-1) >= number of points
+    while ((1LL << (levels - 1)) < cap) ++levels;
+    const int64_t np1 = cap + 1;
     DAB_TRY(dab_ensure(ctx, pr->pm2, sizeof(PmEntry) * (size_t)(rows + WLEN + 1)));
-    DAB_TRY(dab_ensure(ctx, pr->pmoff2, sizeof(int64_t) * 32 + sizeof(unsigned long long) * 4));
-    DAB_TRY(dab_ensure(ctx, pr->back2, sizeof(BackRec) * (size_t)(n_pts + 2)));
+    DAB_TRY(dab_ensure(ctx, pr->back2, sizeof(BackRec) * (size_t)(cap + 2)));
     DAB_TRY(dab_ensure(ctx, pr->lift_up, sizeof(int32_t) * (size_t)(levels * np1)));
     DAB_TRY(dab_ensure(ctx, pr->lift_dep, sizeof(int32_t) * (size_t)(3 * np1)));
-    DAB_TRY(dab_ensure(ctx, pr->path2, sizeof(double) * 5 * (size_t)(n_pts + 1)));
-    DAB_CUDA(cudaMemcpyAsync(pr->pmoff2.p, pm_off, sizeof(int64_t) * (size_t)n_cor, cudaMemcpyHostToDevice, st));
     Dp2LArgs la;
     la.rec = pr->p2_k.as<P2Rec>(); la.p_j = pr->p2_j.as<double>();
-    la.n_points = (int32_t)n_pts;
+    la.n_points = dc + DC_N_PTS2;
     la.cor = pr->corridors.as<dab_corridor>(); la.n_cor = n_cor;
-    la.pm_off = pr->pmoff2.as<int64_t>(); la.pm = pr->pm2.as<PmEntry>();
+    for (int k = 0; k < 32; ++k) la.pm_off[k] = k < n_cor ? pm_off[k] : 0;
+    la.pm = pr->pm2.as<PmEntry>();
     la.back = pr->back2.as<BackRec>();
-    la.result = pr->dpres.as<int32_t>();
-    la.counters = reinterpret_cast<unsigned long long *>(pr->pmoff2.as<int64_t>() + 32);
-    DAB_CUDA(cudaMemsetAsync(la.counters, 0, 4 * sizeof(unsigned long long), st));
+    la.result = dc + DC_DP2_END;
+    la.counters = reinterpret_cast<unsigned long long *>(dc + DC_DP2_CNT);
     if (pr->ctx->opt_dp2_impl == 1) {
       // the one-warp block kernel of round 1 (kept for cross-checks)
       dp2_block_kernel<<<1, 32, 0, st>>>(la);
@@ -1319,63 +1316,45 @@ int dab_run_stage_b(dab_pair *pr, int32_t n_cor, int32_t n_clusters) {
       }
       dp2_scan_kernel<<<1, SC_T, sizeof(ScanShared), st>>>(la);
     }
-    // The DP runs for tens of milliseconds on one warp.  Nothing that depends on it - not even an
-    // event record - is enqueued until it is done: streams share the GPU's 32 hardware queues, and a
-    // dependent command waiting at the head of a queue stalls the other pairs' work mapped to that
-    // queue (with more pairs in flight than queues that costs all the concurrency beyond 32).
-    DAB_CUDA(dab_wait_stream(st));
     DAB_CUDA(cudaEventRecord(pr->ev[18], st));
     int32_t *up = pr->lift_up.as<int32_t>();
     int32_t *dep0 = pr->lift_dep.as<int32_t>(), *dep1 = dep0 + np1, *mark = dep1 + np1;
     const unsigned gl = (unsigned)cdiv(np1, 256);
-    lift_init_kernel<<<gl, 256, 0, st>>>(la.back, (int32_t)n_pts, up, dep0, mark, la.result);
+    const int32_t *n_dev = dc + DC_N_PTS2;
+    lift_init_kernel<<<gl, 256, 0, st>>>(la.back, n_dev, up, dep0, mark, la.result);
     int32_t *din = dep0, *dout = dep1;
     for (int k = 1; k < levels; ++k) {
-      lift_step_kernel<<<gl, 256, 0, st>>>(up + (int64_t)(k - 1) * np1, din, (int32_t)n_pts, up + (int64_t)k * np1, dout);
+      lift_step_kernel<<<gl, 256, 0, st>>>(up + (int64_t)(k - 1) * np1, din, n_dev, up + (int64_t)k * np1, dout);
       int32_t *t = din; din = dout; dout = t;
     }
-    for (int k = levels - 1; k >= 0; --k) lift_mark_kernel<<<gl, 256, 0, st>>>(up + (int64_t)k * np1, (int32_t)n_pts, mark);
+    for (int k = levels - 1; k >= 0; --k) lift_mark_kernel<<<gl, 256, 0, st>>>(up + (int64_t)k * np1, n_dev, mark);
     EmitArgs ea;
     ea.mark = mark; ea.dep = din; ea.back = la.back; ea.result = la.result;
     ea.p_i = pr->p2_i.as<int32_t>(); ea.p_c = pr->p2_c.as<int32_t>(); ea.p_j = la.p_j; ea.p_q = pr->p2_q.as<double>();
-    ea.n = (int32_t)n_pts; ea.rows = pr->path2.as<double>(); ea.n_path = pr->dpres.as<int32_t>() + 1;
+    ea.n_dev = n_dev; ea.rows = pr->path2.as<double>(); ea.n_path = dc + DC_N_PATH2;
     lift_emit_kernel<<<gl, 256, 0, st>>>(ea);
-    ctx->launches += 2 + 2 * levels;
-    DAB_CUDA(dab_readback(pr, &pr->h_counters[12], pr->dpres.as<int32_t>(), 2 * sizeof(int32_t)));
-    DAB_CUDA(dab_readback(pr, &pr->h_counters[16], la.counters, 4 * sizeof(unsigned long long)));
+    ctx->launches += 3 + 2 * levels;
     DAB_CUDA(cudaEventRecord(pr->ev[17], st));
-    DAB_CUDA(dab_wait_stream(st));
-    n_path = reinterpret_cast<int32_t *>(&pr->h_counters[12])[1];
-    pr->stats.n_dp2_queries = pr->h_counters[16];
-    pr->stats.n_dp2_refills = pr->h_counters[17];
-    pr->stats.n_dp2_neighbour = pr->h_counters[18];
-    pr->stats.n_dp2_run_points = pr->h_counters[19];
-  } else if (n_pts > 0) {
-    // ---- generic tree DP ----
-    // rank domain: 1 + total corridor rows
-    int64_t dom = 1;
-    {
-      // corridors were validated by the caller; sizes come from the host copy kept in h_counters[11]
-      dom += pr->h_counters[11];
-    }
-    if (dom > (1LL << (5 * L2N))) { ctx->err = "pass-2 rank domain too large"; return DAB_E_CAPACITY; }
+  } else if (rows > 0) {
+    // ---- generic tree DP (more than 32 corridors, or a line with non-positive slope) ----
+    const int64_t dom = 1 + rows;        // rank domain: 1 + total corridor rows
+    if (dom > (1LL << (5 * L2N))) { dab_set_err(ctx, "pass-2 rank domain too large"); return DAB_E_CAPACITY; }
     int64_t lv[L2N], loff[L2N], tot = 0, m = dom;
     for (int k = 0; k < L2N; ++k) { lv[k] = cdiv(m > 0 ? m : 1, 32) * 32; loff[k] = tot; tot += lv[k]; m = cdiv(m, 32); }
     DAB_TRY(dab_ensure(ctx, pr->tree2, sizeof(Node2) * (size_t)tot + sizeof(int64_t) * L2N));
     DAB_TRY(dab_ensure(ctx, pr->cache2, sizeof(Cell2) * (size_t)(n_v + 1)));
-    DAB_TRY(dab_ensure(ctx, pr->back2, (sizeof(double) + sizeof(double)) * (size_t)(n_clusters + n_pts + 2) + 64));
-    DAB_TRY(dab_ensure(ctx, pr->backid2, sizeof(int32_t) * (size_t)(n_pts + n_clusters + 2)));
-    DAB_TRY(dab_ensure(ctx, pr->len2, sizeof(int32_t) * (size_t)(n_pts + 1)));
-    DAB_TRY(dab_ensure(ctx, pr->cp2, sizeof(int32_t) * (size_t)(n_pts + 1)));
-    DAB_TRY(dab_ensure(ctx, pr->seglist, sizeof(int32_t) * (size_t)(2 * (n_pts / CHECK2 + 16))));
-    DAB_TRY(dab_ensure(ctx, pr->path2, sizeof(double) * 5 * (size_t)(n_pts + 1)));
+    DAB_TRY(dab_ensure(ctx, pr->back2, (sizeof(double) + sizeof(double)) * (size_t)(n_clusters + cap + 2) + 64));
+    DAB_TRY(dab_ensure(ctx, pr->backid2, sizeof(int32_t) * (size_t)(cap + n_clusters + 2)));
+    DAB_TRY(dab_ensure(ctx, pr->len2, sizeof(int32_t) * (size_t)(cap + 1)));
+    DAB_TRY(dab_ensure(ctx, pr->cp2, sizeof(int32_t) * (size_t)(cap + 1)));
+    DAB_TRY(dab_ensure(ctx, pr->seglist, sizeof(int32_t) * (size_t)(2 * (cap / CHECK2 + 16))));
     Node2 *nodes = pr->tree2.as<Node2>();
     int64_t *d_loff = reinterpret_cast<int64_t *>(nodes + tot);
     DAB_CUDA(cudaMemcpyAsync(d_loff, loff, sizeof(int64_t) * L2N, cudaMemcpyHostToDevice, st));
     double *back_cum = pr->back2.as<double>();
-    double *cb_val = back_cum + (n_pts + 1);
+    double *cb_val = back_cum + (cap + 1);
     int32_t *back_id = pr->backid2.as<int32_t>();
-    int32_t *cb_id = back_id + (n_pts + 1);
+    int32_t *cb_id = back_id + (cap + 1);
     int64_t span = tot > n_v ? tot : n_v;
     if (n_clusters > span) span = n_clusters;
     init_dp2_kernel<<<(unsigned)cdiv(span, 256), 256, 0, st>>>(nodes, tot, pr->cache2.as<Cell2>(), n_v, cb_val, cb_id,
@@ -1383,11 +1362,11 @@ int dab_run_stage_b(dab_pair *pr, int32_t n_cor, int32_t n_clusters) {
     Dp2Args da;
     da.p_i = pr->p2_i.as<int32_t>(); da.p_c = pr->p2_c.as<int32_t>(); da.p_rank = pr->p2_rank.as<int32_t>();
     da.p_j = pr->p2_j.as<double>(); da.p_q = pr->p2_q.as<double>();
-    da.n_points = (int32_t)n_pts;
+    da.n_points = dc + DC_N_PTS2;
     for (int k = 0; k < L2N; ++k) da.level[k] = nodes + loff[k];
     da.cache = pr->cache2.as<Cell2>(); da.cb_val = cb_val; da.cb_id = cb_id;
     da.back_id = back_id; da.len = pr->len2.as<int32_t>(); da.cp = pr->cp2.as<int32_t>();
-    da.back_cum = back_cum; da.result = pr->dpres.as<int32_t>();
+    da.back_cum = back_cum; da.result = dc + DC_DP2_END;
     dp2_kernel<<<1, 32, 0, st>>>(da);
     DAB_CUDA(cudaEventRecord(pr->ev[18], st));
     Trace2Args ta;
@@ -1396,17 +1375,36 @@ int dab_run_stage_b(dab_pair *pr, int32_t n_cor, int32_t n_clusters) {
     ta.seg = pr->seglist.as<int32_t>(); ta.rows = pr->path2.as<double>();
     trace2_kernel<<<1, 256, 0, st>>>(ta);
     ctx->launches += 3;
-    DAB_CUDA(dab_readback(pr, &pr->h_counters[12], pr->dpres.as<int32_t>(), 2 * sizeof(int32_t)));
     DAB_CUDA(cudaEventRecord(pr->ev[17], st));
-    DAB_CUDA(dab_wait_stream(st));
-    n_path = reinterpret_cast<int32_t *>(&pr->h_counters[12])[1];
   } else {
     DAB_CUDA(cudaEventRecord(pr->ev[18], st));
     DAB_CUDA(cudaEventRecord(pr->ev[17], st));
   }
-  pr->n_path2 = n_path;
-  pr->stats.n_path2 = n_path;
   pr->ev_used[7] = pr->ev_used[8] = true;
   DAB_CUDA(cudaGetLastError());
   return DAB_OK;
+}
+
+int dab_collect_stage_b(dab_pair *pr) {
+  dab_ctx *ctx = pr->ctx;
+  const int32_t *hc = reinterpret_cast<const int32_t *>(pr->h_counters);
+  if (hc[DC_OVERFLOW_B] & DAB_OVF_ROWCOR) { dab_set_err(ctx, "more than 32 corridors overlap one audio row"); return DAB_E_CAPACITY; }
+  pr->n_points2 = hc[DC_N_PTS2];
+  pr->stats.n_points2 = pr->n_points2;
+  pr->n_path2 = (pr->n_points2 > 0 && hc[DC_DP2_END] >= 0) ? hc[DC_N_PATH2] : 0;
+  pr->stats.n_path2 = pr->n_path2;
+  const int64_t *cnt = reinterpret_cast<const int64_t *>(hc + DC_DP2_CNT);
+  pr->stats.n_dp2_queries = cnt[0];
+  pr->stats.n_dp2_refills = cnt[1];
+  pr->stats.n_dp2_neighbour = cnt[2];
+  pr->stats.n_dp2_run_points = cnt[3];
+  return DAB_OK;
+}
+
+int dab_run_stage_b(dab_pair *pr, int32_t n_cor, int32_t n_clusters) {
+  dab_ctx *ctx = pr->ctx;
+  DAB_TRY(dab_enqueue_stage_b(pr, n_cor, n_clusters));
+  DAB_TRY(dab_enqueue_counts(pr));
+  DAB_CUDA(dab_wait_stream(pr->stream));
+  return dab_collect_stage_b(pr);
 }

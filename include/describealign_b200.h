@@ -43,7 +43,8 @@ enum {
   DAB_E_ARG = 2,        /* invalid argument */
   DAB_E_STATE = 3,      /* call sequence violated (e.g. stage_a before features) */
   DAB_E_CAPACITY = 4,   /* an internal buffer overflowed even after growing */
-  DAB_E_TOO_SHORT = 5   /* track shorter than the 41-frame window */
+  DAB_E_TOO_SHORT = 5,  /* track shorter than the 41-frame window */
+  DAB_E_TIMEOUT = 6     /* dab_engine_next: nothing finished within the timeout */
 };
 
 /* sample formats accepted by dab_pair_set_pcm */
@@ -148,6 +149,12 @@ int dab_pair_set_features(dab_pair *pair, int track, const float *energy, int64_
                           const float *zc, const float *band0, const float *band1, const double *band2,
                           int64_t n);
 
+/* align()'s separate video_energy / audio_desc_energy arguments (:595) decide which frames are "not
+ * quiet" (:629, :657).  The reference's only caller passes features[0] for them (:1121), which is what
+ * the pair uses by default; a caller that passes something else uploads it here after the features
+ * (n_energy must equal len(features[0])). */
+int dab_pair_set_gate_energy(dab_pair *pair, int track, const float *energy, int64_t n_energy);
+
 /* lens[0] = len(energy) (n or n + 1, :555), lens[1..4] = n. */
 int dab_pair_feature_lens(dab_pair *pair, int track, int64_t lens[5]);
 /* Copies features to host buffers of at least lens[] elements; any pointer may be NULL. */
@@ -214,6 +221,73 @@ int dab_pair_get_timings(dab_pair *pair, float ms[16]);
 int dab_pair_get_timeline(dab_pair *pair, void *ref_event, float start_ms[9], float end_ms[9]);
 /* number of kernel launches issued by this context since creation */
 int64_t dab_launch_count(const dab_ctx *ctx);
+
+/* ---- batch engine (reference describealign.py:1077, the per-pair loop of batch mode) -----------------
+ * Many pairs in flight on one GPU without a host thread per pair: the caller submits jobs and then
+ * serves a queue of events.  A pair occupies one of the engine's slots (device buffers + a CUDA stream)
+ * and goes   submit -> [upload, features, stage A on the device] -> DAB_EVENT_STAGE_A
+ *            -> caller runs the host fit (:702-893) and answers with dab_engine_submit_b
+ *            -> [stage B on the device] -> DAB_EVENT_STAGE_B -> caller reads the path, dab_engine_release.
+ * One scheduler thread inside the library enqueues every device stage in one go and polls CUDA events;
+ * it never blocks on a stream.  All result pointers of an event are page-locked host memory owned by the
+ * slot, valid until the slot's next dab_engine_submit_b (stage A results) or dab_engine_release.
+ * The PCM buffers of a job must stay valid until the job's DAB_EVENT_STAGE_A (page-locked memory makes
+ * the uploads asynchronous DMA).  Any thread may call these functions; events are handed out once. */
+typedef struct dab_engine dab_engine;
+
+typedef struct {
+  uint64_t tag;             /* caller's id of the pair, returned with its events */
+  const void *pcm[2];       /* [DAB_TRACK_VIDEO], [DAB_TRACK_AUDIO]: interleaved samples, host or device memory */
+  int64_t samples[2];       /* per channel */
+  int32_t channels[2];      /* 1 or 2 */
+  int32_t format;           /* DAB_PCM_* */
+  int32_t on_device;        /* != 0: pcm[] are device pointers (no upload) */
+} dab_job;
+
+enum { DAB_EVENT_STAGE_A = 1, DAB_EVENT_STAGE_B = 2 };
+
+typedef struct {
+  int32_t kind;             /* DAB_EVENT_* */
+  int32_t slot;             /* handle for dab_engine_submit_b / dab_engine_release */
+  uint64_t tag;
+  int32_t status;           /* DAB_OK, or the DAB_E_* code the pair failed with (dab_engine_slot_error) */
+  int32_t reserved;
+  /* stage A: pass-1 path (audio frame x, video frame y) and the first three feature vectors of each track
+   * (what the host fit reads, :706-741) */
+  int64_t n_path1;
+  const int32_t *path_x, *path_y;
+  const float *features[2][3];
+  int64_t feature_len[2][3];
+  /* stage B: final path rows (video j, audio i, cluster, qual, cum), row-major (n_path2, 5), in frames */
+  int64_t n_path2;
+  const double *rows;
+  dab_stats stats;
+  /* as dab_pair_get_timings, except slots 10-13: [10] scheduler time spent enqueueing this pair's work,
+   * [11] submit -> stage A results on the host, [12] stage-B input -> final path on the host (ms) */
+  float timings_ms[16];
+} dab_event;
+
+/* input of stage B, as dab_pair_stage_b_gains */
+typedef struct {
+  float gain[3], audio_std[3];
+  float audio_energy_max, video_energy_max;
+  int64_t n_audio, n_video;
+  const dab_corridor *corridors;   /* copied by dab_engine_submit_b */
+  int32_t n_corridors, n_clusters;
+} dab_stage_b_in;
+
+int dab_engine_create(dab_ctx *ctx, int32_t slots, dab_engine **out);
+void dab_engine_destroy(dab_engine *engine);
+int dab_engine_submit(dab_engine *engine, const dab_job *job);     /* queued; starts when a slot is free */
+/* timeout_ms < 0: wait for ever; 0: poll.  Returns DAB_OK, DAB_E_TIMEOUT or DAB_E_ARG. */
+int dab_engine_next(dab_engine *engine, dab_event *out, int32_t timeout_ms);
+int dab_engine_submit_b(dab_engine *engine, int32_t slot, const dab_stage_b_in *in);
+int dab_engine_release(dab_engine *engine, int32_t slot);
+const char *dab_engine_slot_error(dab_engine *engine, int32_t slot);
+/* the dab_pair behind a slot, for introspection between DAB_EVENT_STAGE_B and dab_engine_release */
+void *dab_engine_slot_pair(dab_engine *engine, int32_t slot);
+/* out[0] scheduler loop iterations, out[1] iterations that found nothing to do and slept 20 us */
+void dab_engine_counters(dab_engine *engine, int64_t out[4]);
 
 #ifdef __cplusplus
 }

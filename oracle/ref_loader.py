@@ -15,14 +15,26 @@ import sys
 import types
 
 REFERENCE_CANDIDATES = ("/root/reference/describealign.py",)
+# a pip --target install of the reference (the only form of it that travels to the GPU box).  The
+# reference's own packaging does not build from its checkout (setuptools: "multiple top-level packages
+# discovered in a flat-layout"), so this directory normally does not exist; bench.py --impl reference
+# probes it and nothing else.
+INSTALLED_CANDIDATES = (os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref", "describealign.py"),)
 
 
 def reference_available() -> bool:
     return any(os.path.isfile(p) for p in REFERENCE_CANDIDATES)
 
 
-def load_reference():
-    path = next((p for p in REFERENCE_CANDIDATES if os.path.isfile(p)), None)
+def load():
+    """The installed reference (baseline/_ref) or None; never reads /root/reference."""
+    path = next((p for p in INSTALLED_CANDIDATES if os.path.isfile(p)), None)
+    return None if path is None else load_reference(path)
+
+
+def load_reference(path=None):
+    if path is None:
+        path = next((p for p in REFERENCE_CANDIDATES if os.path.isfile(p)), None)
     if path is None:
         raise FileNotFoundError("reference describealign.py not found")
     for name in ("matplotlib", "matplotlib.pyplot", "ffmpeg", "static_ffmpeg",
