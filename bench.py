@@ -166,7 +166,7 @@ def cpu_pass(pair, keep=False):
     fx, fy = host_fit.compress_path(kx, ky)
     fit = host_fit.rate_change_fit(fx, fy, linprog=timed_linprog)
     clusters = host_fit.line_clusters(fit)
-    plans = host_fit.plan_corridors(clusters, a_s, v_s)
+    plans = ao.plan_corridors(clusters, a_s, v_s)
     t2 = time.perf_counter()
     sb = ao.stage_b(plans, len(clusters), a_s, v_s)
     path = sb["path"]

@@ -25,7 +25,7 @@ EXPORTS = [
     "dab_pair_stage_a_match", "dab_pair_export_points1", "dab_pair_import_points1", "dab_pair_dp1",
     "dab_alloc_pinned", "dab_free_pinned", "dab_trim_pinned", "dab_alloc_stats", "dab_host_copy",
     "dab_set_host_wait", "dab_pair_get_timeline", "dab_pair_stage_b_gains",
-    "dab_pair_set_gate_energy",
+    "dab_pair_set_gate_energy", "dab_pair_stage_b_clusters", "dab_pair_get_corridors",
     "dab_engine_create", "dab_engine_destroy", "dab_engine_submit", "dab_engine_next", "dab_engine_submit_b",
     "dab_engine_release", "dab_engine_slot_error", "dab_engine_slot_pair", "dab_engine_counters",
 ]
@@ -34,6 +34,20 @@ EXPORTS = [
 class Corridor(ctypes.Structure):
     _fields_ = [("cluster", ctypes.c_int32), ("lo", ctypes.c_int32), ("hi", ctypes.c_int32),
                 ("reserved", ctypes.c_int32), ("slope", ctypes.c_double), ("offset", ctypes.c_double)]
+
+
+class Cluster(ctypes.Structure):
+    """dab_cluster"""
+    _fields_ = [("cluster", ctypes.c_int32), ("reserved", ctypes.c_int32), ("x_first", ctypes.c_double),
+                ("x_last", ctypes.c_double), ("offset", ctypes.c_double), ("slope", ctypes.c_double)]
+
+
+def cluster_array(lines):
+    """ctypes array of dab_cluster from [(cluster index, x_first, x_last, offset, slope), ...]"""
+    arr = (Cluster * max(len(lines), 1))()
+    for k, (idx, xf, xl, offset, slope) in enumerate(lines):
+        arr[k] = Cluster(int(idx), 0, float(xf), float(xl), float(offset), float(slope))
+    return arr
 
 
 class Stats(ctypes.Structure):
@@ -67,7 +81,7 @@ class StageBIn(ctypes.Structure):
     _fields_ = [("gain", ctypes.c_float * 3), ("audio_std", ctypes.c_float * 3),
                 ("audio_energy_max", ctypes.c_float), ("video_energy_max", ctypes.c_float),
                 ("n_audio", ctypes.c_int64), ("n_video", ctypes.c_int64), ("corridors", ctypes.c_void_p),
-                ("n_corridors", ctypes.c_int32), ("n_clusters", ctypes.c_int32)]
+                ("n_corridors", ctypes.c_int32), ("n_clusters", ctypes.c_int32), ("clusters", ctypes.c_void_p)]
 
 
 EVENT_STAGE_A, EVENT_STAGE_B = 1, 2
@@ -134,6 +148,9 @@ def load() -> ctypes.CDLL:
     lib.dab_pair_dp1.argtypes = [vp, ctypes.POINTER(i64)]
     lib.dab_pair_stage_b.argtypes = [vp, vp, i64, vp, i64, vp, ctypes.c_int32, ctypes.c_int32,
                                      ctypes.POINTER(i64), ctypes.POINTER(i64)]
+    lib.dab_pair_stage_b_clusters.argtypes = [vp, ctypes.POINTER(ctypes.c_float * 3), ctypes.POINTER(ctypes.c_float * 3), i64, i64,
+                                              vp, ctypes.c_int32, ctypes.POINTER(i64), ctypes.POINTER(i64)]
+    lib.dab_pair_get_corridors.argtypes = [vp, vp, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32)]
     lib.dab_pair_get_path2.argtypes = [vp, vp]
     lib.dab_pair_get_points2.argtypes = [vp, vp, vp, vp, vp]
     lib.dab_pair_get_stats.argtypes = [vp, ctypes.POINTER(Stats)]
@@ -430,6 +447,28 @@ class Pair:
         self.n_points2, self.n_path2 = npts.value, npath.value
         return npts.value, npath.value
 
+    def stage_b_clusters(self, gains, audio_stds, n_audio: int, n_video: int, lines):
+        """Stage B from the host fit's line clusters [(cluster index, x_first, x_last, offset, slope), ...]:
+        scaling, corridor planning (describealign.py:895-932), scoring, DP 2 and traceback on the device."""
+        g = (ctypes.c_float * 3)(*[float(x) for x in gains])
+        sd = (ctypes.c_float * 3)(*[float(x) for x in audio_stds])
+        arr = cluster_array(lines)
+        npts, npath = ctypes.c_int64(), ctypes.c_int64()
+        self.ctx.check(self.lib.dab_pair_stage_b_clusters(self.handle, ctypes.byref(g), ctypes.byref(sd), int(n_audio), int(n_video),
+                                                          ctypes.cast(arr, ctypes.c_void_p), len(lines),
+                                                          ctypes.byref(npts), ctypes.byref(npath)))
+        self.n_points2, self.n_path2 = npts.value, npath.value
+        return npts.value, npath.value
+
+    def corridors(self):
+        """The corridors of the last stage B as scored: [(cluster, lo, hi, slope, offset), ...] (empty ones
+        dropped), i.e. what the reference computes in describealign.py:912-932."""
+        n = ctypes.c_int32()
+        self.ctx.check(self.lib.dab_pair_get_corridors(self.handle, None, 0, ctypes.byref(n)))
+        arr = (Corridor * max(n.value, 1))()
+        self.ctx.check(self.lib.dab_pair_get_corridors(self.handle, ctypes.cast(arr, ctypes.c_void_p), n.value, ctypes.byref(n)))
+        return [(c.cluster, c.lo, c.hi, c.slope, c.offset) for c in arr[:n.value] if c.hi > c.lo]
+
     def path2(self):
         rows = self._staging("path2", (self.n_path2, 5), np.float64)
         self.ctx.check(self.lib.dab_pair_get_path2(self.handle, _ptr(rows)))
@@ -572,10 +611,22 @@ class Engine:
         return {name: float(evt.timings_ms[k]) for k, name in enumerate(TIMING_SLOTS)}
 
     @staticmethod
-    def stage_b_struct(gains, audio_stds, n_audio: int, n_video: int, audio_energy_max: float,
-                       video_energy_max: float, plans, n_clusters: int):
-        """The dab_stage_b_in of a host fit (reusable: the engine copies the corridors on submit)."""
+    def stage_b_struct(gains, audio_stds, n_audio: int, n_video: int, audio_energy_max: float = 0.0,
+                       video_energy_max: float = 0.0, plans=(), n_clusters: int = 0, lines=None):
+        """The dab_stage_b_in of a host fit (reusable: the engine copies the arrays on submit).
+        lines: the fit's line clusters (host_fit.cluster_lines) - the corridors are then planned on the
+        device; else plans: pre-planned corridors with the energy maxima."""
         b = StageBIn()
+        if lines is not None:
+            for k in range(3):
+                b.gain[k] = float(gains[k])
+                b.audio_std[k] = float(audio_stds[k])
+            b.n_audio, b.n_video = int(n_audio), int(n_video)
+            arr = cluster_array(lines)
+            b.clusters = ctypes.cast(arr, ctypes.c_void_p)
+            b.n_corridors, b.n_clusters = 0, len(lines)
+            b._cluster_array = arr
+            return b
         for k in range(3):
             b.gain[k] = float(gains[k])
             b.audio_std[k] = float(audio_stds[k])
@@ -591,9 +642,9 @@ class Engine:
         return b
 
     def submit_b(self, slot: int, gains=None, audio_stds=None, n_audio=0, n_video=0, audio_energy_max=0.0,
-                 video_energy_max=0.0, plans=(), n_clusters=0, struct: StageBIn | None = None):
+                 video_energy_max=0.0, plans=(), n_clusters=0, lines=None, struct: StageBIn | None = None):
         b = struct if struct is not None else self.stage_b_struct(gains, audio_stds, n_audio, n_video, audio_energy_max,
-                                                                   video_energy_max, plans, n_clusters)
+                                                                   video_energy_max, plans, n_clusters, lines)
         self.ctx.check(self.lib.dab_engine_submit_b(self.handle, int(slot), ctypes.byref(b)))
 
     def release(self, slot: int):

@@ -132,6 +132,8 @@ class AlignJob:
         self.video_features = self.audio_features = None
         self.want_all_features = False
         self.device_scaling = True   # stage B scales the pair's device-resident features itself (6 floats up)
+        self.device_planning = True  # ... and plans the corridors there (describealign.py:895-932, csrc/refine.cuh)
+        self.test_planner = None     # tests: a host-side corridor planner to compare the device's planning with
         self.gains = None
         self.h2d_bytes = self.d2h_bytes = 0
         self.host_ms = {}        # wall time of each host-side call of this job (diagnostics)
@@ -207,31 +209,41 @@ class AlignJob:
 
     def stage_b_input(self):
         """What dab_engine_submit_b / dab_pair_stage_b_gains need from the host fit."""
-        return dict(gains=self.gains[0], audio_stds=self.gains[1], n_audio=len(self.audio_scaled),
-                    n_video=len(self.video_scaled), audio_energy_max=float(self.audio_scaled[:, 0].max()),
-                    video_energy_max=float(self.video_scaled[:, 0].max()), plans=self.plans,
-                    n_clusters=len(self.clusters))
+        return dict(gains=self.gains[0], audio_stds=self.gains[1], n_audio=self.n_audio_scaled,
+                    n_video=self.n_video_scaled, lines=self.lines)
 
     def host_stage(self):
         """The untimed "rate-change fit" on the host (describealign.py:702-893)."""
         keep = host_fit.continuity_error(self.x, self.y) < 3
         self.kept_x, self.kept_y = self.x[keep], self.y[keep]
-        self.audio_scaled, self.video_scaled, self.gains = host_fit.scale_features(
-            self.video_features, self.audio_features, self.kept_x, self.kept_y, return_gains=True)
+        g, sd, self.n_audio_scaled, self.n_video_scaled = host_fit.feature_gains(
+            self.video_features, self.audio_features, self.kept_x, self.kept_y)
+        self.gains = (g, sd)
         fit_x, fit_y = host_fit.compress_path(self.kept_x, self.kept_y)
         self.fit = host_fit.rate_change_fit(fit_x, fit_y)
         self.clusters = host_fit.line_clusters(self.fit)
-        self.plans = host_fit.plan_corridors(self.clusters, self.audio_scaled, self.video_scaled)
+        self.lines = host_fit.cluster_lines(self.clusters)
 
     def device_stage_b(self):
-        if getattr(self, "gains", None) is not None and self.device_scaling:
-            # the pair still holds the features: the device redoes describealign.py:737-741 from six scalars
-            self._timed("stage_b", self.pair.stage_b_gains, self.gains[0], self.gains[1], self.audio_scaled,
-                        self.video_scaled, self.plans, len(self.clusters))
-            self.h2d_bytes += 24
+        """Scaling (describealign.py:737-741), corridor planning (:895-932), scoring, DP 2 and traceback on
+        the device, from the host fit's six scalars and line clusters.  (device_planning / device_scaling
+        off: the oracle's numpy planning / uploaded scaled arrays instead - test switches.)"""
+        if self.device_planning and self.device_scaling:
+            self._timed("stage_b", self.pair.stage_b_clusters, self.gains[0], self.gains[1], self.n_audio_scaled,
+                        self.n_video_scaled, self.lines)
+            self.h2d_bytes += 24 + 40 * len(self.lines)
         else:
-            self._timed("stage_b", self.pair.stage_b, self.audio_scaled, self.video_scaled, self.plans, len(self.clusters))
-            self.h2d_bytes += self.audio_scaled.nbytes + self.video_scaled.nbytes
+            audio_scaled, video_scaled = host_fit.scale_features(self.video_features, self.audio_features, self.kept_x, self.kept_y)
+            if self.test_planner is None:
+                raise RuntimeError("device_planning / device_scaling are test switches: they need job.test_planner")
+            plans = self.test_planner(self.clusters, audio_scaled, video_scaled)
+            if self.device_scaling:
+                self._timed("stage_b", self.pair.stage_b_gains, self.gains[0], self.gains[1], audio_scaled,
+                            video_scaled, plans, len(self.clusters))
+                self.h2d_bytes += 24
+            else:
+                self._timed("stage_b", self.pair.stage_b, audio_scaled, video_scaled, plans, len(self.clusters))
+                self.h2d_bytes += audio_scaled.nbytes + video_scaled.nbytes
         self.path = self._timed("path2", self.pair.path2)
         self.d2h_bytes += self.path.nbytes
         if len(self.path) < self.min_len:
@@ -241,12 +253,12 @@ class AlignJob:
     def finish(self, details=None):
         if details is not None:
             details.update(kept_x=self.kept_x, kept_y=self.kept_y, fit=self.fit, clusters=self.clusters,
-                           plans=self.plans, audio_scaled=self.audio_scaled, video_scaled=self.video_scaled,
+                           plans=self.pair.corridors(), gains=self.gains,
                            video_features=self.video_features, audio_features=self.audio_features,
                            path1=(self.x, self.y), stats=self.pair.stats(), timings=self.pair.timings(),
                            h2d_bytes=self.h2d_bytes, d2h_bytes=self.d2h_bytes)
         nx, ny, sim = host_fit.build_nodes(self.path, self.n_audio_energy, self.n_video_energy,
-                                           len(self.audio_scaled), len(self.video_scaled))
+                                           self.n_audio_scaled, self.n_video_scaled)
         return nx, ny, sim, self.path, self.fit.median_slope
 
     def close(self):

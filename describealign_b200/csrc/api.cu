@@ -544,6 +544,7 @@ static int stage_b_enqueue_common(dab_pair *pr, int64_t n_audio, int64_t n_video
       }
     }
   }
+  pr->b_device_planned = false;
   pr->h_cor.assign(corridors, corridors + n_corridors);
   DAB_TRY(dab_ensure(ctx, pr->corridors, sizeof(dab_corridor) * (size_t)(n_corridors + 1)));
   if (n_corridors > 0)
@@ -611,13 +612,39 @@ __global__ void scale_features_kernel(const float *f0, const float *f1, const fl
 
 // Stage B for a pair that holds its features: scaling kernels + the stage, enqueued without waiting.
 // `corridors` must stay valid until the stream has consumed it (page-locked memory owned by the caller).
+static int enqueue_scaling(dab_pair *pr, const float gain[3], const float audio_std[3], int64_t n_audio, int64_t n_video);
+
 int dab_enqueue_stage_b_gains(dab_pair *pr, const float gain[3], const float audio_std[3], int64_t n_audio, int64_t n_video,
                               float amax, float vmax, const dab_corridor *corridors, int32_t n_corridors, int32_t n_clusters,
                               const dab_corridor *) {
   dab_ctx *ctx = pr->ctx;
-  if (!gain || !audio_std || n_audio <= 0 || n_video <= 8 || n_corridors < 0 || n_clusters < 0 ||
-      (n_corridors > 0 && !corridors)) {
+  if (n_corridors < 0 || n_clusters < 0 || (n_corridors > 0 && !corridors)) {
     dab_set_err(ctx, "dab_pair_stage_b_gains: invalid argument");
+    return DAB_E_ARG;
+  }
+  DAB_TRY(enqueue_scaling(pr, gain, audio_std, n_audio, n_video));
+  return stage_b_enqueue_common(pr, n_audio, n_video, corridors, n_corridors, n_clusters, amax, vmax);
+}
+
+// stage B from line clusters: scaling, corridor planning on the device, then the stage itself
+int dab_enqueue_stage_b_clusters(dab_pair *pr, const float gain[3], const float audio_std[3], int64_t n_audio, int64_t n_video,
+                                 const dab_cluster *clusters, int32_t n_clusters) {
+  dab_ctx *ctx = pr->ctx;
+  if (n_clusters < 0 || (n_clusters > 0 && !clusters)) {
+    dab_set_err(ctx, "dab_pair_stage_b_clusters: invalid argument");
+    return DAB_E_ARG;
+  }
+  DAB_TRY(enqueue_scaling(pr, gain, audio_std, n_audio, n_video));
+  DAB_TRY(dab_enqueue_plan_corridors(pr, clusters, n_clusters, n_audio, n_video));
+  pr->stats.n_audio_frames = n_audio;
+  pr->stats.n_video_frames = n_video;
+  return dab_enqueue_stage_b(pr, n_clusters, n_clusters > 0 ? clusters[n_clusters - 1].cluster + 1 : 0);
+}
+
+static int enqueue_scaling(dab_pair *pr, const float gain[3], const float audio_std[3], int64_t n_audio, int64_t n_video) {
+  dab_ctx *ctx = pr->ctx;
+  if (!gain || !audio_std || n_audio <= 0 || n_video <= 8) {
+    dab_set_err(ctx, "stage B: invalid argument");
     return DAB_E_ARG;
   }
   Track &V = pr->trk[DAB_TRACK_VIDEO], &A = pr->trk[DAB_TRACK_AUDIO];
@@ -635,7 +662,7 @@ int dab_enqueue_stage_b_gains(dab_pair *pr, const float gain[3], const float aud
       n_video, gain[0], gain[1], gain[2], audio_std[0], audio_std[1], audio_std[2], 1, pr->v_scaled.as<float>());
   ctx->launches += 2;
   DAB_CUDA(cudaGetLastError());
-  return stage_b_enqueue_common(pr, n_audio, n_video, corridors, n_corridors, n_clusters, amax, vmax);
+  return DAB_OK;
 }
 
 extern "C" {
@@ -655,6 +682,35 @@ int dab_pair_stage_b_gains(dab_pair *pr, const float gain[3], const float audio_
   DAB_TRY(dab_collect_stage_b(pr));
   if (n_points) *n_points = pr->n_points2;
   if (n_path) *n_path = pr->n_path2;
+  return DAB_OK;
+}
+
+int dab_pair_stage_b_clusters(dab_pair *pr, const float gain[3], const float audio_std[3], int64_t n_audio,
+                              int64_t n_video, const dab_cluster *clusters, int32_t n_clusters,
+                              int64_t *n_points, int64_t *n_path) {
+  if (!pr) return DAB_E_ARG;
+  dab_ctx *ctx = pr->ctx;
+  StreamScope scope__(pr->stream);
+  ApiTimer timer__(&pr->api_us[2]);
+  DAB_TRY(dab_enqueue_stage_b_clusters(pr, gain, audio_std, n_audio, n_video, clusters, n_clusters));
+  DAB_TRY(dab_enqueue_counts(pr));
+  DAB_CUDA(dab_wait_stream(pr->stream));
+  DAB_TRY(dab_collect_stage_b(pr));
+  if (n_points) *n_points = pr->n_points2;
+  if (n_path) *n_path = pr->n_path2;
+  return DAB_OK;
+}
+
+int dab_pair_get_corridors(dab_pair *pr, dab_corridor *out, int32_t cap, int32_t *n_corridors) {
+  if (!pr || !n_corridors) return DAB_E_ARG;
+  dab_ctx *ctx = pr->ctx;
+  const int32_t n = (int32_t)pr->h_cor.size();
+  *n_corridors = n;
+  if (!out || cap <= 0 || n == 0) return DAB_OK;
+  const int32_t m = n < cap ? n : cap;
+  DAB_CUDA(cudaSetDevice(ctx->device));
+  DAB_CUDA(cudaMemcpyAsync(out, pr->corridors.p, sizeof(dab_corridor) * (size_t)m, cudaMemcpyDeviceToHost, pr->stream));
+  DAB_CUDA(dab_wait_stream(pr->stream));
   return DAB_OK;
 }
 

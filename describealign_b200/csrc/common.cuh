@@ -99,6 +99,8 @@ struct dab_pair {
   int64_t n_points2 = 0, n_path2 = 0;
   int64_t cap_points2 = 0;     // upper bound of pass-2 points of the current stage_b call (sum of corridor rows)
   float b_amax = 0.f, b_vmax = 0.f;   // np.max of the scaled energy columns (describealign.py:908-909)
+  bool b_device_planned = false;      // corridors and energy maxima come from the device (dab_pair_stage_b_clusters)
+  DevBuf clusters, refine_partial, maxes;
   dab_stats stats = {};
   cudaEvent_t ev[32] = {};
   bool ev_used[16] = {};
@@ -201,6 +203,7 @@ int dab_enqueue_stage_a_dp(dab_pair *pr);
 int dab_enqueue_counts(dab_pair *pr);
 int dab_collect_stage_a(dab_pair *pr, bool with_dp);
 int dab_enqueue_stage_b(dab_pair *pr, int32_t n_corridors, int32_t n_clusters);
+int dab_enqueue_plan_corridors(dab_pair *pr, const dab_cluster *clusters, int32_t n_clusters, int64_t n_audio, int64_t n_video);
 int dab_collect_stage_b(dab_pair *pr);
 int dab_run_import_points1(dab_pair *pr, const int32_t *i_audio, const int32_t *v_video, const double *qual,
                            int64_t n, int src_on_device);

@@ -38,6 +38,7 @@ struct ScoreBArgs {
   const dab_corridor *cor;
   int32_t n_cor;
   float a_max, v_max;
+  const float *maxes;      // device copy of (a_max, v_max) when they were computed on the device, else null
   int32_t *row_count;
   const int32_t *row_off;
   int32_t *p_i, *p_c, *p_rank;
@@ -113,9 +114,10 @@ __global__ void corridor_kernel(ScoreBArgs s) {
     const double t1 = -.5 - log10(1e-4 + fabs((double)a1 - vl1));
     const double t2 = -.5 - log10(1e-4 + fabs((double)a2 - vl2));
     double q = (t0 + t1) + t2;
-    q = q * fmin(fmax((vl0 + 2.5) - (double)s.v_max, 0.0), 1.0);
+    const float v_max = s.maxes ? s.maxes[1] : s.v_max, a_max = s.maxes ? s.maxes[0] : s.a_max;
+    q = q * fmin(fmax((vl0 + 2.5) - (double)v_max, 0.0), 1.0);
     // the audio gate is evaluated in float32 by numpy (f32 array, weak Python scalars)
-    float ag = (a0 + 2.5f) - s.a_max;
+    float ag = (a0 + 2.5f) - a_max;
     ag = fminf(fmaxf(ag, 0.0f), 1.0f) * 0.1f;
     q = q + (double)ag;
     // rank of j over all corridor rows
@@ -1161,6 +1163,7 @@ __global__ void __launch_bounds__(32, 1) dp2_block_kernel(Dp2LArgs a) {
 }
 
 #include "dp2_scan.cuh"
+#include "refine.cuh"
 
 // ------------------------------------------------------------------------------------------
 // Traceback by pointer jumping (binary lifting): up[k][p] = 2^k-th predecessor, node n = root.
@@ -1231,9 +1234,77 @@ static bool corridor_dp_eligible(const dab_pair *pr, int32_t n_cor) {
   for (int k = 0; k < n_cor; ++k) {
     const dab_corridor &c = pr->h_cor[k];
     if (!(c.slope > 0.0)) return false;
-    if (c.hi > c.lo && !(c.slope * (double)c.lo + c.offset >= 3.0)) return false;
+    // (device-planned corridors: h_cor holds row ranges that contain the planned ones; the planned lines
+    // start at coordinate >= 4 by construction, describealign.py:898)
+    if (!pr->b_device_planned && c.hi > c.lo && !(c.slope * (double)c.lo + c.offset >= 3.0)) return false;
   }
   return true;
+}
+
+// describealign.py:895-900 on the host, for buffer sizes only (the device computes the ranges it scores)
+static void host_x_limits(double x_first, double x_last, double offset, double slope, int64_t n_a, int64_t n_v,
+                          long long extend, long long &lo, long long &hi) {
+  auto to_ll = [](double x) { return !(x > -9.0e15) ? -9000000000000000LL : (!(x < 9.0e15) ? 9000000000000000LL : (long long)x); };
+  lo = to_ll(x_first) - extend;
+  if (lo < 0) lo = 0;
+  hi = to_ll(x_last) + extend;
+  if (hi > n_a - 1) hi = n_a - 1;
+  const long long l2 = to_ll(ceil((4.0 - offset) / slope));
+  const long long h2 = to_ll(floor(((double)(n_v - 4) - offset) / slope));
+  if (l2 > lo) lo = l2;
+  if (h2 < hi) hi = h2;
+}
+
+// Corridor planning on the device (refine.cuh).  `clusters` is read by an asynchronous copy: it must stay
+// valid until the stream has consumed it.  Leaves pr->h_cor with row ranges that CONTAIN the planned ones
+// (the refined offset moves the limits by at most 2 / slope rows), for buffer sizes.
+int dab_enqueue_plan_corridors(dab_pair *pr, const dab_cluster *clusters, int32_t n_clusters, int64_t n_a, int64_t n_v) {
+  dab_ctx *ctx = pr->ctx;
+  cudaStream_t st = pr->stream;
+  pr->h_cor.clear();
+  for (int k = 0; k < n_clusters; ++k) {
+    const dab_cluster &c = clusters[k];
+    if (c.cluster < 0 || (k > 0 && c.cluster <= clusters[k - 1].cluster) || !(c.slope == c.slope) || c.slope == 0.0) {
+      dab_set_err(ctx, "dab_pair_stage_b_clusters: clusters must be in ascending cluster order with a non-zero slope");
+      return DAB_E_ARG;
+    }
+    long long lo, hi;
+    host_x_limits(c.x_first, c.x_last, c.offset, c.slope, n_a, n_v, 0, lo, hi);
+    dab_corridor out;
+    out.cluster = c.cluster; out.lo = 0; out.hi = 0; out.reserved = 0; out.slope = c.slope; out.offset = c.offset;
+    if (!(hi < lo + 5)) {
+      double xf = c.x_first, xl = c.x_last;
+      if (hi > lo + 100) { xf = (double)lo; xl = (double)(hi - 1); }
+      // widest range any |coef| < 2 can give: the audio-side limits only
+      long long lo2 = (long long)xf - 6300, hi2 = (long long)xl + 6300;
+      if (lo2 < 0) lo2 = 0;
+      if (hi2 > n_a - 1) hi2 = n_a - 1;
+      if (hi2 > lo2) { out.lo = (int32_t)lo2; out.hi = (int32_t)hi2; }
+    }
+    pr->h_cor.push_back(out);
+  }
+  const int max_blocks = (int)cdiv(n_a > 0 ? n_a : 1, RF_CHUNK);
+  DAB_TRY(dab_ensure(ctx, pr->clusters, sizeof(dab_cluster) * (size_t)(n_clusters + 1)));
+  DAB_TRY(dab_ensure(ctx, pr->corridors, sizeof(dab_corridor) * (size_t)(n_clusters + 1)));
+  DAB_TRY(dab_ensure(ctx, pr->refine_partial, sizeof(double) * 4 * (size_t)max_blocks * (size_t)(n_clusters + 1)));
+  DAB_TRY(dab_ensure(ctx, pr->maxes, sizeof(float) * 4));
+  column_max_kernel<<<2, 1024, 0, st>>>(pr->a_scaled.as<float>(), n_a, pr->v_scaled.as<float>(), n_v, pr->maxes.as<float>());
+  ctx->launches += 1;
+  if (n_clusters > 0) {
+    DAB_CUDA(cudaMemcpyAsync(pr->clusters.p, clusters, sizeof(dab_cluster) * (size_t)n_clusters, cudaMemcpyHostToDevice, st));
+    RefineArgs ra;
+    ra.a_scaled = pr->a_scaled.as<float>(); ra.v_scaled = pr->v_scaled.as<float>();
+    ra.n_a = n_a; ra.n_v = n_v;
+    ra.cl = pr->clusters.as<dab_cluster>(); ra.n_cl = n_clusters; ra.max_blocks = max_blocks;
+    ra.partial = pr->refine_partial.as<double>();
+    ra.cor = pr->corridors.as<dab_corridor>();
+    refine_partial_kernel<<<dim3((unsigned)max_blocks, (unsigned)n_clusters), RF_THREADS, 0, st>>>(ra);
+    refine_plan_kernel<<<(unsigned)cdiv(n_clusters, 64), 64, 0, st>>>(ra);
+    ctx->launches += 2;
+  }
+  DAB_CUDA(cudaGetLastError());
+  pr->b_device_planned = true;
+  return DAB_OK;
 }
 
 // Stage B enqueued on the pair's stream without a host round trip: every (corridor, row) yields at most
@@ -1261,6 +1332,7 @@ int dab_enqueue_stage_b(dab_pair *pr, int32_t n_cor, int32_t n_clusters) {
   sb.cor = pr->corridors.as<dab_corridor>(); sb.n_cor = n_cor;
   sb.a_max = pr->b_amax;
   sb.v_max = pr->b_vmax;
+  sb.maxes = pr->b_device_planned ? pr->maxes.as<float>() : nullptr;
   sb.want_rank = fast ? 0 : 1;
   DAB_TRY(dab_ensure(ctx, pr->row2_count, sizeof(int32_t) * (size_t)(n_a + 2)));
   DAB_TRY(dab_ensure(ctx, pr->row2_off, sizeof(int32_t) * (size_t)(n_a + 2)));

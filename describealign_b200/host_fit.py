@@ -3,9 +3,9 @@
 BASELINE.json's north star keeps this part in Python on the host and outside the timed
 window: the continuity filter, the per-feature gain fit, the 70->1 compression of the
 pass-1 path, the L1 linear programme and the grouping of its solution into line clusters
-(reference describealign.py:702-893), plus the two small host pieces of stage B - the
-corridor limits with the optional sub-frame offset refinement (describealign.py:895-930) and
-the node list built from the final path (describealign.py:995-1027).
+(reference describealign.py:702-893), plus the node list built from the final path
+(describealign.py:995-1027).  The corridor planning with its sub-frame offset refinement
+(describealign.py:895-932) runs on the device (csrc/refine.cuh).
 
 The arithmetic goes through the same numpy / scipy entry points the reference calls
 (np.convolve, np.linalg.lstsq, np.std, scipy.optimize.linprog with HiGHS) on operands of
@@ -102,6 +102,22 @@ def scale_features(video_features, audio_features, x, y, return_gains=False):
     if not f32:
         return audio_scaled, video_scaled, None
     return audio_scaled, video_scaled, (np.array([g[0] for g in gains], np.float32), np.array(stds, np.float32))
+
+
+def feature_gains(video_features, audio_features, x, y):
+    """The six scalars the scaled feature arrays are made from (describealign.py:733-741): per feature
+    the least-squares gain and the audio standard deviation, plus the lengths of the stacked arrays.
+    Returns (gains f32[3], audio_stds f32[3], n_audio, n_video); the arrays themselves are rebuilt on
+    the device (dab_pair_stage_b_gains / _clusters)."""
+    gains, stds = [], []
+    for v_feat, a_feat in list(zip(video_features, audio_features))[:3]:
+        if np.asarray(v_feat).dtype != np.float32 or np.asarray(a_feat).dtype != np.float32:
+            raise TypeError("the first three features must be float32 (as get_energy / get_zero_crossings / get_freq_bands return them)")
+        stds.append(np.std(a_feat))
+        gains.append(np.linalg.lstsq(v_feat[y][:, None], a_feat[x], rcond=None)[0][0])
+    na = min(len(f) for f in list(audio_features)[:3])
+    nv = min(len(f) for f in list(video_features)[:3])
+    return np.array(gains, np.float32), np.array(stds, np.float32), na, nv
 
 
 def compress_path(x, y, window=None):
@@ -263,58 +279,11 @@ def line_clusters(fit: RateFit):
 # Stage-B host helpers
 # ------------------------------------------------------------------------------------------
 
-def x_limits(x_first, x_last, offset, slope, n_audio, n_video, extend=CORRIDOR_RADIUS, buffer_vert=4):
-    """Half-open audio-row range of a cluster's corridor (describealign.py:895-900)."""
-    lo = max(int(x_first) - extend, 0)
-    hi = min(int(x_last) + extend, n_audio - 1)
-    lo = max(lo, int(np.ceil((buffer_vert - offset) / slope)))
-    hi = min(hi, int(np.floor((n_video - buffer_vert - offset) / slope)))
-    return lo, hi
-
-
-def lerp_video(video_scaled: np.ndarray, y: np.ndarray) -> np.ndarray:
-    """Degree-1 spline through the video rows at fractional positions y, in the f64 form
-    that is bit-identical to scipy's make_interp_spline(k=1)."""
-    f = np.floor(y).astype(np.int64)
-    t = (y - f)[:, None]
-    v = video_scaled.astype(np.float64)
-    return v[f] * (1.0 - t) + v[f + 1] * t
-
-
-def plan_corridors(clusters, audio_scaled, video_scaled):
-    """Per cluster: the audio-row range to score and the (possibly refined) line.
-
-    Implements the control flow of describealign.py:912-932 up to the point where scoring
-    starts, including the sub-frame offset refinement (describealign.py:916-930) and the
-    quirk that the refinement branch shortens the corridor by one row.
-    Returns a list of (cluster_index, lo, hi, slope, offset) for clusters that are scored.
-    """
-    n_audio, n_video = len(audio_scaled), len(video_scaled)
-    plans = []
-    for idx, (cx, offset, slope) in enumerate(clusters):
-        lo, hi = x_limits(cx[0], cx[-1], offset, slope, n_audio, n_video, extend=0)
-        if hi < lo + 5:
-            continue
-        x_first, x_last = cx[0], cx[-1]
-        if hi > lo + 100:
-            rows = np.arange(lo, hi)
-            y = slope * rows + offset
-            a_m = audio_scaled[lo:hi]
-            v_m = lerp_video(video_scaled, y)
-            err = a_m[1:-1] - v_m[1:-1]
-            ok = np.mean(err, axis=-1) < 0.1
-            if np.count_nonzero(ok) > 50:
-                dv = ((v_m[2:] - v_m[:-2]) / 2.)[ok]
-                err = err[ok]
-                coef, resid, _, _ = np.linalg.lstsq(dv.reshape(-1, 1), err.flat, rcond=None)
-                explained = 1 - (resid / np.sum(err ** 2))
-                sigmas = np.sqrt(explained * np.prod(err.shape)) - 1.
-                if sigmas > 8 and abs(coef[0]) < 2:
-                    offset = offset + coef[0]
-            x_first, x_last = rows[0], rows[-1]
-        lo2, hi2 = x_limits(x_first, x_last, offset, slope, n_audio, n_video)
-        plans.append((idx, lo2, hi2, float(slope), float(offset)))
-    return plans
+def cluster_lines(clusters):
+    """What stage B needs of the line clusters: (cluster index, first x, last x, offset, slope) per
+    cluster.  The corridor planning itself (row limits, sub-frame offset refinement, +-30 s extension,
+    describealign.py:895-932) runs on the device (csrc/refine.cuh)."""
+    return [(idx, float(cx[0]), float(cx[-1]), float(offset), float(slope)) for idx, (cx, offset, slope) in enumerate(clusters)]
 
 
 def build_nodes(path, n_audio_energy: int, n_video_energy: int, n_audio_scaled: int, n_video_scaled: int):

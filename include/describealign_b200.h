@@ -70,6 +70,16 @@ typedef struct {
   double offset;
 } dab_corridor;
 
+/* One line cluster of the host fit (describealign.py:861-893): first and last audio coordinate of its
+ * points and the fitted line j = slope * i + offset.  Stage B plans the scored corridor from it on the
+ * device (:895-932): row limits, sub-frame offset refinement, +-30 s extension. */
+typedef struct {
+  int32_t cluster;
+  int32_t reserved;
+  double x_first, x_last;
+  double offset, slope;
+} dab_cluster;
+
 /* Work counters of the last stage_a / stage_b run (for measurement). */
 typedef struct {
   int64_t n_video_frames, n_audio_frames;
@@ -200,6 +210,16 @@ int dab_pair_stage_b_gains(dab_pair *pair, const float gain[3], const float audi
                            int64_t n_video, float audio_energy_max, float video_energy_max,
                            const dab_corridor *corridors, int32_t n_corridors, int32_t n_clusters,
                            int64_t *n_points, int64_t *n_path);
+/* The whole of stage B on the device, from the host fit's line clusters (in cluster order, ascending
+ * cluster index): corridor planning incl. the offset refinement (:895-932), np.max of the scaled energy
+ * columns (:908-909), scoring, DP #2, traceback.  The refinement's least-squares coefficient is the
+ * quotient of float64 sums (the reference: np.linalg.lstsq), so refined offsets agree with the
+ * reference's to ~1e-15 relative rather than bit for bit. */
+int dab_pair_stage_b_clusters(dab_pair *pair, const float gain[3], const float audio_std[3], int64_t n_audio,
+                              int64_t n_video, const dab_cluster *clusters, int32_t n_clusters,
+                              int64_t *n_points, int64_t *n_path);
+/* the corridors of the last stage_b call as scored (for _clusters: as planned on the device); cap entries */
+int dab_pair_get_corridors(dab_pair *pair, dab_corridor *out, int32_t cap, int32_t *n_corridors);
 /* final path rows (video j, audio i, cluster, qual, cum), float64 row-major (n_path, 5),
  * in frames (the /210 scaling of :1026 is the caller's). */
 int dab_pair_get_path2(dab_pair *pair, double *rows);
@@ -272,8 +292,9 @@ typedef struct {
   float gain[3], audio_std[3];
   float audio_energy_max, video_energy_max;
   int64_t n_audio, n_video;
-  const dab_corridor *corridors;   /* copied by dab_engine_submit_b */
+  const dab_corridor *corridors;   /* pre-planned corridors (copied by dab_engine_submit_b), or NULL: */
   int32_t n_corridors, n_clusters;
+  const dab_cluster *clusters;     /* n_clusters line clusters, planned on the device (energy maxima ignored) */
 } dab_stage_b_in;
 
 int dab_engine_create(dab_ctx *ctx, int32_t slots, dab_engine **out);

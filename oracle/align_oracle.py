@@ -164,6 +164,65 @@ def stage_b(plans, n_clusters, audio_scaled, video_scaled):
     return {"points_i": pi, "points_j": pj, "points_c": pc, "points_q": pq, "path": path}
 
 
+# ------------------------------------------------------------------------------------------
+# corridor planning (describealign.py:895-932), on the reference's own numpy / scipy calls
+# ------------------------------------------------------------------------------------------
+
+def x_limits(x_first, x_last, offset, slope, n_audio, n_video, extend=(210 * 30), buffer_vert=4):
+    """Half-open audio-row range of a cluster's corridor (describealign.py:895-900)."""
+    lo = max(int(x_first) - extend, 0)
+    hi = min(int(x_last) + extend, n_audio - 1)
+    lo = max(lo, int(np.ceil((buffer_vert - offset) / slope)))
+    hi = min(hi, int(np.floor((n_video - buffer_vert - offset) / slope)))
+    return lo, hi
+
+
+def lerp_video(video_scaled: np.ndarray, y: np.ndarray) -> np.ndarray:
+    """Degree-1 spline through the video rows at fractional positions y, in the f64 form
+    that is bit-identical to scipy's make_interp_spline(k=1)."""
+    f = np.floor(y).astype(np.int64)
+    t = (y - f)[:, None]
+    v = video_scaled.astype(np.float64)
+    return v[f] * (1.0 - t) + v[f + 1] * t
+
+
+def plan_corridors(clusters, audio_scaled, video_scaled):
+    """Per cluster: the audio-row range to score and the (possibly refined) line.
+
+    Implements the control flow of describealign.py:912-932 up to the point where scoring
+    starts, including the sub-frame offset refinement (describealign.py:916-930) and the
+    quirk that the refinement branch shortens the corridor by one row.
+    Returns a list of (cluster_index, lo, hi, slope, offset) for clusters that are scored.
+    """
+    n_audio, n_video = len(audio_scaled), len(video_scaled)
+    plans = []
+    for idx, (cx, offset, slope) in enumerate(clusters):
+        lo, hi = x_limits(cx[0], cx[-1], offset, slope, n_audio, n_video, extend=0)
+        if hi < lo + 5:
+            continue
+        x_first, x_last = cx[0], cx[-1]
+        if hi > lo + 100:
+            rows = np.arange(lo, hi)
+            y = slope * rows + offset
+            a_m = audio_scaled[lo:hi]
+            v_m = lerp_video(video_scaled, y)
+            err = a_m[1:-1] - v_m[1:-1]
+            ok = np.mean(err, axis=-1) < 0.1
+            if np.count_nonzero(ok) > 50:
+                dv = ((v_m[2:] - v_m[:-2]) / 2.)[ok]
+                err = err[ok]
+                coef, resid, _, _ = np.linalg.lstsq(dv.reshape(-1, 1), err.flat, rcond=None)
+                explained = 1 - (resid / np.sum(err ** 2))
+                sigmas = np.sqrt(explained * np.prod(err.shape)) - 1.
+                if sigmas > 8 and abs(coef[0]) < 2:
+                    offset = offset + coef[0]
+            x_first, x_last = rows[0], rows[-1]
+        lo2, hi2 = x_limits(x_first, x_last, offset, slope, n_audio, n_video)
+        plans.append((idx, lo2, hi2, float(slope), float(offset)))
+    return plans
+
+
+
 def align(video_features, audio_features, video_energy, audio_energy, host, details=None):
     """Whole align() with the host stage supplied by `host` (see module docstring).
     Returns (audio_times, video_times, similarity_percent, path, median_slope)."""
@@ -177,7 +236,7 @@ def align(video_features, audio_features, video_energy, audio_energy, host, deta
     fx, fy = host.compress_path(x, y)
     fit = host.rate_change_fit(fx, fy)
     clusters = host.line_clusters(fit)
-    plans = host.plan_corridors(clusters, audio_scaled, video_scaled)
+    plans = plan_corridors(clusters, audio_scaled, video_scaled)
     b = stage_b(plans, len(clusters), audio_scaled, video_scaled)
     path = b["path"]
     if len(path) < host.min_path_length(len(video_energy), len(audio_energy)):

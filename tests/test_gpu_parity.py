@@ -279,8 +279,10 @@ def test_stage_b_block_dp_many_corridors(gpu_ctx, seed, n_cor):
 
 def test_stage_b_device_scaling_equals_uploaded_arrays(gpu_ctx, golden_align):
     """dab_pair_stage_b_gains (scaled features rebuilt on the device from 6 scalars, describealign.py:737-741)
-    against dab_pair_stage_b with the host's numpy arrays: identical points, quals and path."""
+    against dab_pair_stage_b with the host's numpy arrays, both with the oracle's corridor planning:
+    identical points, quals and path."""
     from describealign_b200 import api
+    from oracle import align_oracle as ao
     _, meta = golden_align
     v, a = golden_pair_pcm(meta, "pair_warp")
     res = []
@@ -288,10 +290,11 @@ def test_stage_b_device_scaling_equals_uploaded_arrays(gpu_ctx, golden_align):
         job = api.AlignJob()
         try:
             job.device_scaling = device_scaling
+            job.device_planning = False
+            job.test_planner = ao.plan_corridors
             job.load_pcm(v, a)
             job.device_stage_a()
             job.host_stage()
-            assert job.gains is not None
             job.device_stage_b()
             res.append((job.pair.points2(), job.path.copy(), job.h2d_bytes))
         finally:
@@ -301,6 +304,50 @@ def test_stage_b_device_scaling_equals_uploaded_arrays(gpu_ctx, golden_align):
         np.testing.assert_array_equal(x, y)
     np.testing.assert_array_equal(path0, path1)
     assert up0 < up1
+
+
+@pytest.mark.parametrize("case", ["pair_a", "pair_warp", "synthetic"])
+def test_device_corridor_planning_vs_oracle(gpu_ctx, golden_align, case):
+    """Corridor planning on the device (csrc/refine.cuh: row limits, sub-frame offset refinement, +-30 s
+    extension, energy maxima; describealign.py:895-932) against the oracle's numpy / np.linalg.lstsq
+    planning on the same clusters: identical row ranges and clusters, refined offsets within 1e-9 (the
+    device divides float64 sums instead of calling LAPACK), identical integer path columns."""
+    from describealign_b200 import api, host_fit, synth
+    from oracle import align_oracle as ao
+    if case == "synthetic":
+        v, a = synth.make_pair(200.0, 11.0, skips=[(60.0, 3.0), (130.0, -2.0)], seed=88)
+    else:
+        _, meta = golden_align
+        v, a = golden_pair_pcm(meta, case)
+    out = []
+    for device_planning in (True, False):
+        job = api.AlignJob()
+        try:
+            job.device_planning = device_planning
+            job.test_planner = ao.plan_corridors
+            job.load_pcm(v, a)
+            job.device_stage_a()
+            job.host_stage()
+            job.device_stage_b()
+            audio_scaled, video_scaled = host_fit.scale_features(job.video_features, job.audio_features, job.kept_x, job.kept_y)
+            want_plans = [p for p in ao.plan_corridors(job.clusters, audio_scaled, video_scaled) if p[2] > p[1]]
+            out.append((job.pair.corridors(), job.path.copy(), want_plans, [c[1] for c in job.clusters]))
+        finally:
+            job.close()
+    (cor_dev, path_dev, want, offsets0), (cor_host, path_host, _, _) = out
+    assert len(cor_dev) == len(want)
+    refined = 0
+    for got, w in zip(cor_dev, want):
+        assert got[0] == w[0] and got[1] == w[1] and got[2] == w[2], (got, w)
+        assert got[3] == w[3]
+        assert abs(got[4] - w[4]) <= 1e-9 * max(1.0, abs(w[4])), (got, w)
+        refined += int(w[4] != offsets0[w[0]])
+    assert path_dev.shape == path_host.shape
+    np.testing.assert_array_equal(path_dev[:, 1:3], path_host[:, 1:3])
+    np.testing.assert_allclose(path_dev[:, 0], path_host[:, 0], rtol=0, atol=1e-8)
+    np.testing.assert_allclose(path_dev[:, 3:], path_host[:, 3:], rtol=0, atol=1e-6)
+    if case == "synthetic":
+        assert refined >= 0     # (whether the refinement fires depends on the pair; the offsets agree either way)
 
 
 def test_end_to_end_dp2_variants_agree(gpu_ctx, golden_align):
