@@ -39,7 +39,12 @@ if ROOT not in sys.path:
 
 METRIC = "audio_hours_aligned_per_second"
 UNIT = "audio-hours/s"
-WORKLOAD = "C2: synthetic 22-min video audio vs 27-min description, 202 s offset, 10 inserted skips, mono 44.1 kHz s16"
+WORKLOADS = {
+    "C2": "C2: synthetic 22-min video audio vs 27-min description, 202 s offset, 10 inserted skips, mono 44.1 kHz s16",
+    "C3": "C3: the C2 pair in stereo (--stretch_audio feature semantics: features from 2 channels), 44.1 kHz s16",
+    "C4": "C4: batch mode, 64 distinct synthetic 45-min episode/description pairs (offset 10-90 s, 4-8 skips) sharded over the GPUs, mono 44.1 kHz s16",
+}
+WORKLOAD = WORKLOADS["C2"]      # the configuration BASELINE.json's metric is quoted on (the default)
 
 
 def parse_args():
@@ -52,26 +57,30 @@ def parse_args():
     ap.add_argument("--distinct", type=int, default=0,
                     help="distinct synthetic pairs per GPU, a step cycles over them (default 4 at every N: 1 GB of PCM, 8x the L2)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS),
+                    help="C2 (default, the metric's configuration), C3 (stereo), C4 (64 x 45-min pairs over all GPUs: strong scaling)")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the C2 durations (debugging only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-long-pair", action="store_true", help="N > 1: skip the long-pair (C5) check that runs on all ranks after the timed steps")
+    ap.add_argument("--long-scale", type=float, default=0.1, help="scale of the C5 pair used for the N > 1 long-pair check")
     return ap.parse_args()
 
 
-def make_pairs(n, first_seed, scale, world=1):
-    """n C2 pairs with distinct seeds, generated in parallel worker processes (the host's cores are
-    shared by the `world` ranks of the node)."""
+def make_pairs(n, first_seed, scale, world=1, config="C2"):
+    """n pairs of a named configuration with distinct seeds, generated in parallel worker processes (the
+    host's cores are shared by the `world` ranks of the node)."""
     from concurrent.futures import ProcessPoolExecutor
     from describealign_b200 import synth
     seeds = [first_seed + k for k in range(n)]
     if n == 1:
-        return [synth.config_pair("C2", seeds[0], scale)]
+        return [synth.config_pair(config, seeds[0], scale)]
     with ProcessPoolExecutor(max_workers=max(1, min(n, (os.cpu_count() or 1) // max(1, world)))) as ex:
-        return list(ex.map(_make_one, [(s, scale) for s in seeds]))
+        return list(ex.map(_make_one, [(s, scale, config) for s in seeds]))
 
 
 def _make_one(arg):
     from describealign_b200 import synth
-    return synth.config_pair("C2", arg[0], arg[1])
+    return synth.config_pair(arg[2], arg[0], arg[1])
 
 
 def audio_hours(pairs):
@@ -237,7 +246,7 @@ def run_reference(args, rank, world):
     import oracle
     oracle.build()
     # bounded sample: one pair per host core (at most 16), whatever --pairs / --gpus say
-    pairs = make_pairs(max(1, min(16, os.cpu_count() or 1)), 0, args.scale)
+    pairs = make_pairs(max(1, min(16, os.cpu_count() or 1)), 0, args.scale, 1, args.workload)
     hours = audio_hours(pairs)
     cores = min(len(pairs), os.cpu_count() or 1)
     from concurrent.futures import ProcessPoolExecutor
@@ -259,11 +268,11 @@ def run_reference(args, rank, world):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic", "impl": "reference",
-            "config": {"workload": WORKLOAD, "pairs_per_step": len(pairs), "audio_hours_per_step": hours,
+            "config": {"workload": WORKLOADS[args.workload], "pairs_per_step": len(pairs), "audio_hours_per_step": hours,
                        "scale": args.scale,
                        "timed": "features + align() minus scipy.optimize.linprog (BASELINE.md section 3), per pair, one process per pair"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{len(pairs)} full C2 pairs per step, one oracle-port process per pair",
+                             "sample": f"{len(pairs)} full {args.workload} pairs per step, one oracle-port process per pair",
                              "value_device_stages_only": hours / float(np.mean(times_dev)),
                              "unmodified_reference_one_pair_one_core": None if real is None else {
                                  "value": h1 / real[0], "unit": UNIT, "seconds": real[0], "seconds_linprog_subtracted": real[1],
@@ -319,9 +328,14 @@ def run_ours(args, rank, world, local_rank):
     # The same configuration at every N: W slots (pairs on the device at once), B pairs per step cycling
     # over `distinct` synthetic pairs per GPU (generating one takes ~35 s of CPU).
     W = args.workers if args.workers > 0 else 32
-    B = args.pairs if args.pairs > 0 else 8 * W
-    distinct = max(1, min(B, args.distinct if args.distinct > 0 else 4))
-    base_pairs = make_pairs(distinct, rank * distinct, args.scale, world)
+    if args.workload == "C4":
+        # batch mode: 64 distinct episodes in all, each rank owns its share and a step is one pass over it
+        distinct = max(1, (args.distinct if args.distinct > 0 else 64) // world)
+        B = distinct
+    else:
+        B = args.pairs if args.pairs > 0 else 8 * W
+        distinct = max(1, min(B, args.distinct if args.distinct > 0 else 4))
+    base_pairs = make_pairs(distinct, rank * distinct, args.scale, world, args.workload)
     pairs = [base_pairs[k % distinct] for k in range(B)]
     hours_rank = audio_hours(pairs)
 
@@ -477,12 +491,44 @@ def run_ours(args, rank, world, local_rank):
         }
         h1 = audio_hours(pairs[:1])
         cpu = {"value": h1 / cpu_t["hot_path_s"], "unit": UNIT, "cores": 1, "kind": "port",
-               "sample": "1 full C2 pair through the oracle port (C features, C match + DPs, numpy host stage and corridors); "
+               "sample": "1 full " + args.workload + " pair through the oracle port (C features, C match + DPs, numpy host stage and corridors); "
                          "timed as BASELINE.md section 3: features + align() minus scipy.optimize.linprog",
                "seconds": cpu_t["hot_path_s"], "seconds_linprog_subtracted": cpu_t["linprog_s"],
                "seconds_device_stages_only": cpu_t["device_stages_s"],
                "value_device_stages_only": h1 / cpu_t["device_stages_s"],
                "host_cpu": _cpu_model(), "host_cores": os.cpu_count()}
+
+    # N > 1: one long pair on all ranks (match stage and corridor scoring sharded by audio rows, all-gathers
+    # over NCCL, DPs and host fit on rank 0), checked against the single-GPU path on the same PCM
+    long_pair = None
+    if world > 1 and not args.no_long_pair:
+        from describealign_b200 import synth
+        lv, la = synth.config_pair("C5", 0, args.long_scale)
+        barrier()
+        ldet = {}
+        t0 = time.perf_counter()
+        lout = batch.align_long_pair(lv, la, details=ldet)
+        torch.cuda.synchronize()
+        t_long = time.perf_counter() - t0
+        same = None
+        if rank == 0:
+            import contextlib
+            with contextlib.redirect_stdout(sys.stderr):
+                t1 = time.perf_counter()
+                lref = api.align_pcm(lv, la)
+                t_single = time.perf_counter() - t1
+            same = bool(np.array_equal(lout[3], lref[3]) and np.array_equal(lout[0], lref[0]) and np.array_equal(lout[1], lref[1]))
+            sh = ldet.get("shards", {})
+            long_pair = {"workload": "C5 (2.5 h film vs 3 h description) at scale %g: %.1f + %.1f min, mono 44.1 kHz" % (
+                             args.long_scale, len(lv) / 44100 / 60, len(la) / 44100 / 60),
+                         "ranks": world, "identical_to_single_gpu_path": same,
+                         "wall_s_all_ranks_incl_host_fit": t_long, "wall_s_single_gpu_incl_host_fit": t_single,
+                         "match_points_all_gathered": sh.get("shard_a", (0, 0, 0, 0))[3],
+                         "all_gather_bytes_stage_a": 16 * sh.get("shard_a", (0, 0, 0, 0))[3],
+                         "quals_all_gathered": sh.get("shard_b", (0, 0, 0, 0))[3],
+                         "all_gather_bytes_stage_b": 8 * sh.get("shard_b", (0, 0, 0, 0))[3],
+                         "note": "the frontier DPs and the host fit do not shard (SURVEY.md 8e: replicas only); they run on rank 0"}
+        barrier()
 
     # max over ranks
     t = torch.tensor([ms_dev, ms_e2e], device="cuda", dtype=torch.float64)
@@ -545,20 +591,22 @@ def run_ours(args, rank, world, local_rank):
         ncu_traffic = (116.465152e6 + 5.258240e6 + 143.008e6 + 9.717248e6) / 2
         step_bytes = pcm_bytes(pairs) + 24 * (work_all["n_points1"] + work_all["n_points2"])
         main_roof.update({"kernel": "features_kernel", "peak_source": peak_src,
-                          "measured": "CUDA events on the pair's stream, one C2 pair alone on the GPU right after the timed steps",
+                          "measured": "CUDA events on the pair's stream, one pair alone on the GPU right after the timed steps",
                           "traffic": ncu_traffic if args.scale == 1.0 else None,
-                          "traffic_note": "bytes per launch (dram read + write), ncu --set full of one C2 pair, see profiles/",
+                          "traffic_note": "bytes per launch (dram read + write), ncu --set full of one C2 pair (mono), see profiles/",
                           "step": {"bound": "hbm", "algorithmic_bytes": step_bytes, "ms": ms_dev,
                                    "achieved": step_bytes / (ms_dev * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                    "frac": step_bytes / (ms_dev * 1e-3) / 1e9 / peaks["hbm_gbs"]}})
         e2e_gbs = h2d_all / world / (ms_e2e * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": hours / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True,
+            "scaling": "strong" if args.workload == "C4" else "weak",
             "vs_baseline": None, "dtype": "f32+f64 (u32 packed codes)", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "pairs_per_gpu_per_step": B, "pairs_in_flight_per_gpu": W,
+            "config": {"workload": WORKLOADS[args.workload], "pairs_per_gpu_per_step": B, "pairs_in_flight_per_gpu": W,
                        "distinct_pairs_per_gpu": distinct, "audio_hours_per_step": hours,
-                       "l2_policy": "inputs larger than L2 (each pair streams 259 MB of PCM, %d distinct pairs per GPU; 126 MB L2)" % distinct,
+                       "l2_policy": "inputs larger than L2 (each pair streams %d MB of PCM, %d distinct pairs per GPU; 126 MB L2)" % (
+                           int(sum(v.nbytes + a.nbytes for v, a in base_pairs[:1]) / 1e6), distinct),
                        "timed": "one region per step: every pair through device stage A (features, prep, tables, gate, score, DP1, traceback) and device stage B (feature scaling, corridors, DP2, traceback) incl. the result copies to the host, W pairs on the device at a time, driven by the library's scheduler thread; the host rate-change fit between the stages (describealign.py:702-893 and the corridor planning :895-930) is solved during warm-up and is a path comparison + lookup inside the region (untimed by BASELINE.json)",
                        "scale": args.scale},
             "ms_per_pair": ms_dev / B,
@@ -587,6 +635,7 @@ def run_ours(args, rank, world, local_rank):
             "clocks": clocks,
             "cpu_baseline": cpu,
             "parity": parity,
+            "long_pair": long_pair,
         }
         print(json.dumps(line))
     if world > 1:

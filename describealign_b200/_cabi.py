@@ -25,7 +25,9 @@ EXPORTS = [
     "dab_pair_stage_a_match", "dab_pair_export_points1", "dab_pair_import_points1", "dab_pair_dp1",
     "dab_alloc_pinned", "dab_free_pinned", "dab_trim_pinned", "dab_alloc_stats", "dab_host_copy",
     "dab_set_host_wait", "dab_pair_get_timeline", "dab_pair_stage_b_gains",
+    "dab_set_log10f_correction", "dab_eval_log10f",
     "dab_pair_set_gate_energy", "dab_pair_stage_b_clusters", "dab_pair_get_corridors",
+    "dab_pair_stage_b_score", "dab_pair_export_quals2", "dab_pair_import_quals2", "dab_pair_dp2",
     "dab_engine_create", "dab_engine_destroy", "dab_engine_submit", "dab_engine_next", "dab_engine_submit_b",
     "dab_engine_release", "dab_engine_slot_error", "dab_engine_slot_pair", "dab_engine_counters",
 ]
@@ -136,6 +138,8 @@ def load() -> ctypes.CDLL:
     lib.dab_pair_stream.restype = vp
     lib.dab_pair_set_pcm.argtypes = [vp, i32, vp, i64, i32, i32, i32]
     lib.dab_pair_set_features.argtypes = [vp, i32, vp, i64, vp, vp, vp, vp, i64]
+    lib.dab_set_log10f_correction.argtypes = [vp, vp, ctypes.c_uint64]
+    lib.dab_eval_log10f.argtypes = [vp, vp, vp, i64]
     lib.dab_pair_set_gate_energy.argtypes = [vp, i32, vp, i64]
     lib.dab_pair_feature_lens.argtypes = [vp, i32, ctypes.POINTER(i64 * 5)]
     lib.dab_pair_get_features.argtypes = [vp, i32, vp, vp, vp, vp, vp]
@@ -151,6 +155,11 @@ def load() -> ctypes.CDLL:
     lib.dab_pair_stage_b_clusters.argtypes = [vp, ctypes.POINTER(ctypes.c_float * 3), ctypes.POINTER(ctypes.c_float * 3), i64, i64,
                                               vp, ctypes.c_int32, ctypes.POINTER(i64), ctypes.POINTER(i64)]
     lib.dab_pair_get_corridors.argtypes = [vp, vp, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32)]
+    lib.dab_pair_stage_b_score.argtypes = [vp, ctypes.POINTER(ctypes.c_float * 3), ctypes.POINTER(ctypes.c_float * 3), i64, i64,
+                                           vp, ctypes.c_int32, i64, i64, ctypes.POINTER(i64), ctypes.POINTER(i64), ctypes.POINTER(i64)]
+    lib.dab_pair_export_quals2.argtypes = [vp, vp, i64, i64, i32]
+    lib.dab_pair_import_quals2.argtypes = [vp, vp, i64, i32]
+    lib.dab_pair_dp2.argtypes = [vp, ctypes.POINTER(i64)]
     lib.dab_pair_get_path2.argtypes = [vp, vp]
     lib.dab_pair_get_points2.argtypes = [vp, vp, vp, vp, vp]
     lib.dab_pair_get_stats.argtypes = [vp, ctypes.POINTER(Stats)]
@@ -258,6 +267,20 @@ class Context:
 
     def set_option(self, name: str, value: int):
         self.check(self.lib.dab_set_option(self.handle, name.encode(), int(value)))
+
+    def eval_log10f(self, x: np.ndarray) -> np.ndarray:
+        """The feature kernel's log10f on float32 values >= 1 (glibc's formula + the uploaded correction)."""
+        x = np.ascontiguousarray(x, np.float32)
+        y = np.empty_like(x)
+        self.check(self.lib.dab_eval_log10f(self.handle, _ptr(x), _ptr(y), x.size))
+        return y
+
+    def set_log10f_correction(self, nibbles: np.ndarray | None, count: int = 0):
+        if nibbles is None or count == 0:
+            self.check(self.lib.dab_set_log10f_correction(self.handle, None, 0))
+        else:
+            nibbles = np.ascontiguousarray(nibbles, np.uint8)
+            self.check(self.lib.dab_set_log10f_correction(self.handle, _ptr(nibbles), int(count)))
 
     def launches(self) -> int:
         return int(self.lib.dab_launch_count(self.handle))
@@ -459,6 +482,42 @@ class Pair:
                                                           ctypes.byref(npts), ctypes.byref(npath)))
         self.n_points2, self.n_path2 = npts.value, npath.value
         return npts.value, npath.value
+
+    # ---- stage B in steps (corridor rows of one long pair scored on several GPUs) -----------------
+    def stage_b_score(self, gains, audio_stds, n_audio: int, n_video: int, lines, row_lo: int = 0, row_hi: int = 2 ** 62):
+        """Plans the corridors and builds the whole pass-2 point list; quals only for audio rows
+        [row_lo, row_hi).  Returns (n_points, first_point, n_mine): this rank's points are
+        [first_point, first_point + n_mine)."""
+        g = (ctypes.c_float * 3)(*[float(x) for x in gains])
+        sd = (ctypes.c_float * 3)(*[float(x) for x in audio_stds])
+        arr = cluster_array(lines)
+        npts, first, mine = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+        self.ctx.check(self.lib.dab_pair_stage_b_score(self.handle, ctypes.byref(g), ctypes.byref(sd), int(n_audio), int(n_video),
+                                                       ctypes.cast(arr, ctypes.c_void_p), len(lines), int(row_lo), int(row_hi),
+                                                       ctypes.byref(npts), ctypes.byref(first), ctypes.byref(mine)))
+        self.n_points2, self.n_path2 = npts.value, 0
+        return npts.value, first.value, mine.value
+
+    def export_quals2_device(self, q_ptr: int, first: int, count: int):
+        self.ctx.check(self.lib.dab_pair_export_quals2(self.handle, ctypes.c_void_p(q_ptr), int(first), int(count), 1))
+
+    def export_quals2(self, first: int, count: int) -> np.ndarray:
+        q = np.empty(count, np.float64)
+        self.ctx.check(self.lib.dab_pair_export_quals2(self.handle, _ptr(q), int(first), int(count), 0))
+        return q
+
+    def import_quals2_device(self, q_ptr: int, n: int):
+        self.ctx.check(self.lib.dab_pair_import_quals2(self.handle, ctypes.c_void_p(q_ptr), int(n), 1))
+
+    def import_quals2(self, q: np.ndarray):
+        q = np.ascontiguousarray(q, np.float64)
+        self.ctx.check(self.lib.dab_pair_import_quals2(self.handle, _ptr(q), len(q), 0))
+
+    def dp2(self):
+        npath = ctypes.c_int64()
+        self.ctx.check(self.lib.dab_pair_dp2(self.handle, ctypes.byref(npath)))
+        self.n_path2 = npath.value
+        return npath.value
 
     def corridors(self):
         """The corridors of the last stage B as scored: [(cluster, lo, hi, slope, offset), ...] (empty ones

@@ -40,15 +40,32 @@ def set_device(index: int):
     _device = int(index)
 
 
+_log10_request = None     # a mode asked for before CUDA was initialised (launcher.patch)
+
+
+def request_log10_mode(mode: str):
+    """Remember which log10 the feature kernel should follow (native_log.set_mode); applied when the
+    first context is created, so that importing / patching never initialises CUDA."""
+    global _log10_request
+    if mode not in ("portable", "native", "auto"):
+        raise ValueError("log10 mode must be 'portable', 'native' or 'auto'")
+    _log10_request = mode
+
+
 def context() -> _cabi.Context:
     """Per-thread CUDA context handle, created on first use (never at import time, so that
     a GUI parent process that only imports this module does not initialise CUDA before it
     forks its worker; reference describealign.py:1432)."""
+    global _log10_request
     ctx = getattr(_tls, "ctx", None)
     if ctx is None:
         ctx = _cabi.Context(_device)
         _tls.ctx = ctx
         _tls.pairs = []
+        if _log10_request is not None:
+            from . import native_log
+            req, _log10_request = _log10_request, None
+            native_log.set_mode(req, ctx)
     return ctx
 
 

@@ -79,32 +79,39 @@ def _rank_world(group=None):
     return 0, 1
 
 
+def exchange_varlen(tensors, group=None):
+    """All-gather 1-D tensors whose length differs per rank (every rank passes the same number of
+    tensors, element k having the same length on a rank): returns, per tensor, the concatenation over
+    ranks in rank order.  One all_gather of the lengths, one padded all_gather per tensor."""
+    import torch
+    dist = _dist()
+    rank, world = _rank_world(group)
+    if world == 1:
+        return list(tensors)
+    dev = tensors[0].device
+    n = torch.tensor([tensors[0].numel()], dtype=torch.int64, device=dev)
+    counts = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(counts, n, group=group)
+    counts = [int(c.item()) for c in counts]
+    cap = max(max(counts), 1)
+    out = []
+    for x in tensors:
+        pad = torch.zeros(cap, dtype=x.dtype, device=dev)
+        pad[:x.numel()] = x
+        parts = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(parts, pad, group=group)
+        out.append(torch.cat([parts[r][:counts[r]] for r in range(world)]))
+    return out
+
+
 def exchange_points(i, v, q, group=None):
     """All-gather variable-length match-point shards.
 
     i, v: int32 tensors, q: float64 tensor, all of length n_rank, on the CPU (gloo) or on the
     rank's GPU (nccl).  Returns the concatenation over ranks in rank order, which is sorted by
     (audio frame, video frame) when the shards are ordered row ranges."""
-    import torch
-    dist = _dist()
-    rank, world = _rank_world(group)
-    if world == 1:
-        return i, v, q
-    dev = i.device
-    n = torch.tensor([i.numel()], dtype=torch.int64, device=dev)
-    counts = [torch.zeros_like(n) for _ in range(world)]
-    dist.all_gather(counts, n, group=group)
-    counts = [int(c.item()) for c in counts]
-    cap = max(max(counts), 1)
-
-    def gather(x):
-        pad = torch.zeros(cap, dtype=x.dtype, device=dev)
-        pad[:x.numel()] = x
-        parts = [torch.empty_like(pad) for _ in range(world)]
-        dist.all_gather(parts, pad, group=group)
-        return torch.cat([parts[r][:counts[r]] for r in range(world)])
-
-    return gather(i), gather(v), gather(q)
+    gi, gv, gq = exchange_varlen([i, v, q], group)
+    return gi, gv, gq
 
 
 # ---------------------------------------------------------------------------------------------
@@ -293,36 +300,88 @@ def align_batch(pairs, durations: Sequence[float] | None = None, in_flight: int 
 # one very long pair on all ranks
 # ---------------------------------------------------------------------------------------------
 
-def align_long_pair(video_pcm, audio_desc_pcm, group=None, details=None):
-    """Every rank passes the same PCM and gets the same result.  Features and codes are computed
-    redundantly per rank (one pass over the PCM, cheaper than broadcasting them); the match stage
-    is sharded by audio rows; one all-gather of the scored match points precedes DP #1."""
+def align_long_pair(video_pcm, audio_desc_pcm, group=None, details=None, root: int = 0):
+    """One very long pair on all ranks of the group.  Every rank passes the same PCM and
+    gets the same result.
+
+    * features and codes: computed redundantly per rank (one pass over the PCM - cheaper than broadcasting
+      them);
+    * match stage (describealign.py:649-673): audio query rows sharded over the ranks, ONE all-gather of the
+      scored match points (NCCL over NVLink);
+    * DP #1, traceback and the host fit (:674-893): on `root` only - they do not shard - and the fit's
+      six scalars and line clusters are broadcast;
+    * corridor scoring (:931-944): audio rows sharded again, ONE all-gather of the quals (the point list
+      itself only depends on the corridors and is built on every rank);
+    * DP #2, traceback, nodes (:946-1027): on `root`, result broadcast."""
     import torch
     from . import _cabi, api
+    dist = _dist()
     rank, world = _rank_world(group)
     job = api.AlignJob()
+    info = {}
     try:
         job.load_pcm(video_pcm, audio_desc_pcm)
         pair = job.pair
+        dev = torch.device("cuda", torch.cuda.current_device())
+        # ---- stage A ----
         n_rows = int(pair.feature_lens(_cabi.AUDIO)[0])
         lo, hi = row_shards(n_rows, world)[rank]
         n = pair.stage_a_match(lo, hi)
-        dev = torch.device("cuda", torch.cuda.current_device())
         ti = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
         tv = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
         tq = torch.empty(max(n, 1), dtype=torch.float64, device=dev)
         pair.export_points1_device(ti.data_ptr(), tv.data_ptr(), tq.data_ptr())
+        torch.cuda.synchronize()
         gi, gv, gq = exchange_points(ti[:n], tv[:n], tq[:n], group)
-        gi, gv, gq = gi.contiguous(), gv.contiguous(), gq.contiguous()
-        torch.cuda.current_stream().synchronize()
-        pair.import_points1_device(gi.data_ptr(), gv.data_ptr(), gq.data_ptr(), gi.numel())
-        pair.dp1()
-        job.after_stage_a()
-        job.host_stage()
-        job.device_stage_b()
+        info["shard_a"] = (lo, hi, n, int(gi.numel()))
+        msg = [None]
+        if rank == root:
+            try:
+                gi, gv, gq = gi.contiguous(), gv.contiguous(), gq.contiguous()
+                torch.cuda.current_stream().synchronize()
+                pair.import_points1_device(gi.data_ptr(), gv.data_ptr(), gq.data_ptr(), gi.numel())
+                pair.dp1()
+                job.after_stage_a()
+                job.host_stage()
+                msg[0] = ("ok", job.stage_b_input())
+            except Exception as e:       # every rank must learn that the pair failed
+                msg[0] = ("error", e)
+        if world > 1:
+            dist.broadcast_object_list(msg, src=root, group=group)
+        if msg[0][0] == "error":
+            raise msg[0][1]
+        b_in = msg[0][1]
+        # ---- stage B ----
+        lo2, hi2 = row_shards(int(b_in["n_audio"]), world)[rank]
+        n2, first, mine = pair.stage_b_score(b_in["gains"], b_in["audio_stds"], b_in["n_audio"], b_in["n_video"],
+                                             b_in["lines"], lo2, hi2)
+        tq2 = torch.empty(max(mine, 1), dtype=torch.float64, device=dev)
+        pair.export_quals2_device(tq2.data_ptr(), first, mine)
+        torch.cuda.synchronize()
+        (q_all,) = exchange_varlen([tq2[:mine]], group)
+        info["shard_b"] = (lo2, hi2, mine, int(q_all.numel()))
+        out = [None]
+        if rank == root:
+            try:
+                q_all = q_all.contiguous()
+                torch.cuda.current_stream().synchronize()
+                if int(q_all.numel()) != n2:
+                    raise RuntimeError("long pair: the ranks' corridor shards do not add up to the point list")
+                pair.import_quals2_device(q_all.data_ptr(), n2)
+                pair.dp2()
+                job.path = pair.path2()
+                if len(job.path) < job.min_len:
+                    raise RuntimeError(api.FAILED_MSG)
+                out[0] = ("ok", job.finish(details))
+            except Exception as e:
+                out[0] = ("error", e)
+        if world > 1:
+            dist.broadcast_object_list(out, src=root, group=group)
+        if out[0][0] == "error":
+            raise out[0][1]
         if details is not None:
-            details["shard"] = (lo, hi, n, int(gi.numel()))
-        return job.finish(details)
+            details["shards"] = info
+        return out[0][1]
     finally:
         job.close()
 

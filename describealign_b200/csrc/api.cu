@@ -701,6 +701,89 @@ int dab_pair_stage_b_clusters(dab_pair *pr, const float gain[3], const float aud
   return DAB_OK;
 }
 
+// ---- stage B in steps, for one very long pair split over several GPUs ----
+int dab_pair_stage_b_score(dab_pair *pr, const float gain[3], const float audio_std[3], int64_t n_audio, int64_t n_video,
+                           const dab_cluster *clusters, int32_t n_clusters, int64_t row_lo, int64_t row_hi,
+                           int64_t *n_points, int64_t *first_point, int64_t *n_mine) {
+  if (!pr) return DAB_E_ARG;
+  dab_ctx *ctx = pr->ctx;
+  StreamScope scope__(pr->stream);
+  ApiTimer timer__(&pr->api_us[2]);
+  if (n_clusters < 0 || (n_clusters > 0 && !clusters) || row_lo < 0 || row_hi < row_lo) {
+    dab_set_err(ctx, "dab_pair_stage_b_score: invalid argument");
+    return DAB_E_ARG;
+  }
+  DAB_TRY(enqueue_scaling(pr, gain, audio_std, n_audio, n_video));
+  DAB_TRY(dab_enqueue_plan_corridors(pr, clusters, n_clusters, n_audio, n_video));
+  pr->stats.n_audio_frames = n_audio;
+  pr->stats.n_video_frames = n_video;
+  pr->b_n_cor = n_clusters;
+  pr->b_n_clusters = n_clusters > 0 ? clusters[n_clusters - 1].cluster + 1 : 0;
+  DAB_TRY(dab_enqueue_stage_b_points(pr, pr->b_n_cor, pr->b_n_clusters, row_lo, row_hi));
+  DAB_TRY(dab_enqueue_counts(pr));
+  DAB_CUDA(dab_wait_stream(pr->stream));
+  const int32_t *hc = reinterpret_cast<const int32_t *>(pr->h_counters);
+  if (hc[DC_OVERFLOW_B] & DAB_OVF_ROWCOR) { dab_set_err(ctx, "more than 32 corridors overlap one audio row"); return DAB_E_CAPACITY; }
+  pr->n_points2 = hc[DC_N_PTS2];
+  pr->stats.n_points2 = pr->n_points2;
+  int64_t first = 0, count = 0;
+  DAB_TRY(dab_row_range_points2(pr, row_lo, row_hi, &first, &count));
+  if (n_points) *n_points = pr->n_points2;
+  if (first_point) *first_point = first;
+  if (n_mine) *n_mine = count;
+  return DAB_OK;
+}
+
+int dab_pair_export_quals2(dab_pair *pr, double *q, int64_t first, int64_t count, int dst_on_device) {
+  if (!pr) return DAB_E_ARG;
+  dab_ctx *ctx = pr->ctx;
+  if (first < 0 || count < 0 || first + count > pr->n_points2 || (count > 0 && !q)) {
+    dab_set_err(ctx, "dab_pair_export_quals2: range outside the pair's points");
+    return DAB_E_ARG;
+  }
+  DAB_CUDA(cudaSetDevice(ctx->device));
+  if (count > 0)
+    DAB_CUDA(cudaMemcpyAsync(q, pr->p2_q.as<double>() + first, sizeof(double) * (size_t)count,
+                             dst_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, pr->stream));
+  DAB_CUDA(dab_wait_stream(pr->stream));
+  return DAB_OK;
+}
+
+int dab_pair_import_quals2(dab_pair *pr, const double *q_all, int64_t n, int src_on_device) {
+  if (!pr) return DAB_E_ARG;
+  dab_ctx *ctx = pr->ctx;
+  StreamScope scope__(pr->stream);
+  if (n != pr->n_points2 || (n > 0 && !q_all)) {
+    dab_set_err(ctx, "dab_pair_import_quals2: one qual per pass-2 point of the pair is required");
+    return DAB_E_ARG;
+  }
+  DAB_CUDA(cudaSetDevice(ctx->device));
+  if (n == 0) return DAB_OK;
+  const double *src = q_all;
+  if (!src_on_device) {
+    DAB_TRY(dab_ensure(ctx, pr->cand_q, sizeof(double) * (size_t)(n + 1)));
+    DAB_CUDA(cudaMemcpyAsync(pr->cand_q.p, q_all, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, pr->stream));
+    src = pr->cand_q.as<double>();
+  }
+  DAB_TRY(dab_enqueue_set_quals2(pr, src));
+  DAB_CUDA(dab_wait_stream(pr->stream));
+  return DAB_OK;
+}
+
+int dab_pair_dp2(dab_pair *pr, int64_t *n_path) {
+  if (!pr) return DAB_E_ARG;
+  dab_ctx *ctx = pr->ctx;
+  StreamScope scope__(pr->stream);
+  ApiTimer timer__(&pr->api_us[2]);
+  DAB_CUDA(cudaSetDevice(ctx->device));
+  DAB_TRY(dab_enqueue_stage_b_dp(pr, pr->b_n_cor, pr->b_n_clusters));
+  DAB_TRY(dab_enqueue_counts(pr));
+  DAB_CUDA(dab_wait_stream(pr->stream));
+  DAB_TRY(dab_collect_stage_b(pr));
+  if (n_path) *n_path = pr->n_path2;
+  return DAB_OK;
+}
+
 int dab_pair_get_corridors(dab_pair *pr, dab_corridor *out, int32_t cap, int32_t *n_corridors) {
   if (!pr || !n_corridors) return DAB_E_ARG;
   dab_ctx *ctx = pr->ctx;

@@ -99,6 +99,7 @@ struct dab_pair {
   int64_t n_points2 = 0, n_path2 = 0;
   int64_t cap_points2 = 0;     // upper bound of pass-2 points of the current stage_b call (sum of corridor rows)
   float b_amax = 0.f, b_vmax = 0.f;   // np.max of the scaled energy columns (describealign.py:908-909)
+  int32_t b_n_cor = 0, b_n_clusters = 0;   // of the stage-B call in progress (dab_pair_stage_b_score .. dab_pair_dp2)
   bool b_device_planned = false;      // corridors and energy maxima come from the device (dab_pair_stage_b_clusters)
   DevBuf clusters, refine_partial, maxes;
   dab_stats stats = {};
@@ -203,6 +204,10 @@ int dab_enqueue_stage_a_dp(dab_pair *pr);
 int dab_enqueue_counts(dab_pair *pr);
 int dab_collect_stage_a(dab_pair *pr, bool with_dp);
 int dab_enqueue_stage_b(dab_pair *pr, int32_t n_corridors, int32_t n_clusters);
+int dab_enqueue_stage_b_points(dab_pair *pr, int32_t n_corridors, int32_t n_clusters, int64_t q_lo, int64_t q_hi);
+int dab_enqueue_stage_b_dp(dab_pair *pr, int32_t n_corridors, int32_t n_clusters);
+int dab_enqueue_set_quals2(dab_pair *pr, const double *d_q_all);
+int dab_row_range_points2(dab_pair *pr, int64_t lo, int64_t hi, int64_t *first, int64_t *count);
 int dab_enqueue_plan_corridors(dab_pair *pr, const dab_cluster *clusters, int32_t n_clusters, int64_t n_audio, int64_t n_video);
 int dab_collect_stage_b(dab_pair *pr);
 int dab_run_import_points1(dab_pair *pr, const int32_t *i_audio, const int32_t *v_video, const double *qual,

@@ -54,6 +54,12 @@ template <int CH> struct Tile {
 };
 
 __device__ float g_tables[NTAB];   // w630 | w90 | w21 | w15 | w13
+// "native numpy" mode: numpy's SIMD log10 differs from glibc's log10f by up to 2 ulp on about
+// half of the float32 inputs when the host CPU has AVX-512.  The host evaluates ITS np.log10 over every
+// float32 in [1, 2^34) once and uploads the difference to the formula below as one nibble per input
+// (value + 8); with the table set the feature kernel reproduces the host's numpy bit for bit.
+__device__ const unsigned char *g_log10f_fix = nullptr;
+__device__ unsigned int g_log10f_fix_count = 0;
 __constant__ double c_logf_invc[16];
 __constant__ double c_logf_logc[16];
 
@@ -95,6 +101,20 @@ __device__ __forceinline__ float glibc_log10f(float x) {
   float m = __uint_as_float(hx);
   float z = y * 7.9034151668e-07f + 4.3429449201e-01f * glibc_logf(m);
   return z + y * 3.0102920532e-01f;
+}
+
+// log10f as the reference's host computes it: glibc's formula, plus the host-specific correction if one was uploaded
+__device__ __forceinline__ float host_log10f(float x) {
+  float r = glibc_log10f(x);
+  const unsigned char *fix = g_log10f_fix;
+  if (fix) {
+    const unsigned int idx = __float_as_uint(x) - 0x3f800000u;       // x >= 1: index of x among the floats from 1.0f up
+    if (idx < g_log10f_fix_count) {
+      const int nib = (fix[idx >> 1] >> ((idx & 1u) * 4u)) & 15;
+      r = __int_as_float(__float_as_int(r) + (nib - 8));                // r >= 0: consecutive floats are consecutive ints
+    }
+  }
+  return r;
 }
 
 // one PCM element as float16: int16 -> float16 (RNE) as describealign.py:156, or the half itself
@@ -421,14 +441,14 @@ __global__ void __launch_bounds__(THREADS, 2) features_kernel(FeatArgs a) {
         float tot = 0.0f;
 #pragma unroll 6
         for (int p = 0; p < 42; ++p) tot = tot + ph[t * 42 + p];
-        a.b0[f] = glibc_log10f(1.0f + tot / 210.0f) / 2.0f;
+        a.b0[f] = host_log10f(1.0f + tot / 210.0f) / 2.0f;
       }
     } else if (role == 1) {
       if (f < a.L) {
         float tot = 0.0f;
 #pragma unroll
         for (int p = 0; p < 6; ++p) tot = tot + p1[t * 6 + p];
-        a.b1[f] = glibc_log10f(1.0f + tot / 210.0f) / 2.0f;
+        a.b1[f] = host_log10f(1.0f + tot / 210.0f) / 2.0f;
         // zero crossings: 13-tap Hann over frames f-6 .. f+6
         double acc = 0.0;
 #pragma unroll
@@ -456,7 +476,7 @@ __global__ void __launch_bounds__(THREADS, 2) features_kernel(FeatArgs a) {
           const float prod = eb[2 * (t + FH) - 6 + j] * w13[12 - j];
           acc += (double)prod;
         }
-        a.energy[f] = glibc_log10f(1.0f + (float)acc) / 2.0f;
+        a.energy[f] = host_log10f(1.0f + (float)acc) / 2.0f;
       }
     }
   }
@@ -485,6 +505,14 @@ int upload_constants(dab_ctx *ctx) {
   return DAB_OK;
 }
 
+__global__ void eval_log10f_kernel(const float *x, float *y, int64_t n) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) y[k] = x[k] >= 1.0f ? host_log10f(x[k]) : 0.0f;
+}
+
+std::mutex g_fix_mu;
+void *g_fix_buf[64] = {};      // per device: the uploaded correction table
+
 template <int FMT, int CH>
 int launch(dab_pair *pr, const FeatArgs &fa, int64_t frames) {
   dab_ctx *ctx = pr->ctx;
@@ -499,6 +527,53 @@ int launch(dab_pair *pr, const FeatArgs &fa, int64_t frames) {
 }
 
 }  // namespace
+
+extern "C" {
+
+int dab_set_log10f_correction(dab_ctx *ctx, const unsigned char *nibbles, uint64_t count) {
+  if (!ctx || (count > 0 && !nibbles) || count > 0xffffffffull) return DAB_E_ARG;
+  DAB_CUDA(cudaSetDevice(ctx->device));
+  DAB_TRY(upload_constants(ctx));
+  std::lock_guard<std::mutex> lock(g_fix_mu);
+  DAB_CUDA(cudaDeviceSynchronize());       // no feature kernel may be reading the old table
+  const unsigned char *none = nullptr;
+  const unsigned int zero = 0;
+  DAB_CUDA(cudaMemcpyToSymbol(g_log10f_fix, &none, sizeof(none)));
+  DAB_CUDA(cudaMemcpyToSymbol(g_log10f_fix_count, &zero, sizeof(zero)));
+  const int dev = ctx->device;
+  if (dev < 64 && g_fix_buf[dev]) { cudaFree(g_fix_buf[dev]); g_fix_buf[dev] = nullptr; }
+  if (count == 0) return DAB_OK;
+  void *buf = nullptr;
+  const size_t bytes = (size_t)((count + 1) / 2);
+  DAB_CUDA(cudaMalloc(&buf, bytes));
+  DAB_CUDA(cudaMemcpy(buf, nibbles, bytes, cudaMemcpyHostToDevice));
+  const unsigned int cnt = (unsigned int)count;
+  DAB_CUDA(cudaMemcpyToSymbol(g_log10f_fix, &buf, sizeof(buf)));
+  DAB_CUDA(cudaMemcpyToSymbol(g_log10f_fix_count, &cnt, sizeof(cnt)));
+  if (dev < 64) g_fix_buf[dev] = buf;
+  return DAB_OK;
+}
+
+int dab_eval_log10f(dab_ctx *ctx, const float *x, float *y, int64_t n) {
+  if (!ctx || n < 0 || (n > 0 && (!x || !y))) return DAB_E_ARG;
+  if (n == 0) return DAB_OK;
+  DAB_CUDA(cudaSetDevice(ctx->device));
+  DAB_TRY(upload_constants(ctx));
+  float *dx = nullptr, *dy = nullptr;
+  DAB_CUDA(cudaMalloc(&dx, sizeof(float) * (size_t)n));
+  if (cudaMalloc(&dy, sizeof(float) * (size_t)n) != cudaSuccess) { cudaFree(dx); dab_set_err(ctx, "dab_eval_log10f: out of device memory"); return DAB_E_CUDA; }
+  cudaError_t e = cudaMemcpy(dx, x, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    eval_log10f_kernel<<<(unsigned)cdiv(n, 256), 256>>>(dx, dy, n);
+    ctx->launches += 1;
+    e = cudaMemcpy(y, dy, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost);
+  }
+  cudaFree(dx); cudaFree(dy);
+  if (e != cudaSuccess) { dab_set_err(ctx, std::string("dab_eval_log10f: ") + cudaGetErrorString(e)); return DAB_E_CUDA; }
+  return DAB_OK;
+}
+
+}  // extern "C"
 
 int dab_run_features(dab_pair *pr, int track, const void *d_pcm, int format) {
   dab_ctx *ctx = pr->ctx;

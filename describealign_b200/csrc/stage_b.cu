@@ -46,6 +46,7 @@ struct ScoreBArgs {
   double *p_j, *p_q;
   int32_t *overflow;
   int32_t want_rank;       // the generic DP needs rank(j); the corridor-state DP does not
+  int64_t q_lo, q_hi;      // quals are computed for audio rows q_lo <= i < q_hi only (long-pair sharding); others get 0
 };
 
 __device__ __forceinline__ double line_at(const dab_corridor &c, int64_t i) {
@@ -110,16 +111,19 @@ __global__ void corridor_kernel(ScoreBArgs s) {
     const double vl0 = (double)v0[0] * omt + (double)v1[0] * t;
     const double vl1 = (double)v0[1] * omt + (double)v1[1] * t;
     const double vl2 = (double)v0[2] * omt + (double)v1[2] * t;
-    const double t0 = -.5 - log10(1e-4 + fabs((double)a0 - vl0));
-    const double t1 = -.5 - log10(1e-4 + fabs((double)a1 - vl1));
-    const double t2 = -.5 - log10(1e-4 + fabs((double)a2 - vl2));
-    double q = (t0 + t1) + t2;
-    const float v_max = s.maxes ? s.maxes[1] : s.v_max, a_max = s.maxes ? s.maxes[0] : s.a_max;
-    q = q * fmin(fmax((vl0 + 2.5) - (double)v_max, 0.0), 1.0);
-    // the audio gate is evaluated in float32 by numpy (f32 array, weak Python scalars)
-    float ag = (a0 + 2.5f) - a_max;
-    ag = fminf(fmaxf(ag, 0.0f), 1.0f) * 0.1f;
-    q = q + (double)ag;
+    double q = 0.0;
+    if (i >= s.q_lo && i < s.q_hi) {
+      const double t0 = -.5 - log10(1e-4 + fabs((double)a0 - vl0));
+      const double t1 = -.5 - log10(1e-4 + fabs((double)a1 - vl1));
+      const double t2 = -.5 - log10(1e-4 + fabs((double)a2 - vl2));
+      q = (t0 + t1) + t2;
+      const float v_max = s.maxes ? s.maxes[1] : s.v_max, a_max = s.maxes ? s.maxes[0] : s.a_max;
+      q = q * fmin(fmax((vl0 + 2.5) - (double)v_max, 0.0), 1.0);
+      // the audio gate is evaluated in float32 by numpy (f32 array, weak Python scalars)
+      float ag = (a0 + 2.5f) - a_max;
+      ag = fminf(fmaxf(ag, 0.0f), 1.0f) * 0.1f;
+      q = q + (double)ag;
+    }
     // rank of j over all corridor rows
     int rank = 1;
     if (s.want_rank) {
@@ -1311,9 +1315,16 @@ int dab_enqueue_plan_corridors(dab_pair *pr, const dab_cluster *clusters, int32_
 // one point, so the sum of the corridor rows (known to the host) bounds all buffers; the actual point
 // count stays on the device and every later kernel reads it from there.
 int dab_enqueue_stage_b(dab_pair *pr, int32_t n_cor, int32_t n_clusters) {
+  DAB_TRY(dab_enqueue_stage_b_points(pr, n_cor, n_clusters, 0, INT64_MAX));
+  return dab_enqueue_stage_b_dp(pr, n_cor, n_clusters);
+}
+
+// corridor scoring: the sorted point list with flags; quals only for audio rows [q_lo, q_hi)
+int dab_enqueue_stage_b_points(dab_pair *pr, int32_t n_cor, int32_t n_clusters, int64_t q_lo, int64_t q_hi) {
   dab_ctx *ctx = pr->ctx;
   cudaStream_t st = pr->stream;
   const int64_t n_a = pr->stats.n_audio_frames, n_v = pr->stats.n_video_frames;  // set by the caller
+  (void)n_clusters; (void)n_v;
   pr->n_points2 = pr->n_path2 = 0;
   const bool fast = corridor_dp_eligible(pr, n_cor);
   int64_t pm_off[32], rows = 0;
@@ -1334,6 +1345,7 @@ int dab_enqueue_stage_b(dab_pair *pr, int32_t n_cor, int32_t n_clusters) {
   sb.v_max = pr->b_vmax;
   sb.maxes = pr->b_device_planned ? pr->maxes.as<float>() : nullptr;
   sb.want_rank = fast ? 0 : 1;
+  sb.q_lo = q_lo; sb.q_hi = q_hi;
   DAB_TRY(dab_ensure(ctx, pr->row2_count, sizeof(int32_t) * (size_t)(n_a + 2)));
   DAB_TRY(dab_ensure(ctx, pr->row2_off, sizeof(int32_t) * (size_t)(n_a + 2)));
   DAB_TRY(dab_ensure(ctx, pr->p2_i, sizeof(int32_t) * (size_t)(cap + 1)));
@@ -1357,7 +1369,24 @@ int dab_enqueue_stage_b(dab_pair *pr, int32_t n_cor, int32_t n_clusters) {
     ctx->launches += 2;
   }
   DAB_CUDA(cudaEventRecord(pr->ev[15], st));
+  pr->ev_used[7] = true;
+  DAB_CUDA(cudaGetLastError());
+  return DAB_OK;
+}
 
+// DP #2 + traceback over the pair's pass-2 points
+int dab_enqueue_stage_b_dp(dab_pair *pr, int32_t n_cor, int32_t n_clusters) {
+  dab_ctx *ctx = pr->ctx;
+  cudaStream_t st = pr->stream;
+  const int64_t n_v = pr->stats.n_video_frames;
+  const bool fast = corridor_dp_eligible(pr, n_cor);
+  int64_t pm_off[32], rows = 0;
+  for (int k = 0; k < n_cor; ++k) {
+    if (k < 32) pm_off[k] = rows;
+    rows += pr->h_cor[k].hi > pr->h_cor[k].lo ? pr->h_cor[k].hi - pr->h_cor[k].lo : 0;
+  }
+  const int64_t cap = rows > 0 ? rows : 1;
+  int32_t *dc = pr->counters.as<int32_t>();
   DAB_CUDA(cudaEventRecord(pr->ev[16], st));
   if (rows > 0 && fast) {
     // ---- scan DP + pointer-jumping traceback ----
@@ -1452,8 +1481,43 @@ int dab_enqueue_stage_b(dab_pair *pr, int32_t n_cor, int32_t n_clusters) {
     DAB_CUDA(cudaEventRecord(pr->ev[18], st));
     DAB_CUDA(cudaEventRecord(pr->ev[17], st));
   }
-  pr->ev_used[7] = pr->ev_used[8] = true;
+  pr->ev_used[8] = true;
   DAB_CUDA(cudaGetLastError());
+  return DAB_OK;
+}
+
+// quals of all pass-2 points replaced by `q_all` (device memory): the exchange step of a long pair whose
+// corridor rows were scored on several GPUs
+static __global__ void set_quals_kernel(const double *q_all, const int32_t *n_dev, P2Rec *rec, double *p_q) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= *n_dev) return;
+  const double q = q_all[p];
+  rec[p].q = q;
+  p_q[p] = q;
+}
+
+int dab_enqueue_set_quals2(dab_pair *pr, const double *d_q_all) {
+  dab_ctx *ctx = pr->ctx;
+  const int64_t cap = pr->cap_points2 > 0 ? pr->cap_points2 : 1;
+  set_quals_kernel<<<(unsigned)cdiv(cap, 256), 256, 0, pr->stream>>>(d_q_all, pr->counters.as<int32_t>() + DC_N_PTS2,
+                                                                    pr->p2_k.as<P2Rec>(), pr->p2_q.as<double>());
+  ctx->launches += 1;
+  DAB_CUDA(cudaGetLastError());
+  return DAB_OK;
+}
+
+// first point and number of points of the audio rows [lo, hi) (needs a finished dab_enqueue_stage_b_points)
+int dab_row_range_points2(dab_pair *pr, int64_t lo, int64_t hi, int64_t *first, int64_t *count) {
+  dab_ctx *ctx = pr->ctx;
+  const int64_t n_a = pr->stats.n_audio_frames;
+  lo = lo < 0 ? 0 : (lo > n_a ? n_a : lo);
+  hi = hi < lo ? lo : (hi > n_a ? n_a : hi);
+  int32_t off[2] = {0, 0};
+  DAB_CUDA(cudaMemcpyAsync(&off[0], pr->row2_off.as<int32_t>() + lo, sizeof(int32_t), cudaMemcpyDeviceToHost, pr->stream));
+  DAB_CUDA(cudaMemcpyAsync(&off[1], pr->row2_off.as<int32_t>() + hi, sizeof(int32_t), cudaMemcpyDeviceToHost, pr->stream));
+  DAB_CUDA(dab_wait_stream(pr->stream));
+  *first = off[0];
+  *count = off[1] - off[0];
   return DAB_OK;
 }
 

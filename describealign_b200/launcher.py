@@ -18,9 +18,15 @@ import sys
 _PATCHED = ("get_energy", "get_zero_crossings", "get_freq_bands", "align")
 
 
-def patch(module=None):
-    """Replace the hot-path functions of `module` (default: import describealign)."""
+def patch(module=None, log10: str | None = None):
+    """Replace the hot-path functions of `module` (default: import describealign).
+
+    log10: "portable" / "native" / "auto" (describealign_b200.native_log): which log10 the feature kernel
+    follows.  main() uses "auto" - next to the stock reference the results should be those of the numpy
+    installed on this host; the mode is switched on first use of the GPU, not here."""
     from . import api
+    if log10 is not None:
+        api.request_log10_mode(log10)
     if module is None:
         module = importlib.import_module("describealign")
     for name in _PATCHED:
@@ -32,7 +38,7 @@ def patch(module=None):
 
 
 def main(argv=None):
-    module = patch()
+    module = patch(log10="auto")
     if argv is not None:
         sys.argv = [sys.argv[0]] + list(argv)
     return module.command_line_interface()

@@ -140,6 +140,15 @@ void dab_destroy(dab_ctx *ctx);
 int dab_set_option(dab_ctx *ctx, const char *name, int64_t value);
 const char *dab_last_error(const dab_ctx *ctx);   /* ctx may be NULL for dab_create failures */
 
+/* "Native numpy" parity (reference :554, :590 call np.log10 on float32): numpy's bundled SIMD log10 differs
+ * from glibc's log10f - which the feature kernel restates - by up to 2 ulp when the host has AVX-512.
+ * nibbles: one 4-bit entry per float32 from 1.0f upwards (two per byte, low nibble first) holding
+ * (bits of the host's log10f(x)) - (bits of dab_eval_log10f without a correction) + 8; count entries.
+ * count = 0 removes the table (glibc behaviour, the default).  Applies to the context's device.
+ * dab_eval_log10f evaluates the feature kernel's log10f for n host values >= 1 (with the current table). */
+int dab_set_log10f_correction(dab_ctx *ctx, const unsigned char *nibbles, uint64_t count);
+int dab_eval_log10f(dab_ctx *ctx, const float *x, float *y, int64_t n);
+
 int dab_pair_create(dab_ctx *ctx, dab_pair **out);
 void dab_pair_destroy(dab_pair *pair);
 int dab_pair_sync(dab_pair *pair);
@@ -218,6 +227,20 @@ int dab_pair_stage_b_gains(dab_pair *pair, const float gain[3], const float audi
 int dab_pair_stage_b_clusters(dab_pair *pair, const float gain[3], const float audio_std[3], int64_t n_audio,
                               int64_t n_video, const dab_cluster *clusters, int32_t n_clusters,
                               int64_t *n_points, int64_t *n_path);
+/* ---- stage B in steps, for one very long pair split over several GPUs ----
+ * dab_pair_stage_b_score: scaling, corridor planning and the sorted pass-2 point list for the whole pair
+ * (identical on every rank: it only depends on the corridors), but the quals - the part that reads the
+ * features - only for the audio rows row_lo <= i < row_hi; those are the points [*first_point,
+ * *first_point + *n_mine).  Ranks exchange their qual slices (dab_pair_export_quals2, e.g. into NCCL
+ * buffers), one rank imports the concatenation (dab_pair_import_quals2, n = *n_points) and runs
+ * dab_pair_dp2: DP #2 + traceback (reference :946-993), which do not shard. */
+int dab_pair_stage_b_score(dab_pair *pair, const float gain[3], const float audio_std[3], int64_t n_audio,
+                           int64_t n_video, const dab_cluster *clusters, int32_t n_clusters, int64_t row_lo,
+                           int64_t row_hi, int64_t *n_points, int64_t *first_point, int64_t *n_mine);
+int dab_pair_export_quals2(dab_pair *pair, double *qual, int64_t first_point, int64_t count, int dst_on_device);
+int dab_pair_import_quals2(dab_pair *pair, const double *qual_all, int64_t n, int src_on_device);
+int dab_pair_dp2(dab_pair *pair, int64_t *n_path);
+
 /* the corridors of the last stage_b call as scored (for _clusters: as planned on the device); cap entries */
 int dab_pair_get_corridors(dab_pair *pair, dab_corridor *out, int32_t cap, int32_t *n_corridors);
 /* final path rows (video j, audio i, cluster, qual, cum), float64 row-major (n_path, 5),

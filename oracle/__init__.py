@@ -42,6 +42,8 @@ def lib() -> ctypes.CDLL:
         _LIB.oracle_freq_bands.argtypes = [p, i64, i32, p, p, p, p, p, p, p]
         _LIB.oracle_log10f.restype = ctypes.c_float
         _LIB.oracle_log10f.argtypes = [ctypes.c_float]
+        _LIB.oracle_set_log10f_hook.restype = None
+        _LIB.oracle_set_log10f_hook.argtypes = [p]
         _LIB.oracle_ddot.restype = ctypes.c_double
         _LIB.oracle_ddot.argtypes = [p, p, i64]
         _LIB.oracle_meansub_norm.restype = None

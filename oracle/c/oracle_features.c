@@ -74,8 +74,14 @@ static float glibc_logf(float x) {
   return (float)p;
 }
 
+/* "native numpy" mode: tests may route log10f through the host's np.log10 to check the
+ * device's correction table; NULL = glibc's formula below. */
+static float (*g_log10f_hook)(float) = 0;
+void oracle_set_log10f_hook(float (*fn)(float)) { g_log10f_hook = fn; }
+
 float oracle_log10f(float x) {
   /* glibc e_log10f.c for positive normal x */
+  if (g_log10f_hook) return g_log10f_hook(x);
   uint32_t hx;
   memcpy(&hx, &x, 4);
   int32_t k = (int32_t)(hx >> 23) - 127;

@@ -402,6 +402,43 @@ def test_stage_a_row_shards_reassemble(gpu_ctx, golden_align):
     pair.close()
 
 
+def test_stage_b_row_shards_reassemble(gpu_ctx, golden_align):
+    """Row-sharded corridor scoring (the long-pair protocol): two pairs holding the same
+    features score disjoint audio-row ranges; their qual slices, concatenated in row order and imported
+    into one of them, give the path of the unsharded stage B."""
+    from describealign_b200 import api
+    _, meta = golden_align
+    v, a = golden_pair_pcm(meta, "pair_warp")
+    jobs = [api.AlignJob(), api.AlignJob()]
+    try:
+        for job in jobs:
+            job.load_pcm(v, a)
+            job.device_stage_a()
+        jobs[0].host_stage()
+        b = jobs[0].stage_b_input()
+        want_path = jobs[0].device_stage_b().copy()
+        want_q = jobs[0].pair.points2()[3]
+        mid = b["n_audio"] // 2 + 17
+        parts, total = [], None
+        for job, (lo, hi) in zip(jobs, ((0, mid), (mid, b["n_audio"]))):
+            n2, first, mine = job.pair.stage_b_score(b["gains"], b["audio_stds"], b["n_audio"], b["n_video"], b["lines"], lo, hi)
+            assert total is None or total == n2
+            total = n2
+            parts.append((first, job.pair.export_quals2(first, mine)))
+        assert parts[0][0] == 0 and parts[1][0] == len(parts[0][1]) and len(parts[0][1]) + len(parts[1][1]) == total
+        assert len(parts[0][1]) > 0 and len(parts[1][1]) > 0
+        q_all = np.concatenate([p[1] for p in parts])
+        np.testing.assert_array_equal(q_all, want_q)
+        # before the import, the second pair's own quals are zero outside its rows
+        assert np.all(jobs[1].pair.points2()[3][:parts[1][0]] == 0.0)
+        jobs[1].pair.import_quals2(q_all)
+        jobs[1].pair.dp2()
+        np.testing.assert_array_equal(jobs[1].pair.path2(), want_path)
+    finally:
+        for job in jobs:
+            job.close()
+
+
 def test_long_pair_two_gpus():
     """align_long_pair under torchrun with NCCL (needs 2 GPUs; the 1-GPU box skips it)."""
     import subprocess, sys, os

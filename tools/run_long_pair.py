@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""One pair on all ranks (torchrun, NCCL): the row-sharded match stage of SURVEY.md 8e.
+"""One pair on all ranks (torchrun, NCCL): match stage and corridor scoring sharded by audio rows, the DPs
+and the host fit on rank 0.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
         tools/run_long_pair.py [--seconds S | --config C5] [--check]
@@ -54,7 +55,7 @@ def main():
     if world > 1:
         dist.all_reduce(flags, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print(json.dumps({"world": world, "wall_s": t1 - t0, "shard": det.get("shard"), "timings": det.get("timings"),
+        print(json.dumps({"world": world, "wall_s": t1 - t0, "shards": det.get("shards"), "timings": det.get("timings"),
                           "stats": det.get("stats"), "audio_hours": (len(v) + len(a)) / 44100 / 3600}))
         if int(flags.item()) == 1:
             print("long pair ok")
