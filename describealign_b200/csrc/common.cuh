@@ -31,7 +31,7 @@ struct dab_ctx {
   int sm_count = 148;
   int opt_dp2_generic = 0;   // force the tree DP for pass 2 (testing)
   int opt_dp_reserve_kb = 0; // dynamic shared memory the pass-2 DP kernel asks for without using it (see dab_set_option)
-  int opt_dp2_impl = 0;      // 0 block kernel, 1 corridor-state kernel, 2 tree DP, 3 lane-per-corridor kernel (all exact)
+  int opt_dp2_impl = 0;      // 0 scan kernel (dp2_scan.cuh), 2 generic tree DP (both exact; the tests compare them)
 };
 
 // Features and prep data of one track, device resident.
@@ -61,11 +61,13 @@ struct dab_pair {
   cudaStream_t stream = nullptr;
   Track trk[2];
   // scan scratch
-  DevBuf scan_tmp;
+  DevBuf scan_tmp;            // single-pass scan: ticket counter + tile status words
+  unsigned int scan_epoch = 0;
   // tables
   DevBuf tbl_count;   // i32 [5*NCODE + 1]
   DevBuf tbl_start;   // i32 [5*NCODE + 1]
   DevBuf tbl_items;   // i32 sel-ranks
+  DevBuf v_rec;       // uint4[2] per hashed video frame: its five digit packs (gate)
   // gate / scoring
   DevBuf row_count, row_off;   // i32 [n_queries + 1]
   DevBuf cand_tmp, cand_s, cand_i;  // i32 [n_cand]

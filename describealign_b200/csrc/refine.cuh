@@ -139,18 +139,32 @@ __global__ void refine_plan_kernel(RefineArgs a) {
   a.cor[c] = out;
 }
 
-// np.max of the energy columns of the scaled arrays (describealign.py:908-909)
-__global__ void column_max_kernel(const float *a_scaled, int64_t n_a, const float *v_scaled, int64_t n_v, float *out) {
+// np.max of the energy columns of the scaled arrays (describealign.py:908-909): block maxima combined with
+// an atomic max on an order-preserving integer image of the float; decoded by refine_plan_kernel / the
+// decode kernel below into out[0] (audio), out[1] (video).
+__device__ __forceinline__ unsigned int rf_ordered(float f) {
+  const unsigned int b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float rf_unordered(unsigned int k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+__global__ void column_max_kernel(const float *a_scaled, int64_t n_a, const float *v_scaled, int64_t n_v, unsigned int *keys) {
   __shared__ float red[32];
-  const float *src = blockIdx.x == 0 ? a_scaled : v_scaled;
-  const int64_t n = blockIdx.x == 0 ? n_a : n_v;
+  const float *src = blockIdx.y == 0 ? a_scaled : v_scaled;
+  const int64_t n = blockIdx.y == 0 ? n_a : n_v;
   float m = -INFINITY;
-  for (int64_t k = threadIdx.x; k < n; k += blockDim.x) m = fmaxf(m, src[3 * k]);
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) m = fmaxf(m, src[3 * k]);
   for (int o = 16; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
   __syncthreads();
   if (threadIdx.x == 0) {
     for (int x = 1; x < (int)(blockDim.x >> 5); ++x) m = fmaxf(m, red[x]);
-    out[blockIdx.x] = m;
+    atomicMax(keys + blockIdx.y, rf_ordered(m));
   }
+}
+
+__global__ void column_max_decode_kernel(const unsigned int *keys, float *out) {
+  if (threadIdx.x < 2) out[threadIdx.x] = rf_unordered(keys[threadIdx.x]);
 }

@@ -154,59 +154,78 @@ __device__ __forceinline__ int64_t scan_len(int64_t n, const int32_t *n_dev) {
   return m < n ? (m < 0 ? 0 : m) : n;
 }
 
-__global__ void scan_reduce_kernel(const int32_t *in, int64_t n, const int32_t *n_dev, int32_t *block_sums) {
-  __shared__ int sm[33];
-  n = scan_len(n, n_dev);
-  const int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
-  int s = 0;
-#pragma unroll
-  for (int k = 0; k < SCAN_ITEMS; ++k) {
-    int64_t i = base + (int64_t)threadIdx.x * SCAN_ITEMS + k;
-    if (i < n) s += in[i];
-  }
-  int total;
-  block_exclusive_scan(s, &total, sm);
-  if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
-}
+// Single-pass exclusive scan (decoupled look-back): one launch per scan.  Tiles take their index from an
+// atomic ticket, so a tile's predecessors have always started; a tile publishes its aggregate, then walks
+// back over its predecessors' published (aggregate | inclusive prefix) words until it meets an inclusive
+// prefix.  Status words carry the epoch of the scan call, so the array needs no clearing between calls;
+// the last tile to finish resets the ticket counter.
+//   status[t] = epoch << 34 | kind << 32 | value      kind 1 = aggregate, 2 = inclusive prefix
+struct ScanArgs {
+  const int32_t *in;
+  int32_t *out;
+  int64_t n;
+  const int32_t *n_dev;
+  unsigned long long *status;      // [tiles]
+  unsigned int *ticket;            // [0] next tile, [1] tiles finished
+  unsigned int epoch;              // 1 .. 2^30 - 1, different from the previous call's on this array
+  int32_t *total_out;
+};
 
-// single block: exclusive scan of the block sums in place, total to sums[nblocks]
-__global__ void scan_sums_kernel(int32_t *sums, int nblocks, int32_t *total_out) {
+__global__ void __launch_bounds__(SCAN_THREADS) scan_onepass_kernel(ScanArgs a) {
   __shared__ int sm[33];
-  int carry = 0;
-  for (int base = 0; base < nblocks; base += SCAN_THREADS) {
-    int i = base + threadIdx.x;
-    int v = (i < nblocks) ? sums[i] : 0;
-    int total;
-    int ex = block_exclusive_scan(v, &total, sm);
-    if (i < nblocks) sums[i] = ex + carry;
-    carry += total;
-  }
-  if (threadIdx.x == 0) {
-    sums[nblocks] = carry;
-    if (total_out) *total_out = carry;
-  }
-}
-
-__global__ void scan_apply_kernel(const int32_t *in, int32_t *out, int64_t n, const int32_t *n_dev,
-                                  const int32_t *block_sums, int nblocks) {
-  __shared__ int sm[33];
-  n = scan_len(n, n_dev);
-  const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+  __shared__ unsigned int s_tile;
+  __shared__ int s_prefix;
+  const int64_t n = scan_len(a.n, a.n_dev);
+  if (threadIdx.x == 0) s_tile = atomicAdd(a.ticket, 1u);
+  __syncthreads();
+  const unsigned int tile = s_tile;
+  const int64_t base = (int64_t)tile * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
   int v[SCAN_ITEMS];
   int s = 0;
 #pragma unroll
   for (int k = 0; k < SCAN_ITEMS; ++k) {
-    v[k] = (base + k < n) ? in[base + k] : 0;
+    v[k] = (base + k < n) ? a.in[base + k] : 0;
     s += v[k];
   }
   int total;
-  int ex = block_exclusive_scan(s, &total, sm) + block_sums[blockIdx.x];
+  const int ex = block_exclusive_scan(s, &total, sm);
+  if (threadIdx.x == 0) {
+    const unsigned long long tag = (unsigned long long)a.epoch << 34;
+    volatile unsigned long long *st = a.status;
+    int prefix = 0;
+    if (tile > 0) {
+      st[tile] = tag | (1ull << 32) | (unsigned int)total;
+      __threadfence();
+      for (int t = (int)tile - 1; t >= 0; --t) {
+        unsigned long long w;
+        do { w = st[t]; } while ((w >> 34) != a.epoch);
+        prefix += (int)(unsigned int)w;
+        if (((w >> 32) & 3ull) == 2ull) break;
+      }
+    }
+    st[tile] = tag | (2ull << 32) | (unsigned int)(prefix + total);
+    __threadfence();
+    s_prefix = prefix;
+  }
+  __syncthreads();
+  int run = ex + s_prefix;
 #pragma unroll
   for (int k = 0; k < SCAN_ITEMS; ++k) {
-    if (base + k < n) out[base + k] = ex;
-    ex += v[k];
+    if (base + k < n) a.out[base + k] = run;
+    run += v[k];
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = block_sums[nblocks];
+  // the tile that holds position n (or the last tile) writes the total
+  const int64_t last_tile = n / SCAN_TILE;
+  if ((int64_t)tile == last_tile && threadIdx.x == 0) {
+    // total of all elements = prefix of this tile + its own total (elements past n are zero)
+    a.out[n] = s_prefix + total;
+    if (a.total_out) *a.total_out = s_prefix + total;
+  }
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int done = atomicAdd(a.ticket + 1, 1u);
+    if (done == gridDim.x - 1) { a.ticket[0] = 0u; a.ticket[1] = 0u; __threadfence(); }
+  }
 }
 
 __global__ void notquiet_flag_kernel(const float *energy, int64_t n, int32_t *flag) {
@@ -268,18 +287,47 @@ __global__ void table_kernel(const uint32_t *pack, int64_t nstride, const int32_
 // ------------------------------------------------------------------------------------------
 // gate
 // ------------------------------------------------------------------------------------------
-// low bit of every 3-bit field that is non-zero
-__device__ __forceinline__ uint32_t nz_fields(uint32_t m) { return (m | (m >> 1) | (m >> 2)) & 0x49249u; }
+// The gate compares the 7 quantised digits of an audio frame with those of a video frame, per feature
+// (SURVEY.md A.4): the frames match in a feature when every audio digit equals the video digit, or the
+// video digit + 1 where that digit is flagged (fraction > .6, stored under both codes, :622-633).
+// Digits live one per nibble: bits 0-2 the digit (0..6), bit 3 the flag (video) / a guard bit (audio).
+//   d = (audio | 0x8888888) - (video digits)         per nibble 8 + a - v, no borrow between nibbles
+//   d ^ 0x8888888                                    a - v for a >= v (0..6), >= 10 for a < v
+//   ... & ~flags                                     0 exactly when a - v is 0, or 1 on a flagged digit
+// i.e. five integer instructions per feature instead of a per-digit loop.
+__device__ __forceinline__ uint32_t nibbles_of(uint32_t pk) {      // 7 x 3-bit digits -> one per nibble
+  uint32_t r = 0u;
+#pragma unroll
+  for (int k = 0; k < 7; ++k) r |= ((pk >> (3 * k)) & 7u) << (4 * k);
+  return r;
+}
 
-// does audio digit pack `a` fall into video entry `v` (digits + flags)?  
-__device__ __forceinline__ bool digits_match(uint32_t a, uint32_t v) {
-  const uint32_t vd = v & 0x1FFFFFu;
-  const uint32_t fl = v >> 21;
-  // spread the 7 flag bits to the low bit of each 3-bit field
-  uint32_t sp = (fl & 1u) | ((fl & 2u) << 2) | ((fl & 4u) << 4) | ((fl & 8u) << 6) | ((fl & 16u) << 8) |
-                ((fl & 32u) << 10) | ((fl & 64u) << 12);
-  const uint32_t vplus = vd + sp;   // flagged digits are <= 5, no carry between fields
-  return (nz_fields(a ^ vd) & nz_fields(a ^ vplus)) == 0u;
+__device__ __forceinline__ uint32_t video_nibbles(uint32_t pk) {  // digits + flag bits 21-27 -> nibbles with the flag in bit 3
+  uint32_t r = nibbles_of(pk);
+#pragma unroll
+  for (int k = 0; k < 7; ++k) r |= ((pk >> (21 + k)) & 1u) << (4 * k + 3);
+  return r;
+}
+
+__device__ __forceinline__ bool digits_match(uint32_t a_guarded, uint32_t v) {
+  const uint32_t d = (a_guarded - (v & 0x7777777u)) ^ 0x8888888u;
+  return (d & ~((v >> 3) & 0x1111111u)) == 0u;
+}
+
+// The five digit words (one digit per nibble, see digits_match) of every hashed video frame side by side
+// (32 bytes per frame, indexed by the
+// frame's rank in the hashed list): a bucket entry then costs the gate ONE 32-byte sector instead of a
+// rank -> frame look-up plus five gathers from five arrays.
+__global__ void video_records_kernel(const uint32_t *pack, int64_t nstride, const int32_t *sel, const int32_t *dc, uint4 *rec) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= dc[DC_N_VSEL]) return;
+  const int32_t v = sel[s];
+  uint4 r0, r1;
+  r0.x = video_nibbles(pack[v]); r0.y = video_nibbles(pack[nstride + v]); r0.z = video_nibbles(pack[2 * nstride + v]);
+  r0.w = video_nibbles(pack[3 * nstride + v]);
+  r1.x = video_nibbles(pack[4 * nstride + v]); r1.y = (uint32_t)v; r1.z = 0u; r1.w = 0u;
+  rec[2 * s] = r0;
+  rec[2 * s + 1] = r1;
 }
 
 struct GateArgs {
@@ -289,9 +337,7 @@ struct GateArgs {
   const int32_t *a_list;    // not-quiet audio frames
   const int32_t *dc;        // device counts: query range [DC_Q_LO, DC_Q_HI) of the list
   int64_t q_cap;            // launch size (rows)
-  const uint32_t *v_pack;   // [5][v_nstride]
-  int64_t v_nstride;
-  const int32_t *v_sel;     // selected video frames (rank -> frame)
+  const uint4 *v_rec;       // per hashed video frame (rank): its five digit packs, 32 bytes = one sector
   const int32_t *start;     // [5*NCODE + 1]
   const int32_t *items;
   int32_t *row_count;       // count pass output
@@ -318,7 +364,7 @@ __global__ void gate_kernel(GateArgs g) {
   int32_t st[5], en[5];
 #pragma unroll
   for (int f = 0; f < 5; ++f) {
-    ap[f] = g.a_pack[(int64_t)f * g.a_nstride + i] & 0x1FFFFFu;
+    ap[f] = nibbles_of(g.a_pack[(int64_t)f * g.a_nstride + i] & 0x1FFFFFu) | 0x8888888u;
     const int64_t slot = (int64_t)f * DAB_NCODE + g.a_code[(int64_t)f * g.a_nstride + i];
     st[f] = g.start[slot];
     en[f] = g.start[slot + 1];
@@ -340,10 +386,11 @@ __global__ void gate_kernel(GateArgs g) {
       int32_t s = 0;
       if (e < cnt) {
         s = g.items[s0 + e];
-        const int32_t v = g.v_sel[s];
+        const uint4 r0 = __ldg(g.v_rec + 2 * (int64_t)s), r1 = __ldg(g.v_rec + 2 * (int64_t)s + 1);
+        const uint32_t vp[5] = {r0.x, r0.y, r0.z, r0.w, r1.x};
         bool m[5];
 #pragma unroll
-        for (int f = 0; f < 5; ++f) m[f] = digits_match(ap[f], g.v_pack[(int64_t)f * g.v_nstride + v]);
+        for (int f = 0; f < 5; ++f) m[f] = digits_match(ap[f], vp[f]);
         ok = ((int)m[0] + (int)m[1] + (int)m[2] >= 2) && (m[3] || m[4]);
         if (pass == 1 && m[fa]) ok = false;   // already enumerated from the first bucket
       }
@@ -364,6 +411,15 @@ __global__ void gate_kernel(GateArgs g) {
   if (off + found > g.cand_cap) return;
   __syncwarp();
   // order the row's candidates by video rank: position = number of smaller entries
+  if (found <= 32) {
+    // the usual case: one candidate per lane, ranks by 32 register shuffles instead of found^2 memory reads
+    const int32_t x = lane < found ? g.cand_tmp[off + lane] : 0x7fffffff;
+    int r = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) r += (__shfl_sync(0xffffffffu, x, j) < x);
+    if (lane < found) { g.cand_s[off + r] = x; g.cand_i[off + r] = i; }
+    return;
+  }
   for (int k = lane; k < found; k += 32) {
     const int32_t x = g.cand_tmp[off + k];
     int r = 0;
@@ -507,12 +563,38 @@ __global__ void __launch_bounds__(32, 1) dp1_kernel(Dp1Args a) {
           len += stop ? __ffs(stop) - 1 : 31 - t;
         }
         if (len > cnt - t) len = cnt - t;
-        double c = top_cum, my_cum = 0.0;
-        for (int u = 0; u < len; ++u) {
-          c = c + s_q[buf][t + u];
-          if (lane == t + u) my_cum = c;
-        }
         const bool in_run = lane >= t && lane < t + len;
+        // The cums of the run are top_cum + q, + q, ... added one after the other in float64 (the
+        // reference's order).  While the sums stay inside the binade of top_cum every such add is exact
+        // arithmetic on multiples of that binade's unit once q is rounded to it (fl(x + q) = x + rn_u(q),
+        // ties aside), so a warp prefix sum gives all of them in five steps; each lane then checks its
+        // value against the one rounded add the reference performs, and only a run that fails the check
+        // (binade crossing, rounding tie) is added up serially.
+        double my_cum = 0.0;
+        {
+          const double my_q = in_run ? s_q[buf][lane] : 0.0;
+          const unsigned long long tb = (unsigned long long)__double_as_longlong(top_cum);
+          const double big = __longlong_as_double((long long)((tb & 0x7ff0000000000000ull) | 0x0008000000000000ull));  // 1.5 * 2^e
+          double ps = in_run ? __dadd_rn(__dadd_rn(my_q, big), -big) : 0.0;       // q rounded to the unit of top_cum's binade
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const double y = __shfl_up_sync(0xffffffffu, ps, o);
+            if (lane >= t + o) ps = ps + y;
+          }
+          const double spec = top_cum + ps;
+          double prev = __shfl_up_sync(0xffffffffu, spec, 1);
+          if (lane == t) prev = top_cum;
+          const bool ok = !in_run || (top_cum > 0.0 && __double_as_longlong(prev + my_q) == __double_as_longlong(spec));
+          if (__all_sync(0xffffffffu, ok)) {
+            my_cum = spec;
+          } else {
+            double c = top_cum;
+            for (int u = 0; u < len; ++u) {
+              c = c + s_q[buf][t + u];
+              if (lane == t + u) my_cum = c;
+            }
+          }
+        }
         const bool first = lane == t;
         double old_cum = __shfl_up_sync(0xffffffffu, my_cum, 1);
         int old_id = base + lane - 1, old_rank = prev_r;
@@ -668,13 +750,22 @@ __global__ void fill_nodes_kernel(Node1 *p, int64_t n) {
 int dab_exclusive_scan(dab_pair *pr, const int32_t *in, int32_t *out, int64_t n, const int32_t *n_dev,
                        int32_t *total_out) {
   dab_ctx *ctx = pr->ctx;
-  const int nblocks = (int)cdiv(n > 0 ? n : 1, SCAN_TILE);
-  DAB_TRY(dab_ensure(ctx, pr->scan_tmp, sizeof(int32_t) * (size_t)(nblocks + 1)));
-  int32_t *sums = pr->scan_tmp.as<int32_t>();
-  scan_reduce_kernel<<<nblocks, SCAN_THREADS, 0, pr->stream>>>(in, n, n_dev, sums);
-  scan_sums_kernel<<<1, SCAN_THREADS, 0, pr->stream>>>(sums, nblocks, total_out);
-  scan_apply_kernel<<<nblocks, SCAN_THREADS, 0, pr->stream>>>(in, out, n, n_dev, sums, nblocks);
-  pr->ctx->launches += 3;
+  // tiles cover positions 0 .. n inclusive, so that the tile holding position n exists and writes the total
+  const int nblocks = (int)(n / SCAN_TILE) + 1;
+  const size_t need = sizeof(unsigned long long) * (size_t)(nblocks + 2);
+  if (need > pr->scan_tmp.cap || !pr->scan_tmp.p) {
+    DAB_TRY(dab_ensure(ctx, pr->scan_tmp, need + 4096));
+    DAB_CUDA(cudaMemsetAsync(pr->scan_tmp.p, 0, pr->scan_tmp.cap, pr->stream));   // epoch 0 = never written; ticket = 0
+    pr->scan_epoch = 0;
+  }
+  ScanArgs sa;
+  sa.in = in; sa.out = out; sa.n = n; sa.n_dev = n_dev; sa.total_out = total_out;
+  sa.ticket = pr->scan_tmp.as<unsigned int>();
+  sa.status = pr->scan_tmp.as<unsigned long long>() + 1;
+  pr->scan_epoch = pr->scan_epoch >= 0x3ffffffe ? 1 : pr->scan_epoch + 1;
+  sa.epoch = pr->scan_epoch;
+  scan_onepass_kernel<<<nblocks, SCAN_THREADS, 0, pr->stream>>>(sa);
+  pr->ctx->launches += 1;
   DAB_CUDA(cudaGetLastError());
   return DAB_OK;
 }
@@ -826,7 +917,11 @@ int dab_enqueue_stage_a_match(dab_pair *pr, int64_t row_lo, int64_t row_hi) {
   GateArgs ga;
   ga.a_code = A.code.as<int32_t>(); ga.a_pack = A.pack.as<uint32_t>(); ga.a_nstride = a_nstride;
   ga.a_list = A.nq_list.as<int32_t>(); ga.dc = dc; ga.q_cap = q_ub;
-  ga.v_pack = V.pack.as<uint32_t>(); ga.v_nstride = v_nstride; ga.v_sel = V.nq_list.as<int32_t>();
+  DAB_TRY(dab_ensure(ctx, pr->v_rec, sizeof(uint4) * 2 * (size_t)(vsel_ub + 1)));
+  video_records_kernel<<<(unsigned)cdiv(vsel_ub, 256), 256, 0, st>>>(V.pack.as<uint32_t>(), v_nstride, V.nq_list.as<int32_t>(), dc,
+                                                                    pr->v_rec.as<uint4>());
+  ctx->launches += 1;
+  ga.v_rec = pr->v_rec.as<uint4>();
   ga.start = pr->tbl_start.as<int32_t>(); ga.items = pr->tbl_items.as<int32_t>();
   ga.row_count = pr->row_count.as<int32_t>(); ga.row_off = pr->row_off.as<int32_t>();
   ga.cand_tmp = pr->cand_tmp.as<int32_t>(); ga.cand_s = pr->cand_s.as<int32_t>(); ga.cand_i = pr->cand_i.as<int32_t>();

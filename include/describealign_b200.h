@@ -131,12 +131,10 @@ int dab_set_host_wait(int device, int mode);
 /* device < 0: current device. */
 int dab_create(int device, dab_ctx **out);
 void dab_destroy(dab_ctx *ctx);
-/* Tuning / testing switches.  "dp2_generic" = 1 forces the tree-based pass-2 DP instead of the
- * corridor-state DP (both are exact; the tests compare them).  "dp2_impl" = 0..3 selects among the
- * exact pass-2 DP kernels (0 = block kernel, the default).  "dp_reserve_kb" = 0..176: dynamic shared
- * memory the one-warp pass-2 DP kernel requests without using it, which keeps large-shared-memory CTAs of
- * other pairs (the feature kernel) off its SM when many pairs are in flight.  Unknown names return
- * DAB_E_ARG. */
+/* Testing switches.  "dp2_generic" = 1 or "dp2_impl" = 2 force the generic tree-based pass-2 DP (the
+ * fallback for more than 32 corridors or non-positive slopes) instead of the scan DP ("dp2_impl" = 0, the
+ * default); both are exact and the tests compare them.  "dp_reserve_kb" is accepted and ignored (it tuned
+ * the one-warp DP kernel of an earlier version).  Unknown names return DAB_E_ARG. */
 int dab_set_option(dab_ctx *ctx, const char *name, int64_t value);
 const char *dab_last_error(const dab_ctx *ctx);   /* ctx may be NULL for dab_create failures */
 

@@ -24,8 +24,8 @@ def _stage_b_case(seed, **kw):
 @pytest.mark.parametrize("seed,kw,nb", [(3, dict(crossing=False), 1024), (4, dict(crossing=True), 64),
                                         (6, dict(crossing=False, n_a=14000, n_v=14000, n_cor=8), 1024)])
 def test_scan_model_equals_sequential_rules_and_oracle(seed, kw, nb):
-    import dp2_block_model as M
     import dp2_scan_model as S
+    M = S
     from oracle import align_oracle as ao
     audio, video, plans, n_clusters = _stage_b_case(seed, **kw)
     pi, pj, pc, pq = ao.score_corridors(plans, audio, video)
