@@ -41,7 +41,7 @@ template <int CH> struct Tile {
   // shared memory carve-up, in bytes, every section 16-byte aligned
   static constexpr int O_TAB = 0;
   static constexpr int O_SIG = O_TAB + NTAB * 4;
-  static constexpr int O_RAW = O_SIG + NS * 2;                                  // stereo only: half2 per sample
+  static constexpr int O_RAW = O_SIG + (NS + 16) * 2;                           // stereo only: half2 per sample
   static constexpr int O_LP1 = O_RAW + (CH == 2 ? NF * 210 * 4 : 0);
   static constexpr int O_BE0 = O_LP1 + ((N1 * 4 + 15) & ~15);
   static constexpr int O_LP2 = O_BE0 + NF * 42 * 4;
@@ -172,6 +172,29 @@ __device__ __forceinline__ float energy_lane(FX X, int l) {
   return acc;
 }
 
+// lanes l and l + 1 (l even) of the same block as one packed accumulator
+template <int CNT, typename FX>
+__device__ __forceinline__ float2 energy_lanes2(FX X, int l) {
+  float2 acc = make_float2(0.0f, 0.0f);
+  int q = 0;
+#pragma unroll 2
+  for (; q + 16 <= CNT; q += 16) {
+#pragma unroll
+    for (int c4 = 3; c4 >= 0; --c4) {
+      const float2 x = make_float2(X(q + 4 * c4 + l), X(q + 4 * c4 + l + 1));
+      acc = __fadd2_rn(acc, __fmul2_rn(x, x));
+    }
+  }
+#pragma unroll
+  for (; q < CNT; q += 4) {
+    // tail: lanes past the end of the block add nothing (they are skipped, not zero-filled, in the scalar form;
+    // x = 0 adds +0, which leaves a non-negative accumulator unchanged)
+    const float2 x = make_float2(q + l < CNT ? X(q + l) : 0.0f, q + l + 1 < CNT ? X(q + l + 1) : 0.0f);
+    if (q + l < CNT) acc = __fadd2_rn(acc, __fmul2_rn(x, x));
+  }
+  return acc;
+}
+
 template <int FMT, int CH>
 __global__ void __launch_bounds__(THREADS, 2) features_kernel(FeatArgs a) {
   using T = Tile<CH>;
@@ -200,6 +223,7 @@ __global__ void __launch_bounds__(THREADS, 2) features_kernel(FeatArgs a) {
   // ---- tables, zero-crossing counters ------------------------------------------------------
   for (int k = tid; k < NTAB; k += THREADS) tab[k] = g_tables[k];
   for (int k = tid; k < NF; k += THREADS) zi[k] = 0;
+  if (tid < 16) sig[NS + tid] = __float2half_rn(0.0f);      // read (never used) by the last lp1 task
 
   // ---- stage the mono / mid signal as float16, zero outside [0, Sb) ------------------------
   // 8 samples per step; s0 is a multiple of 8 samples, so a 16-byte aligned source stays aligned
@@ -250,30 +274,31 @@ __global__ void __launch_bounds__(THREADS, 2) features_kernel(FeatArgs a) {
   const float w15r[15] = {w15[0], w15[1], w15[2], w15[3], w15[4], w15[5], w15[6], w15[7],
                           w15[8], w15[9], w15[10], w15[11], w15[12], w15[13], w15[14]};
 
-  // ---- block energies (einsum order): 4 lane threads per 105-sample block --------------------
-  for (int k = tid; k < 2 * NF * 4; k += THREADS) {
-    const int kb = k >> 2, l = k & 3;
+  // ---- block energies (einsum order): 2 threads per 105-sample block, each running two of the four
+  //      lane accumulators as one packed f32x2 (FMUL2 / FADD2: per lane the same separately rounded
+  //      multiply and add as before) ---------------------------------------------------------------
+  for (int k = tid; k < 2 * NF * 2; k += THREADS) {
+    const int kb = k >> 1, l = (k & 1) * 2;           // lanes l, l + 1
     const int64_t b = 2 * f0 + kb;
-    float acc = 0.0f;
+    float2 acc = make_float2(0.0f, 0.0f);
     const bool valid = b >= 0 && b < a.nb;
     if (valid) {
       if ((b + 1) * 105 <= Sb) {
         if (CH == 1) {
           const __half *src = sig + PADS + kb * 105;
-          acc = energy_lane<105>([&](int e) { return __half2float(src[e]); }, l);
+          acc = energy_lanes2<105>([&](int e) { return __half2float(src[e]); }, l);
         } else {
           const __half *src = reinterpret_cast<const __half *>(raw + kb * 105);
-          acc = energy_lane<210>([&](int e) { return __half2float(src[e]); }, l);
+          acc = energy_lanes2<210>([&](int e) { return __half2float(src[e]); }, l);
         }
       } else {
         // the one block past the band signal (S mod 210 >= 105) is not staged: read it from HBM
         const int64_t base = b * 105 * CH;
-        acc = energy_lane<105 * CH>([&](int e) { return __half2float(elem_half<FMT>(a.pcm, base + e)); }, l);
+        acc = energy_lanes2<105 * CH>([&](int e) { return __half2float(elem_half<FMT>(a.pcm, base + e)); }, l);
       }
     }
-    const float o1 = __shfl_xor_sync(0xffffffffu, acc, 1);
-    const float s01 = (l & 1) ? o1 + acc : acc + o1;        // l0 + l1  /  l2 + l3 (left operand = lower lane)
-    const float o2 = __shfl_xor_sync(0xffffffffu, s01, 2);
+    const float s01 = acc.x + acc.y;                          // l0 + l1  /  l2 + l3
+    const float o2 = __shfl_xor_sync(0xffffffffu, s01, 1);
     if (l == 0) eb[kb] = valid ? (s01 + o2) / (float)(105 * CH) : 0.0f;
   }
 
@@ -305,46 +330,65 @@ __global__ void __launch_bounds__(THREADS, 2) features_kernel(FeatArgs a) {
     }
   }
 
-  // ---- lp1 = downsample_blur(m, 5, 3): 5 phases x 3 taps, f32 accumulators (B.2 ii) ---------
+  // ---- lp1 = downsample_blur(m, 5, 3): 5 phases x 3 taps, f32 accumulators (B.2 ii).  Four adjacent
+  //      outputs per thread: their windows overlap (30 samples instead of 60 are loaded and converted)
+  //      and two outputs share every instruction as one packed f32x2 ---------------------------------
   const int64_t n1_first = f0 * 42 - 7;          // global lp1 index of lp1[0]
   const int64_t len1 = a.L * 42;
-  for (int k = tid; k < N1; k += THREADS) {
-    const int64_t n = n1_first + k;
-    float total = 0.0f;
-    if (n >= 0 && n < len1) {
-      // staged index of m[(n-1)*5]; samples outside [0, Sb) are staged as zero, which is exactly
-      // the zero padding of the phase signals
-      const __half *src = sig + (int)((n - 1) * 5 - s0);
-      float x[15];
+  for (int u = tid; u < (N1 + 3) / 4; u += THREADS) {
+    const int k = 4 * u;
+    // lp1[k] reads the staged samples 5k .. 5k+14 (samples outside [0, Sb) are staged as zero, which is
+    // exactly the zero padding of the phase signals); 5k is a multiple of 20 halves: 8-byte aligned
+    const uint2 *src = reinterpret_cast<const uint2 *>(sig + 5 * k);
+    float x[32];
 #pragma unroll
-      for (int e = 0; e < 15; ++e) x[e] = __half2float(src[e]);
+    for (int e = 0; e < 8; ++e) {
+      const uint2 w = e < 7 ? src[e] : make_uint2(reinterpret_cast<const unsigned *>(src)[14], 0u);
+      const float2 lo = __half22float2(*reinterpret_cast<const __half2 *>(&w.x));
+      const float2 hi = __half22float2(*reinterpret_cast<const __half2 *>(&w.y));
+      x[4 * e] = lo.x; x[4 * e + 1] = lo.y; x[4 * e + 2] = hi.x; x[4 * e + 3] = hi.y;
+    }
+    float2 tot[2] = {make_float2(0.0f, 0.0f), make_float2(0.0f, 0.0f)};
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {                  // outputs (k, k+1) and (k+2, k+3)
 #pragma unroll
       for (int p = 0; p < 5; ++p) {
-        float acc = 0.0f;
+        float2 acc = make_float2(0.0f, 0.0f);
 #pragma unroll
-        for (int j = 0; j < 3; ++j) acc = acc + x[j * 5 + p] * w15r[p + (2 - j) * 5];
-        total = total + acc;
+        for (int j = 0; j < 3; ++j) {
+          const float wv = w15r[p + (2 - j) * 5];
+          acc = __fadd2_rn(acc, __fmul2_rn(make_float2(x[10 * h + j * 5 + p], x[10 * h + j * 5 + p + 5]), make_float2(wv, wv)));
+        }
+        tot[h] = __fadd2_rn(tot[h], acc);
       }
     }
-    lp1[k] = total;
+    const float r[4] = {tot[0].x, tot[0].y, tot[1].x, tot[1].y};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int64_t n = n1_first + k + e;
+      if (k + e < N1) lp1[k + e] = (n >= 0 && n < len1) ? r[e] : 0.0f;
+    }
   }
   __syncthreads();
 
   // ---- band-0 residual energy at 8820 Hz and lp2 = downsample_blur(lp1, 7, 3) ----------------
-  for (int k = tid; k < NF * 42; k += THREADS) {
+  for (int u = tid; u < NF * 21; u += THREADS) {
+    const int k = 2 * u;                              // outputs k, k + 1: staged samples 5k+40 .. 5k+49
     const int64_t n = f0 * 42 + k;
-    float acc = 0.0f;
-    if (n >= 0 && n < len1) {
-      const float lo = lp1[k + 7];
-      const __half *src = sig + (int)(n * 5 - s0);
+    const __half2 *src = reinterpret_cast<const __half2 *>(sig + 5 * k + PADS);
+    float x[10];
 #pragma unroll
-      for (int i = 0; i < 5; ++i) {
-        const float d = __half2float(src[i]) - lo;
-        const float sq = d * d;
-        acc = (i == 0) ? sq : acc + sq;
-      }
+    for (int e = 0; e < 5; ++e) { const float2 v = __half22float2(src[e]); x[2 * e] = v.x; x[2 * e + 1] = v.y; }
+    const float2 nlo = make_float2(-lp1[k + 7], -lp1[k + 8]);
+    float2 acc = make_float2(0.0f, 0.0f);
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const float2 d = __fadd2_rn(make_float2(x[i], x[i + 5]), nlo);        // x - lo
+      const float2 sq = __fmul2_rn(d, d);
+      acc = (i == 0) ? sq : __fadd2_rn(acc, sq);
     }
-    be0[k] = acc;
+    be0[k] = (n >= 0 && n < len1) ? acc.x : 0.0f;
+    be0[k + 1] = (n + 1 >= 0 && n + 1 < len1) ? acc.y : 0.0f;
   }
   const int64_t len2 = a.L * 6;
   for (int k = tid; k < NF * 6; k += THREADS) {
@@ -416,16 +460,18 @@ __global__ void __launch_bounds__(THREADS, 2) features_kernel(FeatArgs a) {
 #pragma unroll
       for (int j = 0; j < 15; ++j) wr[j] = w[(14 - j) * np];
 #pragma unroll
-      for (int t = 0; t < TC; ++t) {
-        if (tb + t < FT) {
-          double acc = 0.0;
+      for (int t = 0; t < TC; t += 2) {
+        // two adjacent frames share their multiplies as packed f32x2; each product is rounded to f32 and
+        // accumulated in f64 in tap order, as before
+        double acc0 = 0.0, acc1 = 0.0;
 #pragma unroll
-          for (int j = 0; j < 15; ++j) {
-            const float prod = win[t + j] * wr[j];
-            acc += (double)prod;
-          }
-          dst[(tb + t) * np] = (float)acc;
+        for (int j = 0; j < 15; ++j) {
+          const float2 prod = __fmul2_rn(make_float2(win[t + j], win[t + 1 + j]), make_float2(wr[j], wr[j]));
+          acc0 += (double)prod.x;
+          acc1 += (double)prod.y;
         }
+        if (tb + t < FT) dst[(tb + t) * np] = (float)acc0;
+        if (tb + t + 1 < FT) dst[(tb + t + 1) * np] = (float)acc1;
       }
     }
   }

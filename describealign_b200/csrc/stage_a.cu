@@ -37,28 +37,30 @@ __device__ __forceinline__ double feat_at(const PrepArgs &a, int f, int64_t t) {
   return f < 4 ? (double)a.f32[f][t] : a.f64[t];
 }
 
-__global__ void meansub_kernel(PrepArgs a) {
+// 256 outputs of one feature per block; the 296 inputs they read are converted to float64 once and staged
+// in shared memory (every input is used by 41 outputs).
+__global__ void __launch_bounds__(256) meansub_kernel(PrepArgs a) {
+  __shared__ double tile[256 + 40];
   const int f = blockIdx.y;
   const int64_t n = a.len[f];
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t t0 = (int64_t)blockIdx.x * 256, base = t0 - 20;
+  if (t0 >= n) return;
+  for (int e = threadIdx.x; e < 256 + 40; e += 256) {
+    const int64_t g = base + e;
+    tile[e] = (g >= 0 && g < n) ? feat_at(a, f, g) : 0.0;
+  }
+  __syncthreads();
+  const int64_t t = t0 + threadIdx.x;
   if (t >= n) return;
   int64_t lo = t - 20, hi = t + 21, klo = 0;
   if (lo < 0) { klo = -lo; lo = 0; }
   if (hi > n) hi = n;
   const int m = (int)(hi - lo);
-  double mean;
-  if (f < 4) {
-    const float *src = a.f32[f] + lo;
-    auto X = [&](int i) { return (double)src[i]; };
-    auto Y = [&](int i) { return c_hflip[klo + i]; };
-    mean = (m == 41) ? ddot41_skx(X, Y) : ddot_skx(X, Y, m);
-  } else {
-    const double *src = a.f64 + lo;
-    auto X = [&](int i) { return src[i]; };
-    auto Y = [&](int i) { return c_hflip[klo + i]; };
-    mean = (m == 41) ? ddot41_skx(X, Y) : ddot_skx(X, Y, m);
-  }
-  a.ms[(int64_t)f * a.stride + t] = feat_at(a, f, t) - mean;
+  const double *src = tile + (lo - base);
+  auto X = [&](int i) { return src[i]; };
+  auto Y = [&](int i) { return c_hflip[klo + i]; };
+  const double mean = (m == 41) ? ddot41_skx(X, Y) : ddot_skx(X, Y, m);
+  a.ms[(int64_t)f * a.stride + t] = tile[t - base] - mean;
 }
 
 // nrm[t] = max(1e-3, sqrt(sum_{k<41} ms[t+k]^2)) and the digit codes of frame t.
@@ -86,19 +88,31 @@ __global__ void norm_codes_kernel(CodeArgs a) {
   if (f < 3) a.nrm[(int64_t)f * a.nstride + t] = nr;
   uint32_t pk = 0;
   int32_t code = 0, p7 = 1;
+  // The digits are floor(8 * (m / nr) + offset) and the flags compare its fraction with .6: integers.  The
+  // quotient is first taken as m * (1 / nr) - within 2 ulp of the true quotient - and only a value that
+  // lands within 1e-9 of a boundary (an integer, an integer + .6, the clip limits) is divided exactly, so
+  // the digits are those of the exact arithmetic with one division per frame instead of seven.
+  const double inv = 1.0 / nr;
 #pragma unroll
   for (int k = 0; k < 7; ++k) {
-    double d = m[2 + 6 * k] / nr;
-    d = 8.0 * d;
+    const double mk = m[2 + 6 * k];
+    double d = 8.0 * (mk * inv) + (a.is_video ? 3.3 : 3.5);
+    {
+      const double fr = d - floor(d);
+      const bool risky = fr < 1e-9 || fr > 1.0 - 1e-9 || (a.is_video && fabs(fr - 0.6) < 1e-9) || !(fabs(d) < 1e6);
+      if (risky) {
+        d = mk / nr;
+        d = 8.0 * d;
+        d = d + (a.is_video ? 3.3 : 3.5);
+      }
+    }
     int dig;
     if (a.is_video) {
-      d = d + 3.3;
       d = fmin(fmax(d, 0.0), 6.0);
       double fl = floor(d);
       if (d - fl > 0.6) pk |= 1u << (21 + k);
       dig = (int)fl;
     } else {
-      d = d + 3.5;
       double fl = floor(d);
       fl = fmin(fmax(fl, 0.0), 6.0);
       dig = (int)fl;
@@ -445,8 +459,9 @@ struct ScoreArgs {
 };
 
 __global__ void score_kernel(ScoreArgs s) {
-  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= s.dc[DC_N_CAND]) return;
+  // the launch is a fixed number of blocks (the candidate count is only known to the device): grid stride
+  const int64_t n_cand = s.dc[DC_N_CAND];
+  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_cand; c += (int64_t)gridDim.x * blockDim.x) {
   const int32_t i = s.cand_i[c];
   const int32_t v = s.v_sel[s.cand_s[c]];
   double prob = 1.0;
@@ -465,13 +480,15 @@ __global__ void score_kernel(ScoreArgs s) {
   if (!(prob > 1e-8)) qual = fmin(50.0, pow(prob / 1e-12, -1.0 / 3));
   s.qual[c] = qual;
   s.keep[c] = qual >= 0.0 ? 1 : 0;
+  }
 }
 
 __global__ void gather_points_kernel(const int32_t *keep, const int32_t *off, const int32_t *dc,
                                      const int32_t *cand_i, const int32_t *cand_s, const double *qual,
                                      int32_t *pt_i, int32_t *pt_s, double *pt_q) {
-  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c < dc[DC_N_CAND] && keep[c]) {
+  const int64_t n_cand = dc[DC_N_CAND];
+  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_cand; c += (int64_t)gridDim.x * blockDim.x) {
+    if (!keep[c]) continue;
     const int o = off[c];
     pt_i[o] = cand_i[c];
     pt_s[o] = cand_s[c];
@@ -952,9 +969,10 @@ int dab_enqueue_stage_a_match(dab_pair *pr, int64_t row_lo, int64_t row_hi) {
   sa.a_nrm = A.nrm.as<double>(); sa.v_nrm = V.nrm.as<double>();
   sa.a_nstride = a_nstride; sa.v_nstride = v_nstride;
   sa.qual = pr->cand_q.as<double>(); sa.keep = pr->keep_flag.as<int32_t>();
-  score_kernel<<<(unsigned)cdiv(cap_c, 128), 128, 0, st>>>(sa);
+  const unsigned n_fixed = (unsigned)(4 * ctx->sm_count);     // grid-stride kernels over a device-side count
+  score_kernel<<<n_fixed, 128, 0, st>>>(sa);
   DAB_TRY(dab_exclusive_scan(pr, pr->keep_flag.as<int32_t>(), pr->keep_off.as<int32_t>(), cap_c, dc + DC_N_CAND, dc + DC_N_PTS1));
-  gather_points_kernel<<<(unsigned)cdiv(cap_c, 256), 256, 0, st>>>(
+  gather_points_kernel<<<n_fixed, 256, 0, st>>>(
       pr->keep_flag.as<int32_t>(), pr->keep_off.as<int32_t>(), dc, pr->cand_i.as<int32_t>(),
       pr->cand_s.as<int32_t>(), pr->cand_q.as<double>(), pr->pt_i.as<int32_t>(), pr->pt_s.as<int32_t>(),
       pr->pt_q.as<double>());
