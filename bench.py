@@ -61,6 +61,7 @@ def parse_args():
                     help="C2 (default, the metric's configuration), C3 (stereo), C4 (64 x 45-min pairs over all GPUs: strong scaling)")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the C2 durations (debugging only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the rank to the CPUs of its GPU's NUMA node")
     ap.add_argument("--no-long-pair", action="store_true", help="N > 1: skip the long-pair (C5) check that runs on all ranks after the timed steps")
     ap.add_argument("--long-scale", type=float, default=0.1, help="scale of the C5 pair used for the N > 1 long-pair check")
     return ap.parse_args()
@@ -336,6 +337,9 @@ def run_ours(args, rank, world, local_rank):
         B = args.pairs if args.pairs > 0 else 8 * W
         distinct = max(1, min(B, args.distinct if args.distinct > 0 else 4))
     base_pairs = make_pairs(distinct, rank * distinct, args.scale, world, args.workload)
+    # before any page-locked buffer or engine thread exists (and after the generator's worker processes have
+    # used all cores): run on, and allocate from, the GPU's own NUMA node
+    numa = batch.bind_to_gpu_numa_node(local_rank) if not args.no_numa_bind else {"bound": False, "disabled": True}
     pairs = [base_pairs[k % distinct] for k in range(B)]
     hours_rank = audio_hours(pairs)
 
@@ -628,7 +632,7 @@ def run_ours(args, rank, world, local_rank):
                                   "cpu_port_same_pair": 1e3 * cpu["seconds_device_stages_only"] if cpu else None,
                                   "note": "one C2 pair (22-min video, 27-min description) alone on the GPU, PCM device-resident; wall time from submit to the stage-A results on the host plus stage-B input to the final path on the host"},
             "kernel_ms_last_step": agg,
-            "host_side": {**sched, **{k: eng.counters()[k] - sched0[k] for k in sched0},
+            "host_side": {"numa_binding_rank0": numa, **sched, **{k: eng.counters()[k] - sched0[k] for k in sched0},
                           "python_threads": 1, "scheduler_threads": 1},
             "allocator_activity_in_timed_steps": {k: alloc1[k] - alloc0[k] for k in alloc1},
             "work": work_all,

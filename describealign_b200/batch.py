@@ -386,6 +386,40 @@ def align_long_pair(video_pcm, audio_desc_pcm, group=None, details=None, root: i
         job.close()
 
 
+def bind_to_gpu_numa_node(device_index: int) -> dict:
+    """Pin this process (and therefore the page-locked buffers it allocates from now on) to the CPUs of
+    the NUMA node the GPU hangs off, read from sysfs.  Uploads from the far socket cross the inter-socket
+    link and share it between all ranks of a box.  Returns what was found; does nothing on a single-node
+    host or when the topology cannot be read."""
+    info = {"device": int(device_index), "numa_node": None, "cpus": None, "bound": False}
+    try:
+        import subprocess
+        out = subprocess.run(["nvidia-smi", "-i", str(int(device_index)), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if not out:
+            return info
+        bdf = out[-12:] if len(out) >= 12 else out          # 00000000:1B:00.0 -> 0000:1b:00.0
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        info["numa_node"] = node
+        if node < 0:
+            return info
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        info["cpus"] = len(allowed)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info["bound"] = True
+    except Exception as e:       # best effort: an unreadable topology must never stop a run
+        info["error"] = repr(e)
+    return info
+
+
 def init_from_env(backend: str = "nccl"):
     """torchrun plumbing: RANK / WORLD_SIZE / LOCAL_RANK / MASTER_* from the environment."""
     import torch

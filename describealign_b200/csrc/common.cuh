@@ -70,6 +70,7 @@ struct dab_pair {
   DevBuf v_rec;       // uint4[2] per hashed video frame: its five digit packs (gate)
   // gate / scoring
   DevBuf row_count, row_off;   // i32 [n_queries + 1]
+  DevBuf row_stash;            // i32 [n_queries][4]: first candidates of each row (gate count pass)
   DevBuf cand_tmp, cand_s, cand_i;  // i32 [n_cand]
   DevBuf cand_q;               // f64 [n_cand]
   DevBuf keep_flag, keep_off;  // i32 [n_cand + 1]

@@ -172,12 +172,22 @@ __device__ __forceinline__ float energy_lane(FX X, int l) {
   return acc;
 }
 
-// lanes l and l + 1 (l even) of the same block as one packed accumulator
+// acc + a * b per lane with the product rounded on its own.  ptxas contracts mul.rn.f32x2 followed by
+// add.rn.f32x2 into one FFMA2 (a single rounding) even under -fmad=false, which it never does for the
+// scalar .rn forms; so the multiply is packed and the two adds are scalar.
+__device__ __forceinline__ float2 mul2_then_add(float2 acc, float2 a, float2 b) {
+  const float2 p = __fmul2_rn(a, b);
+  return make_float2(__fadd_rn(acc.x, p.x), __fadd_rn(acc.y, p.y));
+}
+
+// lanes l and l + 1 (l even) of the same block as one packed accumulator.  (Here the contraction into
+// FFMA2 is harmless and wanted: the samples are float16 values, so x * x is exact in float32 and
+// fma(x, x, acc) rounds exactly what acc + x * x rounds.)
 template <int CNT, typename FX>
 __device__ __forceinline__ float2 energy_lanes2(FX X, int l) {
   float2 acc = make_float2(0.0f, 0.0f);
   int q = 0;
-#pragma unroll 2
+#pragma unroll 1
   for (; q + 16 <= CNT; q += 16) {
 #pragma unroll
     for (int c4 = 3; c4 >= 0; --c4) {
@@ -271,8 +281,6 @@ __global__ void __launch_bounds__(THREADS, 2) features_kernel(FeatArgs a) {
     *reinterpret_cast<uint4 *>(sig + 8 * v) = *reinterpret_cast<const uint4 *>(h);
   }
   __syncthreads();
-  const float w15r[15] = {w15[0], w15[1], w15[2], w15[3], w15[4], w15[5], w15[6], w15[7],
-                          w15[8], w15[9], w15[10], w15[11], w15[12], w15[13], w15[14]};
 
   // ---- block energies (einsum order): 2 threads per 105-sample block, each running two of the four
   //      lane accumulators as one packed f32x2 (FMUL2 / FADD2: per lane the same separately rounded
@@ -330,44 +338,37 @@ __global__ void __launch_bounds__(THREADS, 2) features_kernel(FeatArgs a) {
     }
   }
 
-  // ---- lp1 = downsample_blur(m, 5, 3): 5 phases x 3 taps, f32 accumulators (B.2 ii).  Four adjacent
-  //      outputs per thread: their windows overlap (30 samples instead of 60 are loaded and converted)
-  //      and two outputs share every instruction as one packed f32x2 ---------------------------------
+  // ---- lp1 = downsample_blur(m, 5, 3): 5 phases x 3 taps, f32 accumulators (B.2 ii).  Two adjacent
+  //      outputs per thread: their windows overlap (20 samples instead of 30 are loaded and converted)
+  //      and their multiplies are one packed FMUL2 ---------------------------------------------------
   const int64_t n1_first = f0 * 42 - 7;          // global lp1 index of lp1[0]
   const int64_t len1 = a.L * 42;
-  for (int u = tid; u < (N1 + 3) / 4; u += THREADS) {
-    const int k = 4 * u;
+  {
+  const float w15r[15] = {w15[0], w15[1], w15[2], w15[3], w15[4], w15[5], w15[6], w15[7],
+                          w15[8], w15[9], w15[10], w15[11], w15[12], w15[13], w15[14]};
+  for (int u = tid; u < N1 / 2; u += THREADS) {
+    const int k = 2 * u;
     // lp1[k] reads the staged samples 5k .. 5k+14 (samples outside [0, Sb) are staged as zero, which is
-    // exactly the zero padding of the phase signals); 5k is a multiple of 20 halves: 8-byte aligned
-    const uint2 *src = reinterpret_cast<const uint2 *>(sig + 5 * k);
-    float x[32];
+    // exactly the zero padding of the phase signals); 5k is a multiple of 10 halves: 4-byte aligned
+    const __half2 *src = reinterpret_cast<const __half2 *>(sig + 5 * k);
+    float x[20];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const uint2 w = e < 7 ? src[e] : make_uint2(reinterpret_cast<const unsigned *>(src)[14], 0u);
-      const float2 lo = __half22float2(*reinterpret_cast<const __half2 *>(&w.x));
-      const float2 hi = __half22float2(*reinterpret_cast<const __half2 *>(&w.y));
-      x[4 * e] = lo.x; x[4 * e + 1] = lo.y; x[4 * e + 2] = hi.x; x[4 * e + 3] = hi.y;
-    }
-    float2 tot[2] = {make_float2(0.0f, 0.0f), make_float2(0.0f, 0.0f)};
+    for (int e = 0; e < 10; ++e) { const float2 v = __half22float2(src[e]); x[2 * e] = v.x; x[2 * e + 1] = v.y; }
+    float2 tot = make_float2(0.0f, 0.0f);
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {                  // outputs (k, k+1) and (k+2, k+3)
+    for (int p = 0; p < 5; ++p) {
+      float2 acc = make_float2(0.0f, 0.0f);
 #pragma unroll
-      for (int p = 0; p < 5; ++p) {
-        float2 acc = make_float2(0.0f, 0.0f);
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          const float wv = w15r[p + (2 - j) * 5];
-          acc = __fadd2_rn(acc, __fmul2_rn(make_float2(x[10 * h + j * 5 + p], x[10 * h + j * 5 + p + 5]), make_float2(wv, wv)));
-        }
-        tot[h] = __fadd2_rn(tot[h], acc);
+      for (int j = 0; j < 3; ++j) {
+        const float wv = w15r[p + (2 - j) * 5];
+        acc = mul2_then_add(acc, make_float2(x[j * 5 + p], x[j * 5 + p + 5]), make_float2(wv, wv));
       }
+      tot = __fadd2_rn(tot, acc);
     }
-    const float r[4] = {tot[0].x, tot[0].y, tot[1].x, tot[1].y};
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int64_t n = n1_first + k + e;
-      if (k + e < N1) lp1[k + e] = (n >= 0 && n < len1) ? r[e] : 0.0f;
-    }
+    const int64_t n = n1_first + k;
+    lp1[k] = (n >= 0 && n < len1) ? tot.x : 0.0f;
+    lp1[k + 1] = (n + 1 >= 0 && n + 1 < len1) ? tot.y : 0.0f;
+  }
   }
   __syncthreads();
 
@@ -384,8 +385,7 @@ __global__ void __launch_bounds__(THREADS, 2) features_kernel(FeatArgs a) {
 #pragma unroll
     for (int i = 0; i < 5; ++i) {
       const float2 d = __fadd2_rn(make_float2(x[i], x[i + 5]), nlo);        // x - lo
-      const float2 sq = __fmul2_rn(d, d);
-      acc = (i == 0) ? sq : __fadd2_rn(acc, sq);
+      acc = (i == 0) ? __fmul2_rn(d, d) : mul2_then_add(acc, d, d);
     }
     be0[k] = (n >= 0 && n < len1) ? acc.x : 0.0f;
     be0[k + 1] = (n + 1 >= 0 && n + 1 < len1) ? acc.y : 0.0f;
@@ -460,18 +460,16 @@ __global__ void __launch_bounds__(THREADS, 2) features_kernel(FeatArgs a) {
 #pragma unroll
       for (int j = 0; j < 15; ++j) wr[j] = w[(14 - j) * np];
 #pragma unroll
-      for (int t = 0; t < TC; t += 2) {
-        // two adjacent frames share their multiplies as packed f32x2; each product is rounded to f32 and
-        // accumulated in f64 in tap order, as before
-        double acc0 = 0.0, acc1 = 0.0;
+      for (int t = 0; t < TC; ++t) {
+        if (tb + t < FT) {
+          double acc = 0.0;
 #pragma unroll
-        for (int j = 0; j < 15; ++j) {
-          const float2 prod = __fmul2_rn(make_float2(win[t + j], win[t + 1 + j]), make_float2(wr[j], wr[j]));
-          acc0 += (double)prod.x;
-          acc1 += (double)prod.y;
+          for (int j = 0; j < 15; ++j) {
+            const float prod = win[t + j] * wr[j];
+            acc += (double)prod;
+          }
+          dst[(tb + t) * np] = (float)acc;
         }
-        if (tb + t < FT) dst[(tb + t) * np] = (float)acc0;
-        if (tb + t + 1 < FT) dst[(tb + t + 1) * np] = (float)acc1;
       }
     }
   }
@@ -511,7 +509,7 @@ __global__ void __launch_bounds__(THREADS, 2) features_kernel(FeatArgs a) {
         // band 2: one 15-tap f64 filter = OpenBLAS ddot tail, a sequential FMA chain (B.2 iv)
         double acc = 0.0;
 #pragma unroll
-        for (int j = 0; j < 15; ++j) acc = fma((double)w15r[14 - j], be2[t + 1 + j], acc);
+        for (int j = 0; j < 15; ++j) acc = fma((double)w15[14 - j], be2[t + 1 + j], acc);
         a.b2[f] = log10(1.0 + acc / 210.0) / 2.0;
       }
       if (f < a.Le) {

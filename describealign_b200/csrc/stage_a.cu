@@ -344,6 +344,8 @@ __global__ void video_records_kernel(const uint32_t *pack, int64_t nstride, cons
   rec[2 * s + 1] = r1;
 }
 
+constexpr int GATE_STASH = 4;   // rows with at most this many candidates (nearly all) are not enumerated a second time
+
 struct GateArgs {
   const int32_t *a_code;    // [5][a_nstride]
   const uint32_t *a_pack;
@@ -358,6 +360,7 @@ struct GateArgs {
   const int32_t *row_off;   // fill pass input
   int32_t *cand_tmp, *cand_s, *cand_i;
   int64_t cand_cap;
+  int32_t *stash;           // [q_cap][GATE_STASH]: the first candidates of every row, kept by the count pass
   unsigned long long *enumerated;
 };
 
@@ -374,6 +377,20 @@ __global__ void gate_kernel(GateArgs g) {
   // second pass: only the rows that have candidates (one row in six at the Ask-Dad shape) enumerate again
   if (FILL && ((g.dc[DC_OVERFLOW] & DAB_OVF_CAND) || g.row_off[q + 1] == g.row_off[q])) return;
   const int32_t i = g.a_list[g.dc[DC_Q_LO] + q];
+  if (FILL) {
+    const int64_t off0 = g.row_off[q];
+    const int n_row = g.row_off[q + 1] - (int)off0;
+    if (n_row <= GATE_STASH) {
+      // the count pass kept this row's candidates: order them by video rank and write them out
+      if (off0 + n_row > g.cand_cap) return;
+      const int32_t x = lane < n_row ? g.stash[q * GATE_STASH + lane] : 0x7fffffff;
+      int r = 0;
+#pragma unroll
+      for (int j = 0; j < GATE_STASH; ++j) r += (__shfl_sync(0xffffffffu, x, j) < x);
+      if (lane < n_row) { g.cand_s[off0 + r] = x; g.cand_i[off0 + r] = i; }
+      return;
+    }
+  }
   uint32_t ap[5];
   int32_t st[5], en[5];
 #pragma unroll
@@ -409,6 +426,10 @@ __global__ void gate_kernel(GateArgs g) {
         if (pass == 1 && m[fa]) ok = false;   // already enumerated from the first bucket
       }
       const unsigned bal = __ballot_sync(0xffffffffu, ok);
+      if (!FILL && ok) {
+        const int idx = found + __popc(bal & ((1u << lane) - 1u));
+        if (idx < GATE_STASH) g.stash[q * GATE_STASH + idx] = s;
+      }
       if (FILL && ok) {
         const int64_t pos = off + found + __popc(bal & ((1u << lane) - 1u));
         if (pos < g.cand_cap) g.cand_tmp[pos] = s;
@@ -943,6 +964,8 @@ int dab_enqueue_stage_a_match(dab_pair *pr, int64_t row_lo, int64_t row_hi) {
   ga.row_count = pr->row_count.as<int32_t>(); ga.row_off = pr->row_off.as<int32_t>();
   ga.cand_tmp = pr->cand_tmp.as<int32_t>(); ga.cand_s = pr->cand_s.as<int32_t>(); ga.cand_i = pr->cand_i.as<int32_t>();
   ga.cand_cap = cap_c;
+  DAB_TRY(dab_ensure(ctx, pr->row_stash, sizeof(int32_t) * GATE_STASH * (size_t)(q_ub + 1)));
+  ga.stash = pr->row_stash.as<int32_t>();
   ga.enumerated = reinterpret_cast<unsigned long long *>(dc + DC_ENUM_LO);
   DAB_CUDA(cudaEventRecord(pr->ev[8], st));
   const unsigned gb = (unsigned)cdiv(q_ub * 32, 256);
