@@ -148,6 +148,8 @@ def engine(slots: int = 32):
 
 def _interleaved_pcm(p):
     from . import api
+    if isinstance(p, tuple):
+        return p                          # (device pointer, samples, channels): PCM already on the GPU
     p = np.asarray(p)
     if p.dtype == np.float16 and p.ndim == 2 and p.shape[0] in (1, 2) and p.shape[1] > 2:
         return api._interleaved(p)        # the reference's (ch, S) float16 arrays
@@ -195,6 +197,7 @@ def run_engine(pairs, in_flight: int = 32, host_workers: int = 0, host_stage: Ca
                 try:
                     v, a = p() if callable(p) else p
                     jobs[submitted] = api.AlignJob(detached=True)
+                    jobs[submitted].tag = submitted
                     eng.submit(submitted, _interleaved_pcm(v), _interleaved_pcm(a))
                 except Exception as e:      # reported per pair; the batch goes on
                     fail(submitted, None, e)
@@ -244,13 +247,14 @@ def run_engine(pairs, in_flight: int = 32, host_workers: int = 0, host_stage: Ca
     return results
 
 
-def run_local(pairs, in_flight: int = 32, runner: Callable | None = None):
+def run_local(pairs, in_flight: int = 32, runner: Callable | None = None, **engine_kw):
     """Run `pairs` on this process's GPU with up to `in_flight` pairs in progress at once.
     A pair that fails (e.g. RuntimeError("Alignment failed, ...")) yields its exception.
-    With the default runner the pairs go through the batch engine (run_engine); a custom runner
-    (CPU tests, instrumentation) is called once per pair from a thread pool."""
+    With the default runner the pairs go through the batch engine (run_engine, which takes engine_kw:
+    host_workers, host_stage, finish); a custom runner (CPU tests, instrumentation) is called once per
+    pair from a thread pool."""
     if runner is None or runner is gpu_runner:
-        return run_engine(pairs, in_flight)
+        return run_engine(pairs, in_flight, **engine_kw)
 
     def one(p):
         try:
@@ -265,20 +269,25 @@ def run_local(pairs, in_flight: int = 32, runner: Callable | None = None):
 
 
 def align_batch(pairs, durations: Sequence[float] | None = None, in_flight: int = 32, group=None,
-                runner: Callable | None = None):
+                runner: Callable | None = None, gather: bool = True, **engine_kw):
     """Align a list of (video_pcm, description_pcm) pairs (or zero-argument loaders returning
     such a pair) over all ranks of the current process group.
 
-    Every rank must call this with the same list (loaders are only invoked on the owning rank).
+    Every rank must call this with the same list (loaders are only invoked on the owning rank; entries a
+    rank does not own are never touched and may be None when durations are given).
     Returns, on rank 0, one result per pair in input order - the tuple `align()` returns, or the
-    exception the pair raised; other ranks return None."""
+    exception the pair raised; other ranks return None.  gather=False: no collective at the end, every
+    rank gets [(pair index, result), ...] for its own pairs."""
     rank, world = _rank_world(group)
     if durations is None:
         if any(callable(p) for p in pairs):
             raise ValueError("durations are required when pairs are given as loaders")
         durations = [pair_duration(p) for p in pairs]
     mine = assign_pairs(durations, world)[rank]
-    local = run_local([pairs[k] for k in mine], in_flight, runner)
+    local = run_local([pairs[k] for k in mine], in_flight, runner, **engine_kw)
+    if not gather:
+        # every rank keeps its own results: [(pair index, result), ...]
+        return list(zip(mine, local))
     if world == 1:
         out = [None] * len(pairs)
         for k, res in zip(mine, local):

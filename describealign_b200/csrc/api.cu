@@ -232,6 +232,8 @@ cudaError_t dab_readback(dab_pair *pr, void *host_dst, const void *dev_src, size
 
 extern "C" {
 
+void dab_pair_destroy(dab_pair *pr);
+
 int dab_pair_create(dab_ctx *ctx, dab_pair **out) {
   if (!ctx || !out) return DAB_E_ARG;
   *out = nullptr;
@@ -239,13 +241,21 @@ int dab_pair_create(dab_ctx *ctx, dab_pair **out) {
   dab_pair *pr = new (std::nothrow) dab_pair();
   if (!pr) return DAB_E_CUDA;
   pr->ctx = ctx;
-  DAB_CUDA(cudaStreamCreateWithFlags(&pr->stream, cudaStreamNonBlocking));
-  for (int k = 0; k < 32; ++k) DAB_CUDA(cudaEventCreate(&pr->ev[k]));
+  // on a failure half-way the pair built so far is torn down again (dab_pair_destroy copes with missing parts)
+  cudaError_t e = cudaStreamCreateWithFlags(&pr->stream, cudaStreamNonBlocking);
+  for (int k = 0; k < 32 && e == cudaSuccess; ++k) e = cudaEventCreate(&pr->ev[k]);
   // mapped: kernels write the counts the host waits for straight into this block (dab_readback)
-  DAB_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&pr->h_counters), sizeof(int64_t) * 32,
-                         cudaHostAllocMapped | cudaHostAllocPortable));
-  memset(pr->h_counters, 0, sizeof(int64_t) * 32);
-  DAB_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void **>(&pr->d_counters_map), pr->h_counters, 0));
+  if (e == cudaSuccess)
+    e = cudaHostAlloc(reinterpret_cast<void **>(&pr->h_counters), sizeof(int64_t) * 32, cudaHostAllocMapped | cudaHostAllocPortable);
+  if (e == cudaSuccess) {
+    memset(pr->h_counters, 0, sizeof(int64_t) * 32);
+    e = cudaHostGetDevicePointer(reinterpret_cast<void **>(&pr->d_counters_map), pr->h_counters, 0);
+  }
+  if (e != cudaSuccess) {
+    dab_set_err(ctx, std::string("dab_pair_create: ") + cudaGetErrorString(e));
+    dab_pair_destroy(pr);
+    return DAB_E_CUDA;
+  }
   *out = pr;
   return DAB_OK;
 }

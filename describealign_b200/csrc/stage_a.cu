@@ -1121,9 +1121,10 @@ int dab_run_stage_a(dab_pair *pr) {
 
 // ---- row-sharded match stage: exchange of match points -----------------------------------
 namespace {
-// video frame -> rank in the selected-frame list (binary search; every frame of a point is in the list)
-__global__ void frames_to_ranks_kernel(const int32_t *v_frame, int64_t n, const int32_t *v_sel, int32_t n_sel,
-                                       int32_t *rank, int32_t *bad) {
+// video frame -> rank in the selected-frame list (binary search; every frame of a point is in the list).
+// Also checks what dp1_kernel relies on: points sorted by (audio frame, video frame) and quals > 0.
+__global__ void frames_to_ranks_kernel(const int32_t *i_audio, const int32_t *v_frame, const double *qual, int64_t n,
+                                       const int32_t *v_sel, int32_t n_sel, int32_t *rank, int32_t *bad) {
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   const int32_t v = v_frame[k];
@@ -1132,7 +1133,12 @@ __global__ void frames_to_ranks_kernel(const int32_t *v_frame, int64_t n, const 
     const int mid = lo + ((hi - lo) >> 1);
     if (v_sel[mid] < v) lo = mid + 1; else hi = mid;
   }
-  if (lo >= n_sel || v_sel[lo] != v) { atomicExch(bad, 1); lo = 0; }
+  if (lo >= n_sel || v_sel[lo] != v) { atomicOr(bad, 1); lo = 0; }
+  if (!(qual[k] > 0.0)) atomicOr(bad, 2);
+  if (k > 0) {
+    const int32_t ip = i_audio[k - 1], ic = i_audio[k];
+    if (ip > ic || (ip == ic && v_frame[k - 1] >= v)) atomicOr(bad, 4);
+  }
   rank[k] = lo;
 }
 }  // namespace
@@ -1157,14 +1163,17 @@ int dab_run_import_points1(dab_pair *pr, const int32_t *i_audio, const int32_t *
     DAB_CUDA(cudaMemcpyAsync(pr->cand_tmp.p, v_video, sizeof(int32_t) * (size_t)n, kind, st));
     DAB_CUDA(cudaMemcpyAsync(pr->pt_q.p, qual, sizeof(double) * (size_t)n, kind, st));
     DAB_CUDA(cudaMemsetAsync(pr->dpres.as<int32_t>() + 8, 0, sizeof(int32_t), st));
-    frames_to_ranks_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(pr->cand_tmp.as<int32_t>(), n, V.nq_list.as<int32_t>(),
-                                                                    (int32_t)V.n_list, pr->pt_s.as<int32_t>(),
+    frames_to_ranks_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(pr->pt_i.as<int32_t>(), pr->cand_tmp.as<int32_t>(), pr->pt_q.as<double>(), n,
+                                                                    V.nq_list.as<int32_t>(), (int32_t)V.n_list, pr->pt_s.as<int32_t>(),
                                                                     pr->dpres.as<int32_t>() + 8);
     ctx->launches += 1;
     DAB_CUDA(dab_readback(pr, &pr->h_counters[22], pr->dpres.as<int32_t>() + 8, sizeof(int32_t)));
     DAB_CUDA(dab_wait_stream(st));
-    if ((int32_t)pr->h_counters[22] != 0) {
-      dab_set_err(ctx, "import_points1: a point's video frame is not one of this pair's hashed video frames");
+    const int32_t badbits = (int32_t)pr->h_counters[22];
+    if (badbits != 0) {
+      dab_set_err(ctx, badbits & 1 ? "import_points1: a point's video frame is not one of this pair's hashed video frames"
+                        : (badbits & 2 ? "import_points1: match qualities must be > 0"
+                                       : "import_points1: points must be sorted by (audio frame, video frame), without duplicates"));
       return DAB_E_ARG;
     }
   }

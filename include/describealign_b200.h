@@ -192,7 +192,8 @@ int dab_pair_get_points1(dab_pair *pair, int32_t *i_audio, int32_t *v_video, dou
  * audio frames row_lo <= i < row_hi (pass 0, INT64_MAX for all rows); the match points stay on the
  * device.  Ranks exchange them with dab_pair_export_points1 / dab_pair_import_points1 (pointers may be
  * device pointers, e.g. NCCL buffers, when *_on_device != 0); imported points must be sorted by
- * (audio frame, video frame) - concatenating the shards in row order gives exactly that.
+ * (audio frame, video frame) without duplicates, have quals > 0 and lie on hashed video frames of this pair
+ * - concatenating the shards in row order gives exactly that; anything else is rejected with DAB_E_ARG.
  * dab_pair_dp1 then runs frontier DP #1 + traceback (reference :674-700) on the pair's points. */
 int dab_pair_stage_a_match(dab_pair *pair, int64_t row_lo, int64_t row_hi, int64_t *n_points);
 int dab_pair_export_points1(dab_pair *pair, int32_t *i_audio, int32_t *v_video, double *qual, int dst_on_device);
