@@ -48,7 +48,7 @@ struct Track {
   // stage A prep (features 0..2 keep ms / nrm for scoring; 3, 4 only feed the codes)
   DevBuf ms;           // f64 [3][Lp]   Lp = min feature length
   DevBuf nrm;          // f64 [3][Lp-40]
-  DevBuf pack;         // u32 [5][Lp-40] 3-bit digits (bits 0-20) + flags (bits 21-27, video)
+  DevBuf pack;         // u32 [5][Lp-40] one digit per nibble (bits 0-2), bit 3 of the nibble = flag (video)
   DevBuf code;         // i32 [5][Lp-40] base-7 code (audio: lookup key)
   DevBuf nq_flag;      // i32 [n] not-quiet flags, then reused
   DevBuf nq_list;      // i32 selected frame list (video: every 4th not-quiet; audio: all not-quiet)
@@ -67,6 +67,8 @@ struct dab_pair {
   DevBuf tbl_count;   // i32 [5*NCODE + 1]
   DevBuf tbl_start;   // i32 [5*NCODE + 1]
   DevBuf tbl_items;   // i32 sel-ranks
+  DevBuf tbl_ecount;  // i32 [2][5 * vsel_cap + 1]: codes per (frame, table) and their exclusive scan
+  DevBuf tbl_pos;     // i32 [entries]: position of every expanded entry inside its bucket
   DevBuf v_rec;       // uint4[2] per hashed video frame: its five digit packs (gate)
   // gate / scoring
   DevBuf row_count, row_off;   // i32 [n_queries + 1]

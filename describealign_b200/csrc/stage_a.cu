@@ -110,14 +110,14 @@ __global__ void norm_codes_kernel(CodeArgs a) {
     if (a.is_video) {
       d = fmin(fmax(d, 0.0), 6.0);
       double fl = floor(d);
-      if (d - fl > 0.6) pk |= 1u << (21 + k);
+      if (d - fl > 0.6) pk |= 8u << (4 * k);
       dig = (int)fl;
     } else {
       double fl = floor(d);
       fl = fmin(fmax(fl, 0.0), 6.0);
       dig = (int)fl;
     }
-    pk |= (uint32_t)dig << (3 * k);
+    pk |= (uint32_t)dig << (4 * k);
     code += dig * p7;
     p7 *= 7;
   }
@@ -203,23 +203,35 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_onepass_kernel(ScanArgs a) 
   }
   int total;
   const int ex = block_exclusive_scan(s, &total, sm);
-  if (threadIdx.x == 0) {
+  if (threadIdx.x < 32) {
+    // warp 0 publishes the tile's aggregate, then looks back 32 predecessors at a time
+    const int lane = threadIdx.x;
     const unsigned long long tag = (unsigned long long)a.epoch << 34;
     volatile unsigned long long *st = a.status;
     int prefix = 0;
     if (tile > 0) {
-      st[tile] = tag | (1ull << 32) | (unsigned int)total;
-      __threadfence();
-      for (int t = (int)tile - 1; t >= 0; --t) {
-        unsigned long long w;
-        do { w = st[t]; } while ((w >> 34) != a.epoch);
-        prefix += (int)(unsigned int)w;
-        if (((w >> 32) & 3ull) == 2ull) break;
+      if (lane == 0) { st[tile] = tag | (1ull << 32) | (unsigned int)total; __threadfence(); }
+      int end = (int)tile;                      // tiles [.., end) are still to be accounted for
+      while (end > 0) {
+        const int t = end - 1 - lane;           // lane 0 = nearest predecessor
+        unsigned long long w = 0ull;
+        if (t >= 0) { do { w = st[t]; } while ((w >> 34) != a.epoch); }
+        const bool is_prefix = t >= 0 && ((w >> 32) & 3ull) == 2ull;
+        const unsigned pm = __ballot_sync(0xffffffffu, is_prefix);
+        const int stop = pm ? __ffs(pm) - 1 : 32;             // nearest lane holding an inclusive prefix
+        int v = (t >= 0 && lane <= stop) ? (int)(unsigned int)w : 0;
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        prefix += v;
+        if (pm) break;
+        end -= 32;
       }
     }
-    st[tile] = tag | (2ull << 32) | (unsigned int)(prefix + total);
-    __threadfence();
-    s_prefix = prefix;
+    if (lane == 0) {
+      st[tile] = tag | (2ull << 32) | (unsigned int)(prefix + total);
+      __threadfence();
+      s_prefix = prefix;
+    }
   }
   __syncthreads();
   int run = ex + s_prefix;
@@ -263,36 +275,55 @@ __device__ __forceinline__ int32_t pack_to_code(uint32_t pk) {
   int32_t c = 0, p7 = 1;
 #pragma unroll
   for (int k = 0; k < 7; ++k) {
-    c += (int32_t)((pk >> (3 * k)) & 7u) * p7;
+    c += (int32_t)((pk >> (4 * k)) & 7u) * p7;
     p7 *= 7;
   }
   return c;
 }
 
-// One thread per (selected video frame, table).  FILL = false: count; FILL = true: place.
+// One thread per (selected video frame, table).  A frame is stored under every code reachable through its
+// flagged digits (2^flags codes, :630-633).  Three steps without a second round of atomics:
+//   table_expand_kernel   how many codes each (frame, table) expands to -> scan -> where its entries' bucket
+//                         positions are kept
+//   table_kernel<false>   atomicAdd on the code's counter; the value it returns IS the entry's position in
+//                         its bucket and is kept
+//   table_kernel<true>    after the scan of the counters: items[start[code] + position] = frame, plain stores
+__global__ void table_expand_kernel(const uint32_t *pack, int64_t nstride, const int32_t *sel, const int32_t *dc, int64_t vsel_cap,
+                                    int32_t *ecount) {
+  const int f = blockIdx.y;
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= vsel_cap) return;
+  int32_t c = 0;
+  if (s < dc[DC_N_VSEL]) c = 1 << __popc(pack[(int64_t)f * nstride + sel[s]] & 0x8888888u);
+  ecount[(int64_t)f * vsel_cap + s] = c;
+}
+
 template <bool FILL>
-__global__ void table_kernel(const uint32_t *pack, int64_t nstride, const int32_t *sel, const int32_t *dc,
-                             int32_t *count, const int32_t *start, int32_t *items, int64_t items_cap) {
+__global__ void table_kernel(const uint32_t *pack, int64_t nstride, const int32_t *sel, const int32_t *dc, int64_t vsel_cap,
+                             const int32_t *ebase, int32_t *tpos, int32_t *count, const int32_t *start, int32_t *items,
+                             int64_t items_cap) {
   const int f = blockIdx.y;
   const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= dc[DC_N_VSEL]) return;
-  if (FILL && (dc[DC_OVERFLOW] & DAB_OVF_ENTRIES)) return;
+  if (dc[DC_OVERFLOW] & DAB_OVF_ENTRIES) return;
   const uint32_t pk = pack[(int64_t)f * nstride + sel[s]];
-  const uint32_t fl = pk >> 21;
+  const uint32_t fl = pk & 0x8888888u;             // flag bits, one per nibble
   const int32_t base = pack_to_code(pk);
   const int32_t P7[7] = {1, 7, 49, 343, 2401, 16807, 117649};
-  for (uint32_t sub = fl;; sub = (sub - 1) & fl) {
+  int64_t e = ebase[(int64_t)f * vsel_cap + s];
+  for (uint32_t sub = fl;; sub = (sub - 1) & fl, ++e) {
     int32_t c = base;
 #pragma unroll
     for (int k = 0; k < 7; ++k)
-      if (sub & (1u << k)) c += P7[k];
+      if (sub & (8u << (4 * k))) c += P7[k];
     const int64_t slot = (int64_t)f * DAB_NCODE + c;
-    if (!FILL) {
-      atomicAdd(&count[slot], 1);
-    } else {
-      int pos = atomicSub(&count[slot], 1) - 1;   // consumes the counts back to zero
-      const int64_t at = (int64_t)start[slot] + pos;
-      if (at < items_cap) items[at] = (int32_t)s;
+    if (e < items_cap) {
+      if (!FILL) {
+        tpos[e] = atomicAdd(&count[slot], 1);
+      } else {
+        const int64_t at = (int64_t)start[slot] + tpos[e];
+        if (at < items_cap) items[at] = (int32_t)s;
+      }
     }
     if (sub == 0) break;
   }
@@ -304,25 +335,12 @@ __global__ void table_kernel(const uint32_t *pack, int64_t nstride, const int32_
 // The gate compares the 7 quantised digits of an audio frame with those of a video frame, per feature
 // (SURVEY.md A.4): the frames match in a feature when every audio digit equals the video digit, or the
 // video digit + 1 where that digit is flagged (fraction > .6, stored under both codes, :622-633).
-// Digits live one per nibble: bits 0-2 the digit (0..6), bit 3 the flag (video) / a guard bit (audio).
+// Digits live one per nibble (the format norm_codes_kernel writes): bits 0-2 the digit (0..6), bit 3 the
+// flag (video) / a guard bit set by the gate (audio).
 //   d = (audio | 0x8888888) - (video digits)         per nibble 8 + a - v, no borrow between nibbles
 //   d ^ 0x8888888                                    a - v for a >= v (0..6), >= 10 for a < v
 //   ... & ~flags                                     0 exactly when a - v is 0, or 1 on a flagged digit
 // i.e. five integer instructions per feature instead of a per-digit loop.
-__device__ __forceinline__ uint32_t nibbles_of(uint32_t pk) {      // 7 x 3-bit digits -> one per nibble
-  uint32_t r = 0u;
-#pragma unroll
-  for (int k = 0; k < 7; ++k) r |= ((pk >> (3 * k)) & 7u) << (4 * k);
-  return r;
-}
-
-__device__ __forceinline__ uint32_t video_nibbles(uint32_t pk) {  // digits + flag bits 21-27 -> nibbles with the flag in bit 3
-  uint32_t r = nibbles_of(pk);
-#pragma unroll
-  for (int k = 0; k < 7; ++k) r |= ((pk >> (21 + k)) & 1u) << (4 * k + 3);
-  return r;
-}
-
 __device__ __forceinline__ bool digits_match(uint32_t a_guarded, uint32_t v) {
   const uint32_t d = (a_guarded - (v & 0x7777777u)) ^ 0x8888888u;
   return (d & ~((v >> 3) & 0x1111111u)) == 0u;
@@ -337,9 +355,8 @@ __global__ void video_records_kernel(const uint32_t *pack, int64_t nstride, cons
   if (s >= dc[DC_N_VSEL]) return;
   const int32_t v = sel[s];
   uint4 r0, r1;
-  r0.x = video_nibbles(pack[v]); r0.y = video_nibbles(pack[nstride + v]); r0.z = video_nibbles(pack[2 * nstride + v]);
-  r0.w = video_nibbles(pack[3 * nstride + v]);
-  r1.x = video_nibbles(pack[4 * nstride + v]); r1.y = (uint32_t)v; r1.z = 0u; r1.w = 0u;
+  r0.x = pack[v]; r0.y = pack[nstride + v]; r0.z = pack[2 * nstride + v]; r0.w = pack[3 * nstride + v];
+  r1.x = pack[4 * nstride + v]; r1.y = (uint32_t)v; r1.z = 0u; r1.w = 0u;
   rec[2 * s] = r0;
   rec[2 * s + 1] = r1;
 }
@@ -395,7 +412,7 @@ __global__ void gate_kernel(GateArgs g) {
   int32_t st[5], en[5];
 #pragma unroll
   for (int f = 0; f < 5; ++f) {
-    ap[f] = nibbles_of(g.a_pack[(int64_t)f * g.a_nstride + i] & 0x1FFFFFu) | 0x8888888u;
+    ap[f] = g.a_pack[(int64_t)f * g.a_nstride + i] | 0x8888888u;
     const int64_t slot = (int64_t)f * DAB_NCODE + g.a_code[(int64_t)f * g.a_nstride + i];
     st[f] = g.start[slot];
     en[f] = g.start[slot + 1];
@@ -935,15 +952,19 @@ int dab_enqueue_stage_a_match(dab_pair *pr, int64_t row_lo, int64_t row_hi) {
   const int64_t a_nstride = (A.Le > A.L ? A.Le : A.L) - 40;
   DAB_CUDA(cudaEventRecord(pr->ev[6], st));
   dim3 gt((unsigned)cdiv(vsel_ub, 128), 5);
-  table_kernel<false><<<gt, 128, 0, st>>>(V.pack.as<uint32_t>(), v_nstride, V.nq_list.as<int32_t>(), dc,
-                                          pr->tbl_count.as<int32_t>(), nullptr, nullptr, 0);
-  ctx->launches += 1;
-  DAB_TRY(dab_exclusive_scan(pr, pr->tbl_count.as<int32_t>(), pr->tbl_start.as<int32_t>(), nslots, nullptr, dc + DC_N_ENTRIES));
+  DAB_TRY(dab_ensure(ctx, pr->tbl_ecount, sizeof(int32_t) * (size_t)(2 * (5 * vsel_ub + 2))));
+  DAB_TRY(dab_ensure(ctx, pr->tbl_pos, sizeof(int32_t) * (size_t)(cap_e + 1)));
+  int32_t *ecount = pr->tbl_ecount.as<int32_t>(), *ebase = ecount + (5 * vsel_ub + 1);
+  table_expand_kernel<<<gt, 128, 0, st>>>(V.pack.as<uint32_t>(), v_nstride, V.nq_list.as<int32_t>(), dc, vsel_ub, ecount);
+  DAB_TRY(dab_exclusive_scan(pr, ecount, ebase, 5 * vsel_ub, nullptr, dc + DC_N_ENTRIES));
   check_capacity_kernel<<<1, 32, 0, st>>>(dc, DC_N_ENTRIES, cap_e, DAB_OVF_ENTRIES);
-  table_kernel<true><<<gt, 128, 0, st>>>(V.pack.as<uint32_t>(), v_nstride, V.nq_list.as<int32_t>(), dc,
-                                         pr->tbl_count.as<int32_t>(), pr->tbl_start.as<int32_t>(),
+  table_kernel<false><<<gt, 128, 0, st>>>(V.pack.as<uint32_t>(), v_nstride, V.nq_list.as<int32_t>(), dc, vsel_ub, ebase,
+                                          pr->tbl_pos.as<int32_t>(), pr->tbl_count.as<int32_t>(), nullptr, nullptr, cap_e);
+  DAB_TRY(dab_exclusive_scan(pr, pr->tbl_count.as<int32_t>(), pr->tbl_start.as<int32_t>(), nslots));
+  table_kernel<true><<<gt, 128, 0, st>>>(V.pack.as<uint32_t>(), v_nstride, V.nq_list.as<int32_t>(), dc, vsel_ub, ebase,
+                                         pr->tbl_pos.as<int32_t>(), pr->tbl_count.as<int32_t>(), pr->tbl_start.as<int32_t>(),
                                          pr->tbl_items.as<int32_t>(), cap_e);
-  ctx->launches += 2;
+  ctx->launches += 4;
   DAB_CUDA(cudaEventRecord(pr->ev[7], st));
 
   // ---- gate: count, scan, fill ----
