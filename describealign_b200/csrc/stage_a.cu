@@ -193,6 +193,14 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_onepass_kernel(ScanArgs a) 
   if (threadIdx.x == 0) s_tile = atomicAdd(a.ticket, 1u);
   __syncthreads();
   const unsigned int tile = s_tile;
+  if ((int64_t)tile > n / SCAN_TILE) {
+    // past the tile that holds position n (a device-side count far below the capacity): nobody looks back here
+    if (threadIdx.x == 0) {
+      const unsigned int done = atomicAdd(a.ticket + 1, 1u);
+      if (done == gridDim.x - 1) { a.ticket[0] = 0u; a.ticket[1] = 0u; __threadfence(); }
+    }
+    return;
+  }
   const int64_t base = (int64_t)tile * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
   int v[SCAN_ITEMS];
   int s = 0;
@@ -311,21 +319,43 @@ __global__ void table_kernel(const uint32_t *pack, int64_t nstride, const int32_
   const int32_t base = pack_to_code(pk);
   const int32_t P7[7] = {1, 7, 49, 343, 2401, 16807, 117649};
   int64_t e = ebase[(int64_t)f * vsel_cap + s];
-  for (uint32_t sub = fl;; sub = (sub - 1) & fl, ++e) {
-    int32_t c = base;
+  // four codes per step: the four atomics (count pass) / the four position and start loads (fill pass) are
+  // issued before the first result is used, so their latencies overlap instead of adding up
+  uint32_t sub = fl;
+  bool more = true;
+  while (more) {
+    int64_t slot[4];
+    bool live[4];
 #pragma unroll
-    for (int k = 0; k < 7; ++k)
-      if (sub & (8u << (4 * k))) c += P7[k];
-    const int64_t slot = (int64_t)f * DAB_NCODE + c;
-    if (e < items_cap) {
-      if (!FILL) {
-        tpos[e] = atomicAdd(&count[slot], 1);
-      } else {
-        const int64_t at = (int64_t)start[slot] + tpos[e];
-        if (at < items_cap) items[at] = (int32_t)s;
+    for (int u = 0; u < 4; ++u) {
+      live[u] = more;
+      int32_t c = base;
+#pragma unroll
+      for (int k = 0; k < 7; ++k)
+        if (sub & (8u << (4 * k))) c += P7[k];
+      slot[u] = (int64_t)f * DAB_NCODE + c;
+      if (more) { if (sub == 0) more = false; else sub = (sub - 1) & fl; }
+    }
+    int32_t v0[4], v1[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      v0[u] = v1[u] = 0;
+      if (live[u] && e + u < items_cap) {
+        if (!FILL) v0[u] = atomicAdd(&count[slot[u]], 1);
+        else { v0[u] = tpos[e + u]; v1[u] = start[slot[u]]; }
       }
     }
-    if (sub == 0) break;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (live[u] && e + u < items_cap) {
+        if (!FILL) tpos[e + u] = v0[u];
+        else {
+          const int64_t at = (int64_t)v1[u] + v0[u];
+          if (at < items_cap) items[at] = (int32_t)s;
+        }
+      }
+    }
+    e += 4;
   }
 }
 
@@ -408,51 +438,57 @@ __global__ void gate_kernel(GateArgs g) {
       return;
     }
   }
+  // lanes 0-4 fetch the query's five digit words and bucket ranges, one feature each; then broadcast
+  uint32_t my_ap = 0u;
+  int32_t my_st = 0, my_en = 0;
+  if (lane < 5) {
+    my_ap = g.a_pack[(int64_t)lane * g.a_nstride + i] | 0x8888888u;
+    const int64_t slot = (int64_t)lane * DAB_NCODE + g.a_code[(int64_t)lane * g.a_nstride + i];
+    my_st = g.start[slot];
+    my_en = g.start[slot + 1];
+  }
   uint32_t ap[5];
-  int32_t st[5], en[5];
+  int32_t st[5], nb[5];
 #pragma unroll
   for (int f = 0; f < 5; ++f) {
-    ap[f] = g.a_pack[(int64_t)f * g.a_nstride + i] | 0x8888888u;
-    const int64_t slot = (int64_t)f * DAB_NCODE + g.a_code[(int64_t)f * g.a_nstride + i];
-    st[f] = g.start[slot];
-    en[f] = g.start[slot + 1];
+    ap[f] = __shfl_sync(0xffffffffu, my_ap, f);
+    st[f] = __shfl_sync(0xffffffffu, my_st, f);
+    nb[f] = __shfl_sync(0xffffffffu, my_en, f) - st[f];
   }
-  const int n0 = en[0] - st[0], n1 = en[1] - st[1], n2 = en[2] - st[2], n3 = en[3] - st[3], n4 = en[4] - st[4];
   // every candidate lies in at least one bucket of any pair out of {0,1,2}, and in bucket 3 or 4
-  int fa = 0, fb = 1, best = n0 + n1;
-  if (n0 + n2 < best) { best = n0 + n2; fa = 0; fb = 2; }
-  if (n1 + n2 < best) { best = n1 + n2; fa = 1; fb = 2; }
-  if (n3 + n4 < best) { best = n3 + n4; fa = 3; fb = 4; }
+  int fa = 0, fb = 1, best = nb[0] + nb[1];
+  if (nb[0] + nb[2] < best) { best = nb[0] + nb[2]; fa = 0; fb = 2; }
+  if (nb[1] + nb[2] < best) { best = nb[1] + nb[2]; fa = 1; fb = 2; }
+  if (nb[3] + nb[4] < best) { best = nb[3] + nb[4]; fa = 3; fb = 4; }
   int found = 0;
   const int64_t off = FILL ? g.row_off[q] : 0;
-  for (int pass = 0; pass < 2; ++pass) {
-    const int fcur = pass == 0 ? fa : fb;
-    const int s0 = st[fcur], cnt = en[fcur] - st[fcur];
-    for (int base = 0; base < cnt; base += 32) {
-      const int e = base + lane;
-      bool ok = false;
-      int32_t s = 0;
-      if (e < cnt) {
-        s = g.items[s0 + e];
-        const uint4 r0 = __ldg(g.v_rec + 2 * (int64_t)s), r1 = __ldg(g.v_rec + 2 * (int64_t)s + 1);
-        const uint32_t vp[5] = {r0.x, r0.y, r0.z, r0.w, r1.x};
-        bool m[5];
+  // the two buckets are walked as one list of `best` entries, 32 per step
+  const int sa = st[fa], ca = nb[fa], sb = st[fb];
+  for (int base = 0; base < best; base += 32) {
+    const int e = base + lane;
+    bool ok = false;
+    int32_t s = 0;
+    if (e < best) {
+      const bool second = e >= ca;
+      s = g.items[second ? sb + (e - ca) : sa + e];
+      const uint4 r0 = __ldg(g.v_rec + 2 * (int64_t)s), r1 = __ldg(g.v_rec + 2 * (int64_t)s + 1);
+      const uint32_t vp[5] = {r0.x, r0.y, r0.z, r0.w, r1.x};
+      bool m[5];
 #pragma unroll
-        for (int f = 0; f < 5; ++f) m[f] = digits_match(ap[f], vp[f]);
-        ok = ((int)m[0] + (int)m[1] + (int)m[2] >= 2) && (m[3] || m[4]);
-        if (pass == 1 && m[fa]) ok = false;   // already enumerated from the first bucket
-      }
-      const unsigned bal = __ballot_sync(0xffffffffu, ok);
-      if (!FILL && ok) {
-        const int idx = found + __popc(bal & ((1u << lane) - 1u));
-        if (idx < GATE_STASH) g.stash[q * GATE_STASH + idx] = s;
-      }
-      if (FILL && ok) {
-        const int64_t pos = off + found + __popc(bal & ((1u << lane) - 1u));
-        if (pos < g.cand_cap) g.cand_tmp[pos] = s;
-      }
-      found += __popc(bal);
+      for (int f = 0; f < 5; ++f) m[f] = digits_match(ap[f], vp[f]);
+      ok = ((int)m[0] + (int)m[1] + (int)m[2] >= 2) && (m[3] || m[4]);
+      if (second && m[fa]) ok = false;   // already enumerated from the first bucket
     }
+    const unsigned bal = __ballot_sync(0xffffffffu, ok);
+    if (!FILL && ok) {
+      const int idx = found + __popc(bal & ((1u << lane) - 1u));
+      if (idx < GATE_STASH) g.stash[q * GATE_STASH + idx] = s;
+    }
+    if (FILL && ok) {
+      const int64_t pos = off + found + __popc(bal & ((1u << lane) - 1u));
+      if (pos < g.cand_cap) g.cand_tmp[pos] = s;
+    }
+    found += __popc(bal);
   }
   if (!FILL) {
     if (lane == 0) g.row_count[q] = found;
