@@ -266,10 +266,10 @@ void dab_pair_destroy(dab_pair *pr) {
   if (pr->stream) dab_wait_stream(pr->stream);
   for (int t = 0; t < 2; ++t) {
     Track &k = pr->trk[t];
-    DevBuf *bs[] = {&k.pcm, &k.energy, &k.zc, &k.b0, &k.b1, &k.b2, &k.gate, &k.ms, &k.nrm, &k.pack, &k.code, &k.nq_flag, &k.nq_list};
+    DevBuf *bs[] = {&k.pcm, &k.feat_ticket, &k.energy, &k.zc, &k.b0, &k.b1, &k.b2, &k.gate, &k.ms, &k.nrm, &k.pack, &k.code, &k.nq_flag, &k.nq_list};
     for (DevBuf *b : bs) free_buf(*b);
   }
-  DevBuf *bs[] = {&pr->scan_tmp, &pr->tbl_count, &pr->tbl_start, &pr->tbl_items, &pr->tbl_ecount, &pr->tbl_pos, &pr->v_rec, &pr->clusters, &pr->refine_partial, &pr->maxes, &pr->row_count, &pr->row_off, &pr->row_stash,
+  DevBuf *bs[] = {&pr->scan_tmp, &pr->tbl_count, &pr->tbl_start, &pr->tbl_items, &pr->tbl_ecount, &pr->tbl_pos, &pr->v_rec, &pr->clusters, &pr->refine_partial, &pr->maxes, &pr->row_count, &pr->row_off, &pr->row_stash, &pr->gate_rec, &pr->gate_best, &pr->gate_big,
                   &pr->cand_tmp, &pr->cand_s, &pr->cand_i, &pr->cand_q, &pr->keep_flag, &pr->keep_off, &pr->pt_i,
                   &pr->pt_s, &pr->pt_q, &pr->counters, &pr->tree1, &pr->back1, &pr->len1, &pr->cp1, &pr->dpres,
                   &pr->seglist, &pr->path1_x, &pr->path1_y, &pr->a_scaled, &pr->v_scaled, &pr->corridors,

@@ -43,6 +43,7 @@ struct Track {
   bool have_features = false;
   DevBuf pcm;          // staging for host PCM
   DevBuf energy, zc, b0, b1, b2;   // f32 x4, f64
+  DevBuf feat_ticket;  // u32: tile ticket of the persistent feature kernel
   DevBuf gate;         // the separate *_energy argument of align() when it is not features[0] (:629, :657)
   bool have_gate = false;
   // stage A prep (features 0..2 keep ms / nrm for scoring; 3, 4 only feed the codes)
@@ -73,6 +74,8 @@ struct dab_pair {
   // gate / scoring
   DevBuf row_count, row_off;   // i32 [n_queries + 1]
   DevBuf row_stash;            // i32 [n_queries][4]: first candidates of each row (gate count pass)
+  DevBuf gate_big;             // i32: rows with more than 4 candidates (work list of the fill pass)
+  DevBuf gate_rec, gate_best;  // per query: digit words + its two buckets (32 B); bucket entries to visit and their scan
   DevBuf cand_tmp, cand_s, cand_i;  // i32 [n_cand]
   DevBuf cand_q;               // f64 [n_cand]
   DevBuf keep_flag, keep_off;  // i32 [n_cand + 1]
@@ -188,6 +191,7 @@ enum {
   DC_Q_LO = 10, DC_Q_HI = 11, DC_N_Q = 12,    // query range of this shard in the not-quiet audio list
   DC_OVERFLOW = 13,    // bit 0 table entries, bit 1 candidates, bit 2 > 32 corridors on a row, bit 3 pass-2 points
   DC_BAD_IMPORT = 14,
+  DC_N_BIGROWS = 15,   // gate rows with more than GATE_STASH candidates
   DC_N_PTS2 = 16,
   DC_OVERFLOW_B = 17,  // stage B: bit 2 more than 32 corridors on one audio row
   DC_DP2_END = 18,     // end id, path length, then the frontier value (double at words 20-21)

@@ -34,7 +34,8 @@ constexpr int THREADS = 512;
 constexpr int NTAB = 772;         // 630 + 90 + 21 + 15 + 13 = 769 floats, padded
 
 template <int CH> struct Tile {
-  static constexpr int FT = CH == 1 ? 104 : 48;      // output frames per CTA
+  static constexpr int FT = CH == 1 ? 100 : 48;      // output frames per tile
+  static constexpr int TC = CH == 1 ? 10 : 8;         // frames per phase task: 48 * FT / TC tasks (480 / 288), one round of the 512 threads
   static constexpr int NF = FT + 2 * FH;              // frames staged
   static constexpr int NS = NF * 210 + 2 * PADS;      // samples staged (multiple of 8)
   static constexpr int N1 = NF * 42 + 14;             // lp1 entries staged (+-7)
@@ -51,6 +52,7 @@ template <int CH> struct Tile {
   static constexpr int O_ZI = O_EB + 2 * NF * 4;
   static constexpr int O_P1 = O_ZI + NF * 4;                                    // band-1 phase sums FT*6
   static constexpr int BYTES = O_P1 + FT * 6 * 4;
+  static_assert(NS % 8 == 0 && N1 % 2 == 0 && (NS * 2) % 16 == 0 && O_SIG % 16 == 0 && FT * 42 <= N1, "tile layout");
 };
 
 __device__ float g_tables[NTAB];   // w630 | w90 | w21 | w15 | w13
@@ -143,6 +145,8 @@ struct FeatArgs {
   int64_t nb;     // S / 105
   int64_t Le;     // ceil(nb / 2)
   int vec_ok;     // pcm is 16-byte aligned
+  int64_t tiles;  // tiles of FT output frames
+  unsigned int *ticket;   // next tile (zeroed before the launch)
   float *energy, *zc, *b0, *b1;
   double *b2;
 };
@@ -205,11 +209,51 @@ __device__ __forceinline__ float2 energy_lanes2(FX X, int l) {
   return acc;
 }
 
+// ---- mbarrier / 1-D bulk copy (TMA) helpers: the raw PCM of the next tile is fetched by the copy engine into
+//      the shared-memory signal buffer while the current tile's filter stages run ------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+  // the buffer was last touched through the generic proxy (all threads, before the CTA barrier that precedes this call)
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// Persistent kernel: 2 CTAs per SM, each taking tiles of FT output frames from an atomic ticket.  Per tile:
+//   S0   the staged signal arrives (bulk copy issued during the previous tile, converted int16 -> float16 in place;
+//        edge tiles and stereo tracks are staged by the threads themselves)
+//   S1   lp1 = downsample_blur(m, 5, 3) and, from the same register window, the band-0 residual energies
+//   S2   block energies, zero crossings, lp2 = downsample_blur(lp1, 7, 3) with the band-1 residual energies from
+//        the same window and the band-2 frame energies by warp shuffles; the signal buffer is dead after this
+//        stage: the next tile's bulk copy is issued here and overlaps S3 / S4
+//   S3   the 42 + 6 polyphase 15-tap filters at 210 Hz (f32 products accumulated in f64)
+//   S4   the five outputs
 template <int FMT, int CH>
 __global__ void __launch_bounds__(THREADS, 2) features_kernel(FeatArgs a) {
   using T = Tile<CH>;
-  constexpr int FT = T::FT, NF = T::NF, NS = T::NS, N1 = T::N1;
+  constexpr int FT = T::FT, NF = T::NF, NS = T::NS, N1 = T::N1, TC = T::TC;
   extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ int s_next;
   float *tab = reinterpret_cast<float *>(smem + T::O_TAB);
   const float *w630 = tab, *w90 = tab + 630, *w21 = tab + 720, *w15 = tab + 741, *w13 = tab + 756;
   __half *sig = reinterpret_cast<__half *>(smem + T::O_SIG);
@@ -224,305 +268,369 @@ __global__ void __launch_bounds__(THREADS, 2) features_kernel(FeatArgs a) {
   int *zi = reinterpret_cast<int *>(smem + T::O_ZI);
   float *p1 = reinterpret_cast<float *>(smem + T::O_P1);
 
-  const int tid = threadIdx.x;
-  const int64_t t0 = (int64_t)blockIdx.x * FT;          // first output frame of this tile
-  const int64_t f0 = t0 - FH;                           // first staged frame (may be < 0)
-  const int64_t s0 = f0 * 210 - PADS;                   // first staged sample (may be < 0)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t Sb = a.L * 210;                         // band signal length (:577)
+  const int64_t len1 = a.L * 42, len2 = a.L * 6;
 
-  // ---- tables, zero-crossing counters ------------------------------------------------------
+  // a tile whose staged window lies inside the band signal is fetched by the copy engine (mono tracks)
+  auto bulk_ok = [&](int64_t tile) {
+    if (CH != 1 || !a.vec_ok || tile >= a.tiles) return false;
+    const int64_t s = (tile * FT - FH) * 210 - PADS;
+    return s >= 0 && s + NS <= Sb;
+  };
+  auto bulk_issue = [&](int64_t tile) {
+    const int64_t s = (tile * FT - FH) * 210 - PADS;
+    mbar_expect_tx(&s_bar, NS * 2);
+    bulk_load(sig, reinterpret_cast<const unsigned short *>(a.pcm) + s, NS * 2, &s_bar);
+  };
+
+  // ---- once per CTA: tables, the pad behind the signal, the first tile ------------------------------------
   for (int k = tid; k < NTAB; k += THREADS) tab[k] = g_tables[k];
-  for (int k = tid; k < NF; k += THREADS) zi[k] = 0;
   if (tid < 16) sig[NS + tid] = __float2half_rn(0.0f);      // read (never used) by the last lp1 task
+  if (tid == 0) {
+    mbar_init(&s_bar, 1);
+    s_next = (int)atomicAdd(a.ticket, 1u);
+  }
+  __syncthreads();
+  int64_t tile = s_next;
+  if (tid == 0 && bulk_ok(tile)) bulk_issue(tile);
+  uint32_t parity = 0;
 
-  // ---- stage the mono / mid signal as float16, zero outside [0, Sb) ------------------------
-  // 8 samples per step; s0 is a multiple of 8 samples, so a 16-byte aligned source stays aligned
-  for (int v = tid; v < NS / 8; v += THREADS) {
-    const int64_t g = s0 + 8 * (int64_t)v;
-    __align__(16) __half h[8];
-    if (a.vec_ok && g >= 0 && g + 8 <= Sb) {
-      if (CH == 1) {
-        const uint4 w = __ldg(reinterpret_cast<const uint4 *>(reinterpret_cast<const unsigned short *>(a.pcm) + g));
-        const unsigned u[4] = {w.x, w.y, w.z, w.w};
+  while (tile < a.tiles) {
+    const int64_t t0 = tile * FT;                         // first output frame of this tile
+    const int64_t f0 = t0 - FH;                           // first staged frame (may be < 0)
+    const int64_t s0 = f0 * 210 - PADS;                   // first staged sample (may be < 0)
+
+    // ---- S0: the mono / mid signal as float16, zero outside [0, Sb) ----------------------------------------
+    for (int k = tid; k < NF; k += THREADS) zi[k] = 0;
+    if (bulk_ok(tile)) {
+      mbar_wait(&s_bar, parity);
+      parity ^= 1u;
+      if (FMT == DAB_PCM_S16) {
+        // int16 -> float16 (RNE, describealign.py:156) in place, 8 samples per step
+        for (int v = tid; v < NS / 8; v += THREADS) {
+          const uint4 w = *reinterpret_cast<const uint4 *>(sig + 8 * v);
+          const unsigned u[4] = {w.x, w.y, w.z, w.w};
+          __align__(16) __half h[8];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          h[2 * e] = bits_half<FMT>((unsigned short)(u[e] & 0xffffu));
-          h[2 * e + 1] = bits_half<FMT>((unsigned short)(u[e] >> 16));
-        }
-      } else {
-        const uint4 *src = reinterpret_cast<const uint4 *>(reinterpret_cast<const unsigned short *>(a.pcm) + 2 * g);
-        const uint4 w0 = __ldg(src), w1 = __ldg(src + 1);
-        const unsigned u[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-        const int fr = 8 * v - PADS;                      // index into raw (frame samples only)
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const __half l = bits_half<FMT>((unsigned short)(u[e] & 0xffffu));
-          const __half r = bits_half<FMT>((unsigned short)(u[e] >> 16));
-          h[e] = mid_half(l, r);
-          if (fr + e >= 0 && fr + e < NF * 210) raw[fr + e] = __halves2half2(l, r);
+          for (int e = 0; e < 4; ++e) {
+            h[2 * e] = __short2half_rn((short)(u[e] & 0xffffu));
+            h[2 * e + 1] = __short2half_rn((short)(u[e] >> 16));
+          }
+          *reinterpret_cast<uint4 *>(sig + 8 * v) = *reinterpret_cast<const uint4 *>(h);
         }
       }
     } else {
+      // 8 samples per step; s0 is a multiple of 8 samples, so a 16-byte aligned source stays aligned
+      for (int v = tid; v < NS / 8; v += THREADS) {
+        const int64_t g = s0 + 8 * (int64_t)v;
+        __align__(16) __half h[8];
+        if (a.vec_ok && g >= 0 && g + 8 <= Sb) {
+          if (CH == 1) {
+            const uint4 w = __ldg(reinterpret_cast<const uint4 *>(reinterpret_cast<const unsigned short *>(a.pcm) + g));
+            const unsigned u[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int64_t ge = g + e;
-        __half x = __float2half_rn(0.0f), l = x, r = x;
-        if (ge >= 0 && ge < Sb) {
-          if (CH == 1) x = elem_half<FMT>(a.pcm, ge);
-          else { l = elem_half<FMT>(a.pcm, 2 * ge); r = elem_half<FMT>(a.pcm, 2 * ge + 1); x = mid_half(l, r); }
-        }
-        h[e] = x;
-        if (CH == 2) {
-          const int fr = 8 * v - PADS + e;
-          if (fr >= 0 && fr < NF * 210) raw[fr] = __halves2half2(l, r);
-        }
-      }
-    }
-    *reinterpret_cast<uint4 *>(sig + 8 * v) = *reinterpret_cast<const uint4 *>(h);
-  }
-  __syncthreads();
-
-  // ---- block energies (einsum order): 2 threads per 105-sample block, each running two of the four
-  //      lane accumulators as one packed f32x2 (FMUL2 / FADD2: per lane the same separately rounded
-  //      multiply and add as before) ---------------------------------------------------------------
-  for (int k = tid; k < 2 * NF * 2; k += THREADS) {
-    const int kb = k >> 1, l = (k & 1) * 2;           // lanes l, l + 1
-    const int64_t b = 2 * f0 + kb;
-    float2 acc = make_float2(0.0f, 0.0f);
-    const bool valid = b >= 0 && b < a.nb;
-    if (valid) {
-      if ((b + 1) * 105 <= Sb) {
-        if (CH == 1) {
-          const __half *src = sig + PADS + kb * 105;
-          acc = energy_lanes2<105>([&](int e) { return __half2float(src[e]); }, l);
+            for (int e = 0; e < 4; ++e) {
+              h[2 * e] = bits_half<FMT>((unsigned short)(u[e] & 0xffffu));
+              h[2 * e + 1] = bits_half<FMT>((unsigned short)(u[e] >> 16));
+            }
+          } else {
+            const uint4 *src = reinterpret_cast<const uint4 *>(reinterpret_cast<const unsigned short *>(a.pcm) + 2 * g);
+            const uint4 w0 = __ldg(src), w1 = __ldg(src + 1);
+            const unsigned u[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+            const int fr = 8 * v - PADS;                      // index into raw (frame samples only)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const __half l = bits_half<FMT>((unsigned short)(u[e] & 0xffffu));
+              const __half r = bits_half<FMT>((unsigned short)(u[e] >> 16));
+              h[e] = mid_half(l, r);
+              if (fr + e >= 0 && fr + e < NF * 210) raw[fr + e] = __halves2half2(l, r);
+            }
+          }
         } else {
-          const __half *src = reinterpret_cast<const __half *>(raw + kb * 105);
-          acc = energy_lanes2<210>([&](int e) { return __half2float(src[e]); }, l);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int64_t ge = g + e;
+            __half x = __float2half_rn(0.0f), l = x, r = x;
+            if (ge >= 0 && ge < Sb) {
+              if (CH == 1) x = elem_half<FMT>(a.pcm, ge);
+              else { l = elem_half<FMT>(a.pcm, 2 * ge); r = elem_half<FMT>(a.pcm, 2 * ge + 1); x = mid_half(l, r); }
+            }
+            h[e] = x;
+            if (CH == 2) {
+              const int fr = 8 * v - PADS + e;
+              if (fr >= 0 && fr < NF * 210) raw[fr] = __halves2half2(l, r);
+            }
+          }
         }
-      } else {
-        // the one block past the band signal (S mod 210 >= 105) is not staged: read it from HBM
-        const int64_t base = b * 105 * CH;
-        acc = energy_lanes2<105 * CH>([&](int e) { return __half2float(elem_half<FMT>(a.pcm, base + e)); }, l);
+        *reinterpret_cast<uint4 *>(sig + 8 * v) = *reinterpret_cast<const uint4 *>(h);
       }
     }
-    const float s01 = acc.x + acc.y;                          // l0 + l1  /  l2 + l3
-    const float o2 = __shfl_xor_sync(0xffffffffu, s01, 1);
-    if (l == 0) eb[kb] = valid ? (s01 + o2) / (float)(105 * CH) : 0.0f;
-  }
+    __syncthreads();
 
-  // ---- zero crossings: 14 chunks of 15 samples per frame and channel ----------------------------
-  for (int k = tid; k < NF * 14 * CH; k += THREADS) {
-    const int kf = k / (14 * CH), rem = k - kf * 14 * CH;
-    const int c = CH == 1 ? 0 : rem / 14, ck = CH == 1 ? rem : rem - c * 14;
-    const int64_t f = f0 + kf;
-    if (f >= 0 && f < a.L) {
-      int cnt = 0;
-      if (CH == 1) {
-        const unsigned short *src = reinterpret_cast<const unsigned short *>(sig) + PADS + kf * 210 + ck * 15;
-        unsigned prev = src[-1] >> 15;          // staged zero (+0) in front of sample 0: np.diff prepend=False
+    // ---- S1: lp1 = downsample_blur(m, 5, 3): 5 phases x 3 taps, f32 accumulators (B.2 ii).  Two adjacent
+    //      outputs per thread: their windows overlap (20 samples instead of 30 are loaded and converted) and
+    //      their multiplies are one packed FMUL2.  The band-0 residual energy at 8820 Hz of lp1 entry k sums
+    //      (x - lp1[k])^2 over the MIDDLE five samples of the very window lp1[k] was filtered from, so it is
+    //      formed here from the registers ---------------------------------------------------------------------
+    const int64_t n1_first = f0 * 42 - 7;          // global lp1 index of lp1[0]
+    {
+    const float w15r[15] = {w15[0], w15[1], w15[2], w15[3], w15[4], w15[5], w15[6], w15[7],
+                            w15[8], w15[9], w15[10], w15[11], w15[12], w15[13], w15[14]};
+    for (int u = tid; u < N1 / 2; u += THREADS) {
+      const int k = 2 * u;
+      // lp1[k] reads the staged samples 5k .. 5k+14 (samples outside [0, Sb) are staged as zero, which is
+      // exactly the zero padding of the phase signals); 5k is a multiple of 10 halves: 4-byte aligned
+      const __half2 *src = reinterpret_cast<const __half2 *>(sig + 5 * k);
+      float x[20];
 #pragma unroll
-        for (int e = 0; e < 15; ++e) { const unsigned cur = src[e] >> 15; cnt += (int)(cur ^ prev); prev = cur; }
-      } else {
-        const unsigned short *src = reinterpret_cast<const unsigned short *>(raw) + 2 * (kf * 210 + ck * 15) + c;
-        unsigned prev;
-        if (kf == 0 && ck == 0) {
-          const int64_t n = f * 210;
-          prev = n == 0 ? 0u : (unsigned)(__half_as_ushort(elem_half<FMT>(a.pcm, (n - 1) * 2 + c)) >> 15);
-        } else {
-          prev = src[-2] >> 15;
+      for (int e = 0; e < 10; ++e) { const float2 v = __half22float2(src[e]); x[2 * e] = v.x; x[2 * e + 1] = v.y; }
+      float2 tot = make_float2(0.0f, 0.0f);
+#pragma unroll
+      for (int p = 0; p < 5; ++p) {
+        float2 acc = make_float2(0.0f, 0.0f);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const float wv = w15r[p + (2 - j) * 5];
+          acc = mul2_then_add(acc, make_float2(x[j * 5 + p], x[j * 5 + p + 5]), make_float2(wv, wv));
         }
-#pragma unroll
-        for (int e = 0; e < 15; ++e) { const unsigned cur = src[2 * e] >> 15; cnt += (int)(cur ^ prev); prev = cur; }
+        tot = __fadd2_rn(tot, acc);
       }
-      atomicAdd(&zi[kf], cnt);
-    }
-  }
-
-  // ---- lp1 = downsample_blur(m, 5, 3): 5 phases x 3 taps, f32 accumulators (B.2 ii).  Two adjacent
-  //      outputs per thread: their windows overlap (20 samples instead of 30 are loaded and converted)
-  //      and their multiplies are one packed FMUL2 ---------------------------------------------------
-  const int64_t n1_first = f0 * 42 - 7;          // global lp1 index of lp1[0]
-  const int64_t len1 = a.L * 42;
-  {
-  const float w15r[15] = {w15[0], w15[1], w15[2], w15[3], w15[4], w15[5], w15[6], w15[7],
-                          w15[8], w15[9], w15[10], w15[11], w15[12], w15[13], w15[14]};
-  for (int u = tid; u < N1 / 2; u += THREADS) {
-    const int k = 2 * u;
-    // lp1[k] reads the staged samples 5k .. 5k+14 (samples outside [0, Sb) are staged as zero, which is
-    // exactly the zero padding of the phase signals); 5k is a multiple of 10 halves: 4-byte aligned
-    const __half2 *src = reinterpret_cast<const __half2 *>(sig + 5 * k);
-    float x[20];
-#pragma unroll
-    for (int e = 0; e < 10; ++e) { const float2 v = __half22float2(src[e]); x[2 * e] = v.x; x[2 * e + 1] = v.y; }
-    float2 tot = make_float2(0.0f, 0.0f);
-#pragma unroll
-    for (int p = 0; p < 5; ++p) {
+      const int64_t n = n1_first + k;
+      const bool in0 = n >= 0 && n < len1, in1 = n + 1 >= 0 && n + 1 < len1;
+      const float lo0 = in0 ? tot.x : 0.0f, lo1 = in1 ? tot.y : 0.0f;
+      lp1[k] = lo0;
+      lp1[k + 1] = lo1;
+      // band-0 residuals of the same two entries: staged be0 index = k - 7 (be0[0] <-> lp1 entry f0 * 42)
+      const float2 nlo = make_float2(-lo0, -lo1);
       float2 acc = make_float2(0.0f, 0.0f);
 #pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        const float wv = w15r[p + (2 - j) * 5];
-        acc = mul2_then_add(acc, make_float2(x[j * 5 + p], x[j * 5 + p + 5]), make_float2(wv, wv));
+      for (int i = 0; i < 5; ++i) {
+        const float2 d = __fadd2_rn(make_float2(x[5 + i], x[10 + i]), nlo);        // x - lo
+        acc = (i == 0) ? __fmul2_rn(d, d) : mul2_then_add(acc, d, d);
       }
-      tot = __fadd2_rn(tot, acc);
+      const int kb = k - 7;
+      if (kb >= 0 && kb < NF * 42) be0[kb] = in0 ? acc.x : 0.0f;
+      if (kb + 1 >= 0 && kb + 1 < NF * 42) be0[kb + 1] = in1 ? acc.y : 0.0f;
     }
-    const int64_t n = n1_first + k;
-    lp1[k] = (n >= 0 && n < len1) ? tot.x : 0.0f;
-    lp1[k + 1] = (n + 1 >= 0 && n + 1 < len1) ? tot.y : 0.0f;
-  }
-  }
-  __syncthreads();
+    }
+    __syncthreads();
 
-  // ---- band-0 residual energy at 8820 Hz and lp2 = downsample_blur(lp1, 7, 3) ----------------
-  for (int u = tid; u < NF * 21; u += THREADS) {
-    const int k = 2 * u;                              // outputs k, k + 1: staged samples 5k+40 .. 5k+49
-    const int64_t n = f0 * 42 + k;
-    const __half2 *src = reinterpret_cast<const __half2 *>(sig + 5 * k + PADS);
-    float x[10];
-#pragma unroll
-    for (int e = 0; e < 5; ++e) { const float2 v = __half22float2(src[e]); x[2 * e] = v.x; x[2 * e + 1] = v.y; }
-    const float2 nlo = make_float2(-lp1[k + 7], -lp1[k + 8]);
-    float2 acc = make_float2(0.0f, 0.0f);
-#pragma unroll
-    for (int i = 0; i < 5; ++i) {
-      const float2 d = __fadd2_rn(make_float2(x[i], x[i + 5]), nlo);        // x - lo
-      acc = (i == 0) ? __fmul2_rn(d, d) : mul2_then_add(acc, d, d);
-    }
-    be0[k] = (n >= 0 && n < len1) ? acc.x : 0.0f;
-    be0[k + 1] = (n + 1 >= 0 && n + 1 < len1) ? acc.y : 0.0f;
-  }
-  const int64_t len2 = a.L * 6;
-  for (int k = tid; k < NF * 6; k += THREADS) {
-    const int64_t n2 = f0 * 6 + k;
-    float total = 0.0f;
-    if (n2 >= 0 && n2 < len2) {
-      const float *src = lp1 + (int)((n2 - 1) * 7 - n1_first);   // lp1 is zero outside [0, len1)
-#pragma unroll
-      for (int p = 0; p < 7; ++p) {
-        float acc = 0.0f;
-#pragma unroll
-        for (int j = 0; j < 3; ++j) acc = acc + src[j * 7 + p] * w21[p + (2 - j) * 7];
-        total = total + acc;
+    // ---- S2a: block energies (einsum order): 2 threads per 105-sample block, each running two of the four
+    //      lane accumulators as one packed f32x2 -------------------------------------------------------------
+    for (int k0 = 0; k0 < 2 * NF * 2; k0 += THREADS) {     // whole warps stay in the loop: it ends in a shuffle
+      const int k = k0 + tid;
+      const bool on = k < 2 * NF * 2;
+      const int kb = k >> 1, l = (k & 1) * 2;           // lanes l, l + 1
+      const int64_t b = 2 * f0 + kb;
+      float2 acc = make_float2(0.0f, 0.0f);
+      const bool valid = on && b >= 0 && b < a.nb;
+      if (valid) {
+        if ((b + 1) * 105 <= Sb) {
+          if (CH == 1) {
+            const __half *src = sig + PADS + kb * 105;
+            acc = energy_lanes2<105>([&](int e) { return __half2float(src[e]); }, l);
+          } else {
+            const __half *src = reinterpret_cast<const __half *>(raw + kb * 105);
+            acc = energy_lanes2<210>([&](int e) { return __half2float(src[e]); }, l);
+          }
+        } else {
+          // the one block past the band signal (S mod 210 >= 105) is not staged: read it from HBM
+          const int64_t base = b * 105 * CH;
+          acc = energy_lanes2<105 * CH>([&](int e) { return __half2float(elem_half<FMT>(a.pcm, base + e)); }, l);
+        }
       }
+      const float s01 = acc.x + acc.y;                          // l0 + l1  /  l2 + l3
+      const float o2 = __shfl_xor_sync(0xffffffffu, s01, 1);
+      if (on && l == 0) eb[kb] = valid ? (s01 + o2) / (float)(105 * CH) : 0.0f;
     }
-    lp2[k] = total;
-  }
-  __syncthreads();
 
-  // ---- band-1 residual energy at 1260 Hz, band-2 energy per frame (f64, :583/:588) ----------
-  for (int k = tid; k < NF * 6; k += THREADS) {
-    const int64_t n2 = f0 * 6 + k;
-    float acc = 0.0f;
-    if (n2 >= 0 && n2 < len2) {
-      const float lo = lp2[k];
-      const float *src = lp1 + (int)(n2 * 7 - n1_first);
-#pragma unroll
-      for (int i = 0; i < 7; ++i) {
-        const float d = src[i] - lo;
-        const float sq = d * d;
-        acc = (i == 0) ? sq : acc + sq;
+    // ---- S2b: zero crossings.  Sign changes between neighbouring samples, two samples (mono) or both
+    //      channels of one sample (stereo) per 32-bit word: xor with the word shifted by one sample, keep the
+    //      two sign bits, add them into two 16-bit counters.  Four chunks per frame ---------------------------
+    for (int k = tid; k < NF * 4; k += THREADS) {
+      const int kf = k >> 2, c = k & 3;
+      const int64_t f = f0 + kf;
+      if (f >= 0 && f < a.L) {
+        constexpr int NW = CH == 1 ? 105 : 210;          // words per frame
+        const int wlo = (NW * c) / 4, whi = (NW * (c + 1)) / 4;
+        uint32_t acc = 0u;
+        if (CH == 1) {
+          // frame kf starts at half PADS + 210 kf: word 20 + 105 kf of the signal buffer
+          const uint32_t *W = reinterpret_cast<const uint32_t *>(sig) + (PADS / 2 + 105 * kf);
+          uint32_t prev = W[wlo - 1];                   // the staged zero (+0) in front of sample 0: np.diff prepend=False
+#pragma unroll 9
+          for (int e = wlo; e < whi; ++e) {
+            const uint32_t w = W[e];
+            const uint32_t y = __funnelshift_l(prev, w, 16);      // (sample 2e-1, sample 2e)
+            acc += ((w ^ y) & 0x80008000u) >> 15;
+            prev = w;
+          }
+        } else {
+          const uint32_t *W = reinterpret_cast<const uint32_t *>(raw) + 210 * kf;
+          uint32_t prev;
+          if (kf == 0 && c == 0) {
+            const int64_t n = f * 210;
+            prev = n == 0 ? 0u
+                          : ((uint32_t)__half_as_ushort(elem_half<FMT>(a.pcm, (n - 1) * 2)) |
+                             ((uint32_t)__half_as_ushort(elem_half<FMT>(a.pcm, (n - 1) * 2 + 1)) << 16));
+          } else {
+            prev = W[wlo - 1];
+          }
+#pragma unroll 8
+          for (int e = wlo; e < whi; ++e) {
+            const uint32_t w = W[e];
+            acc += ((w ^ prev) & 0x80008000u) >> 15;
+            prev = w;
+          }
+        }
+        atomicAdd(&zi[kf], (int)((acc & 0xffffu) + (acc >> 16)));
       }
     }
-    be1[k] = acc;
-  }
-  for (int k = tid; k < NF; k += THREADS) {
-    const int64_t f = f0 + k;
-    double acc = 0.0;
-    if (f >= 0 && f < a.L) {
-#pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        const double x = (double)lp2[k * 6 + i];
-        const double sq = x * x;
-        acc = (i == 0) ? sq : acc + sq;
-      }
-    }
-    be2[k] = acc;
-  }
-  __syncthreads();   // lp1 is dead from here on: ph reuses its space
 
-  // ---- band 0: 42 phases x 15 taps and band 1: 6 phases x 15 taps; each phase = f32 products
-  //      accumulated in f64 (B.2 iii).  One thread per (phase, run of TC frames), window in registers.
-  {
-    constexpr int TC = 8;
-    constexpr int NCH = (FT + TC - 1) / TC;
-    for (int u = tid; u < 48 * NCH; u += THREADS) {
-      const int ch = u / 48, pp = u - ch * 48;
-      const bool b0 = pp < 42;
-      const int p = b0 ? pp : pp - 42;
-      const int np = b0 ? 42 : 6;
-      const float *src = (b0 ? be0 : be1) + p;
-      const float *w = (b0 ? w630 : w90) + p;
-      float *dst = (b0 ? ph : p1) + p;
-      const int tb = ch * TC;
-      // output frame t0 + t uses staged frames t + 1 .. t + 15 (tap j <-> frame t + 1 + j)
-      float win[14 + TC], wr[15];
+    // ---- S2c: lp2 = downsample_blur(lp1, 7, 3), 7 phases x 3 taps (f32), the band-1 residual energy at
+    //      1260 Hz from the middle seven entries of the same window, and the band-2 energy of a frame
+    //      (f64, :583/:588) from its six lp2 values by shuffles: a warp takes five frames (30 lanes) ----------
+    {
+      float w21r[21];
 #pragma unroll
-      for (int e = 0; e < 14 + TC; ++e) win[e] = (tb + 1 + e < NF) ? src[(tb + 1 + e) * np] : 0.0f;
+      for (int e = 0; e < 21; ++e) w21r[e] = w21[e];
+      constexpr int NG = (NF + 4) / 5;
+      for (int g = warp; g < NG; g += THREADS / 32) {
+        const int fr = lane / 6, i6 = lane - fr * 6;
+        const int kf = 5 * g + fr;
+        const bool act = lane < 30 && kf < NF;
+        const int k = kf * 6 + i6;
+        const int64_t n2 = f0 * 6 + k;
+        float total = 0.0f, r1 = 0.0f;
+        if (act && n2 >= 0 && n2 < len2) {
+          const float *src = lp1 + 7 * k;                 // lp1 entries (n2 - 1) * 7 .. + 20; lp1 is zero outside [0, len1)
+          float r[21];
 #pragma unroll
-      for (int j = 0; j < 15; ++j) wr[j] = w[(14 - j) * np];
+          for (int e = 0; e < 21; ++e) r[e] = src[e];
 #pragma unroll
-      for (int t = 0; t < TC; ++t) {
-        if (tb + t < FT) {
+          for (int p = 0; p < 7; ++p) {
+            float acc = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) acc = acc + r[j * 7 + p] * w21r[p + (2 - j) * 7];
+            total = total + acc;
+          }
+#pragma unroll
+          for (int i = 0; i < 7; ++i) {
+            const float d = r[7 + i] - total;
+            const float sq = d * d;
+            r1 = (i == 0) ? sq : r1 + sq;
+          }
+        }
+        if (act) { lp2[k] = total; be1[k] = r1; }
+        double acc2 = 0.0;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          const double x = (double)__shfl_sync(0xffffffffu, total, (lane - i6 + i) & 31);
+          const double sq = x * x;
+          acc2 = (i == 0) ? sq : acc2 + sq;
+        }
+        if (act && i6 == 0) {
+          const int64_t f = f0 + kf;
+          be2[kf] = (f >= 0 && f < a.L) ? acc2 : 0.0;
+        }
+      }
+    }
+    __syncthreads();   // sig and lp1 are dead from here on: ph reuses lp1's space, sig receives the next tile
+
+    if (tid == 0) {
+      const int64_t nt = (int64_t)atomicAdd(a.ticket, 1u);
+      s_next = (int)nt;
+      if (bulk_ok(nt)) bulk_issue(nt);
+    }
+
+    // ---- S3: band 0: 42 phases x 15 taps and band 1: 6 phases x 15 taps; each phase = f32 products
+    //      accumulated in f64 (B.2 iii).  One thread per (phase, run of TC frames), window in registers.
+    {
+      constexpr int NCH = (FT + TC - 1) / TC;
+      for (int u = tid; u < 48 * NCH; u += THREADS) {
+        const int ch = u / 48, pp = u - ch * 48;
+        const bool b0 = pp < 42;
+        const int p = b0 ? pp : pp - 42;
+        const int np = b0 ? 42 : 6;
+        const float *src = (b0 ? be0 : be1) + p;
+        const float *w = (b0 ? w630 : w90) + p;
+        float *dst = (b0 ? ph : p1) + p;
+        const int tb = ch * TC;
+        // output frame t0 + t uses staged frames t + 1 .. t + 15 (tap j <-> frame t + 1 + j)
+        float win[14 + TC], wr[15];
+#pragma unroll
+        for (int e = 0; e < 14 + TC; ++e) win[e] = (tb + 1 + e < NF) ? src[(tb + 1 + e) * np] : 0.0f;
+#pragma unroll
+        for (int j = 0; j < 15; ++j) wr[j] = w[(14 - j) * np];
+#pragma unroll
+        for (int t = 0; t < TC; ++t) {
+          if (tb + t < FT) {
+            double acc = 0.0;
+#pragma unroll
+            for (int j = 0; j < 15; ++j) {
+              const float prod = win[t + j] * wr[j];
+              acc += (double)prod;
+            }
+            dst[(tb + t) * np] = (float)acc;
+          }
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- S4: outputs: four thread roles per frame ---------------------------------------------------------
+    for (int u = tid; u < 4 * FT; u += THREADS) {
+      const int role = u / FT, t = u - role * FT;
+      const int64_t f = t0 + t;
+      if (role == 0) {
+        if (f < a.L) {
+          // band 0: phases added sequentially in f32 (B.2 v), /210, log10(1+x)/2
+          float tot = 0.0f;
+#pragma unroll 6
+          for (int p = 0; p < 42; ++p) tot = tot + ph[t * 42 + p];
+          a.b0[f] = host_log10f(1.0f + tot / 210.0f) / 2.0f;
+        }
+      } else if (role == 1) {
+        if (f < a.L) {
+          float tot = 0.0f;
+#pragma unroll
+          for (int p = 0; p < 6; ++p) tot = tot + p1[t * 6 + p];
+          a.b1[f] = host_log10f(1.0f + tot / 210.0f) / 2.0f;
+          // zero crossings: 13-tap Hann over frames f-6 .. f+6
           double acc = 0.0;
 #pragma unroll
-          for (int j = 0; j < 15; ++j) {
-            const float prod = win[t + j] * wr[j];
+          for (int j = 0; j < 13; ++j) {
+            float z = (float)zi[t + FH - 6 + j];
+            if (CH == 1) z = z * 2.0f;
+            const float prod = z * w13[12 - j];
             acc += (double)prod;
           }
-          dst[(tb + t) * np] = (float)acc;
+          a.zc[f] = (float)acc;
+        }
+      } else if (role == 2) {
+        if (f < a.L) {
+          // band 2: one 15-tap f64 filter = OpenBLAS ddot tail, a sequential FMA chain (B.2 iv)
+          double acc = 0.0;
+#pragma unroll
+          for (int j = 0; j < 15; ++j) acc = fma((double)w15[14 - j], be2[t + 1 + j], acc);
+          a.b2[f] = log10(1.0 + acc / 210.0) / 2.0;
+        }
+      } else {
+        if (f < a.Le) {
+          // energy: 13-tap Hann over blocks 2f-6 .. 2f+6, log10(1+x)/2, every second block (:553-555)
+          double acc = 0.0;
+#pragma unroll
+          for (int j = 0; j < 13; ++j) {
+            const float prod = eb[2 * (t + FH) - 6 + j] * w13[12 - j];
+            acc += (double)prod;
+          }
+          a.energy[f] = host_log10f(1.0f + (float)acc) / 2.0f;
         }
       }
     }
-  }
-  __syncthreads();
-
-  // ---- outputs: three thread roles per frame -----------------------------------------------------
-  for (int u = tid; u < 3 * FT; u += THREADS) {
-    const int role = u / FT, t = u - role * FT;
-    const int64_t f = t0 + t;
-    if (role == 0) {
-      if (f < a.L) {
-        // band 0: phases added sequentially in f32 (B.2 v), /210, log10(1+x)/2
-        float tot = 0.0f;
-#pragma unroll 6
-        for (int p = 0; p < 42; ++p) tot = tot + ph[t * 42 + p];
-        a.b0[f] = host_log10f(1.0f + tot / 210.0f) / 2.0f;
-      }
-    } else if (role == 1) {
-      if (f < a.L) {
-        float tot = 0.0f;
-#pragma unroll
-        for (int p = 0; p < 6; ++p) tot = tot + p1[t * 6 + p];
-        a.b1[f] = host_log10f(1.0f + tot / 210.0f) / 2.0f;
-        // zero crossings: 13-tap Hann over frames f-6 .. f+6
-        double acc = 0.0;
-#pragma unroll
-        for (int j = 0; j < 13; ++j) {
-          float z = (float)zi[t + FH - 6 + j];
-          if (CH == 1) z = z * 2.0f;
-          const float prod = z * w13[12 - j];
-          acc += (double)prod;
-        }
-        a.zc[f] = (float)acc;
-      }
-    } else {
-      if (f < a.L) {
-        // band 2: one 15-tap f64 filter = OpenBLAS ddot tail, a sequential FMA chain (B.2 iv)
-        double acc = 0.0;
-#pragma unroll
-        for (int j = 0; j < 15; ++j) acc = fma((double)w15[14 - j], be2[t + 1 + j], acc);
-        a.b2[f] = log10(1.0 + acc / 210.0) / 2.0;
-      }
-      if (f < a.Le) {
-        // energy: 13-tap Hann over blocks 2f-6 .. 2f+6, log10(1+x)/2, every second block (:553-555)
-        double acc = 0.0;
-#pragma unroll
-        for (int j = 0; j < 13; ++j) {
-          const float prod = eb[2 * (t + FH) - 6 + j] * w13[12 - j];
-          acc += (double)prod;
-        }
-        a.energy[f] = host_log10f(1.0f + (float)acc) / 2.0f;
-      }
-    }
+    __syncthreads();   // every buffer of this tile has been consumed; s_next was written before the S3 barrier
+    tile = s_next;
   }
 }
 
@@ -558,13 +666,18 @@ std::mutex g_fix_mu;
 void *g_fix_buf[64] = {};      // per device: the uploaded correction table
 
 template <int FMT, int CH>
-int launch(dab_pair *pr, const FeatArgs &fa, int64_t frames) {
+int launch(dab_pair *pr, const FeatArgs &fa_in, int64_t frames) {
   dab_ctx *ctx = pr->ctx;
   const int64_t tiles = cdiv(frames, Tile<CH>::FT);
   if (tiles <= 0) return DAB_OK;
+  FeatArgs fa = fa_in;
+  fa.tiles = tiles;
   const size_t smem = Tile<CH>::BYTES;
   DAB_CUDA(cudaFuncSetAttribute(features_kernel<FMT, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  features_kernel<FMT, CH><<<(unsigned)tiles, THREADS, smem, pr->stream>>>(fa);
+  // persistent: two CTAs per SM take tiles from the ticket
+  DAB_CUDA(cudaMemsetAsync(fa.ticket, 0, sizeof(unsigned int), pr->stream));
+  const int64_t grid = tiles < 2 * (int64_t)ctx->sm_count ? tiles : 2 * (int64_t)ctx->sm_count;
+  features_kernel<FMT, CH><<<(unsigned)grid, THREADS, smem, pr->stream>>>(fa);
   DAB_LAUNCHED(pr);
   DAB_CUDA(cudaGetLastError());
   return DAB_OK;
@@ -631,7 +744,10 @@ int dab_run_features(dab_pair *pr, int track, const void *d_pcm, int format) {
   DAB_TRY(dab_ensure(ctx, tk.b0, sizeof(float) * (size_t)(L + 1)));
   DAB_TRY(dab_ensure(ctx, tk.b1, sizeof(float) * (size_t)(L + 1)));
   DAB_TRY(dab_ensure(ctx, tk.b2, sizeof(double) * (size_t)(L + 1)));
+  DAB_TRY(dab_ensure(ctx, tk.feat_ticket, 64));
   FeatArgs fa;
+  fa.tiles = 0;
+  fa.ticket = tk.feat_ticket.as<unsigned int>();
   fa.pcm = d_pcm; fa.S = tk.S; fa.L = L; fa.nb = nb; fa.Le = Le;
   fa.vec_ok = (reinterpret_cast<uintptr_t>(d_pcm) & 15u) == 0;
   fa.energy = tk.energy.as<float>(); fa.zc = tk.zc.as<float>();

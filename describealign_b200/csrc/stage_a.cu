@@ -59,7 +59,9 @@ __global__ void __launch_bounds__(256) meansub_kernel(PrepArgs a) {
   const double *src = tile + (lo - base);
   auto X = [&](int i) { return src[i]; };
   auto Y = [&](int i) { return c_hflip[klo + i]; };
-  const double mean = (m == 41) ? ddot41_skx(X, Y) : ddot_skx(X, Y, m);
+  // interior outputs (m == 41 implies klo == 0): the window taps are compile-time constant-bank operands
+  auto Y0 = [&](int i) { return c_hflip[i]; };
+  const double mean = (m == 41) ? ddot41_skx(X, Y0) : ddot_skx(X, Y, m);
   a.ms[(int64_t)f * a.stride + t] = tile[t - base] - mean;
 }
 
@@ -408,112 +410,268 @@ struct GateArgs {
   int32_t *cand_tmp, *cand_s, *cand_i;
   int64_t cand_cap;
   int32_t *stash;           // [q_cap][GATE_STASH]: the first candidates of every row, kept by the count pass
-  unsigned long long *enumerated;
+  int32_t *big_list;        // rows with more than GATE_STASH candidates (fill pass work list)
+  int32_t *big_count;
 };
 
-template <bool FILL>
-__global__ void gate_kernel(GateArgs g) {
-  const int lane = threadIdx.x & 31;
-  const int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (q >= g.q_cap) return;
-  const int32_t n_queries = g.dc[DC_N_Q];
-  if (q >= n_queries) {
-    if (!FILL && lane == 0) g.row_count[q] = 0;
+// Fill pass, rows of up to GATE_STASH candidates (nearly all): thread per query; the candidates the count pass
+// stashed are ordered by video rank and written out.  Larger rows go to a work list for gate_fill_big_kernel.
+__global__ void gate_fill_small_kernel(GateArgs g) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= g.q_cap || q >= g.dc[DC_N_Q]) return;
+  if (g.dc[DC_OVERFLOW] & DAB_OVF_CAND) return;
+  const int64_t off0 = g.row_off[q];
+  const int n_row = g.row_off[q + 1] - (int)off0;
+  if (n_row == 0) return;
+  if (n_row > GATE_STASH) {
+    g.big_list[atomicAdd(g.big_count, 1)] = (int32_t)q;
     return;
   }
-  // second pass: only the rows that have candidates (one row in six at the Ask-Dad shape) enumerate again
-  if (FILL && ((g.dc[DC_OVERFLOW] & DAB_OVF_CAND) || g.row_off[q + 1] == g.row_off[q])) return;
+  if (off0 + n_row > g.cand_cap) return;
   const int32_t i = g.a_list[g.dc[DC_Q_LO] + q];
-  if (FILL) {
-    const int64_t off0 = g.row_off[q];
-    const int n_row = g.row_off[q + 1] - (int)off0;
-    if (n_row <= GATE_STASH) {
-      // the count pass kept this row's candidates: order them by video rank and write them out
-      if (off0 + n_row > g.cand_cap) return;
-      const int32_t x = lane < n_row ? g.stash[q * GATE_STASH + lane] : 0x7fffffff;
+  const int4 st = *reinterpret_cast<const int4 *>(g.stash + q * GATE_STASH);
+  static_assert(GATE_STASH == 4, "the stash is read as one int4");
+  int32_t x[4] = {st.x, n_row > 1 ? st.y : 0x7fffffff, n_row > 2 ? st.z : 0x7fffffff, n_row > 3 ? st.w : 0x7fffffff};
+  // sorting network of four
+  auto cswap = [&](int a, int b) { if (x[b] < x[a]) { const int32_t t = x[a]; x[a] = x[b]; x[b] = t; } };
+  cswap(0, 1); cswap(2, 3); cswap(0, 2); cswap(1, 3); cswap(1, 2);
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (k < n_row) { g.cand_s[off0 + k] = x[k]; g.cand_i[off0 + k] = i; }
+}
+
+// Fill pass, rows with more than GATE_STASH candidates (false-match clusters; a few hundred per pair): a warp per
+// row of the work list enumerates the row's two buckets again and orders what it finds by video rank.
+__global__ void gate_fill_big_kernel(GateArgs g) {
+  const int lane = threadIdx.x & 31;
+  const int n_big = *g.big_count;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_big; w += n_warps) {
+    const int64_t q = g.big_list[w];
+    const int32_t i = g.a_list[g.dc[DC_Q_LO] + q];
+    // lanes 0-4 fetch the query's five digit words and bucket ranges, one feature each; then broadcast
+    uint32_t my_ap = 0u;
+    int32_t my_st = 0, my_en = 0;
+    if (lane < 5) {
+      my_ap = g.a_pack[(int64_t)lane * g.a_nstride + i] | 0x8888888u;
+      const int64_t slot = (int64_t)lane * DAB_NCODE + g.a_code[(int64_t)lane * g.a_nstride + i];
+      my_st = g.start[slot];
+      my_en = g.start[slot + 1];
+    }
+    uint32_t ap[5];
+    int32_t st[5], nb[5];
+#pragma unroll
+    for (int f = 0; f < 5; ++f) {
+      ap[f] = __shfl_sync(0xffffffffu, my_ap, f);
+      st[f] = __shfl_sync(0xffffffffu, my_st, f);
+      nb[f] = __shfl_sync(0xffffffffu, my_en, f) - st[f];
+    }
+    // every candidate lies in at least one bucket of any pair out of {0,1,2}, and in bucket 3 or 4
+    int fa = 0, fb = 1, best = nb[0] + nb[1];
+    if (nb[0] + nb[2] < best) { best = nb[0] + nb[2]; fa = 0; fb = 2; }
+    if (nb[1] + nb[2] < best) { best = nb[1] + nb[2]; fa = 1; fb = 2; }
+    if (nb[3] + nb[4] < best) { best = nb[3] + nb[4]; fa = 3; fb = 4; }
+    int found = 0;
+    const int64_t off = g.row_off[q];
+    // the two buckets are walked as one list of `best` entries, 32 per step
+    const int sa = st[fa], ca = nb[fa], sb = st[fb];
+    for (int base = 0; base < best; base += 32) {
+      const int e = base + lane;
+      bool ok = false;
+      int32_t s = 0;
+      if (e < best) {
+        const bool second = e >= ca;
+        s = g.items[second ? sb + (e - ca) : sa + e];
+        const uint4 r0 = __ldg(g.v_rec + 2 * (int64_t)s), r1 = __ldg(g.v_rec + 2 * (int64_t)s + 1);
+        const uint32_t vp[5] = {r0.x, r0.y, r0.z, r0.w, r1.x};
+        bool m[5];
+#pragma unroll
+        for (int f = 0; f < 5; ++f) m[f] = digits_match(ap[f], vp[f]);
+        ok = ((int)m[0] + (int)m[1] + (int)m[2] >= 2) && (m[3] || m[4]);
+        if (second && m[fa]) ok = false;   // already enumerated from the first bucket
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, ok);
+      if (ok) {
+        const int64_t pos = off + found + __popc(bal & ((1u << lane) - 1u));
+        if (pos < g.cand_cap) g.cand_tmp[pos] = s;
+      }
+      found += __popc(bal);
+    }
+    if (off + found > g.cand_cap) continue;
+    __syncwarp();
+    // order the row's candidates by video rank: position = number of smaller entries
+    if (found <= 32) {
+      // one candidate per lane, ranks by 32 register shuffles instead of found^2 memory reads
+      const int32_t x = lane < found ? g.cand_tmp[off + lane] : 0x7fffffff;
       int r = 0;
 #pragma unroll
-      for (int j = 0; j < GATE_STASH; ++j) r += (__shfl_sync(0xffffffffu, x, j) < x);
-      if (lane < n_row) { g.cand_s[off0 + r] = x; g.cand_i[off0 + r] = i; }
-      return;
+      for (int j = 0; j < 32; ++j) r += (__shfl_sync(0xffffffffu, x, j) < x);
+      if (lane < found) { g.cand_s[off + r] = x; g.cand_i[off + r] = i; }
+      continue;
+    }
+    for (int k = lane; k < found; k += 32) {
+      const int32_t x = g.cand_tmp[off + k];
+      int r = 0;
+      for (int j = 0; j < found; ++j) r += (g.cand_tmp[off + j] < x);
+      g.cand_s[off + r] = x;
+      g.cand_i[off + r] = i;
     }
   }
-  // lanes 0-4 fetch the query's five digit words and bucket ranges, one feature each; then broadcast
-  uint32_t my_ap = 0u;
-  int32_t my_st = 0, my_en = 0;
-  if (lane < 5) {
-    my_ap = g.a_pack[(int64_t)lane * g.a_nstride + i] | 0x8888888u;
-    const int64_t slot = (int64_t)lane * DAB_NCODE + g.a_code[(int64_t)lane * g.a_nstride + i];
-    my_st = g.start[slot];
-    my_en = g.start[slot + 1];
-  }
+}
+
+// ------------------------------------------------------------------------------------------
+// gate, count pass, balanced over bucket ENTRIES instead of queries.  A query visits the entries of its two
+// cheapest buckets; their number ranges from none to several hundred, so a warp per query leaves most lanes
+// idle (ncu: 380 warp instructions per query for 33 entries on average).  Three steps:
+//   gate_plan_kernel      thread per query: digit words, the two buckets, their joint length `best`
+//   scan                  P = exclusive scan of best; its total is the number of entries to test
+//   gate_entries_kernel   tiles of 2048 consecutive entries of the concatenated bucket lists; the tile finds
+//                         the queries it spans by a warp-wide 32-ary search in P, marks where each one starts,
+//                         spreads the owners by a max-scan, and every thread tests 8 consecutive entries.
+//                         Matches are appended to the query's stash through an atomic row counter.
+// The fill pass takes rows of up to GATE_STASH candidates from the stash (gate_fill_small_kernel; in any
+// order - it sorts them by video rank), larger rows are enumerated again by a warp.
+// ------------------------------------------------------------------------------------------
+struct __align__(16) GateQ {
+  uint32_t ap[5];     // guarded digit words of the query
+  int32_t sa, sb;     // bucket starts in items[]
+  uint32_t ca_fa;     // entries in the first bucket | first bucket's feature << 28
+};
+
+__global__ void gate_plan_kernel(GateArgs g, GateQ *rec, int32_t *best_out) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= g.q_cap) return;
+  g.row_count[q] = 0;
+  if (q >= g.dc[DC_N_Q]) { best_out[q] = 0; return; }
+  const int32_t i = g.a_list[g.dc[DC_Q_LO] + q];
   uint32_t ap[5];
   int32_t st[5], nb[5];
 #pragma unroll
   for (int f = 0; f < 5; ++f) {
-    ap[f] = __shfl_sync(0xffffffffu, my_ap, f);
-    st[f] = __shfl_sync(0xffffffffu, my_st, f);
-    nb[f] = __shfl_sync(0xffffffffu, my_en, f) - st[f];
+    ap[f] = g.a_pack[(int64_t)f * g.a_nstride + i] | 0x8888888u;
+    const int64_t slot = (int64_t)f * DAB_NCODE + g.a_code[(int64_t)f * g.a_nstride + i];
+    st[f] = g.start[slot];
+    nb[f] = g.start[slot + 1] - st[f];
   }
   // every candidate lies in at least one bucket of any pair out of {0,1,2}, and in bucket 3 or 4
   int fa = 0, fb = 1, best = nb[0] + nb[1];
   if (nb[0] + nb[2] < best) { best = nb[0] + nb[2]; fa = 0; fb = 2; }
   if (nb[1] + nb[2] < best) { best = nb[1] + nb[2]; fa = 1; fb = 2; }
   if (nb[3] + nb[4] < best) { best = nb[3] + nb[4]; fa = 3; fb = 4; }
-  int found = 0;
-  const int64_t off = FILL ? g.row_off[q] : 0;
-  // the two buckets are walked as one list of `best` entries, 32 per step
-  const int sa = st[fa], ca = nb[fa], sb = st[fb];
-  for (int base = 0; base < best; base += 32) {
-    const int e = base + lane;
-    bool ok = false;
-    int32_t s = 0;
-    if (e < best) {
-      const bool second = e >= ca;
-      s = g.items[second ? sb + (e - ca) : sa + e];
-      const uint4 r0 = __ldg(g.v_rec + 2 * (int64_t)s), r1 = __ldg(g.v_rec + 2 * (int64_t)s + 1);
-      const uint32_t vp[5] = {r0.x, r0.y, r0.z, r0.w, r1.x};
-      bool m[5];
+  GateQ r;
 #pragma unroll
-      for (int f = 0; f < 5; ++f) m[f] = digits_match(ap[f], vp[f]);
-      ok = ((int)m[0] + (int)m[1] + (int)m[2] >= 2) && (m[3] || m[4]);
-      if (second && m[fa]) ok = false;   // already enumerated from the first bucket
-    }
-    const unsigned bal = __ballot_sync(0xffffffffu, ok);
-    if (!FILL && ok) {
-      const int idx = found + __popc(bal & ((1u << lane) - 1u));
-      if (idx < GATE_STASH) g.stash[q * GATE_STASH + idx] = s;
-    }
-    if (FILL && ok) {
-      const int64_t pos = off + found + __popc(bal & ((1u << lane) - 1u));
-      if (pos < g.cand_cap) g.cand_tmp[pos] = s;
-    }
-    found += __popc(bal);
-  }
-  if (!FILL) {
-    if (lane == 0) g.row_count[q] = found;
-    // work counter (bucket entries visited): one atomic per 32 rows
-    if (lane == 0 && (q & 31) == 0) atomicAdd(g.enumerated, (unsigned long long)best * 32ull);
-    return;
-  }
-  if (off + found > g.cand_cap) return;
-  __syncwarp();
-  // order the row's candidates by video rank: position = number of smaller entries
-  if (found <= 32) {
-    // the usual case: one candidate per lane, ranks by 32 register shuffles instead of found^2 memory reads
-    const int32_t x = lane < found ? g.cand_tmp[off + lane] : 0x7fffffff;
-    int r = 0;
+  for (int f = 0; f < 5; ++f) r.ap[f] = ap[f];
+  int32_t sa = 0, sb = 0, ca = 0;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) r += (__shfl_sync(0xffffffffu, x, j) < x);
-    if (lane < found) { g.cand_s[off + r] = x; g.cand_i[off + r] = i; }
-    return;
+  for (int f = 0; f < 5; ++f) {
+    if (f == fa) { sa = st[f]; ca = nb[f]; }
+    if (f == fb) sb = st[f];
   }
-  for (int k = lane; k < found; k += 32) {
-    const int32_t x = g.cand_tmp[off + k];
-    int r = 0;
-    for (int j = 0; j < found; ++j) r += (g.cand_tmp[off + j] < x);
-    g.cand_s[off + r] = x;
-    g.cand_i[off + r] = i;
+  r.sa = sa; r.sb = sb; r.ca_fa = (uint32_t)ca | ((uint32_t)fa << 28);
+  rec[q] = r;
+  best_out[q] = best;
+}
+
+constexpr int GE_THREADS = 256, GE_PER = 8, GE_TILE = GE_THREADS * GE_PER;
+
+// last index q in [0, n] with P[q] <= x (P non-decreasing, P[0] = 0 <= x), found by one warp: 32 probes per round
+__device__ __forceinline__ int warp_last_le(const int32_t *P, int n, int x, int lane) {
+  int lo = 0, hi = n + 1;                 // P[lo] <= x; hi == n + 1 or P[hi] > x
+  while (hi - lo > 1) {
+    const int step = (hi - lo + 31) / 32;
+    const int idx = lo + (lane + 1) * step;
+    const bool le = idx < hi && P[idx] <= x;
+    const int cnt = __popc(__ballot_sync(0xffffffffu, le));     // monotone: the lanes with le form a prefix
+    const int nlo = lo + cnt * step;
+    const int nhi = lo + (cnt + 1) * step;
+    lo = nlo;
+    if (nhi < hi) hi = nhi;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(GE_THREADS) gate_entries_kernel(GateArgs g, const GateQ *rec, const int32_t *P) {
+  __shared__ __align__(16) int owner[GE_TILE];
+  __shared__ int s_q[2];
+  __shared__ int s_wmax[GE_THREADS / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nq = g.dc[DC_N_Q];
+  const int total = g.dc[DC_ENUM_LO];
+  if (g.dc[DC_OVERFLOW] & DAB_OVF_ENTRIES) return;
+  for (int64_t E0l = (int64_t)blockIdx.x * GE_TILE; E0l < total; E0l += (int64_t)gridDim.x * GE_TILE) {
+    const int E0 = (int)E0l;
+    const int E1 = E0 + GE_TILE < total ? E0 + GE_TILE : total;
+    // the queries this tile spans: q0 owns entry E0, q1 owns entry E1 - 1 (both non-empty rows)
+    if (warp < 2) {
+      const int r = warp_last_le(P, nq, warp == 0 ? E0 : E1 - 1, lane);
+      if (lane == 0) s_q[warp] = r;
+    }
+#pragma unroll
+    for (int j = 0; j < GE_PER; ++j) owner[tid + j * GE_THREADS] = 0;
+    __syncthreads();
+    const int q0 = s_q[0], q1 = s_q[1];
+    // every later query that starts inside the tile marks its first entry (empty rows share a position with the
+    // non-empty row that follows them: the largest index wins)
+    for (int q = q0 + 1 + tid; q <= q1; q += GE_THREADS) {
+      const int pos = P[q] - E0;
+      if (pos > 0 && pos < GE_TILE) atomicMax(&owner[pos], q - q0);
+    }
+    __syncthreads();
+    // inclusive max-scan: slot e belongs to the last marked query at or before it
+    int m[GE_PER];
+    {
+      const int4 a = *reinterpret_cast<const int4 *>(&owner[tid * GE_PER]);
+      const int4 b = *reinterpret_cast<const int4 *>(&owner[tid * GE_PER + 4]);
+      m[0] = a.x; m[1] = a.y; m[2] = a.z; m[3] = a.w; m[4] = b.x; m[5] = b.y; m[6] = b.z; m[7] = b.w;
+    }
+#pragma unroll
+    for (int j = 1; j < GE_PER; ++j) m[j] = max(m[j], m[j - 1]);
+    int inc = m[GE_PER - 1];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc = max(inc, y);
+    }
+    if (lane == 31) s_wmax[warp] = inc;
+    int before = __shfl_up_sync(0xffffffffu, inc, 1);
+    if (lane == 0) before = 0;
+    __syncthreads();
+    for (int w = 0; w < warp; ++w) before = max(before, s_wmax[w]);
+    // owners back to shared memory, then entries interleaved over the threads: consecutive lanes read consecutive
+    // bucket items (coalesced) and mostly share a query, whose record is then one broadcast load
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < GE_PER; ++j) owner[tid * GE_PER + j] = max(before, m[j]);
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < GE_PER; ++j) {
+      const int e = E0 + j * GE_THREADS + tid;
+      if (e < E1) {
+        const int q = q0 + owner[j * GE_THREADS + tid];
+        const uint4 *rp = reinterpret_cast<const uint4 *>(rec + q);
+        const uint4 x0 = __ldg(rp), x1 = __ldg(rp + 1);
+        const int el = e - P[q];
+        const int ca = (int)(x1.w & 0x0fffffffu), fa = (int)(x1.w >> 28);
+        const bool second = el >= ca;
+        const int32_t s = g.items[second ? (int32_t)x1.z + (el - ca) : (int32_t)x1.y + el];
+        // features 0-3 are the first 16 bytes of the frame's record; feature 4 is only fetched when it decides
+        const uint4 v0 = __ldg(g.v_rec + 2 * (int64_t)s);
+        const bool m0 = digits_match(x0.x, v0.x), m1 = digits_match(x0.y, v0.y), m2 = digits_match(x0.z, v0.z),
+                   m3 = digits_match(x0.w, v0.w);
+        bool ok = (int)m0 + (int)m1 + (int)m2 >= 2;
+        if (ok && second) {
+          // already enumerated from the first bucket
+          const bool mfa = fa == 0 ? m0 : (fa == 1 ? m1 : m3);
+          if (mfa) ok = false;
+        }
+        if (ok && !m3) ok = digits_match(x1.x, __ldg(reinterpret_cast<const uint32_t *>(g.v_rec + 2 * (int64_t)s + 1)));
+        if (ok) {
+          const int idx = atomicAdd(&g.row_count[q], 1);
+          if (idx < GATE_STASH) g.stash[(int64_t)q * GATE_STASH + idx] = s;
+        }
+      }
+    }
+    __syncthreads();     // owner[] and s_q[] are rewritten by the next tile
   }
 }
 
@@ -1023,14 +1181,23 @@ int dab_enqueue_stage_a_match(dab_pair *pr, int64_t row_lo, int64_t row_hi) {
   ga.cand_cap = cap_c;
   DAB_TRY(dab_ensure(ctx, pr->row_stash, sizeof(int32_t) * GATE_STASH * (size_t)(q_ub + 1)));
   ga.stash = pr->row_stash.as<int32_t>();
-  ga.enumerated = reinterpret_cast<unsigned long long *>(dc + DC_ENUM_LO);
+  DAB_TRY(dab_ensure(ctx, pr->gate_big, sizeof(int32_t) * (size_t)(q_ub + 1)));
+  ga.big_list = pr->gate_big.as<int32_t>();
+  ga.big_count = dc + DC_N_BIGROWS;
   DAB_CUDA(cudaEventRecord(pr->ev[8], st));
-  const unsigned gb = (unsigned)cdiv(q_ub * 32, 256);
-  gate_kernel<false><<<gb, 256, 0, st>>>(ga);
+  // count pass, balanced over bucket entries (see gate_entries_kernel)
+  DAB_TRY(dab_ensure(ctx, pr->gate_rec, sizeof(GateQ) * (size_t)(q_ub + 1)));
+  DAB_TRY(dab_ensure(ctx, pr->gate_best, sizeof(int32_t) * (size_t)(2 * (q_ub + 2))));
+  int32_t *g_best = pr->gate_best.as<int32_t>(), *g_P = g_best + (q_ub + 1);
+  gate_plan_kernel<<<(unsigned)cdiv(q_ub, 128), 128, 0, st>>>(ga, pr->gate_rec.as<GateQ>(), g_best);
+  DAB_TRY(dab_exclusive_scan(pr, g_best, g_P, q_ub, nullptr, dc + DC_ENUM_LO));
+  gate_entries_kernel<<<(unsigned)(8 * ctx->sm_count), GE_THREADS, 0, st>>>(ga, pr->gate_rec.as<GateQ>(), g_P);
+  ctx->launches += 2;
   DAB_TRY(dab_exclusive_scan(pr, pr->row_count.as<int32_t>(), pr->row_off.as<int32_t>(), q_ub, nullptr, dc + DC_N_CAND));
   check_capacity_kernel<<<1, 32, 0, st>>>(dc, DC_N_CAND, cap_c, DAB_OVF_CAND);
-  gate_kernel<true><<<gb, 256, 0, st>>>(ga);
-  ctx->launches += 3;
+  gate_fill_small_kernel<<<(unsigned)cdiv(q_ub, 256), 256, 0, st>>>(ga);
+  gate_fill_big_kernel<<<(unsigned)(2 * ctx->sm_count), 256, 0, st>>>(ga);
+  ctx->launches += 4;
   DAB_CUDA(cudaEventRecord(pr->ev[9], st));
 
   // ---- scoring + compaction ----
