@@ -43,6 +43,7 @@ WORKLOADS = {
     "C2": "C2: synthetic 22-min video audio vs 27-min description, 202 s offset, 10 inserted skips, mono 44.1 kHz s16",
     "C3": "C3: the C2 pair in stereo (--stretch_audio feature semantics: features from 2 channels), 44.1 kHz s16",
     "C4": "C4: batch mode, 64 distinct synthetic 45-min episode/description pairs (offset 10-90 s, 4-8 skips) sharded over the GPUs, mono 44.1 kHz s16",
+    "C5": "C5: long-form, ONE synthetic 2.5-h film vs 3-h description (300 s offset, ~12 skips), match stage and corridor scoring split over the GPUs by audio rows, mono 44.1 kHz s16",
 }
 WORKLOAD = WORKLOADS["C2"]      # the configuration BASELINE.json's metric is quoted on (the default)
 
@@ -58,7 +59,8 @@ def parse_args():
                     help="distinct synthetic pairs per GPU, a step cycles over them (default 4 at every N: 1 GB of PCM, 8x the L2)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS),
-                    help="C2 (default, the metric's configuration), C3 (stereo), C4 (64 x 45-min pairs over all GPUs: strong scaling)")
+                    help="C2 (default, the metric's configuration), C3 (stereo), C4 (64 x 45-min pairs over all GPUs: strong scaling), "
+                         "C5 (one long pair split over all GPUs: strong scaling)")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the C2 durations (debugging only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the rank to the CPUs of its GPU's NUMA node")
@@ -335,6 +337,159 @@ def h2d_probe(pinned, seconds=1.0):
     e1.synchronize()
     del dst
     return nbytes / (e0.elapsed_time(e1) * 1e-3) / 1e9
+
+
+def long_pair_pcm(rank, scale, barrier):
+    """The C5 pair, generated once (rank 0, segments in worker processes) and shared through /dev/shm."""
+    from describealign_b200 import synth
+    base = f"/dev/shm/dab_c5_{os.getuid()}_{scale:g}"
+    if rank == 0:
+        v, a = synth.long_pair(0, scale, workers=max(1, min(10, os.cpu_count() or 1)))
+        np.save(base + "_v.npy", v)
+        np.save(base + "_a.npy", a)
+    barrier()
+    if rank != 0:
+        v, a = np.load(base + "_v.npy"), np.load(base + "_a.npy")
+    barrier()
+    if rank == 0:
+        for suffix in ("_v.npy", "_a.npy"):
+            try:
+                os.remove(base + suffix)
+            except OSError:
+                pass
+    return v, a
+
+
+def run_long(args, rank, world, local_rank):
+    """--workload C5: one long pair per step on ALL ranks (batch.align_long_pair).  Strong scaling: the match
+    stage and the corridor scoring are sharded by audio rows (two all-gathers), both DPs run on rank 0.  The
+    timed figure is device time - CUDA events on each rank around every phase, max over ranks - without the
+    host rate-change fit (solved during warm-up, looked up afterwards: BASELINE.json excludes it)."""
+    import torch
+    import torch.distributed as dist
+    from describealign_b200 import api, batch, build
+    build.build()
+    api.set_device(local_rank)
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    lv, la = long_pair_pcm(rank, args.scale, barrier)
+    hours = audio_hours([(lv, la)])
+    numa = batch.bind_to_gpu_numa_node(local_rank) if not args.no_numa_bind else {"bound": False, "disabled": True}
+    # end-to-end arm: the PCM starts in pinned host memory (the H2D copy is inside align_long_pair's first phase);
+    # device-resident arm: the PCM is handed over as device pointers
+    pv, pa = torch.from_numpy(lv).pin_memory(), torch.from_numpy(la).pin_memory()
+    dv, da_ = pv.cuda(), pa.cuda()
+    dev_in = ((dv.data_ptr(), dv.shape[0], dv.shape[1]), (da_.data_ptr(), da_.shape[0], da_.shape[1]))
+    cache = {}
+
+    def cached_host_stage(job):
+        c = cache.get("fit")
+        if c is not None and np.array_equal(c["x"], job.x) and np.array_equal(c["y"], job.y):
+            for name in c["keep"]:
+                setattr(job, name, c["keep"][name])
+            return
+        job.host_stage()
+        cache["fit"] = {"x": job.x.copy(), "y": job.y.copy(),
+                        "keep": {name: getattr(job, name) for name in
+                                 ("kept_x", "kept_y", "gains", "n_audio_scaled", "n_video_scaled", "fit", "clusters", "lines")}}
+
+    def one_step(host_input):
+        det = {}
+        out = batch.align_long_pair(pv.numpy() if host_input else dev_in[0], pa.numpy() if host_input else dev_in[1],
+                                    details=det, host_stage=cached_host_stage)
+        ph = det["phases_ms"]
+        dev_ms = sum(v for k, v in ph.items() if k != "host_fit_and_broadcast")
+        return dev_ms, det, out
+
+    def run_steps(host_input):
+        for _ in range(args.warmup):
+            one_step(host_input)
+        barrier()
+        tot, det, out = 0.0, None, None
+        phases = {}
+        for _ in range(args.steps):
+            ms, det, out = one_step(host_input)
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            tot += float(t[0])
+            for k, v in det["phases_ms"].items():
+                phases[k] = phases.get(k, 0.0) + v / args.steps
+        barrier()
+        return tot / args.steps, phases, det, out
+
+    ctx = api.context()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.launches()
+    ms_dev, ph_dev, det, out = run_steps(False)
+    launches = (ctx.launches() - l0) * args.steps // (args.steps + args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e, ph_e2e, _, _ = run_steps(True)
+    lt = torch.tensor([float(launches)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+
+    single = cpu = None
+    if rank == 0:
+        import contextlib
+        with contextlib.redirect_stdout(sys.stderr):
+            t1 = time.perf_counter()
+            ref = api.align_pcm(lv, la)
+            t_single = time.perf_counter() - t1
+        single = {"identical_to_single_gpu_path": bool(np.array_equal(out[3], ref[3]) and np.array_equal(out[0], ref[0]) and
+                                                       np.array_equal(out[1], ref[1])),
+                  "wall_s_single_gpu_incl_host_fit": t_single}
+        if not args.no_cpu_baseline:
+            import oracle
+            oracle.build()
+            cpu_t, o = cpu_pass((lv, la), keep=True)
+            cpu = {"value": hours / cpu_t["hot_path_s"], "unit": UNIT, "cores": 1, "kind": "port",
+                   "sample": "the same long pair once through the oracle port; timed as BASELINE.md section 3 (minus linprog)",
+                   "seconds": cpu_t["hot_path_s"], "seconds_linprog_subtracted": cpu_t["linprog_s"],
+                   "host_cpu": _cpu_model(), "host_cores": os.cpu_count()}
+            single["identical_to_oracle_path"] = bool(out[3].shape == o["path"].shape and np.array_equal(out[3][:, 1], o["path"][:, 1]) and
+                                                      np.array_equal(out[3][:, 2], o["path"][:, 2]))
+        peaks, peak_src = measured_peaks()
+        sh = det.get("shards", {})
+        pcm_b = lv.nbytes + la.nbytes
+        feat_ms = ph_dev.get("features", 0.0)
+        line = {"metric": METRIC, "value": hours / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f32+f64 (u32 packed codes)", "data": "synthetic",
+                "config": {"workload": WORKLOADS["C5"], "scale": args.scale,
+                           "pair_minutes": [len(lv) / 44100 / 60, len(la) / 44100 / 60], "audio_hours_per_step": hours,
+                           "l2_policy": "inputs larger than L2 (%d MB of PCM per step; 126 MB L2)" % int(pcm_b / 1e6),
+                           "timed": "per step ONE long pair on all ranks: features (every rank, the PCM once), match stage sharded by audio rows, all-gather of the match points, DP1 + traceback on rank 0, [host rate-change fit on rank 0: solved in warm-up, looked up inside the region, untimed by BASELINE.json], corridor scoring sharded by audio rows, all-gather of the quals, DP2 + traceback on rank 0; CUDA events per phase on every rank, summed without the host-fit wait, max over ranks"},
+                "phases_ms_rank0": ph_dev,
+                "e2e": {"value": hours / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
+                        "h2d_bytes_per_step": float(pcm_b * world), "d2h_bytes_per_step": float(40 * len(out[3])),
+                        "phases_ms_rank0": ph_e2e,
+                        "note": "every rank uploads the whole PCM from pinned host memory inside the region (features are computed redundantly per rank)"},
+                "gpu_launches": int(lt[0]),
+                "collectives": {"all_gather_points": {"elements": sh.get("shard_a", (0, 0, 0, 0))[3], "bytes": 16 * sh.get("shard_a", (0, 0, 0, 0))[3],
+                                                     "ms_rank0": ph_dev.get("all_gather_points")},
+                                "all_gather_quals": {"elements": sh.get("shard_b", (0, 0, 0, 0))[3], "bytes": 8 * sh.get("shard_b", (0, 0, 0, 0))[3],
+                                                    "ms_rank0": ph_dev.get("all_gather_quals")}},
+                "roofline": {"bound": "hbm", "kernel": "features_kernel", "achieved": (pcm_b + 24 * (len(lv) + len(la)) // 210) / (feat_ms * 1e-3) / 1e9 if feat_ms else None,
+                             "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                             "frac": ((pcm_b + 24 * (len(lv) + len(la)) // 210) / (feat_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]) if feat_ms else None,
+                             "peak_source": peak_src, "traffic": None,
+                             "note": "features phase of rank 0 (both tracks, incl. the device-to-device hand-over); the step is bounded by the two single-CTA DPs on rank 0 (latency), see phases_ms_rank0"},
+                "host_fit_s_first_solve": det.get("host_fit_s"),
+                "parity": single, "cpu_baseline": cpu, "clocks": clocks,
+                "host_side": {"numa_binding_rank0": numa}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def run_ours(args, rank, world, local_rank):
@@ -733,6 +888,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+    elif args.workload == "C5":
+        run_long(args, rank, world, local_rank)
     else:
         run_ours(args, rank, world, local_rank)
 

@@ -30,6 +30,7 @@ EXPORTS = [
     "dab_pair_stage_b_score", "dab_pair_export_quals2", "dab_pair_import_quals2", "dab_pair_dp2",
     "dab_engine_create", "dab_engine_destroy", "dab_engine_submit", "dab_engine_next", "dab_engine_submit_b",
     "dab_engine_release", "dab_engine_slot_error", "dab_engine_slot_pair", "dab_engine_counters",
+    "dab_host_continuity_error", "dab_host_continuity_error_f64", "dab_host_compress_path", "dab_host_lp_assemble",
 ]
 
 
@@ -122,6 +123,11 @@ def load() -> ctypes.CDLL:
     lib.dab_alloc_stats.argtypes = [ctypes.POINTER(ctypes.c_int64 * 4)]
     lib.dab_alloc_stats.restype = None
     lib.dab_device_count.restype = i32
+    pd, pl, pi32 = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int32)
+    lib.dab_host_continuity_error.argtypes = [vp, vp, i64, i32, vp]
+    lib.dab_host_continuity_error_f64.argtypes = [vp, vp, vp, vp, i64, i32, vp]
+    lib.dab_host_compress_path.argtypes = [vp, vp, i64, vp, vp, pl]
+    lib.dab_host_lp_assemble.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp, pl]
     lib.dab_set_host_wait.argtypes = [i32, i32]
     lib.dab_set_host_wait.restype = i32
     lib.dab_create.argtypes = [i32, ctypes.POINTER(vp)]

@@ -309,7 +309,7 @@ def align_batch(pairs, durations: Sequence[float] | None = None, in_flight: int 
 # one very long pair on all ranks
 # ---------------------------------------------------------------------------------------------
 
-def align_long_pair(video_pcm, audio_desc_pcm, group=None, details=None, root: int = 0):
+def align_long_pair(video_pcm, audio_desc_pcm, group=None, details=None, root: int = 0, host_stage: Callable | None = None):
     """One very long pair on all ranks of the group.  Every rank passes the same PCM and
     gets the same result.
 
@@ -321,17 +321,35 @@ def align_long_pair(video_pcm, audio_desc_pcm, group=None, details=None, root: i
       six scalars and line clusters are broadcast;
     * corridor scoring (:931-944): audio rows sharded again, ONE all-gather of the quals (the point list
       itself only depends on the corridors and is built on every rank);
-    * DP #2, traceback, nodes (:946-1027): on `root`, result broadcast."""
+    * DP #2, traceback, nodes (:946-1027): on `root`, result broadcast.
+
+    host_stage(job): replaces job.host_stage() on `root` (bench.py caches the rate-change fit there).
+    details["phases_ms"]: device time of each phase on this rank, from CUDA events on the current stream (the
+    rank is synchronised at every exchange anyway); details["host_fit_s"]: wall time of the host fit on `root`."""
+    import time
     import torch
     from . import _cabi, api
     dist = _dist()
     rank, world = _rank_world(group)
     job = api.AlignJob()
     info = {}
+    marks = []
+
+    def mark(name):
+        e = torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e.record()
+        marks.append((name, e))
+
     try:
-        job.load_pcm(video_pcm, audio_desc_pcm)
+        mark("start")
+        if isinstance(video_pcm, tuple):      # device-resident PCM: (device pointer, samples per channel, channels)
+            job.load_pcm_device(video_pcm, audio_desc_pcm)
+        else:
+            job.load_pcm(video_pcm, audio_desc_pcm)
         pair = job.pair
         dev = torch.device("cuda", torch.cuda.current_device())
+        mark("features")
         # ---- stage A ----
         n_rows = int(pair.feature_lens(_cabi.AUDIO)[0])
         lo, hi = row_shards(n_rows, world)[rank]
@@ -340,10 +358,12 @@ def align_long_pair(video_pcm, audio_desc_pcm, group=None, details=None, root: i
         tv = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
         tq = torch.empty(max(n, 1), dtype=torch.float64, device=dev)
         pair.export_points1_device(ti.data_ptr(), tv.data_ptr(), tq.data_ptr())
-        torch.cuda.synchronize()
+        mark("match_shard")
         gi, gv, gq = exchange_points(ti[:n], tv[:n], tq[:n], group)
+        mark("all_gather_points")
         info["shard_a"] = (lo, hi, n, int(gi.numel()))
         msg = [None]
+        host_fit_s = 0.0
         if rank == root:
             try:
                 gi, gv, gq = gi.contiguous(), gv.contiguous(), gq.contiguous()
@@ -351,7 +371,13 @@ def align_long_pair(video_pcm, audio_desc_pcm, group=None, details=None, root: i
                 pair.import_points1_device(gi.data_ptr(), gv.data_ptr(), gq.data_ptr(), gi.numel())
                 pair.dp1()
                 job.after_stage_a()
-                job.host_stage()
+                mark("dp1_trace")
+                t_fit = time.perf_counter()
+                if host_stage is None:
+                    job.host_stage()
+                else:
+                    host_stage(job)
+                host_fit_s = time.perf_counter() - t_fit
                 msg[0] = ("ok", job.stage_b_input())
             except Exception as e:       # every rank must learn that the pair failed
                 msg[0] = ("error", e)
@@ -360,14 +386,16 @@ def align_long_pair(video_pcm, audio_desc_pcm, group=None, details=None, root: i
         if msg[0][0] == "error":
             raise msg[0][1]
         b_in = msg[0][1]
+        mark("host_fit_and_broadcast")       # not device time: the root's host fit and the wait for it (excluded by BASELINE.json)
         # ---- stage B ----
         lo2, hi2 = row_shards(int(b_in["n_audio"]), world)[rank]
         n2, first, mine = pair.stage_b_score(b_in["gains"], b_in["audio_stds"], b_in["n_audio"], b_in["n_video"],
                                              b_in["lines"], lo2, hi2)
         tq2 = torch.empty(max(mine, 1), dtype=torch.float64, device=dev)
         pair.export_quals2_device(tq2.data_ptr(), first, mine)
-        torch.cuda.synchronize()
+        mark("corridor_shard")
         (q_all,) = exchange_varlen([tq2[:mine]], group)
+        mark("all_gather_quals")
         info["shard_b"] = (lo2, hi2, mine, int(q_all.numel()))
         out = [None]
         if rank == root:
@@ -388,8 +416,11 @@ def align_long_pair(video_pcm, audio_desc_pcm, group=None, details=None, root: i
             dist.broadcast_object_list(out, src=root, group=group)
         if out[0][0] == "error":
             raise out[0][1]
+        mark("dp2_trace_and_result")
         if details is not None:
             details["shards"] = info
+            details["phases_ms"] = {b[0]: a[1].elapsed_time(b[1]) for a, b in zip(marks[:-1], marks[1:])}
+            details["host_fit_s"] = host_fit_s
         return out[0][1]
     finally:
         job.close()

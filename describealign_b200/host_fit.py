@@ -12,6 +12,14 @@ The arithmetic goes through the same numpy / scipy entry points the reference ca
 the same dtype and order, because the LP has degenerate optima and anything else would not
 reproduce the reference's segments.  Written from the functional description in
 SURVEY.md appendix A.6/A.7, not from the reference's source text.
+
+Native host stage: the continuity error, the path compression and the assembly
+of the LP are plain array arithmetic and run in C++ inside the library (csrc/host_stage.cpp,
+`dab_host_*`), restating numpy's pairwise sums and OpenBLAS' ddot order; `continuity_error`,
+`compress_path` and `_lp_problem` below call them.  The numpy versions stay as `*_numpy`: they are
+what the native code is tested against, bit for bit (tests/test_host_native.py), next to the
+reference's own intermediate values in tests/golden/.  `np.std`, `np.linalg.lstsq` (LAPACK) and
+`scipy.optimize.linprog` (HiGHS) stay library calls.
 """
 from __future__ import annotations
 
@@ -48,9 +56,37 @@ def min_path_length(n_video_energy: int, n_audio_energy: int) -> float:
     return max(min(n_video_energy, n_audio_energy) / 500.0, 5 * FRAMES_PER_SECOND)
 
 
+def _native():
+    from . import _cabi
+    return _cabi.load()
+
+
+def _ptr(a):
+    return a.ctypes.data
+
+
 def continuity_error(x, y, deriv=False, window=None):
     """Distance of every path point from a line extrapolated from its smoothed future or
-    past neighbours, whichever is closer (describealign.py:706-724)."""
+    past neighbours, whichever is closer (describealign.py:706-724).  Native (dab_host_continuity_error)."""
+    x, y = np.asarray(x), np.asarray(y)
+    n = len(x)
+    if window is not None or n < 51 or len(y) != n:
+        return continuity_error_numpy(x, y, deriv, window)
+    err = np.empty(n - (1 if deriv else 0), dtype=np.float64)
+    lib = _native()
+    if np.issubdtype(x.dtype, np.integer) and np.issubdtype(y.dtype, np.integer):
+        xi, yi = np.ascontiguousarray(x, dtype=np.int64), np.ascontiguousarray(y, dtype=np.int64)
+        rc = lib.dab_host_continuity_error(_ptr(xi), _ptr(yi), n, int(bool(deriv)), _ptr(err))
+    else:
+        xf, yf = np.ascontiguousarray(x, dtype=np.float64), np.ascontiguousarray(y, dtype=np.float64)
+        rc = lib.dab_host_continuity_error_f64(_ptr(xf), _ptr(yf), None, None, n, int(bool(deriv)), _ptr(err))
+    if rc != 0:
+        raise RuntimeError(f"dab_host_continuity_error failed ({rc})")
+    return err
+
+
+def continuity_error_numpy(x, y, deriv=False, window=None):
+    """The numpy statement of continuity_error (describealign.py:706-724): checker of the native code."""
     window = hann41() if window is None else window
     head = window[:SPN - 1]
     head = head / np.sum(head)
@@ -122,7 +158,25 @@ def feature_gains(video_features, audio_features, x, y):
 
 def compress_path(x, y, window=None):
     """Replace well-behaved runs of 70 path points by their mean point and merge entries
-    that share an audio index (describealign.py:743-767), quirks included."""
+    that share an audio index (describealign.py:743-767), quirks included.  Native (dab_host_compress_path)."""
+    x, y = np.asarray(x), np.asarray(y)
+    n = len(x)
+    if window is not None or n < 41 or not (np.issubdtype(x.dtype, np.integer) and np.issubdtype(y.dtype, np.integer)):
+        return compress_path_numpy(x, y, window)
+    if n - 80 <= 10:
+        raise RuntimeError(FAILED_MSG)
+    import ctypes
+    xi, yi = np.ascontiguousarray(x, dtype=np.int64), np.ascontiguousarray(y, dtype=np.int64)
+    ox, oy = np.empty(n, dtype=np.float64), np.empty(n, dtype=np.float64)
+    cnt = ctypes.c_int64(0)
+    rc = _native().dab_host_compress_path(_ptr(xi), _ptr(yi), n, _ptr(ox), _ptr(oy), ctypes.byref(cnt))
+    if rc != 0:
+        raise RuntimeError(f"dab_host_compress_path failed ({rc})")
+    return ox[:cnt.value].copy(), oy[:cnt.value].copy()
+
+
+def compress_path_numpy(x, y, window=None):
+    """The numpy statement of compress_path (describealign.py:743-767): checker of the native code."""
     sx = local_mean(x, window)
     sy = local_mean(y, window)
     slope = np.diff(sy) / np.diff(sx)
@@ -160,12 +214,37 @@ class RateFit:
 
 
 def _lp_problem(x, y, window=None):
+    """Objective, equality constraints (CSC), right-hand side and bounds of the rate-change LP
+    (describealign.py:769-836).  Native assembly (dab_host_lp_assemble)."""
+    n = len(x)
+    if window is not None or n < 51:
+        return _lp_problem_numpy(x, y, window)
+    import ctypes
+    xf, yf = np.ascontiguousarray(x, dtype=np.float64), np.ascontiguousarray(y, dtype=np.float64)
+    cost = np.empty(12 * n - 9, dtype=np.float64)
+    indptr = np.empty(12 * n - 8, dtype=np.int32)
+    indices = np.empty(24 * n, dtype=np.int32)
+    data = np.empty(24 * n, dtype=np.float64)
+    b_eq = np.empty(3 * n - 4, dtype=np.float64)
+    nnz = ctypes.c_int64(0)
+    rc = _native().dab_host_lp_assemble(_ptr(xf), _ptr(yf), n, _ptr(cost), _ptr(indptr), _ptr(indices), _ptr(data),
+                                        _ptr(b_eq), ctypes.byref(nnz))
+    if rc != 0:
+        raise RuntimeError(f"dab_host_lp_assemble failed ({rc})")
+    k = nnz.value
+    a_eq = scipy.sparse.csc_matrix((data[:k].copy(), indices[:k].copy(), indptr), shape=(3 * n - 4, 12 * n - 9))
+    bounds = [[0, None]] * (4 * n - 2) + [[0, 2.0]] * (2 * n) + [[0, None]] * (6 * n - 8) + [[None, None]]
+    return cost, a_eq, b_eq, bounds
+
+
+def _lp_problem_numpy(x, y, window=None):
+    """The numpy / scipy.sparse statement of _lp_problem: checker of the native assembly."""
     n = len(x)
     dx = np.diff(x)
     dy = np.diff(y)
     inv = 1.0 / dx
     jump_cost = np.full(n - 1, 10.0)
-    jump_cost /= np.maximum(1, np.sqrt(continuity_error(x, y, deriv=True, window=window) / 3.0))
+    jump_cost /= np.maximum(1, np.sqrt(continuity_error_numpy(x, y, deriv=True, window=window) / 3.0))
     cost = np.hstack([np.ones(2 * n), jump_cost, jump_cost,
                       np.full(n, .01), np.full(n, .01),
                       np.full(n - 1, 3), np.full(n - 1, 3),

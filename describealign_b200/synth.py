@@ -214,3 +214,43 @@ def config_pair(name: str, seed: int = 0, scale: float = 1.0):
         return make_pair(9000 * s, 300 * s, skips=[(float(t) * s, float(d) * s) for t, d in zip(ts, ds)],
                          seed=seed, tail_s=max(0.0, extra) * s)
     raise ValueError(f"unknown config {name!r}")
+
+
+# ---------------------------------------------------------------------------------------
+# Long-form pair built from independently generated segments (C5 shape, quickly)
+# ---------------------------------------------------------------------------------------
+
+def _segment(arg):
+    video_s, offset_s, skips, seed, tail_s = arg
+    return make_pair(video_s, offset_s, skips=skips, seed=seed, tail_s=tail_s)
+
+
+def long_pair(seed: int = 0, scale: float = 1.0, workers: int = 0, segments: int = 10):
+    """The C5 shape (2.5-h film vs 3-h description, 300 s start offset, ~12 skips) as `segments` independently
+    generated pieces laid end to end, so that the pieces can be made by a pool of worker processes (config_pair("C5")
+    is one sequential pass, ~4 min at full scale).  Piece k is make_pair(video 9000/segments s, intro, one inner skip):
+    the intro of piece 0 is the 300 s start offset, the intros of the later pieces act as inserted unrelated audio at
+    the joins, the last piece carries the tail that brings the description to 10800 s.  Mono; deterministic in
+    (seed, scale, segments)."""
+    s = float(scale)
+    rng = np.random.default_rng(4000 + seed)
+    seg_v = 9000.0 / segments
+    intros = [300.0] + [float(x) for x in rng.uniform(2.0, 8.0, size=segments - 1)]
+    inner_t = rng.uniform(0.2 * seg_v, 0.8 * seg_v, size=segments)
+    inner_d = rng.uniform(2.0, 8.0, size=segments) * rng.choice([-1.0, 1.0], size=segments)
+    has_inner = rng.uniform(size=segments) < 0.3
+    total = sum(intros) + 9000.0 + float(np.sum(inner_d[has_inner]))
+    tail = max(0.0, 10800.0 - total)
+    args = []
+    for k in range(segments):
+        skips = [(float(inner_t[k]) * s, float(inner_d[k]) * s)] if has_inner[k] else []
+        args.append((seg_v * s, intros[k] * s, skips, 100003 * (seed + 1) + k, tail * s if k == segments - 1 else 0.0))
+    if workers and workers > 1:
+        from concurrent.futures import ProcessPoolExecutor
+        with ProcessPoolExecutor(max_workers=min(workers, segments)) as ex:
+            parts = list(ex.map(_segment, args))
+    else:
+        parts = [_segment(a) for a in args]
+    video = np.concatenate([p[0] for p in parts], axis=0)
+    desc = np.concatenate([p[1] for p in parts], axis=0)
+    return video, desc

@@ -332,6 +332,25 @@ void *dab_engine_slot_pair(dab_engine *engine, int32_t slot);
 /* out[0] scheduler loop iterations, out[1] iterations that found nothing to do and slept 20 us */
 void dab_engine_counters(dab_engine *engine, int64_t out[4]);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Host stage in native code: the parts of the "rate-change fit" of align() that are plain
+ * array arithmetic - reference describealign.py:706-724 (continuity error), :743-767 (70 -> 1 compression of
+ * the pass-1 path) and :769-836 (assembly of the L1 programme).  scipy.optimize.linprog itself stays with the
+ * caller.  Every sum is formed in numpy's / OpenBLAS' order (csrc/host_stage.cpp); no device is needed.
+ * --------------------------------------------------------------------------------------------------------- */
+/* err[n - (deriv != 0)]; n >= 51.  x, y: the pass-1 path (audio frame, video frame). */
+int dab_host_continuity_error(const int64_t *x, const int64_t *y, int64_t n, int deriv, double *err);
+/* the same on float64 input (either the float or the integer pair of pointers is given, the other is NULL) */
+int dab_host_continuity_error_f64(const double *x, const double *y, const int64_t *xi, const int64_t *yi, int64_t n,
+                                  int deriv, double *err);
+/* out_x, out_y: room for n entries; *n_out = number of fit points.  DAB_E_ARG when the path is too short
+ * (n <= 90: the reference raises "Alignment failed, are the input files mismatched?"). */
+int dab_host_compress_path(const int64_t *x, const int64_t *y, int64_t n, double *out_x, double *out_y, int64_t *n_out);
+/* cost[12n-9]; A_eq (3n-4 rows x 12n-9 columns) in CSC with sorted row indices: indptr[12n-8], indices / data
+ * with room for 24n entries (23n - 21 are written), *nnz = entries written; b_eq[3n-4].  n >= 51. */
+int dab_host_lp_assemble(const double *x, const double *y, int64_t n, double *cost, int32_t *indptr, int32_t *indices,
+                         double *data, double *b_eq, int64_t *nnz);
+
 #ifdef __cplusplus
 }
 #endif
