@@ -405,7 +405,7 @@ def run_long(args, rank, world, local_rank):
         out = batch.align_long_pair(pv.numpy() if host_input else dev_in[0], pa.numpy() if host_input else dev_in[1],
                                     details=det, host_stage=cached_host_stage)
         ph = det["phases_ms"]
-        dev_ms = sum(v for k, v in ph.items() if k != "host_fit_and_broadcast")
+        dev_ms = sum(v for k, v in ph.items() if k not in batch.HOST_PHASES)
         return dev_ms, det, out
 
     def run_steps(host_input):
@@ -468,7 +468,7 @@ def run_long(args, rank, world, local_rank):
                 "config": {"workload": WORKLOADS["C5"], "scale": args.scale,
                            "pair_minutes": [len(lv) / 44100 / 60, len(la) / 44100 / 60], "audio_hours_per_step": hours,
                            "l2_policy": "inputs larger than L2 (%d MB of PCM per step; 126 MB L2)" % int(pcm_b / 1e6),
-                           "timed": "per step ONE long pair on all ranks: features (every rank, the PCM once), match stage sharded by audio rows, all-gather of the match points, DP1 + traceback on rank 0, [host rate-change fit on rank 0: solved in warm-up, looked up inside the region, untimed by BASELINE.json], corridor scoring sharded by audio rows, all-gather of the quals, DP2 + traceback on rank 0; CUDA events per phase on every rank, summed without the host-fit wait, max over ranks"},
+                           "timed": "per step ONE long pair on all ranks: features (every rank, the PCM once), match stage sharded by audio rows, all-gather of the match points, DP1 + traceback on rank 0, [host rate-change fit on rank 0: solved in warm-up, looked up inside the region, untimed by BASELINE.json], corridor scoring sharded by audio rows, all-gather of the quals, DP2 + traceback on rank 0, final path to the host; [similarity and node list in Python on rank 0, describealign.py:993-1026: untimed like in the C2 arm]; CUDA events per phase on every rank, summed without the two host phases, max over ranks"},
                 "phases_ms_rank0": ph_dev,
                 "e2e": {"value": hours / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                         "h2d_bytes_per_step": float(pcm_b * world), "d2h_bytes_per_step": float(40 * len(out[3])),

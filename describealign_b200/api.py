@@ -98,6 +98,8 @@ def track_features(arr: np.ndarray):
     """All five feature vectors of one track from one pass over the PCM on the GPU.
     The reference calls three functions on the same array; the results are cached per
     array so the PCM is uploaded and scanned once."""
+    if hasattr(arr, "features") and hasattr(arr, "device"):
+        return arr.features()          # a decode.DevicePcm: the samples are already in HBM
     arr = np.asarray(arr)
     ptr = arr.__array_interface__["data"][0]
     for ref, p, shape, feats in _feature_cache:
@@ -324,6 +326,19 @@ def align_pcm(video_pcm, audio_desc_pcm, details=None):
     try:
         job.want_all_features = details is not None
         job.load_pcm(video_pcm, audio_desc_pcm)
+        return job.run(details)
+    finally:
+        job.close()
+
+
+def align_streams(video_stream, audio_desc_stream, details=None):
+    """Two decode.DevicePcm tracks in, alignment out: align_pcm for samples that the decode hand-off
+    (describealign_b200.decode, describealign.py:149-157) already put into HBM."""
+    print("  memorizing video...        \r", end='')
+    job = AlignJob()
+    try:
+        job.want_all_features = details is not None
+        job.load_pcm_device(video_stream.device(), audio_desc_stream.device())
         return job.run(details)
     finally:
         job.close()

@@ -309,6 +309,9 @@ def align_batch(pairs, durations: Sequence[float] | None = None, in_flight: int 
 # one very long pair on all ranks
 # ---------------------------------------------------------------------------------------------
 
+HOST_PHASES = ("host_fit_and_broadcast", "nodes_on_host_and_broadcast")
+
+
 def align_long_pair(video_pcm, audio_desc_pcm, group=None, details=None, root: int = 0, host_stage: Callable | None = None):
     """One very long pair on all ranks of the group.  Every rank passes the same PCM and
     gets the same result.
@@ -324,8 +327,9 @@ def align_long_pair(video_pcm, audio_desc_pcm, group=None, details=None, root: i
     * DP #2, traceback, nodes (:946-1027): on `root`, result broadcast.
 
     host_stage(job): replaces job.host_stage() on `root` (bench.py caches the rate-change fit there).
-    details["phases_ms"]: device time of each phase on this rank, from CUDA events on the current stream (the
-    rank is synchronised at every exchange anyway); details["host_fit_s"]: wall time of the host fit on `root`."""
+    details["phases_ms"]: time between CUDA events recorded after a device synchronisation at the end of each phase on
+    this rank; the phases named in HOST_PHASES are host work on `root` (and the other ranks' wait for it), the rest is
+    device work.  details["host_fit_s"]: wall time of the host fit on `root`."""
     import time
     import torch
     from . import _cabi, api
@@ -406,7 +410,9 @@ def align_long_pair(video_pcm, audio_desc_pcm, group=None, details=None, root: i
                     raise RuntimeError("long pair: the ranks' corridor shards do not add up to the point list")
                 pair.import_quals2_device(q_all.data_ptr(), n2)
                 pair.dp2()
+                mark("dp2_trace")
                 job.path = pair.path2()
+                mark("path_to_host")
                 if len(job.path) < job.min_len:
                     raise RuntimeError(api.FAILED_MSG)
                 out[0] = ("ok", job.finish(details))
@@ -416,7 +422,7 @@ def align_long_pair(video_pcm, audio_desc_pcm, group=None, details=None, root: i
             dist.broadcast_object_list(out, src=root, group=group)
         if out[0][0] == "error":
             raise out[0][1]
-        mark("dp2_trace_and_result")
+        mark("nodes_on_host_and_broadcast")   # not device time: similarity / node list in Python on root (:993-1026), result broadcast
         if details is not None:
             details["shards"] = info
             details["phases_ms"] = {b[0]: a[1].elapsed_time(b[1]) for a, b in zip(marks[:-1], marks[1:])}

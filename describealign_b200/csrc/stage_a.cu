@@ -37,32 +37,57 @@ __device__ __forceinline__ double feat_at(const PrepArgs &a, int f, int64_t t) {
   return f < 4 ? (double)a.f32[f][t] : a.f64[t];
 }
 
-// 256 outputs of one feature per block; the 296 inputs they read are converted to float64 once and staged
-// in shared memory (every input is used by 41 outputs).
-__global__ void __launch_bounds__(256) meansub_kernel(PrepArgs a) {
-  __shared__ double tile[256 + 40];
+// A block walks MS_TILES consecutive tiles of 256 outputs of one feature; the 296 inputs a tile reads are converted to
+// float64 once and staged in shared memory (every input is used by 41 outputs).  The next tile's inputs are fetched
+// into registers before the current tile is computed, so the global-load latency (ncu: 6 of 13 stall cycles per
+// issue were the long scoreboard with one tile per block) hides behind the 76 FP64 operations per output.
+constexpr int MS_TILES = 4;
+
+__global__ void __launch_bounds__(256, 3) meansub_kernel(PrepArgs a) {
+  __shared__ double tile[2][256 + 40];
   const int f = blockIdx.y;
   const int64_t n = a.len[f];
-  const int64_t t0 = (int64_t)blockIdx.x * 256, base = t0 - 20;
-  if (t0 >= n) return;
-  for (int e = threadIdx.x; e < 256 + 40; e += 256) {
-    const int64_t g = base + e;
-    tile[e] = (g >= 0 && g < n) ? feat_at(a, f, g) : 0.0;
-  }
+  const int64_t first = (int64_t)blockIdx.x * (256 * MS_TILES);
+  if (first >= n) return;
+  const int tid = threadIdx.x;
+  auto fetch = [&](int64_t t0, double &r0, double &r1) {
+    const int64_t g0 = t0 - 20 + tid, g1 = g0 + 256;
+    r0 = (g0 >= 0 && g0 < n) ? feat_at(a, f, g0) : 0.0;
+    r1 = (tid < 40 && g1 >= 0 && g1 < n) ? feat_at(a, f, g1) : 0.0;
+  };
+  double r0, r1;
+  fetch(first, r0, r1);
+  tile[0][tid] = r0;
+  if (tid < 40) tile[0][256 + tid] = r1;
   __syncthreads();
-  const int64_t t = t0 + threadIdx.x;
-  if (t >= n) return;
-  int64_t lo = t - 20, hi = t + 21, klo = 0;
-  if (lo < 0) { klo = -lo; lo = 0; }
-  if (hi > n) hi = n;
-  const int m = (int)(hi - lo);
-  const double *src = tile + (lo - base);
-  auto X = [&](int i) { return src[i]; };
-  auto Y = [&](int i) { return c_hflip[klo + i]; };
-  // interior outputs (m == 41 implies klo == 0): the window taps are compile-time constant-bank operands
-  auto Y0 = [&](int i) { return c_hflip[i]; };
-  const double mean = (m == 41) ? ddot41_skx(X, Y0) : ddot_skx(X, Y, m);
-  a.ms[(int64_t)f * a.stride + t] = tile[t - base] - mean;
+#pragma unroll 1
+  for (int k = 0; k < MS_TILES; ++k) {
+    const int64_t t0 = first + 256 * k;
+    if (t0 >= n) break;
+    const bool has_next = k + 1 < MS_TILES && t0 + 256 < n;
+    if (has_next) fetch(t0 + 256, r0, r1);
+    const double *cur = tile[k & 1];
+    const int64_t base = t0 - 20;
+    const int64_t t = t0 + tid;
+    if (t < n) {
+      int64_t lo = t - 20, hi = t + 21, klo = 0;
+      if (lo < 0) { klo = -lo; lo = 0; }
+      if (hi > n) hi = n;
+      const int m = (int)(hi - lo);
+      const double *src = cur + (lo - base);
+      auto X = [&](int i) { return src[i]; };
+      auto Y = [&](int i) { return c_hflip[klo + i]; };
+      // interior outputs (m == 41 implies klo == 0): the window taps are compile-time constant-bank operands
+      auto Y0 = [&](int i) { return c_hflip[i]; };
+      const double mean = (m == 41) ? ddot41_skx(X, Y0) : ddot_skx(X, Y, m);
+      a.ms[(int64_t)f * a.stride + t] = cur[t - base] - mean;
+    }
+    if (has_next) {
+      tile[(k + 1) & 1][tid] = r0;
+      if (tid < 40) tile[(k + 1) & 1][256 + tid] = r1;
+    }
+    __syncthreads();
+  }
 }
 
 // nrm[t] = max(1e-3, sqrt(sum_{k<41} ms[t+k]^2)) and the digit codes of frame t.
@@ -1057,7 +1082,7 @@ static int prep_track(dab_pair *pr, int track) {
   pa.f64 = tk.b2.as<double>();
   pa.len[0] = tk.Le; pa.len[1] = pa.len[2] = pa.len[3] = pa.len[4] = tk.L;
   pa.Lp = Lmin; pa.ms = tk.ms.as<double>(); pa.stride = Lmax;
-  dim3 g1((unsigned)cdiv(Lmax, 256), 5);
+  dim3 g1((unsigned)cdiv(Lmax, 256 * MS_TILES), 5);
   meansub_kernel<<<g1, 256, 0, pr->stream>>>(pa);
   CodeArgs ca;
   ca.ms = tk.ms.as<double>(); ca.stride = Lmax;

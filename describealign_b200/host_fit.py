@@ -370,16 +370,18 @@ def build_nodes(path, n_audio_energy: int, n_video_energy: int, n_audio_scaled: 
     (j, i, cluster, qual, cum) (describealign.py:993-1026).  Scales path[:, :2] in place."""
     y, x, cluster, quals, _ = path.T
     keep = (quals == 0) | (quals > .3)
-    sim_x = float(len(set(x[keep]))) / n_audio_scaled
-    sim_y = float(len(set(y[keep]))) / n_video_scaled
+    sim_x = float(len(np.unique(x[keep]))) / n_audio_scaled       # len(set(...)) of the reference
+    sim_y = float(len(np.unique(y[keep]))) / n_video_scaled
     similarity = 100 * max(sim_x, sim_y)
+    # break-points where the cluster changes, in path order: (point k - .1, point k+1 + .1) per change
+    ch = np.flatnonzero(cluster[:-1] != cluster[1:])
+    px = np.empty(2 * len(ch)); py = np.empty(2 * len(ch))
+    px[0::2], px[1::2] = x[ch] - .1, x[ch + 1] + .1
+    py[0::2], py[1::2] = y[ch] - .1, y[ch + 1] + .1
     nodes = []
     if cluster[0] == cluster[1]:
         nodes.append((x[0], y[0]))
-    for k in range(len(x) - 1):
-        if cluster[k] != cluster[k + 1]:
-            nodes.append((x[k] - .1, y[k] - .1))
-            nodes.append((x[k + 1] + .1, y[k + 1] + .1))
+    nodes.extend(zip(px, py))
     if cluster[-2] == cluster[-1]:
         nodes.append((x[-1], y[-1]))
     nx, ny = np.array(nodes).T / 210.

@@ -351,6 +351,25 @@ int dab_host_compress_path(const int64_t *x, const int64_t *y, int64_t n, double
 int dab_host_lp_assemble(const double *x, const double *y, int64_t n, double *cost, int32_t *indptr, int32_t *indices,
                          double *data, double *b_eq, int64_t *nnz);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Decode hand-off: replaces the tail of parse_audio_from_file, reference
+ * describealign.py:149-157 (ffmpeg's s16le pipe -> bytes -> int16 -> float16 on the host).  A reader thread inside
+ * the library read()s the decoder's pipe into two page-locked chunks in turn and copies each chunk to the device
+ * while the decoder is still running; the int16 -> float16 conversion happens in the feature kernel.
+ * --------------------------------------------------------------------------------------------------------- */
+typedef struct dab_pcm_reader dab_pcm_reader;
+/* fd: read end of the decoder's pipe (or any file descriptor); expected_bytes: size hint (duration x rate x
+ * channels x 2) or 0 - the device buffer then grows geometrically.  Returns at once; reading goes on in a thread. */
+int dab_pcm_reader_open(dab_ctx *ctx, int fd, int64_t expected_bytes, dab_pcm_reader **out);
+int64_t dab_pcm_reader_progress(dab_pcm_reader *reader);       /* bytes handed to the copy engine so far */
+/* Blocks until EOF and until every chunk is on the device.  *device_pcm (int16, interleaved) stays valid until
+ * dab_pcm_reader_close: pass it to dab_pair_set_pcm(pair, track, ptr, bytes / (2 * channels), channels,
+ * DAB_PCM_S16, 1) and close the reader after that pair's features have been computed. */
+int dab_pcm_reader_wait(dab_pcm_reader *reader, void **device_pcm, int64_t *bytes);
+/* the samples back on the host (int16, interleaved), for --stretch_audio (describealign.py:1142-1150) */
+int dab_pcm_reader_copy_to_host(dab_pcm_reader *reader, void *dst, int64_t bytes);
+void dab_pcm_reader_close(dab_pcm_reader *reader);
+
 #ifdef __cplusplus
 }
 #endif
