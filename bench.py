@@ -816,7 +816,7 @@ def run_ours(args, rank, world, local_rank):
         # feature kernel (ncu launch list under profiles/); its roofline is the headline, the step-level
         # figure (all algorithmic bytes of a step over the step time) sits beside it.
         main_roof = dict(roof["features"])
-        ncu_traffic = (116.465152e6 + 5.258240e6 + 143.008e6 + 9.717248e6) / 2
+        ncu_traffic = (116.477696e6 + 19.665920e6 + 142.943232e6 + 22.880000e6) / 2     # profiles/r2_v21_features_gate_full.txt
         step_bytes = pcm_bytes(pairs) + 24 * (work_all["n_points1"] + work_all["n_points2"])
         main_roof.update({"kernel": "features_kernel", "peak_source": peak_src,
                           "measured": "CUDA events on the pair's stream, one pair alone on the GPU right after the timed steps",
