@@ -52,13 +52,29 @@ def request_log10_mode(mode: str):
     _log10_request = mode
 
 
+def _current_device_of_this_thread() -> int:
+    import sys
+    torch = sys.modules.get("torch")
+    try:
+        if torch is not None and torch.cuda.is_available() and torch.cuda.is_initialized():
+            return int(torch.cuda.current_device())
+    except Exception:
+        pass
+    return -1
+
+
 def context() -> _cabi.Context:
     """Per-thread CUDA context handle, created on first use (never at import time, so that
     a GUI parent process that only imports this module does not initialise CUDA before it
     forks its worker; reference describealign.py:1432)."""
-    global _log10_request
+    global _log10_request, _device
     ctx = getattr(_tls, "ctx", None)
     if ctx is None:
+        if _device < 0:
+            # No set_device(): the whole process stays on the GPU that is current in the FIRST thread that
+            # needs a context (what a caller who did torch.cuda.set_device(local_rank) expects) - a fresh
+            # worker thread's own "current device" would be 0 whatever the rank.
+            _device = _current_device_of_this_thread()
         ctx = _cabi.Context(_device)
         _tls.ctx = ctx
         _tls.pairs = []
