@@ -449,7 +449,16 @@ def bind_to_gpu_numa_node(device_index: int) -> dict:
             node = int(f.read().strip())
         info["numa_node"] = node
         if node < 0:
-            return info
+            # sysfs does not say (virtualised PCI topology).  If the host still shows several memory nodes, assume the
+            # usual HGX layout - the first half of the GPUs on the first socket, the second half on the second.
+            import glob
+            nodes = sorted(int(p.rsplit("node", 1)[1]) for p in glob.glob("/sys/devices/system/node/node[0-9]*"))
+            n_gpus = len([ln for ln in subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True, timeout=20).stdout.splitlines()
+                          if ln.startswith("GPU ")])
+            if len(nodes) < 2 or n_gpus < 2:
+                return info
+            node = nodes[min(len(nodes) - 1, int(device_index) * len(nodes) // n_gpus)]
+            info["numa_node_assumed"] = node
         with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
             spec = f.read().strip()
         cpus = set()

@@ -107,7 +107,10 @@ __global__ void __launch_bounds__(TB_THREADS) tb_mark_kernel(TbArgs a) {
     __syncthreads();
   }
   // ancestors of e: after processing level k (from the top), all ancestors at distances whose binary
-  // expansion uses the levels seen so far are marked
+  // expansion uses the levels seen so far are marked.  Within one level a thread may already see a mark another
+  // thread set in the same pass (compute-sanitizer's racecheck reports it): that only marks a further TRUE ancestor
+  // early - marks travel along predecessor links from e and are idempotent byte stores of 1 - so the final set,
+  // all in-chunk ancestors of e, does not depend on the interleaving.
   for (int k = TB_LEVELS - 1; k >= 0; --k) {
 #pragma unroll
     for (int u = 0; u < TB_PER; ++u) {
