@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdescribealign_b200.so")
+LIB_PATH = os.environ.get("DAB_LIB_PATH") or os.path.join(_HERE, "libdescribealign_b200.so")   # override: kernel-variant experiments
 
 PCM_S16, PCM_F16 = 0, 1
 VIDEO, AUDIO = 0, 1

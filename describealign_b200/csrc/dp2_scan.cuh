@@ -19,8 +19,14 @@
 // reached inside the block) S1 is repeated with the refreshed inputs; else the verified prefix is
 // committed and the failing point (binade crossing, rounding tie) evaluated by the one-point rules,
 // as are NEAR / GAP points.  Speculation can only cost time, never exactness.
-constexpr int SC_T = 256;            // threads per pair
-constexpr int SC_K = 4;              // chain slots per thread
+#ifndef DAB_SC_T
+#define DAB_SC_T 512
+#endif
+#ifndef DAB_SC_K
+#define DAB_SC_K 2
+#endif
+constexpr int SC_T = DAB_SC_T;       // threads per pair
+constexpr int SC_K = DAB_SC_K;       // chain slots per thread
 constexpr int SC_NB = SC_T * SC_K;   // points per block
 constexpr int SC_W = SC_T / 32;
 constexpr int SC_MAXP = 3;           // scan passes per block before the verified prefix is committed

@@ -301,8 +301,8 @@ __global__ void __launch_bounds__(THREADS, 2) features_kernel(FeatArgs a) {
     const int64_t f0 = t0 - FH;                           // first staged frame (may be < 0)
     const int64_t s0 = f0 * 210 - PADS;                   // first staged sample (may be < 0)
 
-    // ---- S0: the mono / mid signal as float16, zero outside [0, Sb) ----------------------------------------
-    for (int k = tid; k < NF; k += THREADS) zi[k] = 0;
+    // ---- S0: the mono / mid signal as float16, zero outside [0, Sb).  (Nothing the previous tile's output stage
+    //      still reads is written here: a warp that is done with S4 starts on the next tile's signal at once.) ------
     if (bulk_ok(tile)) {
       mbar_wait(&s_bar, parity);
       parity ^= 1u;
@@ -374,6 +374,7 @@ __global__ void __launch_bounds__(THREADS, 2) features_kernel(FeatArgs a) {
     //      (x - lp1[k])^2 over the MIDDLE five samples of the very window lp1[k] was filtered from, so it is
     //      formed here from the registers ---------------------------------------------------------------------
     const int64_t n1_first = f0 * 42 - 7;          // global lp1 index of lp1[0]
+    for (int k = tid; k < NF; k += THREADS) zi[k] = 0;     // every thread is past the previous tile's S4 (barrier above)
     {
     const float w15r[15] = {w15[0], w15[1], w15[2], w15[3], w15[4], w15[5], w15[6], w15[7],
                             w15[8], w15[9], w15[10], w15[11], w15[12], w15[13], w15[14]};
@@ -629,7 +630,9 @@ __global__ void __launch_bounds__(THREADS, 2) features_kernel(FeatArgs a) {
         }
       }
     }
-    __syncthreads();   // every buffer of this tile has been consumed; s_next was written before the S3 barrier
+    // No barrier here: S4 reads ph (= lp1's space), p1, zi, eb and be2, all of which are next written after the next
+    // tile's first barrier, which no thread passes before every thread has left S4.  s_next was written before the S3
+    // barrier of this tile and is rewritten after the S2 barrier of the next one.
     tile = s_next;
   }
 }

@@ -152,3 +152,20 @@ def test_assign_pairs_and_row_shards():
         assert len(sh) == w and sh[0][0] == 0 and sh[-1][1] == n
         assert all(sh[k][1] == sh[k + 1][0] for k in range(w - 1))
         assert max(h - l for l, h in sh) - min(h - l for l, h in sh) <= 1
+
+
+def test_long_pair_generator_is_deterministic_and_has_the_c5_shape():
+    """synth.long_pair builds the C5 shape from independently generated segments (worker processes or not: same PCM)."""
+    from describealign_b200 import synth
+    v1, a1 = synth.long_pair(3, 0.004, workers=0)
+    v2, a2 = synth.long_pair(3, 0.004, workers=3)
+    assert np.array_equal(v1, v2) and np.array_equal(a1, a2)
+    assert v1.dtype == np.int16 and v1.shape[1] == 1
+    assert abs(v1.shape[0] / 44100 - 9000 * 0.004) < 0.01 and abs(a1.shape[0] / 44100 - 10800 * 0.004) < 0.05
+    v3, _ = synth.long_pair(4, 0.004)
+    assert not np.array_equal(v1, v3)
+
+
+def test_long_pair_host_phases_are_named():
+    from describealign_b200 import batch
+    assert set(batch.HOST_PHASES) == {"host_fit_and_broadcast", "nodes_on_host_and_broadcast"}
