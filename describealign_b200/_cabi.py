@@ -31,7 +31,7 @@ EXPORTS = [
     "dab_engine_create", "dab_engine_destroy", "dab_engine_submit", "dab_engine_next", "dab_engine_submit_b",
     "dab_engine_release", "dab_engine_slot_error", "dab_engine_slot_pair", "dab_engine_counters",
     "dab_host_continuity_error", "dab_host_continuity_error_f64", "dab_host_compress_path", "dab_host_lp_assemble",
-    "dab_pcm_reader_open", "dab_pcm_reader_progress", "dab_pcm_reader_wait", "dab_pcm_reader_close", "dab_pcm_reader_copy_to_host",
+    "dab_pcm_reader_open", "dab_pcm_reader_progress", "dab_pcm_reader_wait", "dab_pcm_reader_close", "dab_pcm_reader_copy_to_host", "dab_stretch_best_jumps",
 ]
 
 
@@ -129,6 +129,7 @@ def load() -> ctypes.CDLL:
     lib.dab_pcm_reader_progress.argtypes = [vp]
     lib.dab_pcm_reader_progress.restype = i64
     lib.dab_pcm_reader_wait.argtypes = [vp, ctypes.POINTER(vp), pl]
+    lib.dab_stretch_best_jumps.argtypes = [vp, vp, i32, i64, i32, vp, i32, vp, vp]
     lib.dab_pcm_reader_copy_to_host.argtypes = [vp, vp, i64]
     lib.dab_pcm_reader_close.argtypes = [vp]
     lib.dab_pcm_reader_close.restype = None

@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdescribealign_b200.so")
-SOURCES = ["api.cu", "features.cu", "stage_a.cu", "stage_b.cu", "engine.cu", "pcm_reader.cu", "host_stage.cpp"]
+SOURCES = ["api.cu", "features.cu", "stage_a.cu", "stage_b.cu", "engine.cu", "pcm_reader.cu", "stretch.cu", "host_stage.cpp"]
 HEADERS = ["common.cuh", "dp2_scan.cuh", "refine.cuh", "traceback.cuh", "hann_tables.h", os.path.join("..", "..", "include", "describealign_b200.h")]
 
 NVCC_FLAGS = [

@@ -370,6 +370,17 @@ int dab_pcm_reader_wait(dab_pcm_reader *reader, void **device_pcm, int64_t *byte
 int dab_pcm_reader_copy_to_host(dab_pcm_reader *reader, void *dst, int64_t bytes);
 void dab_pcm_reader_close(dab_pcm_reader *reader);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * --stretch_audio resynthesis: the jump search of the reference's pitch-preserving time stretch,
+ * describealign.py:252-304 (`get_pearson_corrs_generator`) reduced as :330-333 do.  segment: host pointer to float16
+ * (channels, n) row-major, n >= 1535; jumps: n_jumps distances in [1, 512); negative != 0 when the output is longer
+ * than the input.  loc[n / 512][n_jumps] (int16) = position inside the window with the largest 512-sample Pearson
+ * correlation, best[n / 512][n_jumps] (float64) = that correlation; bit-identical to the reference's float64 running
+ * sums (same pieces, same epsilon, same order).  Host buffers; the copies happen inside the call.
+ * --------------------------------------------------------------------------------------------------------- */
+int dab_stretch_best_jumps(dab_ctx *ctx, const void *segment_f16, int32_t channels, int64_t n, int32_t negative,
+                           const int32_t *jumps, int32_t n_jumps, int16_t *loc, double *best);
+
 #ifdef __cplusplus
 }
 #endif
