@@ -3,7 +3,8 @@
     python -m describealign_b200.launcher <the reference's own arguments>
 
 imports the user's installed `describealign` module, replaces its four hot-path functions
-(describealign.py:545, 557, 575, 595) with the ones from this package and then calls its
+(describealign.py:545, 557, 575, 595) - and `replace_aligned_segments` (:229), the resynthesis of
+`--stretch_audio` - with the ones from this package and then calls its
 unchanged `command_line_interface()` (describealign.py:1773).  Because the replacement is
 done at import time of this module, it also survives the `spawn` start method the GUI worker
 uses on some platforms as long as the worker's target imports describealign_b200.launcher
@@ -16,6 +17,7 @@ import importlib
 import sys
 
 _PATCHED = ("get_energy", "get_zero_crossings", "get_freq_bands", "align")
+_PATCHED_IF_PRESENT = {"replace_aligned_segments": "stretch"}     # --stretch_audio resynthesis (describealign.py:229)
 
 
 def patch(module=None, log10: str | None = None):
@@ -34,6 +36,10 @@ def patch(module=None, log10: str | None = None):
             raise AttributeError(f"{module.__name__} has no function {name!r} to replace")
         setattr(module, "_reference_" + name, getattr(module, name))
         setattr(module, name, getattr(api, name))
+    for name, where in _PATCHED_IF_PRESENT.items():
+        if hasattr(module, name):
+            setattr(module, "_reference_" + name, getattr(module, name))
+            setattr(module, name, getattr(importlib.import_module("." + where, __package__), name))
     return module
 
 
