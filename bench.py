@@ -94,15 +94,16 @@ class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
-    def __init__(self, index):
+    def __init__(self, index, period_ms=200):
         self.index = index
+        self.period_ms = int(period_ms)
         self.proc = None
         self.lines = []
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", str(self.period_ms)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -661,15 +662,27 @@ def run_ours(args, rank, world, local_rank):
         barrier()
         return total / args.steps, ctx.launches() - l0, res
 
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    # every rank samples ITS GPU's clocks during the device-resident steps: the step time is the maximum over ranks, so
+    # one power-capped GPU of the box would set it
+    sampler = ClockSampler(local_rank, 200 if rank == 0 else 1000)
+    sampler.start()
     ms_dev, launches, res_dev = run_steps(False)
     alloc1 = _cabi.alloc_stats()
     alloc_before = dict(alloc0)     # the e2e steps below update the dict run_steps writes to
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop()
     sched0 = eng.counters()
     ms_e2e, _, res_e2e = run_steps(True)
+    per_rank = [{"rank": rank, "ms_per_step": ms_dev, "ms_per_step_e2e": ms_e2e, "sm_mhz": clocks.get("sm_mhz"),
+                 "reasons": clocks.get("reasons"), "scheduler_ms_per_pair": float(np.mean([r["kernel_ms"]["host_in_set_pcm"] for r in res_dev]))}]
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, per_rank[0])
+        per_rank = gathered
+    if rank == 0 and world > 1:
+        # the line's "clocks" must speak for the whole job: the lowest median clock and every throttle reason seen
+        mhz = [p["sm_mhz"] for p in per_rank if p.get("sm_mhz")]
+        clocks = dict(clocks, sm_mhz=min(mhz) if mhz else clocks.get("sm_mhz"),
+                      reasons=sorted({r for p in per_rank for r in (p.get("reasons") or [])}), ranks_sampled=len(mhz))
     # bytes that crossed the link per pair in the end-to-end arm (counted from the arrays copied)
     def bytes_of(k, r):
         v, a = pinned_np[k % distinct]
@@ -861,6 +874,7 @@ def run_ours(args, rank, world, local_rank):
             "allocator_activity_in_timed_steps": {k: alloc1[k] - alloc_before[k] for k in alloc1},
             "work": work_all,
             "clocks": clocks,
+            "per_rank": per_rank,
             "cpu_baseline": cpu,
             "parity": parity,
             "long_pair": long_pair,
