@@ -318,6 +318,29 @@ def run_reference(args, rank, world):
 # GPU arm
 # ------------------------------------------------------------------------------------------------
 
+def d2h_probe(pinned, seconds=1.0):
+    """GB/s this rank reaches copying device buffers of the size of its PCM back into its pinned buffers' twins,
+    back to back for about `seconds` (all ranks at once): the ceiling of the result copies under contention."""
+    import torch
+    src = [torch.empty_like(t, device="cuda") for pair in pinned for t in pair]
+    dst = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in src[:2]]      # host twins of the first pair's tracks
+    stream = torch.cuda.Stream()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    nbytes, t_end = 0, time.perf_counter() + seconds
+    with torch.cuda.stream(stream):
+        e0.record()
+        while time.perf_counter() < t_end:
+            for k, s_ in enumerate(src):
+                d, sv = dst[k % 2].view(-1), s_.view(-1)
+                m = min(d.numel(), sv.numel())
+                d[:m].copy_(sv[:m], non_blocking=True)
+                nbytes += m * sv.element_size()
+            stream.synchronize()
+        e1.record()
+    e1.synchronize()
+    return nbytes / (e0.elapsed_time(e1) * 1e-3) / 1e9
+
+
 def h2d_probe(pinned, seconds=1.0):
     """GB/s this rank's pinned PCM buffers reach when copied back to back for about `seconds` (all ranks
     do this at the same time: the ceiling of the end-to-end number under the box's real contention)."""
@@ -539,7 +562,7 @@ def run_ours(args, rank, world, local_rank):
               for v, a in base_pairs]
     pinned_np = [(v.numpy(), a.numpy()) for v, a in pinned]
     # what the host-to-device link gives: one large pinned copy on an idle box, and every rank copying at once
-    h2d_single = h2d_all_ranks = None
+    h2d_single = h2d_all_ranks = d2h_all_ranks = None
     try:
         src = pinned[0][1]
         dst = torch.empty_like(src, device="cuda")
@@ -552,6 +575,8 @@ def run_ours(args, rank, world, local_rank):
         del dst
         barrier()
         h2d_all_ranks = h2d_probe(pinned)
+        barrier()
+        d2h_all_ranks = d2h_probe(pinned)
         barrier()
     except Exception:
         pass
@@ -666,14 +691,17 @@ def run_ours(args, rank, world, local_rank):
     # one power-capped GPU of the box would set it
     sampler = ClockSampler(local_rank, 200 if rank == 0 else 1000)
     sampler.start()
+    cpu0, wall0 = os.times(), time.perf_counter()
     ms_dev, launches, res_dev = run_steps(False)
+    cpu1, wall1 = os.times(), time.perf_counter()
+    cpu_cores_busy = ((cpu1.user - cpu0.user) + (cpu1.system - cpu0.system)) / max(wall1 - wall0, 1e-9)
     alloc1 = _cabi.alloc_stats()
     alloc_before = dict(alloc0)     # the e2e steps below update the dict run_steps writes to
     clocks = sampler.stop()
     sched0 = eng.counters()
     ms_e2e, _, res_e2e = run_steps(True)
     per_rank = [{"rank": rank, "ms_per_step": ms_dev, "ms_per_step_e2e": ms_e2e, "sm_mhz": clocks.get("sm_mhz"),
-                 "reasons": clocks.get("reasons"), "scheduler_ms_per_pair": float(np.mean([r["kernel_ms"]["host_in_set_pcm"] for r in res_dev]))}]
+                 "reasons": clocks.get("reasons"), "host_cores_busy": cpu_cores_busy, "scheduler_ms_per_pair": float(np.mean([r["kernel_ms"]["host_in_set_pcm"] for r in res_dev]))}]
     if world > 1:
         gathered = [None] * world
         dist.all_gather_object(gathered, per_rank[0])
@@ -774,14 +802,14 @@ def run_ours(args, rank, world, local_rank):
     # max over ranks
     t = torch.tensor([ms_dev, ms_e2e], device="cuda", dtype=torch.float64)
     tot = torch.tensor([hours_rank, float(launches), float(h2d), float(d2h)], device="cuda", dtype=torch.float64)
-    probe = torch.tensor([h2d_all_ranks or 0.0], device="cuda", dtype=torch.float64)
+    probe = torch.tensor([h2d_all_ranks or 0.0, d2h_all_ranks or 0.0], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
         dist.all_reduce(probe, op=dist.ReduceOp.SUM)
     ms_dev, ms_e2e = float(t[0]), float(t[1])
     hours, launches_all, h2d_all, d2h_all = (float(x) for x in tot)
-    h2d_probe_sum = float(probe[0])
+    h2d_probe_sum, d2h_probe_sum = float(probe[0]), float(probe[1])
 
     if rank == 0:
         peaks, peak_src = measured_peaks()
@@ -858,6 +886,8 @@ def run_ours(args, rank, world, local_rank):
                     "h2d_gbs_single_copy_idle_box": h2d_single,
                     "h2d_gbs_probe_all_ranks_at_once_per_gpu": h2d_probe_sum / world if h2d_probe_sum else None,
                     "frac_of_h2d_probe": e2e_gbs / (h2d_probe_sum / world) if h2d_probe_sum else None,
+                    "d2h_gbs_probe_all_ranks_at_once_per_gpu": d2h_probe_sum / world if d2h_probe_sum else None,
+                    "d2h_gbs_needed_per_gpu_device_resident": d2h_all / world / (ms_dev * 1e-3) / 1e9,
                     "note": "PCM is 2 bytes per sample per channel; the end-to-end rate is bounded by the host-to-device link (probe: every rank copying its pinned PCM back to back at the same time)"},
             "gpu_launches": int(launches_all),
             "roofline": main_roof,
@@ -870,7 +900,8 @@ def run_ours(args, rank, world, local_rank):
                                   "note": "one C2 pair (22-min video, 27-min description) alone on the GPU, PCM device-resident; wall time from submit to the stage-A results on the host plus stage-B input to the final path on the host"},
             "kernel_ms_last_step": agg,
             "host_side": {"numa_binding_rank0": numa, **sched, **{k: eng.counters()[k] - sched0[k] for k in sched0},
-                          "python_threads": 1, "scheduler_threads": 1},
+                          "python_threads": 1, "scheduler_threads": 1, "host_cores_busy_rank0": cpu_cores_busy,
+                          "host_cores_per_rank": (os.cpu_count() or 1) / world},
             "allocator_activity_in_timed_steps": {k: alloc1[k] - alloc_before[k] for k in alloc1},
             "work": work_all,
             "clocks": clocks,
