@@ -91,18 +91,19 @@ def audio_hours(pairs):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
-    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """nvidia-smi clocks / throttle reasons sampled during the timed region.  ONE process (rank 0's) watches the GPUs
+    of all local ranks - `indices` - so that the other ranks' host cores are left alone."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
-    def __init__(self, index, period_ms=200):
-        self.index = index
+    def __init__(self, indices, period_ms=200):
+        self.indices = [int(i) for i in (indices if isinstance(indices, (list, tuple)) else [indices])]
         self.period_ms = int(period_ms)
         self.proc = None
         self.lines = []
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", ",".join(str(i) for i in self.indices), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", str(self.period_ms)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
@@ -115,28 +116,36 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self):
+        """Summary over all watched GPUs (lowest median clock, every reason seen) + "per_gpu": {index: summary}."""
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "per_gpu": {}}
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        per = {}
+        mx = None
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
+            if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[0])); mx = float(f[1])
+                idx = int(f[0]); clk = float(f[1]); mx = float(f[2])
             except ValueError:
                 continue
+            g = per.setdefault(idx, {"sm": [], "reasons": set()})
+            g["sm"].append(clk)
             for k, nm in enumerate(names):
-                if f[3 + k].lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                if f[4 + k].lower().startswith("active"):
+                    g["reasons"].add(nm)
+        per_gpu = {i: {"sm_mhz": float(np.median(g["sm"])) if g["sm"] else None, "reasons": sorted(g["reasons"]),
+                       "samples": len(g["sm"])} for i, g in per.items()}
+        meds = [g["sm_mhz"] for g in per_gpu.values() if g["sm_mhz"] is not None]
+        return {"sm_mhz": min(meds) if meds else None, "sm_max_mhz": mx,
+                "reasons": sorted({r for g in per_gpu.values() for r in g["reasons"]}),
+                "samples": sum(g["samples"] for g in per_gpu.values()), "gpus_sampled": len(per_gpu), "per_gpu": per_gpu}
 
 
 def measured_peaks():
@@ -450,7 +459,7 @@ def run_long(args, rank, world, local_rank):
         return tot / args.steps, phases, det, out
 
     ctx = api.context()
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(list(range(world)))        # rank 0 watches every local rank's GPU (one node)
     if rank == 0:
         sampler.start()
     l0 = ctx.launches()
@@ -687,30 +696,31 @@ def run_ours(args, rank, world, local_rank):
         barrier()
         return total / args.steps, ctx.launches() - l0, res
 
-    # every rank samples ITS GPU's clocks during the device-resident steps: the step time is the maximum over ranks, so
-    # one power-capped GPU of the box would set it
-    sampler = ClockSampler(local_rank, 200 if rank == 0 else 1000)
-    sampler.start()
+    # rank 0 samples the clocks of EVERY rank's GPU during the device-resident steps (one nvidia-smi process for the
+    # node): the step time is the maximum over ranks, so one power-capped GPU of the box would set it
+    sampler = ClockSampler(list(range(world)))
+    if rank == 0:
+        sampler.start()
     cpu0, wall0 = os.times(), time.perf_counter()
     ms_dev, launches, res_dev = run_steps(False)
     cpu1, wall1 = os.times(), time.perf_counter()
     cpu_cores_busy = ((cpu1.user - cpu0.user) + (cpu1.system - cpu0.system)) / max(wall1 - wall0, 1e-9)
     alloc1 = _cabi.alloc_stats()
     alloc_before = dict(alloc0)     # the e2e steps below update the dict run_steps writes to
-    clocks = sampler.stop()
+    clocks = sampler.stop() if rank == 0 else None
     sched0 = eng.counters()
     ms_e2e, _, res_e2e = run_steps(True)
-    per_rank = [{"rank": rank, "ms_per_step": ms_dev, "ms_per_step_e2e": ms_e2e, "sm_mhz": clocks.get("sm_mhz"),
-                 "reasons": clocks.get("reasons"), "host_cores_busy": cpu_cores_busy, "scheduler_ms_per_pair": float(np.mean([r["kernel_ms"]["host_in_set_pcm"] for r in res_dev]))}]
+    per_rank = [{"rank": rank, "ms_per_step": ms_dev, "ms_per_step_e2e": ms_e2e, "host_cores_busy": cpu_cores_busy,
+                 "scheduler_ms_per_pair": float(np.mean([r["kernel_ms"]["host_in_set_pcm"] for r in res_dev]))}]
     if world > 1:
         gathered = [None] * world
         dist.all_gather_object(gathered, per_rank[0])
         per_rank = gathered
-    if rank == 0 and world > 1:
-        # the line's "clocks" must speak for the whole job: the lowest median clock and every throttle reason seen
-        mhz = [p["sm_mhz"] for p in per_rank if p.get("sm_mhz")]
-        clocks = dict(clocks, sm_mhz=min(mhz) if mhz else clocks.get("sm_mhz"),
-                      reasons=sorted({r for p in per_rank for r in (p.get("reasons") or [])}), ranks_sampled=len(mhz))
+    if rank == 0:
+        per_gpu = clocks.pop("per_gpu", {})
+        for p_ in per_rank:
+            g = per_gpu.get(p_["rank"]) or {}          # local rank = GPU index on the one node the bench runs on
+            p_["sm_mhz"], p_["reasons"] = g.get("sm_mhz"), g.get("reasons")
     # bytes that crossed the link per pair in the end-to-end arm (counted from the arrays copied)
     def bytes_of(k, r):
         v, a = pinned_np[k % distinct]
