@@ -7,6 +7,7 @@
 //                               (:743-767, quirks included)
 //   dab_host_lp_assemble        objective, equality constraints (CSC, as scipy's coo.tocsc() lays them out) and
 //                               right-hand side of the L1 rate-change fit (:769-836)
+//   dab_host_line_clusters      grouping of the fit's points into co-linear clusters (:861-884)
 //
 // scipy.optimize.linprog itself (HiGHS) stays in Python: the LP has degenerate optima and only the same solver
 // on the same input reproduces the reference's segments - which is why every number handed to it is formed in
@@ -17,7 +18,9 @@
 #include <cstdint>
 #include <cstring>
 #include <limits>
+#include <algorithm>
 #include <unordered_map>
+#include <utility>
 #include <vector>
 
 #include "../../include/describealign_b200.h"
@@ -296,6 +299,94 @@ int dab_host_lp_assemble(const double *x, const double *y, int64_t n, double *co
   *nnz_out = p;
   for (int64_t k = 0; k + 1 < n; ++k) b[k] = dy[k] / dx[k];
   for (int64_t k = n - 1; k < 3 * n - 4; ++k) b[k] = 0.0;
+  return DAB_OK;
+}
+
+// Grouping of the fitted path's points into co-linear clusters (describealign.py:861-884): every point votes, with
+// the slope on either side of it, for the line (slope rounded to 6 decimals, integer offset) through it; the largest
+// groups absorb every other group whose first and last point lie within 3 frames of their line; clusters are sorted,
+// and those spanning more than 10 frames with more than 5 points are kept.  x, y: the n fit points with the fit error
+// removed from y; slopes: the n + 1 slopes (first and last repeated).  Output: the kept clusters' points,
+// concatenated (room for 2n each), and cluster_start[n_clusters + 1] (room for 2n + 1).  The per-cluster line fit
+// (np.linalg.lstsq) stays with the caller.
+int dab_host_line_clusters(const double *x, const double *y, const double *slopes, int64_t n, double *out_x, double *out_y,
+                           int64_t *cluster_start, int64_t *n_clusters) {
+  if (!x || !y || !slopes || !out_x || !out_y || !cluster_start || !n_clusters || n < 1) return DAB_E_ARG;
+  struct Group {
+    double slope;
+    int64_t offset;
+    std::vector<std::pair<double, double>> pts;
+    bool alive = true;
+  };
+  struct Key {
+    uint64_t s;
+    int64_t o;
+    bool operator==(const Key &k) const { return s == k.s && o == k.o; }
+  };
+  struct KeyHash {
+    size_t operator()(const Key &k) const { return (size_t)(k.s * 0x9e3779b97f4a7c15ull) ^ (size_t)(k.o * 0xc2b2ae3d27d4eb4full); }
+  };
+  std::vector<Group> groups;
+  std::unordered_map<Key, size_t, KeyHash> index;
+  for (int64_t k = 0; k < n; ++k) {
+    for (int side = 0; side < 2; ++side) {
+      const double slope = slopes[k + side];
+      if (slope < .1 || slope > 10) continue;
+      // round(np.float64, 6) = rint(v * 1e6) / 1e6; round(np.float64, 0) = rint(v)
+      double ks = std::nearbyint(slope * 1e6) / 1e6;
+      if (ks == 0.0) ks = 0.0;                                       // -0.0 and 0.0 are one dict key
+      const double off = std::nearbyint(y[k] - slope * x[k]);
+      if (!(std::fabs(off) < 9e18)) return DAB_E_ARG;                // int(nan) / int(inf) raise in the reference
+      Key key;
+      std::memcpy(&key.s, &ks, sizeof(double));
+      key.o = (int64_t)off;
+      auto it = index.find(key);
+      size_t g;
+      if (it == index.end()) {
+        g = groups.size();
+        index.emplace(key, g);
+        groups.emplace_back();
+        groups[g].slope = ks;
+        groups[g].offset = key.o;
+      } else {
+        g = it->second;
+      }
+      groups[g].pts.emplace_back(x[k], y[k]);
+    }
+  }
+  // largest first, ties in order of first appearance (sizes as they are now)
+  std::vector<size_t> order(groups.size());
+  for (size_t g = 0; g < groups.size(); ++g) order[g] = g;
+  std::vector<size_t> size0(groups.size());
+  for (size_t g = 0; g < groups.size(); ++g) size0[g] = groups[g].pts.size();
+  std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return size0[a] > size0[b]; });
+  std::vector<size_t> seeds;
+  for (size_t g : order) {
+    if (!groups[g].alive) continue;
+    groups[g].alive = false;
+    const double slope = groups[g].slope;
+    const double offset = (double)groups[g].offset;
+    for (size_t h = 0; h < groups.size(); ++h) {
+      if (!groups[h].alive) continue;
+      const auto &first = groups[h].pts.front();
+      const auto &last = groups[h].pts.back();
+      if (std::fabs(first.second - (first.first * slope + offset)) < 3 && std::fabs(last.second - (last.first * slope + offset)) < 3) {
+        groups[g].pts.insert(groups[g].pts.end(), groups[h].pts.begin(), groups[h].pts.end());
+        groups[h].alive = false;
+      }
+    }
+    seeds.push_back(g);
+  }
+  int64_t at = 0, nc = 0;
+  cluster_start[0] = 0;
+  for (size_t g : seeds) {
+    auto &c = groups[g].pts;
+    std::sort(c.begin(), c.end());
+    if (!(std::fabs(c.front().first - c.back().first) > 10 && c.size() > 5)) continue;
+    for (const auto &p : c) { out_x[at] = p.first; out_y[at] = p.second; ++at; }
+    cluster_start[++nc] = at;
+  }
+  *n_clusters = nc;
   return DAB_OK;
 }
 

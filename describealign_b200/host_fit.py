@@ -13,10 +13,11 @@ the same dtype and order, because the LP has degenerate optima and anything else
 reproduce the reference's segments.  Written from the functional description in
 SURVEY.md appendix A.6/A.7, not from the reference's source text.
 
-Native host stage: the continuity error, the path compression and the assembly
-of the LP are plain array arithmetic and run in C++ inside the library (csrc/host_stage.cpp,
-`dab_host_*`), restating numpy's pairwise sums and OpenBLAS' ddot order; `continuity_error`,
-`compress_path` and `_lp_problem` below call them.  The numpy versions stay as `*_numpy`: they are
+Native host stage: the continuity error, the path compression, the assembly
+of the LP and the grouping of its solution into line clusters run in C++ inside the library
+(csrc/host_stage.cpp, `dab_host_*`), restating numpy's pairwise sums, OpenBLAS' ddot order and
+numpy's scalar rounding; `continuity_error`, `compress_path`, `_lp_problem` and `line_clusters`
+below call them.  The numpy versions stay as `*_numpy`: they are
 what the native code is tested against, bit for bit (tests/test_host_native.py), next to the
 reference's own intermediate values in tests/golden/.  `np.std`, `np.linalg.lstsq` (LAPACK) and
 `scipy.optimize.linprog` (HiGHS) stay library calls.
@@ -318,7 +319,31 @@ def rate_change_fit(x, y, window=None, linprog=None) -> RateFit:
 
 def line_clusters(fit: RateFit):
     """Group the smooth path's points into co-linear clusters and fit a line to each
-    (describealign.py:861-893).  Returns a list of (x array, offset, slope)."""
+    (describealign.py:861-893).  Returns a list of (x array, offset, slope).  The grouping is native
+    (dab_host_line_clusters); the line fit per cluster is the reference's np.linalg.lstsq call."""
+    import ctypes
+    n = len(fit.x)
+    x = np.ascontiguousarray(fit.x, dtype=np.float64)
+    y = np.ascontiguousarray(fit.y - fit.fit_err, dtype=np.float64)
+    slopes = np.ascontiguousarray(np.hstack((fit.slopes[:1], fit.slopes, fit.slopes[-1:])), dtype=np.float64)
+    if n < 1 or len(slopes) != n + 1 or not np.all(np.isfinite(slopes)):
+        return line_clusters_numpy(fit)
+    ox, oy = np.empty(2 * n, dtype=np.float64), np.empty(2 * n, dtype=np.float64)
+    start = np.empty(2 * n + 1, dtype=np.int64)
+    count = ctypes.c_int64(0)
+    rc = _native().dab_host_line_clusters(_ptr(x), _ptr(y), _ptr(slopes), n, _ptr(ox), _ptr(oy), _ptr(start), ctypes.byref(count))
+    if rc != 0:
+        return line_clusters_numpy(fit)
+    out = []
+    for c in range(count.value):
+        cx, cy = ox[start[c]:start[c + 1]].copy(), oy[start[c]:start[c + 1]].copy()
+        sol = np.linalg.lstsq(np.hstack((np.ones((len(cx), 1)), cx[:, None])), cy, rcond=None)[0]
+        out.append((cx, sol[0], sol[1]))
+    return out
+
+
+def line_clusters_numpy(fit: RateFit):
+    """The Python statement of line_clusters (describealign.py:861-893): checker of the native grouping."""
     smooth = list(zip(fit.x, fit.y - fit.fit_err))
     slopes = np.hstack((fit.slopes[:1], fit.slopes, fit.slopes[-1:]))
     groups = {}

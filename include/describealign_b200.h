@@ -348,6 +348,12 @@ int dab_host_continuity_error_f64(const double *x, const double *y, const int64_
 int dab_host_compress_path(const int64_t *x, const int64_t *y, int64_t n, double *out_x, double *out_y, int64_t *n_out);
 /* cost[12n-9]; A_eq (3n-4 rows x 12n-9 columns) in CSC with sorted row indices: indptr[12n-8], indices / data
  * with room for 24n entries (23n - 21 are written), *nnz = entries written; b_eq[3n-4].  n >= 51. */
+/* Grouping of the fitted path into co-linear clusters (describealign.py:861-884).  x, y: the n fit points with the fit
+ * error removed from y; slopes[n + 1].  out_x / out_y: room for 2n points (a point can vote twice); cluster_start: room
+ * for 2n + 1 entries; cluster c is out_*[cluster_start[c] .. cluster_start[c + 1]).  The line fit per cluster
+ * (np.linalg.lstsq, describealign.py:886-891) stays with the caller. */
+int dab_host_line_clusters(const double *x, const double *y, const double *slopes, int64_t n, double *out_x, double *out_y,
+                           int64_t *cluster_start, int64_t *n_clusters);
 int dab_host_lp_assemble(const double *x, const double *y, int64_t n, double *cost, int32_t *indptr, int32_t *indices,
                          double *data, double *b_eq, int64_t *nnz);
 

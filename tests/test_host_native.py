@@ -91,3 +91,55 @@ def test_native_host_stage_reproduces_the_references_intermediates(golden_align,
     assert _same(cost, g["lp_c"]) and _same(b_eq, g["lp_b"])
     assert np.array_equal(a_eq.indptr, g["lp_indptr"]) and np.array_equal(a_eq.indices, g["lp_indices"])
     assert _same(a_eq.data, g["lp_data"])
+
+
+def _random_fit(rng, n, segments):
+    """A RateFit like the LP's output: piece-wise linear path with a few rate changes and jumps, small fit errors."""
+    x = np.cumsum(rng.choice([1.0, 35.0, 70.0, 70.0, 12.5], size=n)) + 100.0
+    bounds = np.sort(rng.choice(np.arange(5, n - 5), size=segments - 1, replace=False))
+    slope_of = np.ones(n - 1)
+    y = np.empty(n)
+    y[0] = 40.0
+    seg = 0
+    cur = 1.0
+    for k in range(1, n):
+        if seg < len(bounds) and k == bounds[seg]:
+            seg += 1
+            cur = float(rng.choice([1.0, 1.000001, 0.98, 1.04, 0.05, 12.0]))
+            y[k] = y[k - 1] + cur * (x[k] - x[k - 1]) + float(rng.choice([0.0, 400.0, -90.0, 2.4]))
+        else:
+            y[k] = y[k - 1] + cur * (x[k] - x[k - 1])
+        slope_of[k - 1] = cur
+    slopes = slope_of + rng.normal(0, 2e-7, size=n - 1) * (rng.uniform(size=n - 1) < 0.3)
+    fit_err = rng.normal(0, 0.3, size=n) * (rng.uniform(size=n) < 0.2)
+    return host_fit.RateFit(x=x, y=y + fit_err, fit_err=fit_err, slopes=slopes, median_slope=1.0)
+
+
+@pytest.mark.parametrize("seed,n,segments", [(31, 60, 2), (32, 400, 5), (33, 2194, 9), (34, 2194, 40), (35, 7, 1)])
+def test_line_clusters_native_equals_python(seed, n, segments):
+    rng = np.random.default_rng(seed)
+    fit = _random_fit(rng, n, segments)
+    want = host_fit.line_clusters_numpy(fit)
+    got = host_fit.line_clusters(fit)
+    assert len(got) == len(want)
+    for (gx, go, gs), (wx, wo, ws) in zip(got, want):
+        assert _same(gx, wx) and _same(go, wo) and _same(gs, ws)
+
+
+@pytest.mark.parametrize("name", ["pair_a", "pair_warp"])
+def test_line_clusters_native_reproduces_the_references_clusters(golden_align, name):
+    """The LP solution recorded from the reference -> the clusters the reference formed from it."""
+    data, _ = golden_align
+    g = data[name]
+    n = len(g["fit_x"])
+    sol = g["lp_x"]
+    fit_err = sol[:n] - sol[n:2 * n]
+    jumps = sol[8 * n - 4:9 * n - 5] - sol[9 * n - 5:10 * n - 6]
+    fit = host_fit.RateFit(x=g["fit_x"], y=g["fit_y"], fit_err=fit_err, slopes=sol[-1] + jumps / np.diff(g["fit_x"]),
+                           median_slope=sol[-1])
+    assert _same(fit.slopes, g["slopes"])
+    clusters = host_fit.line_clusters(fit)
+    assert len(clusters) == int(g["n_clusters"])
+    for k, (cx, offset, slope) in enumerate(clusters[:3]):
+        if f"cluster{k}_x" in g:
+            assert _same(cx, g[f"cluster{k}_x"]) and _same(np.array([offset, slope]), g[f"cluster{k}_line"])
