@@ -90,20 +90,28 @@ def audio_hours(pairs):
     return sum(v.shape[0] + a.shape[0] for v, a in pairs) / 44100.0 / 3600.0
 
 
+def visible_gpu_ids(world):
+    """What `nvidia-smi -i` must be given to see the GPU of local rank 0 .. world-1: the rank itself, or the rank's
+    entry of CUDA_VISIBLE_DEVICES (index or UUID) when the launcher restricted the devices."""
+    vis = [t.strip() for t in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if t.strip()]
+    return [vis[r] if r < len(vis) else str(r) for r in range(world)]
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region.  ONE process (rank 0's) watches the GPUs
-    of all local ranks - `indices` - so that the other ranks' host cores are left alone."""
-    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    of all local ranks - `ids`, one nvidia-smi identifier (index or UUID) per rank - so that the other ranks' host
+    cores are left alone."""
+    Q = "index,uuid,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
-    def __init__(self, indices, period_ms=200):
-        self.indices = [int(i) for i in (indices if isinstance(indices, (list, tuple)) else [indices])]
+    def __init__(self, ids, period_ms=200):
+        self.ids = [str(i) for i in (ids if isinstance(ids, (list, tuple)) else [ids])]
         self.period_ms = int(period_ms)
         self.proc = None
         self.lines = []
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", ",".join(str(i) for i in self.indices), f"--query-gpu={self.Q}",
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", ",".join(self.ids), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", str(self.period_ms)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
@@ -115,8 +123,14 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def _rank_of(self, index, uuid):
+        for r, ident in enumerate(self.ids):
+            if ident == index or (not ident.isdigit() and uuid.startswith(ident)):
+                return r
+        return None
+
     def stop(self):
-        """Summary over all watched GPUs (lowest median clock, every reason seen) + "per_gpu": {index: summary}."""
+        """Summary over all watched GPUs (lowest median clock, every reason seen) + "per_gpu": {local rank: summary}."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "per_gpu": {}}
         self.proc.terminate()
@@ -129,19 +143,22 @@ class ClockSampler:
         mx = None
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
-            if len(f) < 8:
+            if len(f) < 9:
                 continue
             try:
-                idx = int(f[0]); clk = float(f[1]); mx = float(f[2])
+                clk = float(f[2]); mx = float(f[3])
             except ValueError:
                 continue
-            g = per.setdefault(idx, {"sm": [], "reasons": set()})
+            r = self._rank_of(f[0], f[1])
+            if r is None:
+                continue
+            g = per.setdefault(r, {"sm": [], "reasons": set()})
             g["sm"].append(clk)
             for k, nm in enumerate(names):
-                if f[4 + k].lower().startswith("active"):
+                if f[5 + k].lower().startswith("active"):
                     g["reasons"].add(nm)
-        per_gpu = {i: {"sm_mhz": float(np.median(g["sm"])) if g["sm"] else None, "reasons": sorted(g["reasons"]),
-                       "samples": len(g["sm"])} for i, g in per.items()}
+        per_gpu = {r: {"sm_mhz": float(np.median(g["sm"])) if g["sm"] else None, "reasons": sorted(g["reasons"]),
+                       "samples": len(g["sm"])} for r, g in per.items()}
         meds = [g["sm_mhz"] for g in per_gpu.values() if g["sm_mhz"] is not None]
         return {"sm_mhz": min(meds) if meds else None, "sm_max_mhz": mx,
                 "reasons": sorted({r for g in per_gpu.values() for r in g["reasons"]}),
@@ -459,7 +476,7 @@ def run_long(args, rank, world, local_rank):
         return tot / args.steps, phases, det, out
 
     ctx = api.context()
-    sampler = ClockSampler(list(range(world)))        # rank 0 watches every local rank's GPU (one node)
+    sampler = ClockSampler(visible_gpu_ids(world))    # rank 0 watches every local rank's GPU (one node)
     if rank == 0:
         sampler.start()
     l0 = ctx.launches()
@@ -698,7 +715,7 @@ def run_ours(args, rank, world, local_rank):
 
     # rank 0 samples the clocks of EVERY rank's GPU during the device-resident steps (one nvidia-smi process for the
     # node): the step time is the maximum over ranks, so one power-capped GPU of the box would set it
-    sampler = ClockSampler(list(range(world)))
+    sampler = ClockSampler(visible_gpu_ids(world))
     if rank == 0:
         sampler.start()
     cpu0, wall0 = os.times(), time.perf_counter()
