@@ -135,6 +135,16 @@ def track_features(arr: np.ndarray):
     return feats
 
 
+def remember_features(arr: np.ndarray, feats):
+    """Attach already computed features to a host array (launcher: a stereo track decoded straight to the device whose
+    samples --stretch_audio needs on the host as well), so that the feature functions do not upload it again."""
+    try:
+        _feature_cache.append((weakref.ref(arr), arr.__array_interface__["data"][0], arr.shape, feats))
+        del _feature_cache[:-4]
+    except TypeError:
+        pass
+
+
 def get_energy(arr):
     return track_features(arr)[0]
 

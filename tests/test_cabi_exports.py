@@ -105,6 +105,49 @@ def test_launcher_patches_a_module():
         launcher.patch(broken)
 
 
+def test_launcher_optional_patches(monkeypatch):
+    """replace_aligned_segments is patched where the module has it; parse_audio_from_file only on request, and its
+    replacement hands mono tracks over as DevicePcm and stereo tracks as host arrays with remembered features."""
+    import types
+    import numpy as np
+    from describealign_b200 import api, decode, launcher, stretch
+    fake = types.ModuleType("describealign")
+    for n in ("get_energy", "get_zero_crossings", "get_freq_bands", "align", "replace_aligned_segments", "parse_audio_from_file"):
+        setattr(fake, n, lambda *a, **k: None)
+    fake.get_ffmpeg = lambda: "/opt/ffmpeg"
+    original_parse = fake.parse_audio_from_file
+    launcher.patch(fake)
+    assert fake.replace_aligned_segments is stretch.replace_aligned_segments
+    assert fake.parse_audio_from_file is original_parse          # untouched without decode=True
+    launcher.patch(fake, decode=True)
+    assert fake.parse_audio_from_file is not original_parse and fake._reference_parse_audio_from_file is original_parse
+
+    calls = []
+
+    class FakePcm:
+        def __init__(self, ch):
+            self.ch = ch
+        def wait(self):
+            return self
+        def to_host(self):
+            return np.zeros((self.ch, 8), np.float16)
+        def features(self):
+            return ["e", "z", "b0", "b1", "b2"]
+        def close(self):
+            calls.append("closed")
+
+    def fake_parse(media_file, num_channels=2, ffmpeg="ffmpeg", command=None):
+        calls.append((media_file, num_channels, ffmpeg))
+        return FakePcm(num_channels)
+
+    monkeypatch.setattr(decode, "parse_audio_from_file", fake_parse)
+    mono = fake.parse_audio_from_file("a.mkv", 1)
+    assert isinstance(mono, FakePcm) and calls[-1] == ("a.mkv", 1, "/opt/ffmpeg")
+    stereo = fake.parse_audio_from_file("b.mkv", 2)
+    assert isinstance(stereo, np.ndarray) and stereo.shape == (2, 8) and calls[-1] == "closed"
+    assert api.track_features(stereo) == ["e", "z", "b0", "b1", "b2"]       # from the cache: no upload, no device needed
+
+
 def test_host_wait_mode_is_validated(lib):
     lib.dab_set_host_wait.argtypes = [ctypes.c_int, ctypes.c_int]
     lib.dab_set_host_wait.restype = ctypes.c_int
