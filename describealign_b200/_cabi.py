@@ -30,7 +30,7 @@ EXPORTS = [
     "dab_pair_stage_b_score", "dab_pair_export_quals2", "dab_pair_import_quals2", "dab_pair_dp2",
     "dab_engine_create", "dab_engine_destroy", "dab_engine_submit", "dab_engine_next", "dab_engine_submit_b",
     "dab_engine_release", "dab_engine_slot_error", "dab_engine_slot_pair", "dab_engine_counters",
-    "dab_host_continuity_error", "dab_host_continuity_error_f64", "dab_host_compress_path", "dab_host_lp_assemble", "dab_host_line_clusters",
+    "dab_host_continuity_error", "dab_host_continuity_error_f64", "dab_host_compress_path", "dab_host_lp_assemble", "dab_host_line_clusters", "dab_host_stretch_plan",
     "dab_pcm_reader_open", "dab_pcm_reader_progress", "dab_pcm_reader_wait", "dab_pcm_reader_close", "dab_pcm_reader_copy_to_host", "dab_stretch_best_jumps",
 ]
 
@@ -138,6 +138,7 @@ def load() -> ctypes.CDLL:
     lib.dab_host_compress_path.argtypes = [vp, vp, i64, vp, vp, pl]
     lib.dab_host_lp_assemble.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp, pl]
     lib.dab_host_line_clusters.argtypes = [vp, vp, vp, i64, vp, vp, vp, pl]
+    lib.dab_host_stretch_plan.argtypes = [i64, i64, vp, i32, vp, vp, vp, vp, pl]
     lib.dab_set_host_wait.argtypes = [i32, i32]
     lib.dab_set_host_wait.restype = i32
     lib.dab_create.argtypes = [i32, ctypes.POINTER(vp)]

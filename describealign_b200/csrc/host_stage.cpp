@@ -390,4 +390,77 @@ int dab_host_line_clusters(const double *x, const double *y, const double *slope
   return DAB_OK;
 }
 
+// Drift dynamic programme of the pitch-preserving time stretch and its traceback (describealign.py:320-371; SURVEY.md
+// 8f N3): per 512-sample window and drift (0 .. 3072) the cheapest way to have reached it - no jump, or a jump of one
+// of the candidate distances from two windows back at the loss of that window's best position - then the walk back
+// from the last window.  loc / best: [windows][n_jumps] as dab_stretch_best_jumps returns them.  out_at / out_dist:
+// room for `windows` entries; jumps come out in input order, distances still unsigned (the caller flips the sign
+// for a longer output).  Returns DAB_E_ARG where the reference's own index arithmetic would leave the arrays
+// (absurd stretch ratios): the caller then runs the numpy statement, which raises what the reference raises.
+int dab_host_stretch_plan(int64_t n_in, int64_t n_out, const int32_t *jumps, int32_t n_jumps, const int16_t *loc,
+                          const double *best, int64_t *out_at, int64_t *out_dist, int64_t *count) {
+  if (!jumps || !loc || !best || !out_at || !out_dist || !count || n_jumps < 1) return DAB_E_ARG;
+  constexpr int W = 512, MAXD = 3 * 512, WIDTH = 2 * MAXD + 1;
+  const int64_t total = n_out - n_in;
+  const int64_t nw = n_in / W;
+  if (nw < 2) return DAB_E_ARG;
+  auto floordiv = [](int64_t a, int64_t b) { int64_t q = a / b; if ((a % b != 0) && ((a < 0) != (b < 0))) --q; return q; };
+  auto offset_at = [&](int64_t w) {
+    const int64_t c = w < 0 ? 0 : (w > nw - 1 ? nw - 1 : w);
+    return floordiv(total * c, nw - 1);
+  };
+  auto offset_step = [&](int64_t w) { const int64_t d = offset_at(w) - offset_at(w - 1); return d < 0 ? -d : d; };
+  for (int k = 0; k < n_jumps; ++k)
+    if (jumps[k] < 1 || jumps[k] >= WIDTH) return DAB_E_ARG;
+  const double inf = std::numeric_limits<double>::infinity();
+  std::vector<int16_t> back((size_t)nw * WIDTH);
+  std::vector<double> cum(3 * (size_t)WIDTH, inf), next(WIDTH), losses(n_jumps);
+  cum[1 * WIDTH + MAXD] = 0.0;
+  cum[2 * WIDTH + MAXD] = 0.0;
+  int64_t last_step = 0;
+  for (int64_t w = 0; w < nw; ++w) {
+    const int64_t step = offset_step(w), step2 = step + last_step;
+    if (step2 >= WIDTH) return DAB_E_ARG;
+    for (int k = 0; k < n_jumps; ++k) losses[k] = 1.0 - best[w * n_jumps + k];
+    const double *one = cum.data() + ((w + 2) % 3) * WIDTH;      // (w - 1) mod 3
+    const double *two = cum.data() + ((w + 1) % 3) * WIDTH;      // (w - 2) mod 3
+    int16_t *bk = back.data() + (size_t)w * WIDTH;
+    // row 0: no jump
+    for (int c = 0; c < WIDTH; ++c) {
+      next[c] = c < WIDTH - step ? one[c + step] : inf;
+      bk[c] = 0;
+    }
+    // rows 1..: a jump from two windows back; the first minimum of a column wins (np.argmin)
+    for (int k = 0; k < n_jumps; ++k) {
+      const int64_t jump = jumps[k], cut = step2 - jump;
+      const int64_t lo = jump, hi = WIDTH - (cut > 0 ? cut : 0);
+      const double loss = losses[k];
+      const double *src = two + (step2 - jump);
+      for (int64_t c = lo; c < hi; ++c) {
+        const double v = src[c] + loss;
+        if (v < next[c]) { next[c] = v; bk[c] = (int16_t)(k + 1); }
+      }
+    }
+    std::memcpy(cum.data() + (w % 3) * WIDTH, next.data(), sizeof(double) * WIDTH);
+    last_step = step;
+  }
+  int64_t drift = MAXD, m = 0;
+  bool skip = false;
+  for (int64_t w = nw - 1; w >= 0; --w) {
+    drift += offset_step(w + 1);
+    if (skip) { skip = false; continue; }
+    if (drift < 0 || drift >= WIDTH) return DAB_E_ARG;
+    const int k = (int)back[(size_t)w * WIDTH + drift] - 1;
+    if (k == -1) continue;
+    out_at[m] = w * W + (int64_t)loc[w * n_jumps + k];
+    out_dist[m] = jumps[k];
+    ++m;
+    drift -= jumps[k];
+    skip = true;
+  }
+  for (int64_t a = 0, b = m - 1; a < b; ++a, --b) { std::swap(out_at[a], out_at[b]); std::swap(out_dist[a], out_dist[b]); }
+  *count = m;
+  return DAB_OK;
+}
+
 }  // extern "C"

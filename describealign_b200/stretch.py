@@ -9,8 +9,9 @@ candidate jump distance the position with the largest 512-sample Pearson correla
 cross-faded.  The correlation search is the expensive part - 10 to 482 jump distances times every sample - and is the
 part that runs on the GPU here (`best_jumps`, csrc/stretch.cu): one thread per (piece, jump) reproduces the
 reference's float64 running sums in its order, so locations and losses are bit-identical
-(oracle/stretch_oracle.py is the numpy checker).  The dynamic programme over a few thousand windows and the
-cross-fade assembly are host numpy.
+(oracle/stretch_oracle.py is the numpy checker).  The dynamic programme over (window, drift) and its traceback are
+native host code (dab_host_stretch_plan, csrc/host_stage.cpp; plan_jumps_numpy is its checker); the cross-fade
+assembly is host numpy.
 """
 from __future__ import annotations
 
@@ -60,7 +61,30 @@ def jump_distances(total_offset_samples: int):
 def plan_jumps(num_input_samples: int, num_output_samples: int, jumps, loc, best):
     """Dynamic programme over (window, drift) and its traceback (describealign.py:320-371): where in the input to
     jump, and by how much.  loc / best as returned by best_jumps.  Returns an int array (k, 2) of
-    (input index, signed jump distance)."""
+    (input index, signed jump distance).  Native (dab_host_stretch_plan, csrc/host_stage.cpp); plan_jumps_numpy is its
+    checker and the path for inputs whose index arithmetic leaves the arrays (it then raises what the reference raises)."""
+    from . import _cabi
+    nw = num_input_samples // WINDOW
+    jl = np.ascontiguousarray(list(jumps), dtype=np.int32)
+    loc_c = np.ascontiguousarray(loc, dtype=np.int16)
+    best_c = np.ascontiguousarray(best, dtype=np.float64)
+    if nw < 2 or loc_c.shape != (nw, len(jl)) or best_c.shape != (nw, len(jl)) or np.isnan(best_c).any():
+        return plan_jumps_numpy(num_input_samples, num_output_samples, jumps, loc, best)
+    at, dist = np.empty(nw, dtype=np.int64), np.empty(nw, dtype=np.int64)
+    count = ctypes.c_int64(0)
+    rc = _cabi.load().dab_host_stretch_plan(int(num_input_samples), int(num_output_samples), jl.ctypes.data, len(jl),
+                                            loc_c.ctypes.data, best_c.ctypes.data, at.ctypes.data, dist.ctypes.data,
+                                            ctypes.byref(count))
+    if rc != 0:
+        return plan_jumps_numpy(num_input_samples, num_output_samples, jumps, loc, best)
+    chosen = np.array(list(zip(at[:count.value].tolist(), dist[:count.value].tolist())))
+    if num_output_samples - num_input_samples > 0:
+        chosen[:, 1] *= -1
+    return chosen
+
+
+def plan_jumps_numpy(num_input_samples: int, num_output_samples: int, jumps, loc, best):
+    """The numpy statement of plan_jumps (describealign.py:320-371): checker of the native code."""
     width = MAX_DRIFT * 2 + 1
     total = num_output_samples - num_input_samples
     nw = num_input_samples // WINDOW

@@ -384,6 +384,11 @@ void dab_pcm_reader_close(dab_pcm_reader *reader);
  * correlation, best[n / 512][n_jumps] (float64) = that correlation; bit-identical to the reference's float64 running
  * sums (same pieces, same epsilon, same order).  Host buffers; the copies happen inside the call.
  * --------------------------------------------------------------------------------------------------------- */
+/* The drift dynamic programme over (window, drift) of `stretch` and its traceback (describealign.py:320-371), host code.
+ * loc / best as dab_stretch_best_jumps returns them; out_at / out_dist: room for n_in / 512 entries, *count jumps in input
+ * order with unsigned distances.  DAB_E_ARG where the reference's index arithmetic would leave its arrays. */
+int dab_host_stretch_plan(int64_t n_in, int64_t n_out, const int32_t *jumps, int32_t n_jumps, const int16_t *loc,
+                          const double *best, int64_t *out_at, int64_t *out_dist, int64_t *count);
 int dab_stretch_best_jumps(dab_ctx *ctx, const void *segment_f16, int32_t channels, int64_t n, int32_t negative,
                            const int32_t *jumps, int32_t n_jumps, int16_t *loc, double *best);
 

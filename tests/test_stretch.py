@@ -102,3 +102,25 @@ def test_replace_aligned_segments_on_the_gpu_equals_reference_golden(gpu_ctx, na
     case = _cases()[name]
     got = _run(case, None)
     assert hashlib.sha256(np.ascontiguousarray(got).tobytes()).hexdigest() == case["sha256"]
+
+
+@pytest.mark.parametrize("seed,nw,total,jumps", [(1, 300, 4000, "extended"), (2, 300, -4000, "extended"), (3, 900, 30000, "base"),
+                                                  (4, 900, -41000, "base"), (5, 180, 700, "all"), (6, 180, -333, "all"),
+                                                  (7, 2, 40, "all")])
+def test_native_drift_dp_equals_numpy(seed, nw, total, jumps):
+    """dab_host_stretch_plan (C++) against the numpy statement of describealign.py:320-371 on random correlations."""
+    from describealign_b200 import stretch as st
+    rng = np.random.default_rng(seed)
+    jl = {"base": st.jump_distances(20000), "extended": st.jump_distances(5000), "all": st.jump_distances(500)}[jumps]
+    n_in = nw * 512 + int(rng.integers(0, 512))
+    loc = rng.integers(0, 512, size=(nw, len(jl))).astype(np.int16)
+    best = rng.uniform(-0.2, 1.0, size=(nw, len(jl)))
+    best[rng.uniform(size=best.shape) < 0.02] = -np.inf          # windows without a valid position for a jump
+    try:
+        want = st.plan_jumps_numpy(n_in, n_in + total, jl, loc, best)
+    except IndexError:
+        with pytest.raises(IndexError):
+            st.plan_jumps(n_in, n_in + total, jl, loc, best)
+        return
+    got = st.plan_jumps(n_in, n_in + total, jl, loc, best)
+    assert got.shape == want.shape and np.array_equal(got, want)
