@@ -80,3 +80,41 @@ def test_oracle_equals_reference_on_fresh_pairs(seed, ch, video_s, offset_s, ski
     assert out["path_int_identical"], out                                     # (audio i, cluster) of every path row
     assert out["path_float_max"] < 1e-8 and out["nodes_max"] < 1e-9, out
     assert out["similarity_diff"] < 1e-9 and out["median_slope_equal"], out
+
+
+@pytest.mark.skipif(not _reference_present(), reason="the reference is only mounted in the authoring container")
+@pytest.mark.parametrize("seed,ch,nodes", [
+    (411, 1, ([1.5, 9.0, 17.2, 24.0], [0.0, 7.45, 16.0, 22.3])),
+    (412, 2, ([2.0, 12.6, 20.0], [0.0, 10.0, 17.9])),
+])
+def test_stretch_host_logic_and_oracle_equal_the_reference_live(seed, ch, nodes):
+    """replace_aligned_segments (describealign.py:229-416) of the unmodified reference against the product's host logic
+    (native drift DP, numpy cross-fades) fed by the numpy oracle of the jump search, on pairs that are not in the goldens."""
+    import contextlib
+    import io
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    from describealign_b200 import stretch as st, synth
+    from oracle import ref_loader, stretch_oracle as so
+    da = ref_loader.load_reference()
+    v, a = synth.make_pair(28.0, nodes[0][0], seed=seed, ch=ch)
+    va, aa = synth.as_reference_input(v).copy(), synth.as_reference_input(a).copy()
+    xt, yt = np.array(nodes[0]), np.array(nodes[1])
+
+    def oracle_stretcher(segment, output):
+        n_in, n_out = segment.shape[1], output.shape[1]
+        jumps = st.jump_distances(n_out - n_in)
+        loc, best = so.best_jumps(segment, n_out > n_in, jumps)
+        orig = st.best_jumps
+        st.best_jumps = lambda seg, neg, j: (loc, best)
+        try:
+            st.stretch(segment, output)
+        finally:
+            st.best_jumps = orig
+
+    want, got = va.copy(), va.copy()
+    with contextlib.redirect_stdout(io.StringIO()):
+        da.replace_aligned_segments(want, aa, xt, yt, False)
+        st.replace_aligned_segments(got, aa, xt, yt, False, stretcher=oracle_stretcher)
+    assert int(np.sum(want != va)) > 100000                     # something was replaced
+    assert np.array_equal(want.view(np.uint16), got.view(np.uint16))
